@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE -- CPU oracle: a functional restatement of the RSIS hot path.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` /
+`--impl reference` legs may import this module, and only as the checker / the
+reported CPU baseline.  The product package `rsis_b200` never imports it.
+
+What it restates (fp32, NCHW, state_dict in / tensors out, no nn.Module):
+  * ResNet-101 taps        -- /root/reference/src/modules/vision.py:11-21 on top of
+                              torchvision 0.26.0 `models/resnet.py` (`Bottleneck.forward`,
+                              `ResNet._make_layer`; stride on conv2, eps 1e-5). torchvision is a
+                              third-party dependency that is NOT vendored in /root/reference and is
+                              unpinned there (README.md:16-17); 0.26.0 is what this image ships.
+  * FeatureExtractor       -- /root/reference/src/modules/model.py:56-70
+  * ConvLSTMCell           -- /root/reference/src/modules/clstm.py:19-62
+  * RSIS decoder step      -- /root/reference/src/modules/model.py:122-184 (skip_mode='concat')
+  * test() inference loop  -- /root/reference/src/test.py:16-50
+
+Pinning: the reference holds no golden vectors or tests for this path (SURVEY.md
+section 4), so the oracle is pinned against outputs of the UNMODIFIED reference
+modules executed in the build container (`oracle/make_golden.py` ->
+`tests/golden/*.npz`; checked by `tests/test_oracle_golden.py`).
+
+Every arithmetic primitive can be swapped through `conv=` so the same code also
+serves as a precision emulator (split-bf16 / tf32 operand rounding) for design work.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm2d default, used by torchvision and model.py:50-54
+RESNET101_BLOCKS = (3, 4, 23, 3)
+
+
+def _bn_eval(sd, prefix, x):
+    """Eval-mode BatchNorm2d with running statistics."""
+    return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
+                        sd[prefix + ".weight"], sd[prefix + ".bias"], False, 0.0, BN_EPS)
+
+
+def _bn_train(sd, prefix, x):
+    """Train-mode BatchNorm2d: batch statistics (biased variance), no running-stat update here."""
+    return F.batch_norm(x, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.0, BN_EPS)
+
+
+def bottleneck(sd, p, x, stride, conv=F.conv2d, bn=_bn_eval):
+    """torchvision `Bottleneck.forward`: 1x1 -> 3x3(stride) -> 1x1, BN after each, residual add, ReLU."""
+    identity = x
+    out = F.relu(bn(sd, p + ".bn1", conv(x, sd[p + ".conv1.weight"])))
+    out = F.relu(bn(sd, p + ".bn2", conv(out, sd[p + ".conv2.weight"], stride=stride, padding=1)))
+    out = bn(sd, p + ".bn3", conv(out, sd[p + ".conv3.weight"]))
+    if (p + ".downsample.0.weight") in sd:
+        identity = bn(sd, p + ".downsample.1", conv(x, sd[p + ".downsample.0.weight"], stride=stride))
+    return F.relu(out + identity)
+
+
+def resnet101_taps(sd, x, conv=F.conv2d, bn=_bn_eval, prefix="base."):
+    """vision.py:11-21 -> (x5, x4, x3, x2, x1)."""
+    x = conv(x, sd[prefix + "conv1.weight"], stride=2, padding=3)
+    x1 = F.relu(bn(sd, prefix + "bn1", x))
+    x = F.max_pool2d(x1, kernel_size=3, stride=2, padding=1)
+    taps = []
+    for li, nblk in enumerate(RESNET101_BLOCKS, start=1):
+        for b in range(nblk):
+            stride = 2 if (b == 0 and li > 1) else 1
+            x = bottleneck(sd, f"{prefix}layer{li}.{b}", x, stride, conv, bn)
+        taps.append(x)
+    x2, x3, x4, x5 = taps
+    return x5, x4, x3, x2, x1
+
+
+def feature_extractor(sd, x, conv=F.conv2d, bn=_bn_eval, raw=False):
+    """model.py:56-70 -> (x5_skip, x4_skip, x3_skip, x2_skip, x1_skip); heads are conv+bias+BN, no ReLU."""
+    taps = resnet101_taps(sd, x, conv, bn)
+    if raw:
+        return taps
+    feats = []
+    for n, t in zip("54321", taps):
+        k = sd[f"sk{n}.weight"].shape[-1]
+        y = conv(t, sd[f"sk{n}.weight"], padding=0 if k == 1 else 1) + sd[f"sk{n}.bias"].view(1, -1, 1, 1)
+        feats.append(bn(sd, f"bn{n}", y))
+    return tuple(feats)
+
+
+def convlstm_cell(weight, bias, input_, prev_state, conv=F.conv2d):
+    """clstm.py:19-62. Gate order along Cout is [in | remember | out | cell]; Cin order is [input_ | prev_hidden]."""
+    ch = weight.shape[0] // 4
+    if prev_state is None:  # clstm.py:26-37: zero state materialised
+        z = input_.new_zeros((input_.shape[0], ch) + tuple(input_.shape[2:]))
+        prev_state = (z, z)
+    prev_hidden, prev_cell = prev_state
+    stacked = torch.cat((input_, prev_hidden), 1)
+    pad = 0 if weight.shape[-1] == 1 else 1
+    gates = conv(stacked, weight, padding=pad) + bias.view(1, -1, 1, 1)
+    in_gate, remember_gate, out_gate, cell_gate = gates.chunk(4, 1)
+    in_gate = torch.sigmoid(in_gate)
+    remember_gate = torch.sigmoid(remember_gate)
+    out_gate = torch.sigmoid(out_gate)
+    cell_gate = torch.tanh(cell_gate)
+    cell = remember_gate * prev_cell + in_gate * cell_gate
+    hidden = out_gate * torch.tanh(cell)
+    return [hidden, cell]
+
+
+def upsample_bilinear_ac(x, size):
+    """nn.UpsamplingBilinear2d == bilinear interpolation with align_corners=True (model.py:149,163)."""
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=True)
+
+
+def rsis_step(sd, feats, prev_hidden_list, conv=F.conv2d):
+    """model.py:122-184, dropout 0, skip_mode 'concat'.
+
+    Returns (out_mask logits [B,1,H,W], class_probs [B,C], stop logits [B,1], hidden_list).
+    The reference squeezes side features (model.py:169) which drops the batch dim at B=1; this
+    restatement keeps [B,...] and the caller squeezes when it needs the reference's B=1 shapes.
+    """
+    clstm_in = feats[0]
+    skips = feats[1:]
+    side = []
+    hidden_list = []
+    for i in range(len(skips) + 1):
+        st = convlstm_cell(sd[f"clstm_list.{i}.Gates.weight"], sd[f"clstm_list.{i}.Gates.bias"], clstm_in,
+                           None if prev_hidden_list is None else prev_hidden_list[i], conv)
+        hidden_list.append(st)
+        hidden = st[0]
+        side.append(hidden.amax(dim=(2, 3)))  # nn.MaxPool2d(full spatial size), model.py:143
+        if i < len(skips):
+            skip = skips[i]
+            hidden = upsample_bilinear_ac(hidden, tuple(skip.shape[-2:]))
+            clstm_in = torch.cat([hidden, skip], 1)
+        else:
+            clstm_in = upsample_bilinear_ac(hidden, (hidden.shape[-2] * 2, hidden.shape[-1] * 2))
+    k = sd["conv_out.weight"].shape[-1]
+    out_mask = conv(clstm_in, sd["conv_out.weight"], padding=0 if k == 1 else 1) + sd["conv_out.bias"].view(1, -1, 1, 1)
+    side_feats = torch.cat(side, 1)  # [B, 248]
+    class_probs = torch.softmax(F.linear(side_feats, sd["fc_class.weight"], sd["fc_class.bias"]), dim=1)
+    stop = F.linear(side_feats, sd["fc_stop.weight"], sd["fc_stop.bias"])
+    return out_mask, class_probs, stop, hidden_list
+
+
+def test_loop(enc_sd, dec_sd, x, T, conv=F.conv2d):
+    """test.py:16-50: encoder once, T decoder steps, sigmoid on masks and stops.
+
+    Returns (masks [B,T,H,W], classes [B,T,C], stops [B,T,1]).
+    """
+    with torch.no_grad():
+        feats = feature_extractor(enc_sd, x, conv)
+        hidden = None
+        masks, classes, stops = [], [], []
+        for _ in range(T):
+            m, c, s, hidden = rsis_step(dec_sd, feats, hidden, conv)
+            # test.py:39-40 upsamples to x's size; identity when sizes already match
+            if tuple(m.shape[-2:]) != tuple(x.shape[-2:]):
+                m = upsample_bilinear_ac(m, tuple(x.shape[-2:]))
+            masks.append(m)
+            classes.append(c)
+            stops.append(s)
+        masks = torch.cat(masks, 1)
+        classes = torch.stack(classes, 1)
+        stops = torch.stack(stops, 1)
+        return torch.sigmoid(masks), classes, torch.sigmoid(stops)
+
+
+# ----------------------------------------------------------------------------------------------
+# precision emulators (design aids; not part of any parity claim)
+# ----------------------------------------------------------------------------------------------
+def split_bf16(t):
+    hi = t.to(torch.bfloat16).to(torch.float32)
+    lo = (t - hi).to(torch.bfloat16).to(torch.float32)
+    return hi, lo
+
+
+def conv_bf16x3(x, w, **kw):
+    """a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with bf16 operands and fp32 accumulation."""
+    xh, xl = split_bf16(x)
+    wh, wl = split_bf16(w)
+    return F.conv2d(xh, wh, **kw) + F.conv2d(xh, wl, **kw) + F.conv2d(xl, wh, **kw)
+
+
+def conv_bf16(x, w, **kw):
+    return F.conv2d(split_bf16(x)[0], split_bf16(w)[0], **kw)
+
+
+def _tf32_trunc(t):
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def conv_tf32_trunc(x, w, **kw):
+    return F.conv2d(_tf32_trunc(x.contiguous()), _tf32_trunc(w.contiguous()), **kw)
