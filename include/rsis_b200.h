@@ -1,0 +1,148 @@
+/*
+ * rsis_b200 -- C ABI of the B200-native (sm_100a) RSIS hot path.
+ *
+ * The reference (imatge-upc/rsis) has no FFI/plugin layer: its hot path is a set of Python
+ * nn.Modules (`src/modules/{vision,model,clstm}.py`) that dispatch to torch.nn primitives.
+ * This header is therefore the boundary *this* repo defines: one entry point per primitive
+ * group the reference invokes, each citing the reference call site it replaces.  The Python
+ * package `rsis_b200` binds it with ctypes and re-exposes the reference's own module surface
+ * (`FeatureExtractor`, `RSIS`, `ConvLSTMCell`, `test()`).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller
+ *     (PyTorch's caching allocator); the library never allocates or frees tensor memory;
+ *   - every call is asynchronous on the `stream` passed in (a cudaStream_t), performs no
+ *     host synchronisation and is safe under CUDA-graph capture;
+ *   - return value: RSIS_OK (0) or a negative rsis_status; `rsis_strerror` describes it.
+ *     Nothing throws or aborts across the ABI;
+ *   - activations are NHWC ("channels last").  Two element formats exist:
+ *       RSIS_FMT_F32         float32, [N][H][W][C]
+ *       RSIS_FMT_SPLIT_BF16  two bfloat16 planes hi|lo, [2][N][H][W][C], value = hi + lo
+ *                            (the operand format of the split-precision tcgen05 convolutions:
+ *                            a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate);
+ *   - re-entrant; the only process-wide state is an init-once table of function attributes.
+ */
+#ifndef RSIS_B200_H_
+#define RSIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSIS_ABI_VERSION 1
+
+typedef void* rsis_stream_t; /* cudaStream_t */
+
+typedef enum rsis_status {
+  RSIS_OK = 0,
+  RSIS_ERR_BAD_ARG = -1,     /* null pointer, negative size, inconsistent shapes */
+  RSIS_ERR_UNSUPPORTED = -2, /* shape / format combination this build does not implement */
+  RSIS_ERR_CUDA = -3,        /* a CUDA runtime call or kernel launch failed (see rsis_last_cuda_error) */
+  RSIS_ERR_ARCH = -4,        /* current device is not sm_100 (B200) */
+  RSIS_ERR_ALIGN = -5        /* pointer not aligned as the kernel requires (16 B) */
+} rsis_status;
+
+enum { RSIS_FMT_F32 = 0, RSIS_FMT_SPLIT_BF16 = 1 };
+enum { RSIS_IMPL_AUTO = 0, RSIS_IMPL_SIMT = 1, RSIS_IMPL_TCGEN05 = 2 };
+
+/* NHWC activation view. For RSIS_FMT_SPLIT_BF16 `data` points at the hi plane; lo = hi + n*h*w*c elements. */
+typedef struct rsis_tensor {
+  void* data;
+  int32_t fmt;
+  int32_t n, h, w, c;
+} rsis_tensor;
+
+/* Packed convolution weights + folded per-channel affine (bias and eval-mode BatchNorm):
+ *   y[co] = acc[co] * scale[co] + shift[co]
+ * produced by rsis_conv_pack from the reference's OIHW float32 parameters. */
+typedef struct rsis_conv_weights {
+  const float* w_kc;  /* SIMT pack: [KH*KW*Cin][cout_pad] float32, cout_pad = ceil(Cout/64)*64, zero padded */
+  const void* w_umma; /* tcgen05 pack: [2 planes hi|lo][cout_pad16][k_pad] bfloat16, K-major; may be NULL */
+  const float* scale; /* [cout_pad] */
+  const float* shift; /* [cout_pad] */
+  int32_t cout, cin, kh, kw;
+  int32_t gate_interleaved; /* 1: output channel order is (hidden channel, gate) -- ConvLSTM packs */
+} rsis_conv_weights;
+
+/* ---- library -------------------------------------------------------------------------------------------- */
+int rsis_abi_version(void);
+const char* rsis_strerror(int status);
+const char* rsis_last_cuda_error(void); /* text of the last CUDA error seen by this thread ("" if none) */
+int rsis_device_check(void);            /* RSIS_OK iff the current device is compute capability 10.x */
+int rsis_has_tcgen05(void);             /* 1 iff this build carries the tcgen05/TMA convolution kernels */
+
+/* ---- weight packing (once per load_state_dict / optimiser step) ---------------------------------------- */
+/* Sizes, in bytes, of the packed buffers for one convolution. */
+size_t rsis_conv_pack_bytes_simt(int cout, int cin, int kh, int kw);
+size_t rsis_conv_pack_bytes_affine(int cout); /* one of scale / shift */
+/* Folds nn.Conv2d(bias) [+ nn.BatchNorm2d eval statistics] into (packed weights, scale, shift).
+ * Replaces the parameter handling of nn.Conv2d/nn.BatchNorm2d at model.py:43-54, clstm.py:17 and of
+ * torchvision's Bottleneck.  bias / bn_* may be NULL (no bias / no BatchNorm); w_kc may be NULL (affine only).
+ * gate_interleave != 0 reorders output channels from the reference's [in|remember|out|cell] blocks (clstm.py:47)
+ * to (channel, gate) so one thread owns the four gates of a hidden channel. */
+int rsis_conv_pack(const float* w_oihw, const float* bias, const float* bn_weight, const float* bn_bias,
+                   const float* bn_mean, const float* bn_var, float bn_eps, int cout, int cin, int kh, int kw,
+                   int gate_interleave, float* w_kc, float* scale, float* shift, rsis_stream_t stream);
+/* tcgen05 pack.  K is laid out [tap][source][64-channel chunk] (each chunk zero padded to 64) to line up with the
+ * activation TMA boxes of the n_src inputs (channel counts src_c[0..n_src)), rows are output channels padded to a
+ * multiple of 16; two bf16 planes hi|lo. */
+int rsis_conv_umma_kpad(int kh, int kw, int n_src, const int32_t* src_c);
+int rsis_conv_umma_coutpad(int cout);
+size_t rsis_conv_pack_bytes_umma(int cout, int kh, int kw, int n_src, const int32_t* src_c);
+int rsis_conv_pack_umma(const float* w_oihw, int cout, int cin, int kh, int kw, int n_src, const int32_t* src_c,
+                        int gate_interleave, void* w_umma, rsis_stream_t stream);
+
+/* ---- layout / format plumbing ---------------------------------------------------------------------------- */
+/* float32 NCHW (the reference's layout, e.g. the image batch of test.py:35) -> NHWC tensor (either format). */
+int rsis_nchw_to_nhwc(const float* src_nchw, const rsis_tensor* dst, rsis_stream_t stream);
+/* NHWC tensor -> NHWC tensor of the other element format (same shape). */
+int rsis_convert(const rsis_tensor* src, const rsis_tensor* dst, rsis_stream_t stream);
+
+/* ---- encoder primitives ----------------------------------------------------------------------------------- */
+/* conv (+folded BN/bias) (+residual) (+ReLU).  Replaces nn.Conv2d + nn.BatchNorm2d (+ReLU, + `out += identity`)
+ * of vision.py:12-19 / torchvision Bottleneck.forward and the skip heads model.py:59-63.
+ * `srcs` are concatenated along C (n_src = 1 for plain convs).  y2 (optional) receives a second copy of the
+ * result in another element format (e.g. float32 for the API-visible feature + split-bf16 for the decoder). */
+int rsis_conv2d(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
+                const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, int impl,
+                rsis_stream_t stream);
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of vision.py:15. */
+int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
+
+/* ---- decoder primitives ----------------------------------------------------------------------------------- */
+/* One fused ConvLSTM cell step (clstm.py:19-62): gates = conv3x3(cat(srcs)) + bias; i,f,o = sigmoid, g = tanh;
+ * c = f*c_prev + i*g; h = o*tanh(c).  The four gate planes never reach HBM.
+ *   srcs      inputs concatenated along C in the reference's order [input_ ... | prev_hidden]; prev_hidden may
+ *             be omitted (n_src excludes it) when the state is None (clstm.py:26-37: zeros) -- then c_prev=NULL
+ *   w         packed with gate_interleave=1
+ *   c_prev    float32 NHWC [N,H,W,Ch] or NULL (zero state)
+ *   h_out     float32 NHWC; h_split (optional) the same values as split-bf16 for the next consumer
+ *   c_out     float32 NHWC
+ *   side_max  optional: per-(image, channel) running max of h, as order-preserving uint32 keys, at
+ *             side_max[n*side_stride + side_offset + ch] -- the global nn.MaxPool2d of model.py:143.
+ *             Must be zero-filled before the step (key 0 sorts below every float). */
+int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
+                       const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
+                       uint32_t* side_max, int side_stride, int side_offset, int impl, rsis_stream_t stream);
+/* nn.UpsamplingBilinear2d(size=(y.h, y.w)) == bilinear, align_corners=True (model.py:149-150,163-164). */
+int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
+/* conv_out (model.py:167): ksize x ksize (1 or 3), Cin -> 1, on an NHWC float32 input; writes logits [N,H,W] float32 (when
+ * logits != NULL) and, when prob_out != NULL, sigmoid(logit) at prob_out[n*prob_stride_n + pixel] (the stacking + sigmoid of test.py:46,50). */
+int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias, int ksize, float* logits,
+                   float* prob_out, int64_t prob_stride_n, rsis_stream_t stream);
+/* fc_class + Softmax + fc_stop on the side features (model.py:169-182).  side_max holds the uint32 keys written by
+ * rsis_convlstm_cell; feat_out (optional) receives the decoded float features [N, F].  Outputs: class_probs [N,C]
+ * written at class_probs[n*class_stride + c], stop logit at stop_logit[n*stop_stride], and optional sigmoid(stop)
+ * at stop_prob[n*stop_stride] (test.py:50). */
+int rsis_class_stop_heads(const uint32_t* side_max, int n, int f, const float* w_class, const float* b_class,
+                          int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
+                          float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
+                          int64_t stop_stride, rsis_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSIS_B200_H_ */

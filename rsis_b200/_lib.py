@@ -1,0 +1,161 @@
+"""ctypes binding of the C ABI declared in include/rsis_b200.h.
+
+The CUDA library is the product: if it is missing or fails to load this module raises -- there is no
+PyTorch/CPU fallback for any primitive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+FMT_F32 = 0
+FMT_SPLIT_BF16 = 1
+IMPL_AUTO = 0
+IMPL_SIMT = 1
+IMPL_TCGEN05 = 2
+
+
+class Tensor(C.Structure):
+    """`rsis_tensor`: NHWC activation view."""
+    _fields_ = [("data", C.c_void_p), ("fmt", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c", C.c_int32)]
+
+
+class ConvWeights(C.Structure):
+    """`rsis_conv_weights`."""
+    _fields_ = [("w_kc", C.c_void_p), ("w_umma", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("gate_interleaved", C.c_int32)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_TP = C.POINTER(Tensor)
+_WP = C.POINTER(ConvWeights)
+
+# name -> (restype, argtypes); must list every symbol include/rsis_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "rsis_abi_version": (_I, []),
+    "rsis_strerror": (C.c_char_p, [_I]),
+    "rsis_last_cuda_error": (C.c_char_p, []),
+    "rsis_device_check": (_I, []),
+    "rsis_has_tcgen05": (_I, []),
+    "rsis_conv_pack_bytes_simt": (C.c_size_t, [_I, _I, _I, _I]),
+    "rsis_conv_pack_bytes_affine": (C.c_size_t, [_I]),
+    "rsis_conv_pack": (_I, [_P, _P, _P, _P, _P, _P, C.c_float, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "rsis_conv_umma_kpad": (_I, [_I, _I, _I, C.POINTER(C.c_int32)]),
+    "rsis_conv_umma_coutpad": (_I, [_I]),
+    "rsis_conv_pack_bytes_umma": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(C.c_int32)]),
+    "rsis_conv_pack_umma": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _P, _P]),
+    "rsis_nchw_to_nhwc": (_I, [_P, _TP, _P]),
+    "rsis_convert": (_I, [_TP, _TP, _P]),
+    "rsis_conv2d": (_I, [_TP, _I, _WP, _TP, _TP, _TP, _I, _I, _I, _I, _P]),
+    "rsis_maxpool3x3s2": (_I, [_TP, _TP, _P]),
+    "rsis_convlstm_cell": (_I, [_TP, _I, _WP, _P, _TP, _TP, _TP, _P, _I, _I, _I, _P]),
+    "rsis_upsample_bilinear": (_I, [_TP, _TP, _P]),
+    "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),
+    "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Loads librsis_b200.so (building it with nvcc when absent). Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        _build.build()
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:  # pragma: no cover
+        raise RuntimeError(f"rsis_b200: cannot load the CUDA library {path}: {e}. There is no CPU fallback; "
+                           f"build it with `python -m rsis_b200.build`.") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rsis_abi_version() != 1:
+        raise RuntimeError("rsis_b200: ABI version mismatch between the Python package and librsis_b200.so")
+    _lib = lib
+    return lib
+
+
+_launches = 0
+
+
+def count_launch(n: int = 1):
+    """Book-keeping for bench.py's `gpu_launches`: every ABI call that enqueues kernels reports how many."""
+    global _launches
+    _launches += n
+
+
+def check(status: int, what: str):
+    if status != 0:
+        lib = load()
+        msg = lib.rsis_strerror(status).decode()
+        cuda = lib.rsis_last_cuda_error().decode()
+        raise RuntimeError(f"rsis_b200.{what} failed: {msg}" + (f" [{cuda}]" if status == -3 and cuda else ""))
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Act:
+    """An NHWC activation held in a torch tensor: float32 [N,H,W,C] or split-bf16 [2,N,H,W,C] (hi|lo planes)."""
+    __slots__ = ("t", "fmt", "n", "h", "w", "c", "desc", "source_key")
+
+    def __init__(self, t: torch.Tensor, fmt: int):
+        if fmt == FMT_F32:
+            assert t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous()
+            n, h, w, c = t.shape
+        else:
+            assert t.dtype == torch.bfloat16 and t.dim() == 5 and t.shape[0] == 2 and t.is_contiguous()
+            _, n, h, w, c = t.shape
+        self.t, self.fmt, self.n, self.h, self.w, self.c = t, fmt, n, h, w, c
+        self.desc = Tensor(t.data_ptr(), fmt, n, h, w, c)
+        self.source_key = None
+
+    def valid_for(self, src: torch.Tensor) -> bool:
+        """True while `src` (the float32 tensor this operand copy was derived from) is unchanged."""
+        return self.source_key == (src.data_ptr(), src._version, tuple(src.shape))
+
+    @staticmethod
+    def empty(n, h, w, c, fmt, device) -> "Act":
+        if fmt == FMT_F32:
+            return Act(torch.empty((n, h, w, c), dtype=torch.float32, device=device), fmt)
+        return Act(torch.empty((2, n, h, w, c), dtype=torch.bfloat16, device=device), fmt)
+
+    @staticmethod
+    def from_nchw_view(x: torch.Tensor) -> "Act":
+        """Zero-copy when `x` ([N,C,H,W] float32) is channels_last-contiguous; otherwise one torch copy."""
+        assert x.dim() == 4 and x.dtype == torch.float32
+        xl = x.permute(0, 2, 3, 1)
+        if not xl.is_contiguous():
+            xl = xl.contiguous()
+        return Act(xl, FMT_F32)
+
+    def nchw(self) -> torch.Tensor:
+        """float32 activations as the reference's logical [N,C,H,W] (channels_last memory, zero-copy)."""
+        assert self.fmt == FMT_F32
+        return self.t.permute(0, 3, 1, 2)
+
+    def ref(self):
+        return C.byref(self.desc)
+
+    def float(self) -> torch.Tensor:
+        """[N,H,W,C] float32 values (a torch op; tests/debug only)."""
+        if self.fmt == FMT_F32:
+            return self.t
+        return self.t[0].float() + self.t[1].float()

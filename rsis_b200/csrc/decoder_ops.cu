@@ -1,0 +1,259 @@
+// HBM-streaming primitives around the convolutions: max-pool, align-corners bilinear upsampling, the 1-channel
+// mask head and the class/stop heads.  All are element-parallel, read NHWC with 16-byte channel vectors and write
+// each output once.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace rsis {
+
+__device__ __forceinline__ void load4(const View& v, size_t idx, float out[4]) {
+  if (v.fmt == RSIS_FMT_F32) {
+    const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.p) + idx);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(v.p);
+    const uint2 h = *reinterpret_cast<const uint2*>(b + idx);
+    const uint2 l = *reinterpret_cast<const uint2*>(b + idx + v.plane);
+    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&h);
+    const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
+  }
+}
+
+__device__ __forceinline__ void store4v(void* p, size_t plane, int fmt, size_t idx, const float v[4]) {
+  if (fmt == RSIS_FMT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(p);
+    *reinterpret_cast<uint2*>(b + idx) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(b + idx + plane) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+
+// nn.MaxPool2d(kernel_size=3, stride=2, padding=1) -- /root/reference/src/modules/vision.py:15
+__global__ void maxpool3x3s2_kernel(View x, void* y, size_t y_plane, int y_fmt, int N, int H, int W, int C, int Ho,
+                                    int Wo) {
+  const int C4 = C >> 2;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    size_t r = i / C4;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = ho * 2 - 1 + dh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) {
+        const int wi = wo * 2 - 1 + dw;
+        if (wi < 0 || wi >= W) continue;
+        float v[4];
+        load4(x, (((size_t)n * H + hi) * W + wi) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], v[j]);
+      }
+    }
+    store4v(y, y_plane, y_fmt, (((size_t)n * Ho + ho) * Wo + wo) * C + c, best);
+  }
+}
+
+// nn.UpsamplingBilinear2d(size) == bilinear with align_corners=True -- /root/reference/src/modules/model.py:149-150,
+// 163-164.  Index arithmetic follows ATen's area_pixel_compute_source_index(align_corners=true): src = scale * dst with
+// scale = (in - 1) / (out - 1) evaluated in float.
+__global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_fmt, int N, int H, int W, int C,
+                                         int Ho, int Wo, float sh, float sw) {
+  const int C4 = C >> 2;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    size_t r = i / C4;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    const float fh = sh * ho, fw = sw * wo;
+    const int h1 = min((int)fh, H - 1), w1 = min((int)fw, W - 1);  // ATen guard_index_and_lambda
+    const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
+    const float h1l = fminf(fmaxf(fh - h1, 0.f), 1.f), h0l = 1.f - h1l;
+    const float w1l = fminf(fmaxf(fw - w1, 0.f), 1.f), w0l = 1.f - w1l;
+    float v00[4], v01[4], v10[4], v11[4], o[4];
+    const size_t base = (((size_t)n * H + h1) * W + w1) * C + c;
+    load4(x, base, v00);
+    load4(x, base + (size_t)w1p * C, v01);
+    load4(x, base + (size_t)h1p * W * C, v10);
+    load4(x, base + (size_t)h1p * W * C + (size_t)w1p * C, v11);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = h0l * (w0l * v00[j] + w1l * v01[j]) + h1l * (w0l * v10[j] + w1l * v11[j]);
+    store4v(y, y_plane, y_fmt, (((size_t)n * Ho + ho) * Wo + wo) * C + c, o);
+  }
+}
+
+// conv_out (model.py:167): k x k conv (k = 1 or 3), Cin -> 1, + bias; optional sigmoid copy (test.py:50).
+// One thread per output pixel; weights staged in shared memory as [tap][c].
+__global__ void mask_head_kernel(const float* __restrict__ x, const float* __restrict__ w_oihw,
+                                 const float* __restrict__ bias, float* __restrict__ logits,
+                                 float* __restrict__ prob_out, long long prob_stride_n, int N, int H, int W, int C,
+                                 int ks) {
+  extern __shared__ float sw[];
+  const int taps = ks * ks;
+  for (int i = threadIdx.x; i < taps * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    sw[i] = w_oihw[c * taps + tap];
+  }
+  __syncthreads();
+  const float b = bias ? bias[0] : 0.f;
+  const int pad = ks / 2;
+  const size_t HW = (size_t)H * W;
+  const size_t total = (size_t)N * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(i % W);
+    const int hq = (int)((i / W) % H);
+    const size_t n = i / HW;
+    float acc = 0.f;
+    for (int kh = 0; kh < ks; ++kh) {
+      const int hi = hq - pad + kh;
+      if (hi < 0 || hi >= H) continue;
+      for (int kw = 0; kw < ks; ++kw) {
+        const int wi = wq - pad + kw;
+        if (wi < 0 || wi >= W) continue;
+        const float* px = x + ((n * H + hi) * W + wi) * C;
+        const float* pw = sw + (kh * ks + kw) * C;
+        for (int c = 0; c < C; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(px + c);
+          acc = fmaf(v.x, pw[c], acc);
+          acc = fmaf(v.y, pw[c + 1], acc);
+          acc = fmaf(v.z, pw[c + 2], acc);
+          acc = fmaf(v.w, pw[c + 3], acc);
+        }
+      }
+    }
+    acc += b;
+    if (logits) logits[i] = acc;
+    if (prob_out) prob_out[n * prob_stride_n + (i - n * HW)] = sigmoidf_acc(acc);
+  }
+}
+
+// fc_class + Softmax + fc_stop on the max-pooled side features (model.py:169-182). One CTA per image.
+__global__ void class_stop_heads_kernel(const uint32_t* __restrict__ side_max, int F, const float* __restrict__ w_class,
+                                        const float* __restrict__ b_class, int num_classes,
+                                        const float* __restrict__ w_stop, const float* __restrict__ b_stop,
+                                        float* __restrict__ feat_out, float* __restrict__ class_probs,
+                                        long long class_stride, float* __restrict__ stop_logit,
+                                        float* __restrict__ stop_prob, long long stop_stride) {
+  extern __shared__ float sm[];
+  float* feat = sm;            // [F]
+  float* logit = sm + F;       // [num_classes + 1]; the last entry is the stop logit
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    const float v = key_to_float(side_max[(size_t)n * F + i]);
+    feat[i] = v;
+    if (feat_out) feat_out[(size_t)n * F + i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o = warp; o <= num_classes; o += nwarps) {
+    const float* wrow = o < num_classes ? w_class + (size_t)o * F : w_stop;
+    float acc = 0.f;
+    for (int i = lane; i < F; i += 32) acc = fmaf(feat[i], wrow[i], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) logit[o] = acc + (o < num_classes ? b_class[o] : b_stop[0]);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int o = lane; o < num_classes; o += 32) mx = fmaxf(mx, logit[o]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    float sum = 0.f;
+    for (int o = lane; o < num_classes; o += 32) sum += expf(logit[o] - mx);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    for (int o = lane; o < num_classes; o += 32) class_probs[(size_t)n * class_stride + o] = expf(logit[o] - mx) / sum;
+    if (lane == 0) {
+      const float s = logit[num_classes];
+      if (stop_logit) stop_logit[(size_t)n * stop_stride] = s;
+      if (stop_prob) stop_prob[(size_t)n * stop_stride] = sigmoidf_acc(s);
+    }
+  }
+}
+
+}  // namespace rsis
+
+using namespace rsis;
+
+static inline int grid_for(size_t total, int block) {
+  size_t b = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+extern "C" {
+
+int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
+  if (!valid_tensor(x) || !valid_tensor(y)) return RSIS_ERR_BAD_ARG;
+  const int Ho = (x->h + 2 - 3) / 2 + 1, Wo = (x->w + 2 - 3) / 2 + 1;
+  if (y->n != x->n || y->c != x->c || y->h != Ho || y->w != Wo) return RSIS_ERR_BAD_ARG;
+  if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
+  if (!aligned16(x->data) || !aligned16(y->data)) return RSIS_ERR_ALIGN;
+  const size_t total = numel(*y) / 4;
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(*x), y->data, numel(*y), y->fmt,
+                                                                            x->n, x->h, x->w, x->c, Ho, Wo);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
+  if (!valid_tensor(x) || !valid_tensor(y) || y->n != x->n || y->c != x->c) return RSIS_ERR_BAD_ARG;
+  if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
+  if (!aligned16(x->data) || !aligned16(y->data)) return RSIS_ERR_ALIGN;
+  const float sh = y->h > 1 ? (float)(x->h - 1) / (float)(y->h - 1) : 0.f;
+  const float sw = y->w > 1 ? (float)(x->w - 1) / (float)(y->w - 1) : 0.f;
+  const size_t total = numel(*y) / 4;
+  upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      make_view(*x), y->data, numel(*y), y->fmt, x->n, x->h, x->w, x->c, y->h, y->w, sh, sw);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias, int ksize, float* logits,
+                   float* prob_out, int64_t prob_stride_n, rsis_stream_t stream) {
+  if (!valid_tensor(x) || !w_oihw || (!logits && !prob_out)) return RSIS_ERR_BAD_ARG;
+  if (x->fmt != RSIS_FMT_F32 || x->c % 4 != 0 || x->c > 256 || (ksize != 1 && ksize != 3)) return RSIS_ERR_UNSUPPORTED;
+  if (!aligned16(x->data)) return RSIS_ERR_ALIGN;
+  const size_t total = (size_t)x->n * x->h * x->w;
+  const size_t smem = (size_t)ksize * ksize * x->c * sizeof(float);
+  mask_head_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(x->data), w_oihw, bias, logits, prob_out, (long long)prob_stride_n, x->n, x->h,
+      x->w, x->c, ksize);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_class_stop_heads(const uint32_t* side_max, int n, int f, const float* w_class, const float* b_class,
+                          int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
+                          float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
+                          int64_t stop_stride, rsis_stream_t stream) {
+  if (!side_max || !w_class || !b_class || !w_stop || !b_stop || !class_probs) return RSIS_ERR_BAD_ARG;
+  if (n < 1 || f < 1 || num_classes < 1) return RSIS_ERR_BAD_ARG;
+  if (f + num_classes + 1 > 10000) return RSIS_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(f + num_classes + 1) * sizeof(float);
+  class_stop_heads_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(side_max, f, w_class, b_class, num_classes, w_stop,
+                                                                 b_stop, feat_out, class_probs,
+                                                                 (long long)class_stride, stop_logit, stop_prob,
+                                                                 (long long)stop_stride);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+}  // extern "C"

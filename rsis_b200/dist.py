@@ -1,0 +1,68 @@
+"""Data-parallel plumbing: the batch shards per image, one process per GPU.
+
+Replaces the reference's single-process `torch.nn.DataParallel` wrap (/root/reference/src/train.py:269-274,
+eval.py:240-242): weights are resident per rank (no per-forward broadcast), the batch is split on dim 0, the hidden
+state stays rank-local for all T steps and inference needs NO collective.  `torch.distributed` (NCCL on the GPU box,
+gloo in CPU tests) is used only for the rendezvous, barriers and the max-over-ranks timing reduction.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of a batch of n images owned by `rank`; sizes differ by at most one, the
+    remainder going to the lowest ranks (the same split `DataParallel.scatter` / `torch.chunk` would make when
+    n % world == 0, which is the reference's only tested case)."""
+    if world < 1 or not (0 <= rank < world) or n < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """Initialises torch.distributed from torchrun's env (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).
+    Returns (rank, local_rank, world). A single process without the env is (0, 0, 1) and no group is created."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """MAX-reduces a scalar (a device-timed duration) over all ranks; identity for a single process."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -1,0 +1,205 @@
+"""FeatureExtractor / RSIS -- counterparts of /root/reference/src/modules/model.py:15-70 and :72-184.
+
+Same constructor arguments (`args` namespace), attribute names (`base`, `sk1..sk5`, `bn1..bn5`, `clstm_list`,
+`conv_out`, `fc_class`, `fc_stop`), state_dict keys/shapes (661 + 16) and return structure as the reference, so
+`train.py` / `eval.py` / `test.py` / `utils/utils.py` can use them unchanged.  The nn.Parameters (OIHW float32)
+stay the source of truth; kernel-ready packed copies are derived caches rebuilt when a parameter changes.
+
+Tensors crossing this boundary are logical NCHW float32 (`.shape == [N,C,H,W]`) stored channels-last, which is the
+layout the kernels use (NHWC) -- returning them is zero-copy.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import Act, PackedConv
+from .clstm import ConvLSTMCell
+from .vision import ResNet101
+
+SKIP_DIMS_IN = {"resnet101": [2048, 1024, 512, 256, 64]}  # utils/utils.py:129-131
+
+
+def get_skip_dims(model_name):
+    if model_name not in SKIP_DIMS_IN:
+        raise Exception("The base model you chose is not supported !")  # model.py:37 (only resnet101 is in scope)
+    return SKIP_DIMS_IN[model_name]
+
+
+class FeatureExtractor(nn.Module):
+    """Returns base network to extract visual features from image (model.py:15-70)."""
+
+    def __init__(self, args):
+        super().__init__()
+        skip_dims_in = get_skip_dims(args.base_model)
+        # The reference loads ImageNet weights from the network here (model.py:30-31); this build has no network
+        # access, so the base starts from torchvision's random initialisation and real weights arrive through
+        # load_state_dict (the reference's own checkpoint path, utils/utils.py:97-111).
+        self.base = ResNet101()
+        self.hidden_size = int(args.hidden_size)
+        self.kernel_size = int(args.kernel_size)
+        self.padding = 0 if self.kernel_size == 1 else 1
+        hs, k, p = self.hidden_size, self.kernel_size, self.padding
+        self.sk5 = nn.Conv2d(skip_dims_in[0], hs, k, padding=p)
+        self.sk4 = nn.Conv2d(skip_dims_in[1], hs, k, padding=p)
+        self.sk3 = nn.Conv2d(skip_dims_in[2], hs // 2, k, padding=p)
+        self.sk2 = nn.Conv2d(skip_dims_in[3], hs // 4, k, padding=p)
+        self.sk1 = nn.Conv2d(skip_dims_in[4], hs // 8, k, padding=p)
+        self.bn5 = nn.BatchNorm2d(hs)
+        self.bn4 = nn.BatchNorm2d(hs)
+        self.bn3 = nn.BatchNorm2d(hs // 2)
+        self.bn2 = nn.BatchNorm2d(hs // 4)
+        self.bn1 = nn.BatchNorm2d(hs // 8)
+        self._packed = None
+        self._packed_key = None
+
+    def _heads(self):
+        return [(self.sk5, self.bn5), (self.sk4, self.bn4), (self.sk3, self.bn3), (self.sk2, self.bn2),
+                (self.sk1, self.bn1)]
+
+    def packed_heads(self, want_umma: bool):
+        tensors = []
+        for sk, bn in self._heads():
+            tensors += [sk.weight, sk.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (tuple((t.data_ptr(), t._version) for t in tensors), want_umma)
+        if self._packed is None or self._packed_key != key:
+            self._packed = [PackedConv(sk.weight, sk.bias, bn, want_umma=want_umma) for sk, bn in self._heads()]
+            self._packed_key = key
+        return self._packed
+
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False):
+        """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each."""
+        impl = ops.default_impl() if impl is None else impl
+        taps = self.base.forward_act(x, impl)
+        if raw:
+            return taps, None
+        if self.training:
+            raise NotImplementedError("rsis_b200: train-mode BatchNorm is not implemented yet; call .eval()")
+        fmt = ops.activation_format(impl)
+        heads = self.packed_heads(want_umma=(fmt == ops.FMT_SPLIT_BF16))
+        feats, feats_op = [], []
+        for tap, pc in zip(taps, heads):
+            if fmt == ops.FMT_F32:
+                y = ops.conv2d([tap], pc, pad=self.padding, out_fmt=ops.FMT_F32, impl=impl)
+                feats.append(y)
+                feats_op.append(y)
+            else:
+                y, y2 = ops.conv2d([tap], pc, pad=self.padding, out_fmt=ops.FMT_F32, out2_fmt=fmt, impl=impl)
+                feats.append(y)
+                feats_op.append(y2)
+        return feats, feats_op
+
+    def forward(self, x, semseg=False, raw=False):
+        if semseg or raw:
+            taps, _ = self.forward_act(x, raw=True)
+            outs = tuple(ops.act_to_nchw(a) for a in taps)
+            return outs[0] if semseg else outs
+        feats, feats_op = self.forward_act(x)
+        outs = []
+        for f, fo in zip(feats, feats_op):
+            t = f.nchw()
+            if fo is not f:
+                ops.attach_operand_copy(t, fo)  # lets the decoder skip re-deriving the split-bf16 copy
+            outs.append(t)
+        return tuple(outs)
+
+
+class RSIS(nn.Module):
+    """The recurrent decoder (model.py:72-184); `skip_mode='concat'` (the reference default, args.py:109)."""
+
+    def __init__(self, args):
+        super().__init__()
+        get_skip_dims(args.base_model)
+        self.hidden_size = int(args.hidden_size)
+        self.num_classes = int(args.num_classes)
+        self.kernel_size = int(args.kernel_size)
+        padding = 0 if self.kernel_size == 1 else 1
+        self.dropout = args.dropout
+        self.dropout_stop = args.dropout_stop
+        self.dropout_cls = args.dropout_cls
+        self.skip_mode = args.skip_mode
+        if self.skip_mode != "concat":
+            raise NotImplementedError("rsis_b200: only skip_mode='concat' (the reference default) is implemented")
+        if self.dropout > 0 or self.dropout_stop > 0 or self.dropout_cls > 0:
+            raise NotImplementedError("rsis_b200: dropout > 0 is not implemented (reference defaults are 0.0)")
+        hs = self.hidden_size
+        skip_dims_out = [hs, hs // 2, hs // 4, hs // 8, hs // 16]
+        self.clstm_list = nn.ModuleList()
+        for i in range(len(skip_dims_out)):
+            clstm_in_dim = hs if i == 0 else skip_dims_out[i - 1] * 2
+            self.clstm_list.append(ConvLSTMCell(args, clstm_in_dim, skip_dims_out[i], self.kernel_size,
+                                                padding=padding))
+        self.conv_out = nn.Conv2d(skip_dims_out[-1], 1, self.kernel_size, padding=padding)
+        self.fc_dim = sum(skip_dims_out)
+        self.fc_class = nn.Linear(self.fc_dim, self.num_classes)
+        self.fc_stop = nn.Linear(self.fc_dim, 1)
+
+    def step_act(self, feats: Sequence[Act], prev, impl: int, mask_logits: torch.Tensor,
+                 class_probs: torch.Tensor, class_stride: int, stop_logit: Optional[torch.Tensor],
+                 stop_stride: int, mask_prob: Optional[torch.Tensor] = None, mask_prob_stride: int = 0,
+                 stop_prob: Optional[torch.Tensor] = None):
+        """One decoder time-step on NHWC activations.
+
+        feats: the five skip features in the kernels' operand format; prev: None or list of (h Act, c tensor).
+        Outputs are written in place into the given buffers.  Returns the new state list [(h_op Act, h f32 Act,
+        c f32 Act)] per level.
+        """
+        fmt = ops.activation_format(impl)
+        n = feats[0].n
+        dev = feats[0].t.device
+        if self.fc_class.in_features != self.fc_dim:
+            raise RuntimeError("fc_class.in_features does not match the decoder's side-feature width")
+        side = torch.zeros((n, self.fc_dim), dtype=torch.int32, device=dev)
+        inputs: List[Act] = [feats[0]]
+        new_state = []
+        off = 0
+        nlev = len(self.clstm_list)
+        for i, cell in enumerate(self.clstm_list):
+            ph = pc = None
+            if prev is not None:
+                ph, pc = prev[i][0], prev[i][2].t
+            h, c, hs = cell.step_act(inputs, ph, pc, side, off, impl)
+            h_op = hs if hs is not None else h
+            new_state.append((h_op, h, c))
+            off += cell.hidden_size
+            if i + 1 < nlev:
+                skip = feats[i + 1]
+                up = ops.upsample_bilinear(h, skip.h, skip.w, fmt)
+                inputs = [up, skip]
+            else:
+                up = ops.upsample_bilinear(h, h.h * 2, h.w * 2, ops.FMT_F32)
+        ops.mask_head(up, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob, mask_prob_stride)
+        ops.class_stop_heads(side, self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight, self.fc_stop.bias,
+                             class_probs, class_stride, stop_logit, stop_prob, stop_stride)
+        return new_state
+
+    def forward(self, skip_feats, prev_hidden_list):
+        impl = ops.default_impl()
+        fmt = ops.activation_format(impl)
+        ops.require_cuda(skip_feats[0], "RSIS")
+        feats = [ops.act_from_nchw(t, fmt) for t in skip_feats]
+        prev = None
+        if prev_hidden_list is not None:
+            prev = []
+            for h_t, c_t in prev_hidden_list:
+                prev.append((ops.act_from_nchw(h_t, fmt), None, ops.act_from_nchw(c_t, ops.FMT_F32)))
+        n = feats[0].n
+        dev = skip_feats[0].device
+        last = feats[-1]
+        out_mask = torch.empty((n, 1, last.h * 2, last.w * 2), dtype=torch.float32, device=dev)
+        class_probs = torch.empty((n, self.num_classes), dtype=torch.float32, device=dev)
+        stop = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        state = self.step_act(feats, prev, impl, out_mask, class_probs, self.num_classes, stop, 1)
+        hidden_list = []
+        for h_op, h, c in state:
+            ht = h.nchw()
+            if h_op is not h:
+                ops.attach_operand_copy(ht, h_op)
+            hidden_list.append([ht, c.nchw()])
+        if n == 1:  # the reference's `.squeeze()` (model.py:169) drops the batch dimension at B=1
+            class_probs = class_probs.view(-1)
+            stop = stop.view(-1)
+        return out_mask, class_probs, stop, hidden_list

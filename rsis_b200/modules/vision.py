@@ -1,0 +1,119 @@
+"""ResNet-101 feature taps -- counterpart of /root/reference/src/modules/vision.py:6-21.
+
+The reference subclasses torchvision's `ResNet(Bottleneck, [3, 4, 23, 3], 1000)` and returns the five taps
+`(x5, x4, x3, x2, x1)`.  Here the module tree only *holds parameters* (same names, shapes and state_dict keys as
+torchvision's, including the never-executed `avgpool`/`fc`); the arithmetic runs through `rsis_b200.ops`
+(conv + folded BatchNorm (+residual) (+ReLU) in one CUDA kernel per convolution, NHWC activations).
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import Act, PackedConv
+
+RESNET101_BLOCKS = (3, 4, 23, 3)
+
+
+class Bottleneck(nn.Module):
+    """Parameter container laid out like torchvision's `Bottleneck` (stride on conv2, expansion 4)."""
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: bool = False):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                            nn.BatchNorm2d(planes * 4))
+        self.stride = stride
+
+    def forward(self, x):  # pragma: no cover - never called; ResNet101.forward_act drives the packed kernels
+        raise RuntimeError("rsis_b200 Bottleneck holds parameters only; call the enclosing ResNet101")
+
+
+class ResNet101(nn.Module):
+    """Returns intermediate features from ResNet-101 (vision.py:6-21): `forward(x) -> (x5, x4, x3, x2, x1)`."""
+
+    def __init__(self):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(64, RESNET101_BLOCKS[0], 1)
+        self.layer2 = self._make_layer(128, RESNET101_BLOCKS[1], 2)
+        self.layer3 = self._make_layer(256, RESNET101_BLOCKS[2], 2)
+        self.layer4 = self._make_layer(512, RESNET101_BLOCKS[3], 2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))  # constructed by torchvision, unused by the reference forward
+        self.fc = nn.Linear(512 * 4, 1000)            # idem; present in the state_dict
+        for m in self.modules():  # torchvision's initialisation
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self._packed = None
+        self._packed_key = None
+
+    def _make_layer(self, planes: int, blocks: int, stride: int) -> nn.Sequential:
+        layers = [Bottleneck(self.inplanes, planes, stride, downsample=(stride != 1 or self.inplanes != planes * 4))]
+        self.inplanes = planes * 4
+        for _ in range(1, blocks):
+            layers.append(Bottleneck(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    # ---- packed-weight cache (derived from the nn.Parameters; rebuilt when they change) ----------------------
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+
+    def packed(self, want_umma: bool):
+        key = (self._weights_key(), want_umma)
+        if self._packed is None or self._packed_key != key:
+            pk = {"stem": PackedConv(self.conv1.weight, None, self.bn1)}
+            for li in range(1, 5):
+                for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                    p = f"layer{li}.{bi}"
+                    pk[p + ".conv1"] = PackedConv(blk.conv1.weight, None, blk.bn1, want_umma=want_umma)
+                    pk[p + ".conv2"] = PackedConv(blk.conv2.weight, None, blk.bn2, want_umma=want_umma)
+                    pk[p + ".conv3"] = PackedConv(blk.conv3.weight, None, blk.bn3, want_umma=want_umma)
+                    if blk.downsample is not None:
+                        pk[p + ".down"] = PackedConv(blk.downsample[0].weight, None, blk.downsample[1],
+                                                     want_umma=want_umma)
+            self._packed, self._packed_key = pk, key
+        return self._packed
+
+    def forward_act(self, x: torch.Tensor, impl: int = ops.IMPL_AUTO) -> List[Act]:
+        """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1]."""
+        ops.require_cuda(x, "ResNet101")
+        if self.training:
+            raise NotImplementedError("rsis_b200: train-mode BatchNorm (batch statistics) is not implemented yet; "
+                                      "call .eval() (the inference path of /root/reference/src/test.py:29-30)")
+        fmt = ops.activation_format(impl)
+        pk = self.packed(want_umma=(fmt == ops.FMT_SPLIT_BF16))
+        xa = ops.act_from_nchw(x, ops.FMT_F32)
+        x1 = ops.conv2d([xa], pk["stem"], stride=2, pad=3, relu=True, out_fmt=fmt, impl=ops.IMPL_SIMT)
+        cur = ops.maxpool3x3s2(x1)
+        taps = []
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                p = f"layer{li}.{bi}"
+                out = ops.conv2d([cur], pk[p + ".conv1"], relu=True, out_fmt=fmt, impl=impl)
+                out = ops.conv2d([out], pk[p + ".conv2"], stride=blk.stride, pad=1, relu=True, out_fmt=fmt, impl=impl)
+                identity = cur
+                if blk.downsample is not None:
+                    identity = ops.conv2d([cur], pk[p + ".down"], stride=blk.stride, out_fmt=fmt, impl=impl)
+                cur = ops.conv2d([out], pk[p + ".conv3"], relu=True, residual=identity, out_fmt=fmt, impl=impl)
+            taps.append(cur)
+        x2, x3, x4, x5 = taps
+        return [x5, x4, x3, x2, x1]
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        return tuple(ops.act_to_nchw(a) for a in self.forward_act(x))

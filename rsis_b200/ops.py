@@ -1,0 +1,226 @@
+"""Thin functional wrappers over the C ABI (include/rsis_b200.h).  torch supplies device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import FMT_F32, FMT_SPLIT_BF16, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, Act, check  # noqa: F401
+
+
+def launch_count() -> int:
+    """Number of CUDA kernels this process has enqueued through the C ABI so far."""
+    return _lib._launches
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"rsis_b200.{what}: tensors must live on a CUDA device (B200); there is no CPU path")
+
+
+_IMPL_NAMES = {"auto": IMPL_AUTO, "simt": IMPL_SIMT, "tcgen05": IMPL_TCGEN05}
+
+
+def default_impl() -> int:
+    """Kernel family used by the nn.Module surface: env RSIS_B200_IMPL = auto (default) | simt | tcgen05."""
+    name = os.environ.get("RSIS_B200_IMPL", "auto").lower()
+    if name not in _IMPL_NAMES:
+        raise RuntimeError(f"RSIS_B200_IMPL must be one of {sorted(_IMPL_NAMES)}, got {name!r}")
+    return _IMPL_NAMES[name]
+
+
+def has_tcgen05() -> bool:
+    return bool(_lib.load().rsis_has_tcgen05())
+
+
+def activation_format(impl: int) -> int:
+    """Element format activations travel in between kernels for a kernel family: float32 for the CUDA-core
+    path, split-bf16 (hi|lo planes) when the tcgen05 convolutions consume them."""
+    if impl == IMPL_SIMT:
+        return FMT_F32
+    if impl == IMPL_TCGEN05 and not has_tcgen05():
+        raise RuntimeError("rsis_b200: this build of librsis_b200.so has no tcgen05 kernels")
+    return FMT_SPLIT_BF16 if has_tcgen05() else FMT_F32
+
+
+def act_from_nchw(t: torch.Tensor, fmt: int) -> "Act":
+    """Logical [N,C,H,W] float32 tensor -> NHWC activation in `fmt` (zero-copy for channels-last float32)."""
+    require_cuda(t, "act_from_nchw")
+    cached = getattr(t, "_rsis_operand", None)
+    if cached is not None and cached.fmt == fmt and cached.valid_for(t):
+        return cached
+    if t.dim() != 4 or t.dtype != torch.float32:
+        raise RuntimeError("rsis_b200: expected a float32 [N,C,H,W] tensor")
+    xl = t.permute(0, 2, 3, 1)
+    a = Act(xl, FMT_F32) if xl.is_contiguous() else nchw_to_nhwc(t, FMT_F32)
+    return a if fmt == FMT_F32 else convert(a, fmt)
+
+
+def act_to_nchw(a: "Act") -> torch.Tensor:
+    """NHWC activation -> logical [N,C,H,W] float32 tensor (channels-last memory; zero-copy for float32)."""
+    return (a if a.fmt == FMT_F32 else convert(a, FMT_F32)).nchw()
+
+
+def attach_operand_copy(t: torch.Tensor, a: "Act"):
+    """Remembers that `a` holds the same values as `t` in the kernels' operand format (derived cache)."""
+    a.source_key = (t.data_ptr(), t._version, tuple(t.shape))
+    t._rsis_operand = a
+
+
+class PackedConv:
+    """Kernel-ready copy of one convolution's parameters: K-major packed weights + folded bias/BatchNorm affine.
+
+    Derived cache only -- the nn.Parameters (OIHW float32, reference layout) stay the source of truth.
+    """
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn=None, gate_interleave=False,
+                 src_channels: Optional[Sequence[int]] = None, want_umma: bool = False):
+        lib = _lib.load()
+        require_cuda(weight, "PackedConv")
+        w = weight.detach().contiguous().float()
+        cout, cin, kh, kw = w.shape
+        dev = w.device
+        self.cout, self.cin, self.kh, self.kw = cout, cin, kh, kw
+        self.gate_interleave = bool(gate_interleave)
+        self.src_channels = list(src_channels) if src_channels is not None else [cin]
+        assert sum(self.src_channels) == cin
+        self.w_kc = torch.empty(lib.rsis_conv_pack_bytes_simt(cout, cin, kh, kw) // 4, dtype=torch.float32, device=dev)
+        na = lib.rsis_conv_pack_bytes_affine(cout) // 4
+        self.scale = torch.empty(na, dtype=torch.float32, device=dev)
+        self.shift = torch.empty(na, dtype=torch.float32, device=dev)
+        b = None if bias is None else bias.detach().contiguous().float()
+        bnp = [None] * 4
+        eps = 0.0
+        if bn is not None:
+            bnp = [bn.weight.detach().contiguous().float(), bn.bias.detach().contiguous().float(),
+                   bn.running_mean.detach().contiguous().float(), bn.running_var.detach().contiguous().float()]
+            eps = float(bn.eps)
+        st = _lib.stream_ptr()
+        check(lib.rsis_conv_pack(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), eps, cout,
+                                 cin, kh, kw, int(self.gate_interleave), _ptr(self.w_kc), _ptr(self.scale),
+                                 _ptr(self.shift), st), "conv_pack")
+        _lib.count_launch(2)
+        self.w_umma = None
+        self.k_pad = 0
+        if want_umma:
+            sc = (C.c_int32 * len(self.src_channels))(*self.src_channels)
+            nbytes = lib.rsis_conv_pack_bytes_umma(cout, kh, kw, len(self.src_channels), sc)
+            self.k_pad = lib.rsis_conv_umma_kpad(kh, kw, len(self.src_channels), sc)
+            self.w_umma = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
+            check(lib.rsis_conv_pack_umma(_ptr(w), cout, cin, kh, kw, len(self.src_channels), sc,
+                                          int(self.gate_interleave), _ptr(self.w_umma), st), "conv_pack_umma")
+        _lib.count_launch(1)
+        self.desc = _lib.ConvWeights(_ptr(self.w_kc), _ptr(self.w_umma), _ptr(self.scale), _ptr(self.shift), cout, cin,
+                                     kh, kw, int(self.gate_interleave))
+
+    def ref(self):
+        return C.byref(self.desc)
+
+
+def _src_array(srcs: Sequence[Act]):
+    arr = (_lib.Tensor * len(srcs))()
+    for i, s in enumerate(srcs):
+        arr[i] = s.desc
+    return arr
+
+
+def conv2d(srcs: Sequence[Act], pc: PackedConv, stride: int = 1, pad: int = 0, relu: bool = False,
+           residual: Optional[Act] = None, out_fmt: int = FMT_F32, out2_fmt: Optional[int] = None,
+           impl: int = IMPL_AUTO, out: Optional[Act] = None):
+    """conv (+folded BN/bias) (+residual) (+ReLU); inputs concatenated along C. Returns y or (y, y2)."""
+    lib = _lib.load()
+    x = srcs[0]
+    ho = (x.h + 2 * pad - pc.kh) // stride + 1
+    wo = (x.w + 2 * pad - pc.kw) // stride + 1
+    dev = x.t.device
+    y = out if out is not None else Act.empty(x.n, ho, wo, pc.cout, out_fmt, dev)
+    y2 = Act.empty(x.n, ho, wo, pc.cout, out2_fmt, dev) if out2_fmt is not None else None
+    check(lib.rsis_conv2d(_src_array(srcs), len(srcs), pc.ref(), residual.ref() if residual is not None else None,
+                          y.ref(), y2.ref() if y2 is not None else None, stride, pad, int(relu), impl,
+                          _lib.stream_ptr()), "conv2d")
+    _lib.count_launch(1)
+    return (y, y2) if y2 is not None else y
+
+
+def maxpool3x3s2(x: Act) -> Act:
+    lib = _lib.load()
+    y = Act.empty(x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c, x.fmt, x.t.device)
+    check(lib.rsis_maxpool3x3s2(x.ref(), y.ref(), _lib.stream_ptr()), "maxpool3x3s2")
+    _lib.count_launch(1)
+    return y
+
+
+def nchw_to_nhwc(x: torch.Tensor, fmt: int = FMT_F32) -> Act:
+    lib = _lib.load()
+    require_cuda(x, "nchw_to_nhwc")
+    x = x.contiguous().float()
+    n, c, h, w = x.shape
+    y = Act.empty(n, h, w, c, fmt, x.device)
+    check(lib.rsis_nchw_to_nhwc(x.data_ptr(), y.ref(), _lib.stream_ptr()), "nchw_to_nhwc")
+    _lib.count_launch(1)
+    return y
+
+
+def convert(x: Act, fmt: int) -> Act:
+    lib = _lib.load()
+    y = Act.empty(x.n, x.h, x.w, x.c, fmt, x.t.device)
+    check(lib.rsis_convert(x.ref(), y.ref(), _lib.stream_ptr()), "convert")
+    _lib.count_launch(1)
+    return y
+
+
+def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
+                  side_offset: int = 0, want_split: bool = False, impl: int = IMPL_AUTO):
+    """One fused ConvLSTM step. `srcs` = [input_ parts..., prev_hidden] (prev_hidden omitted when the state is None).
+
+    Returns (h Act f32, c Act f32, h_split Act or None). side_max: int32/uint32-viewed [N, F] key buffer (zeroed)."""
+    lib = _lib.load()
+    x = srcs[0]
+    ch = pc.cout // 4
+    dev = x.t.device
+    h = Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
+    c = Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
+    hs = Act.empty(x.n, x.h, x.w, ch, FMT_SPLIT_BF16, dev) if want_split else None
+    stride = side_max.shape[1] if side_max is not None else 0
+    check(lib.rsis_convlstm_cell(_src_array(srcs), len(srcs), pc.ref(), _ptr(c_prev), h.ref(), hs.ref() if hs else None,
+                                 c.ref(), _ptr(side_max), stride, side_offset, impl, _lib.stream_ptr()),
+          "convlstm_cell")
+    _lib.count_launch(1)
+    return h, c, hs
+
+
+def upsample_bilinear(x: Act, ho: int, wo: int, fmt: int = FMT_F32) -> Act:
+    lib = _lib.load()
+    y = Act.empty(x.n, ho, wo, x.c, fmt, x.t.device)
+    check(lib.rsis_upsample_bilinear(x.ref(), y.ref(), _lib.stream_ptr()), "upsample_bilinear")
+    _lib.count_launch(1)
+    return y
+
+
+def mask_head(x: Act, weight: torch.Tensor, bias: Optional[torch.Tensor], logits: Optional[torch.Tensor],
+              prob_out: Optional[torch.Tensor] = None, prob_stride_n: int = 0):
+    """conv_out: writes logits [N,H,W] (any tensor with N*H*W contiguous floats) and optional sigmoid copy."""
+    lib = _lib.load()
+    ks = weight.shape[-1]
+    check(lib.rsis_mask_head(x.ref(), weight.data_ptr(), _ptr(bias), ks, _ptr(logits), _ptr(prob_out),
+                             prob_stride_n, _lib.stream_ptr()), "mask_head")
+    _lib.count_launch(1)
+
+
+def class_stop_heads(side_max: torch.Tensor, w_class, b_class, w_stop, b_stop, class_probs: torch.Tensor,
+                     class_stride: int, stop_logit: Optional[torch.Tensor], stop_prob: Optional[torch.Tensor],
+                     stop_stride: int, feat_out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    n, f = side_max.shape
+    check(lib.rsis_class_stop_heads(side_max.data_ptr(), n, f, w_class.data_ptr(), b_class.data_ptr(),
+                                    w_class.shape[0], w_stop.data_ptr(), b_stop.data_ptr(), _ptr(feat_out),
+                                    class_probs.data_ptr(), class_stride, _ptr(stop_logit), _ptr(stop_prob),
+                                    stop_stride, _lib.stream_ptr()), "class_stop_heads")
+    _lib.count_launch(1)
