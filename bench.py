@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the RSIS hot path (ResNet-101 FeatureExtractor -> T ConvLSTM decoder steps -> sigmoid), the
+`test()` loop of /root/reference/src/test.py:16-50, on BASELINE.json configs[1]: batch 8, 256x256, T=10, 21 classes.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores (rank 0)
+
+Prints ONE JSON line.  metric = masks/sec (images x T per second).  A "step" is one full test() pass over one batch
+of synthetic images per rank (weak scaling: every rank owns its own batch of 8; no data-path collective -- SURVEY.md
+section 8e).  `value` is timed with the batch already resident in HBM; `e2e` goes through the public API with HOST
+(pinned) buffers: H2D of the images and D2H of masks/classes/stops inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "masks/sec (images x T) at 256x256 T=10"
+UNIT = "masks/s"
+B, H, W, T, NUM_CLASSES = 8, 256, 256, 10, 21
+WORKLOAD = "BASELINE.json configs[1]: Pascal VOC inference, batch 8 per GPU, 256x256, T=10, ResNet-101 encoder"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d["bf16_tflops_sustained"]), "source": "measured"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# algorithmic work of the fused ConvLSTM cell (stated again in DESIGN.md)
+# --------------------------------------------------------------------------------------------------------------
+def cell_levels(h, w, hidden=128):
+    """(Cin, Ch, H_l, W_l) of the five decoder levels for an h x w input (model.py:90-104)."""
+    out = []
+    for l in range(5):
+        ch = hidden >> l
+        cin = hidden if l == 0 else 4 * ch
+        out.append((cin, ch, (h // 32) << l, (w // 32) << l))
+    return out
+
+
+def cell_alg_bytes(batch, cin, ch, hl, wl, s=4):
+    px = batch * hl * wl
+    return s * (px * (cin + 2 * ch) + px * 2 * ch + 36 * ch * (cin + ch) + 4 * ch)
+
+
+def cell_alg_flops(batch, cin, ch, hl, wl):
+    return 2 * batch * hl * wl * 4 * ch * 9 * (cin + ch)
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): the reported CPU baseline and the `--impl reference` arm
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_time(steps, warmup, batch=B):
+    """Times the oracle's restatement of test() (oracle/rsis_oracle.py:test_loop, same torch CPU primitives as the
+    reference's modules) on all host cores. Returns (seconds per pass, threads)."""
+    from oracle import rsis_oracle as O, synth_weights as sw
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    esd, dsd = sw.encoder_state_dict(1), sw.decoder_state_dict(1, num_classes=NUM_CLASSES)
+    x = sw.synthetic_images(123, batch, H, W)
+    for _ in range(warmup):
+        O.test_loop(esd, dsd, x, T)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.test_loop(esd, dsd, x, T)
+        times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    times, threads = cpu_reference_time(a.steps, a.warmup)
+    total = sum(times)
+    v = B * T * a.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": B, "height": H, "width": W, "T": T, "num_classes": NUM_CLASSES,
+                   "device": "host CPU", "note": "reference CPU path: the same torch.nn CPU primitives the reference's "
+                   "modules call (src/test.py:16-50), driven by oracle/rsis_oracle.py because /root/reference does "
+                   "not exist on the GPU box; one step = one full test() pass over one batch of 8"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{a.steps} full test() passes (B={B}, {H}x{W}, T={T}) after {a.warmup} warm-up"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------
+def time_cells(rsis_b200, dec, feats_op, state, impl, iters=20):
+    """CUDA-event time of the five fused ConvLSTM cell launches of one decoder step (teacher-forced on a real
+    state), per level.  Between iterations a 512 MiB buffer is written to flush the 126 MB L2."""
+    ops = rsis_b200.ops
+    dev = feats_op[0].t.device
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    n = feats_op[0].n
+    side = torch.zeros((n, dec.fc_dim), dtype=torch.int32, device=dev)
+    fmt = ops.activation_format(impl)
+    # inputs of every level, taken from a real step
+    level_inputs = []
+    inputs = [feats_op[0]]
+    for i, cell in enumerate(dec.clstm_list):
+        level_inputs.append(list(inputs))
+        if i + 1 < len(dec.clstm_list):
+            skip = feats_op[i + 1]
+            up = ops.upsample_bilinear(state[i][1], skip.h, skip.w, fmt)
+            inputs = [up, skip]
+    per_level = [[] for _ in dec.clstm_list]
+    for it in range(iters + 3):
+        flush.fill_(it & 0xFF)
+        for i, cell in enumerate(dec.clstm_list):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            cell.step_act(level_inputs[i], state[i][0], state[i][2].t, side, 0, impl)
+            e1.record()
+            if it >= 3:
+                per_level[i].append((e0, e1))
+    torch.cuda.synchronize(dev)
+    return [statistics.mean(a.elapsed_time(b) for a, b in lv) * 1e-3 for lv in per_level]
+
+
+def run_ours(a):
+    import rsis_b200
+    from rsis_b200 import dist as rdist, inference, ops
+    from oracle import synth_weights as sw  # weights/images generator only (deterministic synthetic data)
+    from oracle import ref_shims as rs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference)")
+    rank, local_rank, world = rdist.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world != a.gpus and rank == 0:
+        print(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    impl = ops.default_impl()
+
+    args = rs.make_args(num_classes=NUM_CLASSES, maxseqlen=T)
+    args.hidden_size = int(args.hidden_size)
+    args.use_gpu = True
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1, num_classes=NUM_CLASSES))
+    enc.to(dev).eval()
+    dec.to(dev).eval()
+    # every rank owns its own batch of B images (weak scaling; different images per rank)
+    x_host = sw.synthetic_images(123 + rank, B, H, W).pin_memory()
+    x_dev = x_host.to(dev)
+
+    sess = inference.InferenceSession(args, enc, dec, x_dev.shape, dev, impl)
+    sess.x.copy_(x_dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- value: inputs resident in HBM, K graph replays, per-step CUDA events, L2 flushed between steps ----
+    for i in range(max(a.warmup, 3)):
+        flush.fill_(i)
+        sess.replay()
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    rdist.barrier()
+    torch.cuda.synchronize(dev)
+    evs = []
+    for i in range(a.steps):
+        flush.fill_(i & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sess.replay()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    local_s = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+    total_s = rdist.max_over_ranks(local_s)
+    value = world * B * T * a.steps / total_s
+    launches = sess.launches * a.steps
+
+    # ---- e2e: public API call with HOST buffers (pinned); H2D + graph + D2H inside the timed region ----
+    masks_h = torch.empty((B, T, H, W), dtype=torch.float32).pin_memory()
+    classes_h = torch.empty((B, T, NUM_CLASSES), dtype=torch.float32).pin_memory()
+    stops_h = torch.empty((B, T, 1), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        m, c, s = rsis_b200.test(args, enc, dec, xd)
+        masks_h.copy_(m, non_blocking=True)
+        classes_h.copy_(c, non_blocking=True)
+        stops_h.copy_(s, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    e2e_s = rdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    e2e_value = world * B * T * a.steps / e2e_s
+    h2d = x_host.numel() * 4
+    d2h = (masks_h.numel() + classes_h.numel() + stops_h.numel()) * 4
+
+    # ---- roofline of the fused ConvLSTM cell kernel (the kernel BASELINE.json's metric names), rank 0 ----
+    roof = None
+    cpu = None
+    if rank == 0:
+        pk = peaks()
+        with torch.no_grad():
+            _, feats_op = enc.forward_act(x_dev, impl)
+            cm = torch.empty((B, T, NUM_CLASSES), device=dev)
+            mk = torch.empty((B, T, H, W), device=dev)
+            sp = torch.empty((B, T, 1), device=dev)
+            state = inference.run_eager(enc, dec, x_dev, 2, impl, mk, cm, sp, feats_op=feats_op)
+            lv_s = time_cells(rsis_b200, dec, feats_op, state, impl)
+        levels = cell_levels(H, W)
+        per_level = []
+        tot_b = tot_f = 0
+        for (cin, ch, hl, wl), s in zip(levels, lv_s):
+            nb, nf = cell_alg_bytes(B, cin, ch, hl, wl), cell_alg_flops(B, cin, ch, hl, wl)
+            tot_b += nb
+            tot_f += nf
+            per_level.append({"level": len(per_level), "us": s * 1e6, "alg_bytes": nb, "alg_flops": nf,
+                              "GBps": nb / s / 1e9, "TFLOPs": nf / s / 1e12})
+        step_s = sum(lv_s)
+        ach = tot_b / step_s / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                "traffic": None, "peak_source": pk["source"] + " (burst copy figure; kernel timed alone, L2 flushed)",
+                "kernel": "fused ConvLSTM cell (5 launches = one decoder step, levels 0-4), CUDA-event timed live",
+                "alg_bytes_per_step": tot_b, "alg_flops_per_step": tot_f, "step_us": step_s * 1e6,
+                "tensor": {"achieved_TFLOPs": tot_f / step_s / 1e12, "peak_bf16_TFLOPs": pk["bf16_tflops"],
+                           "frac_of_bf16_peak": tot_f / step_s / 1e12 / pk["bf16_tflops"]},
+                "impl": {ops.IMPL_SIMT: "simt-fp32", ops.IMPL_AUTO: "auto", ops.IMPL_TCGEN05: "tcgen05"}[impl],
+                "per_level": per_level}
+        # ---- CPU baseline: the reference's CPU path (oracle port) on the host cores, bounded sample ----
+        if not a.no_cpu_baseline:
+            times, threads = cpu_reference_time(a.cpu_passes, 1)
+            cv = B * T * len(times) / sum(times)
+            cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{len(times)} full test() passes of the same workload (B={B}, {H}x{W}, T={T}) after 1 "
+                             f"warm-up; torch CPU fp32, {threads} threads"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "height": H, "width": W,
+                       "T": T, "num_classes": NUM_CLASSES, "parallelism": f"dp{world} (batch sharded per image, "
+                       "no data-path collective)", "l2": "flushed between timed steps (512 MiB fill); per-step CUDA "
+                       "events summed", "cuda_graph": True,
+                       "impl": {ops.IMPL_SIMT: "simt", ops.IMPL_AUTO: "auto", ops.IMPL_TCGEN05: "tcgen05"}[impl],
+                       "tcgen05": bool(ops.has_tcgen05())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / a.steps},
+            "gpu_launches": launches, "launches_per_step": sess.launches,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    rdist.barrier()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-passes", type=int, default=5, help="timed CPU test() passes for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

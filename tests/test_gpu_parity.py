@@ -1,0 +1,424 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of include/rsis_b200.h) against the CPU oracle and the
+committed reference-generated golden vectors.  Run on the B200 box with `-m gpu`.
+
+Tolerance (BASELINE.json north_star): every output tensor within 1e-3 *relative* fp32 of the reference path, measured
+tensor-relative: max|new - ref| / max|ref| <= 1e-3 (SURVEY.md section 8c "parity metric").  The exact-fp32 CUDA-core
+kernels are held to a tighter 2e-5 so that a regression in them cannot hide inside the tensor-core budget.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3        # north_star tolerance, tensor-relative
+TOL_FP32 = 2e-5   # exact-fp32 kernels (reassociation only)
+
+
+def rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float32).cpu()
+    b = torch.as_tensor(b, dtype=torch.float32).cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rsis_b200
+    from rsis_b200 import _lib
+    assert _lib.load().rsis_device_check() == 0, "not a B200 (sm_100) device"
+    return rsis_b200
+
+
+@pytest.fixture(scope="module")
+def sw():
+    from oracle import synth_weights
+    return synth_weights
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import rsis_oracle
+    return rsis_oracle
+
+
+def _args(**kw):
+    from oracle import ref_shims as rs
+    a = rs.make_args(**kw)
+    a.hidden_size = int(a.hidden_size)
+    a.use_gpu = True
+    return a
+
+
+def _models(R, sw, num_classes=21, T=10, seed=1):
+    args = _args(num_classes=num_classes, maxseqlen=T)
+    enc, dec = R.FeatureExtractor(args), R.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(seed))
+    dec.load_state_dict(sw.decoder_state_dict(seed, num_classes=num_classes))
+    return args, enc.cuda().eval(), dec.cuda().eval()
+
+
+IMPLS = ["simt", "auto"]
+
+
+@pytest.fixture(params=IMPLS)
+def impl(request, monkeypatch, R):
+    if request.param != "simt" and not R.ops.has_tcgen05():
+        pytest.skip("library built without tcgen05 kernels")
+    monkeypatch.setenv("RSIS_B200_IMPL", request.param)
+    return request.param
+
+
+def _tol(impl):
+    return TOL_FP32 if impl == "simt" else TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# primitives, teacher-forced against torch CPU fp32 (the oracle's arithmetic)
+# ---------------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # (N, Cin, H, W, Cout, k, stride, pad, bias, bn, relu, residual)
+    (2, 3, 64, 64, 64, 7, 2, 3, False, True, True, False),     # stem, vision.py:12-14
+    (2, 64, 16, 16, 64, 1, 1, 0, False, True, True, False),    # Bottleneck conv1
+    (2, 64, 16, 16, 64, 3, 1, 1, False, True, True, False),    # Bottleneck conv2 s1
+    (2, 128, 16, 16, 128, 3, 2, 1, False, True, True, False),  # Bottleneck conv2 s2
+    (2, 256, 16, 16, 512, 1, 2, 0, False, True, False, False),  # downsample 1x1 s2
+    (2, 64, 16, 16, 256, 1, 1, 0, False, True, True, True),    # conv3 + residual + relu
+    (3, 256, 9, 7, 32, 3, 1, 1, True, True, False, False),     # skip head sk2, ragged M
+    (2, 64, 20, 12, 16, 3, 1, 1, True, True, False, False),    # skip head sk1 (Cout 16)
+    (1, 2048, 4, 4, 128, 3, 1, 1, True, True, False, False),   # sk5, K = 18432
+    (1, 40, 5, 5, 24, 3, 1, 1, True, False, False, False),     # odd channel counts (multiples of 4)
+    (2, 512, 8, 8, 128, 1, 1, 0, True, True, False, False),    # kernel_size=1 heads (args.kernel_size=1)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_matches_oracle(R, impl, case):
+    ops = R.ops
+    N, Cin, H, W, Cout, k, s, p, has_bias, has_bn, relu, has_res = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.rand((N, Cin, H, W), generator=g) * 2 - 1
+    w = (torch.rand((Cout, Cin, k, k), generator=g) * 2 - 1) * (3.0 / (Cin * k * k)) ** 0.5
+    bias = torch.rand(Cout, generator=g) - 0.5 if has_bias else None
+    bn = None
+    if has_bn:
+        bn = torch.nn.BatchNorm2d(Cout)
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+            bn.bias.copy_(torch.rand(Cout, generator=g) - 0.5)
+            bn.running_mean.copy_(torch.rand(Cout, generator=g) - 0.5)
+            bn.running_var.copy_(torch.rand(Cout, generator=g) + 0.5)
+        bn.eval()
+    ref = F.conv2d(x, w, bias, stride=s, padding=p)
+    if bn is not None:
+        with torch.no_grad():
+            ref = bn(ref)
+    res = None
+    if has_res:
+        res = torch.rand(ref.shape, generator=g) * 2 - 1
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    which = ops.default_impl()
+    fmt = ops.activation_format(which)
+    if Cin == 3:
+        which, in_fmt = ops.IMPL_SIMT, ops.FMT_F32  # the stem always runs on the CUDA cores
+    else:
+        in_fmt = fmt
+    pc = ops.PackedConv(w.cuda(), None if bias is None else bias.cuda(), None if bn is None else bn.cuda(),
+                        want_umma=(fmt == ops.FMT_SPLIT_BF16 and Cin != 3))
+    xa = ops.act_from_nchw(x.cuda(), in_fmt)
+    ra = ops.act_from_nchw(res.cuda(), fmt) if res is not None else None
+    y = ops.conv2d([xa], pc, stride=s, pad=p, relu=relu, residual=ra, out_fmt=ops.FMT_F32, impl=which)
+    got = y.nchw()
+    assert tuple(got.shape) == tuple(ref.shape)
+    assert rel(got, ref) < _tol(impl)
+    # second output in the other element format carries the same values
+    y1, y2 = ops.conv2d([xa], pc, stride=s, pad=p, relu=relu, residual=ra, out_fmt=ops.FMT_F32,
+                        out2_fmt=ops.FMT_SPLIT_BF16, impl=which)
+    assert torch.equal(y1.t, y.t)
+    assert rel(y2.float().permute(0, 3, 1, 2), ref) < max(_tol(impl), 2e-5)
+
+
+def test_conv2d_concat_sources(R, impl):
+    """Inputs concatenated along C without materialising the concat (model.py:153 `cat([hidden, skip])`)."""
+    ops = R.ops
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand((2, 64, 12, 12), generator=g) - 0.5
+    b = torch.rand((2, 32, 12, 12), generator=g) - 0.5
+    c = torch.rand((2, 16, 12, 12), generator=g) - 0.5
+    w = (torch.rand((48, 112, 3, 3), generator=g) - 0.5) * 0.1
+    ref = F.conv2d(torch.cat([a, b, c], 1), w, padding=1)
+    which = ops.default_impl()
+    fmt = ops.activation_format(which)
+    pc = ops.PackedConv(w.cuda(), src_channels=[64, 32, 16], want_umma=(fmt == ops.FMT_SPLIT_BF16))
+    srcs = [ops.act_from_nchw(t.cuda(), fmt) for t in (a, b, c)]
+    y = ops.conv2d(srcs, pc, pad=1, impl=which)
+    assert rel(y.nchw(), ref) < _tol(impl)
+
+
+def test_maxpool_and_upsample(R):
+    ops = R.ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand((2, 64, 17, 22), generator=g) * 4 - 2
+    xa = ops.act_from_nchw(x.cuda(), ops.FMT_F32)
+    y = ops.maxpool3x3s2(xa)
+    assert torch.equal(y.nchw().cpu(), F.max_pool2d(x, 3, 2, 1))  # nn.MaxPool2d(3, 2, 1), vision.py:15 -- exact
+    for size in [(34, 44), (17, 22), (40, 31), (18, 23)]:
+        ref = F.interpolate(x, size=size, mode="bilinear", align_corners=True)  # nn.UpsamplingBilinear2d
+        got = ops.upsample_bilinear(xa, size[0], size[1], ops.FMT_F32).nchw()
+        assert rel(got, ref) < 1e-6, size
+        got2 = ops.upsample_bilinear(xa, size[0], size[1], ops.FMT_SPLIT_BF16).float().permute(0, 3, 1, 2)
+        assert rel(got2, ref) < 2e-5, size
+    same = ops.upsample_bilinear(xa, 17, 22, ops.FMT_F32).nchw()
+    assert torch.equal(same.cpu(), x)  # same-size upsample is an exact identity
+
+
+@pytest.mark.parametrize("ks", [3, 1])
+def test_mask_head(R, ks):
+    ops = R.ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand((3, 8, 20, 28), generator=g) * 2 - 1
+    w = torch.rand((1, 8, ks, ks), generator=g) - 0.5
+    b = torch.rand(1, generator=g)
+    ref = F.conv2d(x, w, b, padding=ks // 2)
+    xa = ops.act_from_nchw(x.cuda(), ops.FMT_F32)
+    logits = torch.empty((3, 1, 20, 28), device="cuda")
+    T = 4
+    probs = torch.zeros((3, T, 20, 28), device="cuda")
+    ops.mask_head(xa, w.cuda(), b.cuda(), logits, probs[:, 2], T * 20 * 28)
+    assert rel(logits, ref) < TOL_FP32
+    assert rel(probs[:, 2], torch.sigmoid(ref[:, 0])) < TOL_FP32
+    assert float(probs[:, 0].abs().max()) == 0.0 and float(probs[:, 3].abs().max()) == 0.0
+
+
+def test_class_stop_heads_and_side_keys(R, sw):
+    """fc_class + Softmax + fc_stop (model.py:169-182) on max-pooled features delivered as order-preserving keys."""
+    ops = R.ops
+    g = torch.Generator().manual_seed(13)
+    feat = torch.rand((5, 248), generator=g) * 4 - 2
+    feat[0, 0], feat[1, 1], feat[2, 2] = 0.0, -0.0, -3.5
+    bits = feat.view(torch.int32)
+    keys = torch.where(bits < 0, ~bits, bits | torch.tensor(-2 ** 31, dtype=torch.int32))  # common.cuh float_to_key
+    dsd = sw.decoder_state_dict(1)
+    wc, bc, ws, bs = (dsd[k].cuda() for k in ("fc_class.weight", "fc_class.bias", "fc_stop.weight", "fc_stop.bias"))
+    cls = torch.empty((5, 21), device="cuda")
+    stop = torch.empty((5, 1), device="cuda")
+    stop_p = torch.empty((5, 1), device="cuda")
+    fout = torch.empty((5, 248), device="cuda")
+    ops.class_stop_heads(keys.cuda(), wc, bc, ws, bs, cls, 21, stop, stop_p, 1, feat_out=fout)
+    assert torch.equal(fout.cpu().view(torch.int32), feat.view(torch.int32))  # keys decode bit-exactly (incl. -0.0)
+    ref_c = torch.softmax(F.linear(feat, dsd["fc_class.weight"], dsd["fc_class.bias"]), 1)
+    ref_s = F.linear(feat, dsd["fc_stop.weight"], dsd["fc_stop.bias"])
+    assert rel(cls, ref_c) < TOL_FP32 and rel(stop, ref_s) < TOL_FP32 and rel(stop_p, torch.sigmoid(ref_s)) < TOL_FP32
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ConvLSTM cell: the reference's own outputs (tests/golden/cells_teacher_forced.npz, made by oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+def test_convlstm_cell_matches_reference_golden(R, sw, impl, golden_dir):
+    g = np.load(os.path.join(golden_dir, "cells_teacher_forced.npz"))
+    dsd = sw.decoder_state_dict(1)
+    outs = sw.skip_dims_out(128)
+    for lvl, ch in enumerate(outs):
+        cin = 128 if lvl == 0 else 2 * outs[lvl - 1]
+        cell = R.ConvLSTMCell(_args(), cin, ch, 3, 1)
+        cell.load_state_dict({"Gates.weight": dsd[f"clstm_list.{lvl}.Gates.weight"],
+                              "Gates.bias": dsd[f"clstm_list.{lvl}.Gates.bias"]})
+        cell.cuda()
+        x0 = sw._uniform(7, f"cell{lvl}.x0", (2, cin, 8, 8), -2.0, 2.0).cuda()
+        x1 = sw._uniform(7, f"cell{lvl}.x1", (2, cin, 8, 8), -2.0, 2.0).cuda()
+        h0, c0 = cell(x0, None)                      # clstm.py:26-37 zero state
+        assert tuple(h0.shape) == (2, ch, 8, 8)
+        assert rel(h0, g[f"l{lvl}_h0"]) < _tol(impl) and rel(c0, g[f"l{lvl}_c0"]) < _tol(impl), lvl
+        # teacher-forced second step: feed the REFERENCE's state so errors do not compound
+        hr = torch.from_numpy(g[f"l{lvl}_h0"]).cuda()
+        cr = torch.from_numpy(g[f"l{lvl}_c0"]).cuda()
+        h1, c1 = cell(x1, (hr, cr))
+        assert rel(h1, g[f"l{lvl}_h1"]) < _tol(impl) and rel(c1, g[f"l{lvl}_c1"]) < _tol(impl), lvl
+        # explicit zero state == None state (the reference materialises zeros)
+        z = torch.zeros_like(h0)
+        h0z, c0z = cell(x0, (z, z.clone()))
+        assert rel(h0z, h0) < 1e-6 and rel(c0z, c0) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 128, 3, 5), (3, 64, 16, 17, 9), (2, 32, 8, 33, 31), (2, 512, 32, 6, 6)])
+def test_convlstm_cell_matches_oracle_ragged(R, O, impl, shape):
+    """Ragged spatial sizes / odd batch; global max side feature (model.py:143) fused in the epilogue."""
+    ops = R.ops
+    B, cin, ch, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + cin)
+    x = torch.rand((B, cin, H, W), generator=g) * 4 - 2
+    hp = torch.rand((B, ch, H, W), generator=g) * 2 - 1
+    cp = torch.rand((B, ch, H, W), generator=g) * 4 - 2
+    a = 2.0 / (9 * (cin + ch)) ** 0.5
+    w = (torch.rand((4 * ch, cin + ch, 3, 3), generator=g) * 2 - 1) * a
+    b = torch.rand(4 * ch, generator=g) - 0.5
+    href, cref = O.convlstm_cell(w, b, x, (hp, cp))
+    cell = R.ConvLSTMCell(_args(), cin, ch, 3, 1)
+    cell.load_state_dict({"Gates.weight": w, "Gates.bias": b})
+    cell.cuda()
+    which = ops.default_impl()
+    fmt = ops.activation_format(which)
+    side = torch.zeros((B, ch + 7), dtype=torch.int32, device="cuda")
+    h, c, _ = cell.step_act([ops.act_from_nchw(x.cuda(), fmt)], ops.act_from_nchw(hp.cuda(), fmt),
+                            ops.act_from_nchw(cp.cuda(), ops.FMT_F32).t, side, 3, which)
+    assert rel(h.nchw(), href) < _tol(impl) and rel(c.nchw(), cref) < _tol(impl)
+    # decode the keys on the host: must equal the max of the h the kernel itself wrote, bit for bit
+    k = side[:, 3:3 + ch].cpu()
+    dec = torch.where(k < 0, k & 0x7FFFFFFF, ~k).view(torch.float32)
+    assert torch.equal(dec, h.nchw().amax(dim=(2, 3)).cpu())
+    assert int(side[:, :3].abs().sum()) == 0 and int(side[:, 3 + ch:].abs().sum()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# module surface: encoder features, decoder step, test() end to end -- against reference-generated goldens
+# ---------------------------------------------------------------------------------------------------------
+def _golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = [int(v) for v in g["meta"]]
+    return g, meta
+
+
+@pytest.mark.parametrize("name", ["e2e_b2_64x64_t3", "e2e_b2_96x160_t4_c9", "cfg2_b8_256x256_t10"])
+def test_e2e_matches_reference_golden(R, sw, impl, golden_dir, name):
+    g, (wseed, iseed, B, H, W, T, ncls, stride) = _golden(golden_dir, name)
+    args, enc, dec = _models(R, sw, ncls, T, wseed)
+    x = sw.synthetic_images(iseed, B, H, W).cuda()
+    tol = _tol(impl)
+    with torch.no_grad():
+        feats = enc(x)
+    full = name == "e2e_b2_64x64_t3"
+    for i, f in enumerate(feats):
+        assert f.shape[0] == B and f.dim() == 4
+        got = f if full else f[:, ::4, ::2, ::2]
+        assert rel(got, g[f"feat{i}"]) < tol, f"feat{i}"
+    for graph in (True, False):
+        args.cuda_graph = graph
+        masks, classes, stops = R.test(args, enc, dec, x)
+        assert tuple(masks.shape) == (B, T, H, W) and tuple(classes.shape) == (B, T, ncls)
+        assert tuple(stops.shape) == (B, T, 1)
+        assert rel(masks[:, :, ::stride, ::stride], g["masks"]) < tol
+        assert rel(classes, g["classes"]) < tol
+        assert rel(stops, g["stops"]) < tol
+        if graph:
+            again = R.test(args, enc, dec, x)  # replay of the captured graph
+            assert torch.equal(again[0], masks) and torch.equal(again[1], classes) and torch.equal(again[2], stops)
+
+
+def test_cfg1_single_image_through_modules(R, sw, impl, golden_dir):
+    """BASELINE.json configs[0]: 1 image 256x256, T=5.  The reference's test() cannot run B=1, so the
+    golden was made by calling encoder/decoder directly; same here, including the squeezed B=1 return shapes."""
+    g, (wseed, iseed, B, H, W, T, ncls, stride) = _golden(golden_dir, "cfg1_b1_256x256_t5")
+    args, enc, dec = _models(R, sw, ncls, T, wseed)
+    x = sw.synthetic_images(iseed, B, H, W).cuda()
+    with torch.no_grad():
+        feats = enc(x)
+        hidden = None
+        ms, cs, ss = [], [], []
+        for _ in range(T):
+            m, c, s, hidden = dec(feats, hidden)
+            assert tuple(m.shape) == (1, 1, H, W) and tuple(c.shape) == (ncls,) and tuple(s.shape) == (1,)
+            assert len(hidden) == 5 and all(len(hc) == 2 for hc in hidden)
+            ms.append(m)
+            cs.append(c.view(1, -1))
+            ss.append(s.view(1, -1))
+    masks = torch.sigmoid(torch.cat(ms, 1))
+    tol = _tol(impl)
+    assert rel(masks[:, :, ::stride, ::stride], g["masks"]) < tol
+    assert rel(torch.stack(cs, 1), g["classes"]) < tol
+    assert rel(torch.sigmoid(torch.stack(ss, 1)), g["stops"]) < tol
+    with pytest.raises(RuntimeError, match="batch size 1"):
+        R.test(args, enc, dec, x)
+
+
+def test_decoder_step_teacher_forced(R, O, sw, impl):
+    """RSIS.forward on the ORACLE's features and hidden state (NCHW-contiguous CPU-made tensors moved to the GPU)."""
+    args, enc, dec = _models(R, sw)
+    esd, dsd = sw.encoder_state_dict(1), sw.decoder_state_dict(1)
+    x = sw.synthetic_images(9, 2, 64, 96)
+    with torch.no_grad():
+        feats = O.feature_extractor(esd, x)
+        m0, c0, s0, hid0 = O.rsis_step(dsd, feats, None)
+        m1, c1, s1, hid1 = O.rsis_step(dsd, feats, hid0)
+        gf = [f.cuda() for f in feats]
+        gm0, gc0, gs0, ghid0 = dec(gf, None)
+        gm1, gc1, gs1, ghid1 = dec(gf, [[h.cuda(), c.cuda()] for h, c in hid0])
+    tol = _tol(impl)
+    for got, ref in ((gm0, m0), (gc0, c0), (gs0, s0), (gm1, m1), (gc1, c1), (gs1, s1)):
+        assert rel(got, ref) < tol
+    for lvl in range(5):
+        for j in range(2):
+            assert tuple(ghid1[lvl][j].shape) == tuple(hid1[lvl][j].shape)
+            assert rel(ghid0[lvl][j], hid0[lvl][j]) < tol and rel(ghid1[lvl][j], hid1[lvl][j]) < tol
+
+
+def test_encoder_raw_taps(R, O, sw, impl):
+    """`forward(x, raw=True)` returns the backbone taps (model.py:65-68); `base(x)` is vision.py:11-21."""
+    args, enc, dec = _models(R, sw)
+    x = sw.synthetic_images(4, 2, 64, 64)
+    with torch.no_grad():
+        ref = O.feature_extractor(sw.encoder_state_dict(1), x, raw=True)
+        got = enc(x.cuda(), raw=True)
+        got2 = enc.base(x.cuda())
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in ref]
+    for a, b, r in zip(got, got2, ref):
+        assert rel(a, r) < _tol(impl) and torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------------------
+def test_batch_sharding_is_exact_cfg2(R, sw, impl):
+    """The path shards per image: running a batch of 8 in one piece or as two shards of 4 gives
+    bit-identical results, and a run is deterministic (the only atomics are order-independent maxima)."""
+    args, enc, dec = _models(R, sw, 21, 10)
+    args.cuda_graph = False
+    x = sw.synthetic_images(123, 8, 256, 256).cuda()
+    full = R.test(args, enc, dec, x)
+    again = R.test(args, enc, dec, x)
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)
+    parts = [R.test(args, enc, dec, x[i:i + 4].contiguous()) for i in (0, 4)]
+    for k in range(3):
+        assert torch.equal(full[k], torch.cat([parts[0][k], parts[1][k]], 0))
+    masks, classes, stops = full
+    assert float(masks.min()) >= 0.0 and float(masks.max()) <= 1.0
+    assert float((classes.sum(-1) - 1).abs().max()) < 1e-5  # Softmax rows
+    assert bool(torch.isfinite(masks).all()) and bool(torch.isfinite(classes).all())
+
+
+def test_cityscapes_shape_cfg3_smoke(R, O, sw, impl):
+    """BASELINE.json configs[2] geometry (512x1024, T=20, 9 classes) at batch 1 of the 4: shapes, finiteness, and the
+    first decoder step against the oracle (the full T=20 CPU run is too slow for a unit test)."""
+    args, enc, dec = _models(R, sw, 9, 20)
+    x = sw.synthetic_images(123, 2, 512, 1024)
+    masks, classes, stops = R.test(args, enc, dec, x.cuda())
+    assert tuple(masks.shape) == (2, 20, 512, 1024) and tuple(classes.shape) == (2, 20, 9)
+    assert bool(torch.isfinite(masks).all())
+    with torch.no_grad():
+        feats = O.feature_extractor(sw.encoder_state_dict(1), x)
+        m0, c0, s0, _ = O.rsis_step(sw.decoder_state_dict(1, num_classes=9), feats, None)
+    assert rel(masks[:, 0], torch.sigmoid(m0[:, 0])) < _tol(impl)
+    assert rel(classes[:, 0], c0) < _tol(impl)
+    assert rel(stops[:, 0], torch.sigmoid(s0)) < _tol(impl)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# error behaviour across the ABI
+# ---------------------------------------------------------------------------------------------------------
+def test_errors_are_reported_not_swallowed(R):
+    ops = R.ops
+    w = torch.zeros((8, 16, 3, 3), device="cuda")
+    pc = ops.PackedConv(w)
+    x = ops.act_from_nchw(torch.zeros((1, 12, 8, 8), device="cuda"), ops.FMT_F32)  # 12 != 16 input channels
+    with pytest.raises(RuntimeError, match="bad argument"):
+        ops.conv2d([x], pc, pad=1, impl=ops.IMPL_SIMT)
+    cell = R.ConvLSTMCell(_args(), 16, 8, 3, 1).cuda()
+    with pytest.raises(RuntimeError, match="input channels"):
+        cell(torch.zeros((1, 12, 8, 8), device="cuda"), None)
+    from rsis_b200 import _lib
+    assert _lib.load().rsis_device_check() == 0
