@@ -22,6 +22,7 @@
 // full/empty pipelines.  Every mbarrier wait is bounded (trap instead of hang).
 #include <cuda.h>
 
+#include <cstdio>
 #include <mutex>
 
 #include "common.cuh"
@@ -57,8 +58,9 @@ struct UmmaParams {
   // K loop
   int taps, ksize, stride, pad;
   int n_src;
-  int chunks[kMaxSrc];     // 64-channel chunks of each source (stride 1)
-  int num_k;               // total K chunks
+  int chunks[kMaxSrc];     // 64-channel chunks of each source
+  int chunks_per_tap;      // chunks per filter tap in the packed weight K layout (includes an omitted zero state)
+  int num_k;               // K chunks actually multiplied per tile
   // problem
   int N, Ho, Wo, Cout;
   // conv epilogue
@@ -346,9 +348,6 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_i;
-  (void)tiles_m;
-
   if (warp == 4) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
@@ -362,9 +361,9 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         const int th = mt % p.tiles_h;
         const int ti = mt / p.tiles_h;
         const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
-        int kc = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+          int kc = tap * p.chunks_per_tap;  // chunk index in the packed weight K layout [tap][source][chunk]
           for (int s = 0; s < p.n_src; ++s) {
             for (int cc = 0; cc < p.chunks[s]; ++cc, ++kc) {
               mbar_wait(empty0 + 8 * stage, phase ^ 1u);
@@ -567,11 +566,9 @@ bool common_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weight
   return true;
 }
 
-// Fills geometry, tensor maps and the K loop.  `w_src_c` = channel split the weights were packed with: the sources
-// given plus (for a cell whose state is None) the omitted trailing hidden block, whose K chunks are simply skipped...
-// they cannot be skipped in the packed K order, so the producer still walks them with an all-zero A box: instead we
-// require the caller to pass a zero-channel-free list, and handle the missing tail by pointing at source 0 with an
-// out-of-range channel coordinate (TMA zero-fills).
+// Fills geometry, tensor maps and the K loop.  `missing_tail_c` > 0: a ConvLSTM step whose state is None omits the
+// trailing prev_hidden source (clstm.py:26-37 materialises zeros); its K chunks exist in the packed weights and are
+// simply never multiplied.
 int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, int stride,
           int pad, int missing_tail_c) {
   std::call_once(g_once, init_once);
@@ -603,37 +600,20 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor* srcs, int n_src, con
   p.pad = pad;
   p.scale = w->scale;
   p.shift = w->shift;
-
-  int total_chunks = 0;
+  int present = 0;
   for (int s = 0; s < n_src; ++s) {
     p.chunks[s] = ceil_div(srcs[s].c, kBK);
-    total_chunks += p.chunks[s];
+    present += p.chunks[s];
   }
   p.n_src = n_src;
-  if (missing_tail_c > 0) {
-    // state None (clstm.py:26-37 zeros): walk the hidden block's K chunks with an out-of-range image coordinate on
-    // source 0 -- TMA zero-fills the whole box, so the packed weight layout needs no second variant.
-    if (n_src >= kMaxSrc) return RSIS_ERR_UNSUPPORTED;
-    p.chunks[n_src] = ceil_div(missing_tail_c, kBK);
-    total_chunks += p.chunks[n_src];
-    p.n_src = n_src + 1;
-  }
-  p.num_k = p.taps * total_chunks;
-
+  p.chunks_per_tap = present + (missing_tail_c > 0 ? ceil_div(missing_tail_c, kBK) : 0);
+  p.num_k = p.taps * present;
   const int cout_pad = round_up(w->cout, 16);
-  const int k_pad = p.num_k * kBK;
+  const int k_pad = p.taps * p.chunks_per_tap * kBK;
   if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN)) return e;
   if (stride == 1) {
     for (int s = 0; s < n_src; ++s)
       if (int e = encode_act_map(&maps.a[s], srcs[s], 1, 0, 0, p.BW, p.BH, p.BI)) return e;
-    if (missing_tail_c > 0) {
-      // a 1-image view placed so that every box lands out of range: dims N = 0 is illegal, so use the real tensor and
-      // shift the base of the image coordinate instead (handled by giving this map zero-sized channel extent is also
-      // illegal) -> encode source 0 with the channel dimension truncated to 8 and start the box at channel 64.
-      rsis_tensor z = srcs[0];
-      z.c = srcs[0].c;
-      if (int e = encode_act_map(&maps.a[n_src], z, 1, 0, 0, p.BW, p.BH, p.BI)) return e;
-    }
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
@@ -686,9 +666,8 @@ int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
 }
 
 bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w) {
-  // a state of None (prev_hidden omitted) is served by the CUDA-core kernel for now: it happens once per sequence
-  if (!w || !w->gate_interleaved || !common_supported(srcs, n_src, w, 1, w->kh / 2, false)) return false;
-  return (w->cout / 4) % 8 == 0;
+  if (!w || !w->gate_interleaved || !common_supported(srcs, n_src, w, 1, w->kh / 2, true)) return false;
+  return (w->cout / 4) % 8 == 0;  // the epilogue handles 8 hidden channels (32 gate columns) at a time
 }
 
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
@@ -696,7 +675,10 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        uint32_t* side_max, int side_stride, int side_offset, cudaStream_t st) {
   UmmaMaps maps;
   UmmaParams p{};
-  if (int e = setup(maps, p, srcs, n_src, w, 1, w->kh / 2, 0)) return e;
+  int csum = 0;
+  for (int s = 0; s < n_src; ++s) csum += srcs[s].c;
+  if (csum != w->cin && (c_prev || w->cin - csum != w->cout / 4)) return RSIS_ERR_BAD_ARG;
+  if (int e = setup(maps, p, srcs, n_src, w, 1, w->kh / 2, w->cin - csum)) return e;
   const int Ch = p.Cout / 4;
   auto ok = [&](const rsis_tensor* t, int fmt) {
     return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&
