@@ -7,7 +7,7 @@ torchvision's, including the never-executed `avgpool`/`fc`); the arithmetic runs
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -90,9 +90,10 @@ class ResNet101(nn.Module):
             self._packed, self._packed_key = pk, key
         return self._packed
 
-    def forward_act(self, x: torch.Tensor, impl: int = ops.IMPL_AUTO) -> List[Act]:
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None) -> List[Act]:
         """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1]."""
         ops.require_cuda(x, "ResNet101")
+        impl = ops.default_impl() if impl is None else impl
         if self.training:
             raise NotImplementedError("rsis_b200: train-mode BatchNorm (batch statistics) is not implemented yet; "
                                       "call .eval() (the inference path of /root/reference/src/test.py:29-30)")
