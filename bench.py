@@ -166,35 +166,36 @@ def run_reference(a):
 # --------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------------------------------
-def time_cells(rsis_b200, dec, feats_op, state, impl, iters=20):
-    """CUDA-event time of the five fused ConvLSTM cell launches of one decoder step (teacher-forced on a real
-    state), per level.  Between iterations a 512 MiB buffer is written to flush the 126 MB L2."""
+def time_cells(rsis_b200, dec, ws, impl, iters=20):
+    """CUDA-event time of the five fused ConvLSTM cell launches of one decoder step, per level, on the real state a
+    2-step run left in the decoder workspace `ws` (inputs = its concatenated [up(h) | skip | h_prev] buffers,
+    c_prev = its cell state; outputs go to scratch).  Between iterations a 512 MiB buffer is written to flush L2."""
     ops = rsis_b200.ops
-    dev = feats_op[0].t.device
+    dev = ws.side.device
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    n = feats_op[0].n
-    side = torch.zeros((n, dec.fc_dim), dtype=torch.int32, device=dev)
-    fmt = ops.activation_format(impl)
-    # inputs of every level, taken from a real step
-    level_inputs = []
-    inputs = [feats_op[0]]
-    for i, cell in enumerate(dec.clstm_list):
-        level_inputs.append(list(inputs))
-        if i + 1 < len(dec.clstm_list):
-            skip = feats_op[i + 1]
-            up = ops.upsample_bilinear(state[i][1], skip.h, skip.w, fmt)
-            inputs = [up, skip]
+    side = torch.zeros_like(ws.side)
+    p = ws.t & 1
+    scratch = []
+    for l, cell in enumerate(dec.clstm_list):
+        x = ws.X[l][p]
+        scratch.append((ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_F32, dev),
+                        ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_F32, dev),
+                        ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_SPLIT_BF16, dev),
+                        cell.packed([cell.input_size + cell.hidden_size], want_umma=True)))
     per_level = [[] for _ in dec.clstm_list]
-    for it in range(iters + 3):
-        flush.fill_(it & 0xFF)
-        for i, cell in enumerate(dec.clstm_list):
+    # One (flush, event, cell, event) group per launch: the ~150 us flush kernel lets the host enqueue the cell
+    # and both events before the GPU reaches them, so the interval is kernel time, not host launch latency.
+    for l, cell in enumerate(dec.clstm_list):
+        h, c, h16, pc = scratch[l]
+        for it in range(iters + 3):
+            flush.fill_(it & 0xFF)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            cell.step_act(level_inputs[i], state[i][0], state[i][2].t, side, 0, impl)
+            ops.convlstm_cell_x(ws.X[l][p], pc, ws.c[l].t, side, 0, h_out=h, c_out=c, h16_out=h16, impl=impl)
             e1.record()
             if it >= 3:
-                per_level[i].append((e0, e1))
-    torch.cuda.synchronize(dev)
+                per_level[l].append((e0, e1))
+        torch.cuda.synchronize(dev)
     return [statistics.mean(a.elapsed_time(b) for a, b in lv) * 1e-3 for lv in per_level]
 
 
@@ -288,13 +289,14 @@ def run_ours(a):
     cpu = None
     if rank == 0:
         pk = peaks()
+        if not ops.uses_tcgen05(impl):
+            raise SystemExit("bench.py measures the tcgen05 kernel family (RSIS_B200_IMPL=auto|tcgen05)")
         with torch.no_grad():
-            _, feats_op = enc.forward_act(x_dev, impl)
             cm = torch.empty((B, T, NUM_CLASSES), device=dev)
             mk = torch.empty((B, T, H, W), device=dev)
             sp = torch.empty((B, T, 1), device=dev)
-            state = inference.run_eager(enc, dec, x_dev, 2, impl, mk, cm, sp, feats_op=feats_op)
-            lv_s = time_cells(rsis_b200, dec, feats_op, state, impl)
+            ws = inference.run_eager(enc, dec, x_dev, 2, impl, mk, cm, sp)
+            lv_s = time_cells(rsis_b200, dec, ws, impl)
         levels = cell_levels(H, W)
         per_level = []
         tot_b = tot_f = 0

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 1
+#define RSIS_ABI_VERSION 2
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -48,11 +48,16 @@ typedef enum rsis_status {
 enum { RSIS_FMT_F32 = 0, RSIS_FMT_SPLIT_BF16 = 1 };
 enum { RSIS_IMPL_AUTO = 0, RSIS_IMPL_SIMT = 1, RSIS_IMPL_TCGEN05 = 2 };
 
-/* NHWC activation view. For RSIS_FMT_SPLIT_BF16 `data` points at the hi plane; lo = hi + n*h*w*c elements. */
+/* NHWC activation view.  `cstride` is the pixel pitch in elements (0 means dense, = c): a view with
+ * cstride > c is a channel slice [data, data + c) of a wider NHWC buffer -- this is how the decoder's
+ * `torch.cat([upsampled hidden, skip, prev_hidden], 1)` (model.py:153, clstm.py:43) exists without a copy: the
+ * producers write their slice of one buffer.  For RSIS_FMT_SPLIT_BF16 `data` points at the hi plane;
+ * lo = hi + n*h*w*pitch elements.  Kernels that do not take pitched views return RSIS_ERR_UNSUPPORTED. */
 typedef struct rsis_tensor {
   void* data;
   int32_t fmt;
   int32_t n, h, w, c;
+  int32_t cstride;
 } rsis_tensor;
 
 /* Packed convolution weights + folded per-channel affine (bias and eval-mode BatchNorm):

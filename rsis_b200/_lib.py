@@ -17,12 +17,13 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
+ABI_VERSION = 2
 
 
 class Tensor(C.Structure):
-    """`rsis_tensor`: NHWC activation view."""
+    """`rsis_tensor`: NHWC activation view (cstride = pixel pitch in elements, 0 = dense)."""
     _fields_ = [("data", C.c_void_p), ("fmt", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("c", C.c_int32)]
+                ("c", C.c_int32), ("cstride", C.c_int32)]
 
 
 class ConvWeights(C.Structure):
@@ -85,7 +86,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rsis_abi_version() != 1:
+    if lib.rsis_abi_version() != ABI_VERSION:
         raise RuntimeError("rsis_b200: ABI version mismatch between the Python package and librsis_b200.so")
     _lib = lib
     return lib
@@ -113,19 +114,34 @@ def stream_ptr() -> int:
 
 
 class Act:
-    """An NHWC activation held in a torch tensor: float32 [N,H,W,C] or split-bf16 [2,N,H,W,C] (hi|lo planes)."""
-    __slots__ = ("t", "fmt", "n", "h", "w", "c", "desc", "source_key")
+    """An NHWC activation held in a torch tensor: float32 [N,H,W,C] or split-bf16 [2,N,H,W,C] (hi|lo planes).
 
-    def __init__(self, t: torch.Tensor, fmt: int):
+    `Act.slice(c0, c)` is a pitched channel-slice view of the same storage (rsis_tensor.cstride): producers write
+    their part of a concatenated buffer in place, so `torch.cat(..., 1)` never runs."""
+    __slots__ = ("t", "fmt", "n", "h", "w", "c", "desc", "source_key", "c0", "pitch")
+
+    def __init__(self, t: torch.Tensor, fmt: int, c0: int = 0, c: int = None):
         if fmt == FMT_F32:
             assert t.dtype == torch.float32 and t.dim() == 4 and t.is_contiguous()
-            n, h, w, c = t.shape
+            n, h, w, pitch = t.shape
+            esize = 4
         else:
             assert t.dtype == torch.bfloat16 and t.dim() == 5 and t.shape[0] == 2 and t.is_contiguous()
-            _, n, h, w, c = t.shape
+            _, n, h, w, pitch = t.shape
+            esize = 2
+        c = pitch - c0 if c is None else c
+        assert 0 <= c0 and c > 0 and c0 + c <= pitch
         self.t, self.fmt, self.n, self.h, self.w, self.c = t, fmt, n, h, w, c
-        self.desc = Tensor(t.data_ptr(), fmt, n, h, w, c)
+        self.c0, self.pitch = c0, pitch
+        self.desc = Tensor(t.data_ptr() + c0 * esize, fmt, n, h, w, c, 0 if c == pitch else pitch)
         self.source_key = None
+
+    @property
+    def dense(self) -> bool:
+        return self.c == self.pitch
+
+    def slice(self, c0: int, c: int) -> "Act":
+        return Act(self.t, self.fmt, self.c0 + c0, c)
 
     def valid_for(self, src: torch.Tensor) -> bool:
         """True while `src` (the float32 tensor this operand copy was derived from) is unchanged."""
@@ -138,6 +154,12 @@ class Act:
         return Act(torch.empty((2, n, h, w, c), dtype=torch.bfloat16, device=device), fmt)
 
     @staticmethod
+    def zeros(n, h, w, c, fmt, device) -> "Act":
+        if fmt == FMT_F32:
+            return Act(torch.zeros((n, h, w, c), dtype=torch.float32, device=device), fmt)
+        return Act(torch.zeros((2, n, h, w, c), dtype=torch.bfloat16, device=device), fmt)
+
+    @staticmethod
     def from_nchw_view(x: torch.Tensor) -> "Act":
         """Zero-copy when `x` ([N,C,H,W] float32) is channels_last-contiguous; otherwise one torch copy."""
         assert x.dim() == 4 and x.dtype == torch.float32
@@ -148,7 +170,7 @@ class Act:
 
     def nchw(self) -> torch.Tensor:
         """float32 activations as the reference's logical [N,C,H,W] (channels_last memory, zero-copy)."""
-        assert self.fmt == FMT_F32
+        assert self.fmt == FMT_F32 and self.dense
         return self.t.permute(0, 3, 1, 2)
 
     def ref(self):
@@ -156,6 +178,7 @@ class Act:
 
     def float(self) -> torch.Tensor:
         """[N,H,W,C] float32 values (a torch op; tests/debug only)."""
+        sl = slice(self.c0, self.c0 + self.c)
         if self.fmt == FMT_F32:
-            return self.t
-        return self.t[0].float() + self.t[1].float()
+            return self.t[..., sl]
+        return self.t[0][..., sl].float() + self.t[1][..., sl].float()

@@ -27,9 +27,12 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 static inline size_t numel(const rsis_tensor& t) { return (size_t)t.n * t.h * t.w * t.c; }
+static inline int pitch(const rsis_tensor& t) { return t.cstride > 0 ? t.cstride : t.c; }  // elements per pixel
+static inline bool is_dense(const rsis_tensor& t) { return pitch(t) == t.c; }
+static inline size_t plane_elems(const rsis_tensor& t) { return (size_t)t.n * t.h * t.w * pitch(t); }
 
 static inline bool valid_tensor(const rsis_tensor* t) {
-  return t && t->data && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 &&
+  return t && t->data && t->n > 0 && t->h > 0 && t->w > 0 && t->c > 0 && (t->cstride == 0 || t->cstride >= t->c) &&
          (t->fmt == RSIS_FMT_F32 || t->fmt == RSIS_FMT_SPLIT_BF16);
 }
 
@@ -41,7 +44,7 @@ struct View {  // device-side view of an NHWC activation
   int c;
 };
 
-static inline View make_view(const rsis_tensor& t) { return View{t.data, numel(t), t.fmt, t.c}; }
+static inline View make_view(const rsis_tensor& t) { return View{t.data, plane_elems(t), t.fmt, t.c}; }
 
 __device__ __forceinline__ float load_elem(const View& v, size_t idx) {
   if (v.fmt == RSIS_FMT_F32) return reinterpret_cast<const float*>(v.p)[idx];

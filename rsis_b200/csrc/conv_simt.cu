@@ -314,6 +314,7 @@ static int fill_common(ConvParams& p, const rsis_tensor* srcs, int n_src, const 
   int c = 0;
   for (int s = 0; s < n_src; ++s) {
     if (!valid_tensor(&srcs[s])) return RSIS_ERR_BAD_ARG;
+    if (!is_dense(srcs[s])) return RSIS_ERR_UNSUPPORTED;  // the CUDA-core path reads dense NHWC only
     if (srcs[s].n != srcs[0].n || srcs[s].h != srcs[0].h || srcs[s].w != srcs[0].w) return RSIS_ERR_BAD_ARG;
     if (!aligned16(srcs[s].data)) return RSIS_ERR_ALIGN;
     p.src.v[s] = make_view(srcs[s]);
@@ -357,6 +358,8 @@ int conv2d_simt(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
   if (w->gate_interleaved) return RSIS_ERR_BAD_ARG;
   if (!valid_tensor(y) || y->n != srcs[0].n || y->h != p.Ho || y->w != p.Wo || y->c != p.Cout) return RSIS_ERR_BAD_ARG;
   if (!aligned16(y->data)) return RSIS_ERR_ALIGN;
+  if (!is_dense(*y) || (y2 && valid_tensor(y2) && !is_dense(*y2)) || (residual && valid_tensor(residual) && !is_dense(*residual)))
+    return RSIS_ERR_UNSUPPORTED;
   p.y = y->data;
   p.y_plane = numel(*y);
   p.y_fmt = y->fmt;
@@ -389,6 +392,7 @@ int convlstm_cell_simt(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   };
   if (!ok(h_out, RSIS_FMT_F32) || !ok(c_out, RSIS_FMT_F32)) return RSIS_ERR_BAD_ARG;
   if (h_split && !ok(h_split, RSIS_FMT_SPLIT_BF16)) return RSIS_ERR_BAD_ARG;
+  if (!is_dense(*h_out) || !is_dense(*c_out) || (h_split && !is_dense(*h_split))) return RSIS_ERR_UNSUPPORTED;
   if (side_max && (side_stride < side_offset + Ch || side_offset < 0)) return RSIS_ERR_BAD_ARG;
   p.c_prev = c_prev;
   p.h_out = reinterpret_cast<float*>(h_out->data);

@@ -7,22 +7,32 @@
 //     the global max-pool side feature of model.py:143 (CELL epilogue).
 //
 // GEMM view: D[M = 128 output pixels][N = BN output channels] += A[M][K] * B[N][K]^T, K = taps x channels.
-//   A  activations, split-bf16 planes (hi|lo), NHWC.  One K chunk = 64 channels of one filter tap of one source: a TMA
-//      box {64 ch, BW, BH, BI images, 2 planes} whose (w, h) start is shifted by the tap offset -- out-of-bounds
-//      pixels/channels are zero-filled by TMA, which is the convolution's zero padding.  BW*BH*BI = 128 rows, each row
-//      128 bytes: exactly the K-major SWIZZLE_128B operand layout of tcgen05.mma.
-//      Stride-2 convolutions read one of four (row, column)-parity sub-grids per tap (separate tensor maps).
-//   B  packed weights [2 planes][cout_pad][k_pad] bf16 (rsis_conv_pack_umma), box {64, BN, 2}.
+//   A  activations, split-bf16 planes (hi|lo), NHWC with an arbitrary pixel pitch (so a convolution can read a channel
+//      slice of a wider buffer).  Rows of the smem tile are pixels, 64 bf16 channels = 128 bytes each: the K-major
+//      SWIZZLE_128B operand layout of tcgen05.mma.  Two ways to stage it:
+//        HALO mode (3x3, stride 1, maps at least 8 x 16): one TMA box {64 ch, 10, 18, 1 image, 2 planes} per
+//          64-channel chunk brings the 8x16-pixel output tile's whole 10x18 input halo ONCE; the nine filter taps are
+//          nine tcgen05 matrix descriptors into that tile (start address shifted by (kh*10+kw) rows, 8-row core
+//          matrices 10 rows = 1280 bytes apart), so L2->smem traffic is 1.4x the tile instead of 9x;
+//        TAP mode (1x1, stride 2, small maps): one box {64 ch, BW, BH, BI images, 2 planes} per (tap, chunk), start
+//          shifted by the tap offset.  Stride-2 convolutions read one of four (row, column)-parity sub-grids per tap.
+//      Out-of-bounds pixels/channels are zero-filled by TMA, which is the convolution's zero padding.
+//   B  packed weights [2 planes][cout_pad][k_pad] bf16 (rsis_conv_pack_umma), one box {64, BN, 2} per (tap, chunk),
+//      in its own smem ring (decoupled from A's: in HALO mode one A stage feeds nine B stages).
 //   D  fp32 accumulators in TMEM, two stages of 128 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (three kind::f16 MMAs per 16-wide K step, fp32 accumulate): relative
-//   product error ~2^-16, which keeps the 104-convolution encoder inside the 1e-3 parity budget.
+//   product error ~2^-16, which keeps the 104-convolution encoder and the T-step recurrence inside the 1e-3 parity
+//   budget (single-pass fp16/bf16/tf32 operands do not: DESIGN.md "precision").
+//   K steps that only cover zero padding (channels beyond C in the last chunk) are not issued.
 //
-// Persistent, warp-specialised CTA (192 threads, one per SM): warps 0-3 epilogue (TMEM lane quarters), warp 4 TMA
-// producer, warp 5 MMA issuer; smem ring of kStages x (32 KB A + up to 32 KB B); mbarrier full/empty + TMEM
-// full/empty pipelines.  Every mbarrier wait is bounded (trap instead of hang).
+// Persistent, warp-specialised CTA (320 threads, one per SM): warps 0-7 epilogue (TMEM lane quarter = warp % 4,
+// column half = warp / 4), warp 8 TMA producer, warp 9 MMA issuer; mbarrier full/empty rings for A and B, TMEM
+// full/empty between MMA and epilogue.  BN (32/64/128) is chosen so that small maps still spread over the 148 SMs.
+// Every mbarrier wait is bounded (trap instead of hang).
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -38,13 +48,15 @@ constexpr int kBK = 64;           // bf16 channels per K chunk == one 128-byte s
 constexpr int kMaxBN = 128;       // accumulator columns per TMEM stage
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kMaxBN * kAccStages;  // 256, power of two
-constexpr int kEpiThreads = 128;
-constexpr int kThreadsUmma = 192;
-constexpr int kABytes = 2 * kBM * 128;          // hi + lo planes of the A tile
-constexpr int kMaxSrc = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreadsUmma = kEpiThreads + 64;
+constexpr int kMaxStages = 8;
+constexpr int kHaloBW = 8, kHaloBH = 16;
+constexpr int kHaloRows = (kHaloBW + 2) * (kHaloBH + 2);  // 180 pixels
 
 struct alignas(64) UmmaMaps {
-  CUtensorMap a[kMaxSrc];  // stride 1: one per source; stride 2: one per (row parity, column parity)
+  CUtensorMap a[4];  // stride 1: a[0]; stride 2: one per (row parity, column parity)
   CUtensorMap b;
 };
 
@@ -53,32 +65,39 @@ struct UmmaParams {
   int BW, BH, BI;          // output-pixel box: width x height x images, product 128
   int tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
   int BN;                  // output channels per tile (32 / 64 / 128)
-  int stages, stage_bytes; // smem ring
+  int halo;                // 1: HALO staging, 0: TAP staging
+  int a_stages, b_stages;
+  int a_plane_bytes;       // bytes of one bf16 plane of an A stage (rows * 128)
+  int a_stage_bytes;       // both planes, rounded up to 1024
+  int b_stage_bytes;       // 2 * BN * 128
   uint32_t a_tx_bytes, b_tx_bytes;
+  uint32_t a_sbo;          // bytes between 8-row core matrices of A
+  int base_off_mode;       // debug knob: put (addr >> 7) & 7 into the descriptor's base-offset field
   // K loop
   int taps, ksize, stride, pad;
-  int n_src;
-  int chunks[kMaxSrc];     // 64-channel chunks of each source
-  int chunks_per_tap;      // chunks per filter tap in the packed weight K layout (includes an omitted zero state)
-  int num_k;               // K chunks actually multiplied per tile
+  int chunks;              // 64-channel chunks of the source
+  int last_ksteps;         // 16-wide K steps that carry data in the last chunk (1..4)
   // problem
   int N, Ho, Wo, Cout;
   // conv epilogue
   const float* scale;
   const float* shift;
   View res;
+  int res_cs;
   int has_res, relu;
   void* y;
   size_t y_plane;
-  int y_fmt;
+  int y_fmt, y_cs;
   void* y2;
   size_t y2_plane;
-  int y2_fmt;
+  int y2_fmt, y2_cs;
   // cell epilogue
   const float* c_prev;
   float* h_out;
   float* c_out;
   __nv_bfloat16* h_split;
+  size_t hs_plane;
+  int hs_cs;
   uint32_t* side_max;
   int side_stride, side_offset;
 };
@@ -169,13 +188,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row core matrices `sbo` bytes apart.
+// The swizzle XOR acts on absolute smem address bits, so a start address shifted by whole rows (HALO taps) or by
+// 32 bytes (K step inside the row) addresses the same TMA-written tile.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, int base_off_mode) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major; canonical 1)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)(sbo >> 4) << 32;             // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+  if (base_off_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
@@ -237,10 +259,9 @@ __device__ __forceinline__ void conv_epilogue_chunk(const UmmaParams& p, const u
     v[1] = fmaf(__uint_as_float(r[4 * q + 1]), sc.y, sh.y);
     v[2] = fmaf(__uint_as_float(r[4 * q + 2]), sc.z, sh.z);
     v[3] = fmaf(__uint_as_float(r[4 * q + 3]), sc.w, sh.w);
-    const size_t idx = pix * p.Cout + col;
     if (p.has_res) {
       float t[4];
-      load4r(p.res, idx, t);
+      load4r(p.res, pix * p.res_cs + col, t);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += t[j];
     }
@@ -248,8 +269,8 @@ __device__ __forceinline__ void conv_epilogue_chunk(const UmmaParams& p, const u
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    store4u(p.y, p.y_plane, p.y_fmt, idx, v);
-    if (p.y2) store4u(p.y2, p.y2_plane, p.y2_fmt, idx, v);
+    store4u(p.y, p.y_plane, p.y_fmt, pix * p.y_cs + col, v);
+    if (p.y2) store4u(p.y2, p.y2_plane, p.y2_fmt, pix * p.y2_cs + col, v);
   }
 }
 
@@ -260,7 +281,6 @@ __device__ __forceinline__ void cell_epilogue_chunk(const UmmaParams& p, const u
   const int Ch = p.Cout >> 2;
   const int ch0 = col0 >> 2;
   if (ch0 >= Ch) return;  // uniform across the warp
-  const size_t MCh = (size_t)p.N * p.Ho * p.Wo * Ch;
   float hval[8];
   if (row_ok) {
     const size_t idx = pix * Ch + ch0;
@@ -288,7 +308,7 @@ __device__ __forceinline__ void cell_epilogue_chunk(const UmmaParams& p, const u
     }
     store8(p.c_out, 0, RSIS_FMT_F32, idx, cval);
     store8(p.h_out, 0, RSIS_FMT_F32, idx, hval);
-    if (p.h_split) store8(p.h_split, MCh, RSIS_FMT_SPLIT_BF16, idx, hval);
+    if (p.h_split) store8(p.h_split, p.hs_plane, RSIS_FMT_SPLIT_BF16, pix * p.hs_cs + ch0, hval);
   }
   if (p.side_max) {
     // global nn.MaxPool2d (model.py:143): max over the rows of this warp that belong to the same image, then one
@@ -310,26 +330,36 @@ template <bool CELL>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
 conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 2 * kAccStages];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages];
   __shared__ uint32_t tmem_slot;
 
   // SWIZZLE_128B operand tiles need 1024-byte alignment
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b = smem_a + p.a_stages * p.a_stage_bytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t full0 = smem_u32(&bars[0]);
-  const uint32_t empty0 = smem_u32(&bars[8]);
-  const uint32_t tfull0 = smem_u32(&bars[16]);
-  const uint32_t tempty0 = smem_u32(&bars[16 + kAccStages]);
+  const uint32_t afull0 = smem_u32(&bars[0]);
+  const uint32_t aempty0 = smem_u32(&bars[kMaxStages]);
+  const uint32_t bfull0 = smem_u32(&bars[2 * kMaxStages]);
+  const uint32_t bempty0 = smem_u32(&bars[3 * kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[4 * kMaxStages]);
+  const uint32_t tempty0 = smem_u32(&bars[4 * kMaxStages + kAccStages]);
 
-  if (warp == 4 && lane == 0) {
-    for (int s = 0; s < p.n_src; ++s) prefetch_tmap(&maps.a[s]);
+  if (warp == kEpiWarps && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    if (p.stride == 2) {
+      prefetch_tmap(&maps.a[1]);
+      prefetch_tmap(&maps.a[2]);
+      prefetch_tmap(&maps.a[3]);
+    }
     prefetch_tmap(&maps.b);
   }
-  if (warp == 5 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+  if (warp == kEpiWarps + 1 && lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(afull0 + 8 * s, 1);
+      mbar_init(aempty0 + 8 * s, 1);
+      mbar_init(bfull0 + 8 * s, 1);
+      mbar_init(bempty0 + 8 * s, 1);
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -348,11 +378,15 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 4) {
+  // A "items" per tile: HALO -> one per chunk (nine B items each); TAP -> one per (tap, chunk) (one B item each).
+  const int b_per_a = p.halo ? p.taps : 1;
+  const int a_items = p.halo ? p.chunks : p.taps * p.chunks;
+
+  if (warp == kEpiWarps) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nt = tile % p.tiles_n;
         int mt = tile / p.tiles_n;
@@ -361,18 +395,20 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         const int th = mt % p.tiles_h;
         const int ti = mt / p.tiles_h;
         const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-          int kc = tap * p.chunks_per_tap;  // chunk index in the packed weight K layout [tap][source][chunk]
-          for (int s = 0; s < p.n_src; ++s) {
-            for (int cc = 0; cc < p.chunks[s]; ++cc, ++kc) {
-              mbar_wait(empty0 + 8 * stage, phase ^ 1u);
-              const uint32_t sa = smem_base + stage * p.stage_bytes;
-              const uint32_t sb = sa + kABytes;
-              const uint32_t bar = full0 + 8 * stage;
-              mbar_arrive_expect_tx(bar, p.a_tx_bytes + p.b_tx_bytes);
+        for (int ai = 0; ai < a_items; ++ai) {
+          const int cc = p.halo ? ai : ai % p.chunks;
+          const int tap0 = p.halo ? 0 : ai / p.chunks;
+          mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+          {
+            const uint32_t sa = smem_a + as * p.a_stage_bytes;
+            const uint32_t bar = afull0 + 8 * as;
+            mbar_arrive_expect_tx(bar, p.a_tx_bytes);
+            if (p.halo) {
+              tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
+            } else {
+              const int kh = tap0 / p.ksize, kw = tap0 - kh * p.ksize;
               if (p.stride == 1) {
-                tma_load_5d(sa, &maps.a[s], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
+                tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
               } else {
                 // input pixel = 2*out + k - pad: parity (k - pad) & 1, sub-grid index out + floor((k - pad) / 2)
                 const int dh = kh - p.pad, dw = kw - p.pad;
@@ -380,47 +416,75 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
                 tma_load_5d(sa, &maps.a[ph * 2 + pw], bar, cc * kBK, w0 + ((dw - pw) >> 1), h0 + ((dh - ph) >> 1), i0,
                             0);
               }
-              tma_load_3d(sb, &maps.b, bar, kc * kBK, nt * p.BN, 0);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
+            }
+          }
+          if (++as == p.a_stages) {
+            as = 0;
+            aph ^= 1u;
+          }
+          for (int bi = 0; bi < b_per_a; ++bi) {
+            const int tap = tap0 + bi;
+            mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+            const uint32_t bar = bfull0 + 8 * bs;
+            mbar_arrive_expect_tx(bar, p.b_tx_bytes);
+            tma_load_3d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, (tap * p.chunks + cc) * kBK, nt * p.BN, 0);
+            if (++bs == p.b_stages) {
+              bs = 0;
+              bph ^= 1u;
             }
           }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kEpiWarps + 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((kBM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * kMaxBN;
-        for (int kc = 0; kc < p.num_k; ++kc) {
-          mbar_wait(full0 + 8 * stage, phase);
+        uint32_t accumulate = 0;
+        for (int ai = 0; ai < a_items; ++ai) {
+          const int cc = p.halo ? ai : ai % p.chunks;
+          const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+          mbar_wait(afull0 + 8 * as, aph);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sb = sa + kABytes;
-          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + kBM * 128);
-          const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + p.BN * 128);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
-            umma_bf16(d, a_hi + adv, b_hi + adv, idesc, (kc | k) ? 1u : 0u);
-            umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+          const uint32_t sa = smem_a + as * p.a_stage_bytes;
+          for (int bi = 0; bi < b_per_a; ++bi) {
+            mbar_wait(bfull0 + 8 * bs, bph);
+            tc_fence_after();
+            const uint32_t sb = smem_b + bs * p.b_stage_bytes;
+            uint32_t sat = sa;
+            if (p.halo) {
+              const int kh = bi / 3, kw = bi - kh * 3;
+              sat += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
+            }
+            const uint64_t a_hi = make_smem_desc(sat, p.a_sbo, p.base_off_mode);
+            const uint64_t a_lo = make_smem_desc(sat + p.a_plane_bytes, p.a_sbo, p.base_off_mode);
+            const uint64_t b_hi = make_smem_desc(sb, 1024, 0), b_lo = make_smem_desc(sb + p.BN * 128, 1024, 0);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
+              umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
+              umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+            if (++bs == p.b_stages) {
+              bs = 0;
+              bph ^= 1u;
+            }
           }
-          umma_commit(empty0 + 8 * stage);  // smem slot free once these MMAs have read it
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
+          umma_commit(aempty0 + 8 * as);  // activation slot free
+          if (++as == p.a_stages) {
+            as = 0;
+            aph ^= 1u;
           }
         }
         umma_commit(tfull0 + 8 * acc);  // accumulator complete
@@ -431,8 +495,10 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
       }
     }
   } else {
-    // =============================== epilogue (warps 0-3) ===============================
-    const int row = threadIdx.x;  // accumulator row == TMEM lane
+    // =============================== epilogue (warps 0-7) ===============================
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = warp >> 2;         // which 32-column chunks (even / odd) this warp handles
+    const int row = quarter * 32 + lane;  // accumulator row == TMEM lane
     const int wl = row % p.BW;
     const int hl = (row / p.BW) % p.BH;
     const int il = row / (p.BW * p.BH);
@@ -452,8 +518,8 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
       const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * kMaxBN;
-      for (int c32 = 0; c32 < p.BN; c32 += 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
+      for (int c32 = half * 32; c32 < p.BN; c32 += 64) {
         const int col0 = nt * p.BN + c32;
         if (col0 >= p.Cout) break;
         uint32_t r[32];
@@ -489,12 +555,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 int g_init_status = RSIS_OK;
+int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
+int g_base_off_mode = 0;   // RSIS_B200_HALO_BASEOFF=1 sets the descriptor base-offset field (debug)
+int g_min_ctas = 120;      // BN is shrunk until a launch has at least this many tiles (RSIS_B200_MIN_CTAS)
 std::once_flag g_once;
 
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kDynSmem = kSmemLimit - 1024;  // static barriers live beside it
 
 void init_once() {
+  if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_HALO_BASEOFF")) g_base_off_mode = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_MIN_CTAS")) g_min_ctas = atoi(e);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -522,12 +594,13 @@ int next_pow2(int v) {
   return r;
 }
 
-// 5-D view {C, W', H', N, plane} of a split-bf16 NHWC activation; (sub = 2: one parity sub-grid of a stride-2 conv).
+// 5-D view {C, W', H', N, plane} of a split-bf16 NHWC activation with pixel pitch `cs` elements
+// (sub = 2: one parity sub-grid of a stride-2 conv).
 int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw, int BW, int BH, int BI) {
-  const size_t C = t.c, W = t.w, H = t.h, N = t.n;
-  char* base = reinterpret_cast<char*>(t.data) + ((size_t)ph * W + pw) * C * 2;
+  const size_t C = t.c, W = t.w, H = t.h, N = t.n, P = pitch(t);
+  char* base = reinterpret_cast<char*>(t.data) + ((size_t)ph * W + pw) * P * 2;
   cuuint64_t dims[5] = {C, W / sub, H / sub, N, 2};
-  cuuint64_t strides[4] = {C * 2 * sub, W * C * 2 * sub, H * W * C * 2, N * H * W * C * 2};
+  cuuint64_t strides[4] = {P * 2 * sub, W * P * 2 * sub, H * W * P * 2, N * H * W * P * 2};
   cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, 2};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
@@ -547,77 +620,95 @@ int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int k_pad, in
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
 }
 
-bool common_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, int stride, int pad,
-                      bool allow_missing_tail) {
-  if (!srcs || !w || n_src < 1 || n_src > 3 || !w->w_umma || !w->scale || !w->shift) return false;
+bool split_ok(const rsis_tensor* t) {
+  return valid_tensor(t) && t->fmt == RSIS_FMT_SPLIT_BF16 && aligned16(t->data) && pitch(*t) % 8 == 0;
+}
+bool out_ok(const rsis_tensor* t) { return valid_tensor(t) && aligned16(t->data) && pitch(*t) % 4 == 0; }
+
+bool common_supported(const rsis_tensor* x, const rsis_conv_weights* w, int stride, int pad) {
+  if (!x || !w || !w->w_umma || !w->scale || !w->shift) return false;
   if (w->kh != w->kw || (w->kh != 1 && w->kh != 3) || pad != w->kh / 2) return false;
   if (stride != 1 && stride != 2) return false;
   if (w->cout % 4 != 0 || w->cout < 4) return false;
-  int c = 0;
-  for (int s = 0; s < n_src; ++s) {
-    if (!valid_tensor(&srcs[s]) || srcs[s].fmt != RSIS_FMT_SPLIT_BF16) return false;
-    if (srcs[s].c % 8 != 0 || !aligned16(srcs[s].data)) return false;
-    if (srcs[s].n != srcs[0].n || srcs[s].h != srcs[0].h || srcs[s].w != srcs[0].w) return false;
-    c += srcs[s].c;
-  }
-  if (c != w->cin && !(allow_missing_tail && c < w->cin)) return false;
-  if (stride == 2 && (n_src != 1 || (srcs[0].h & 1) || (srcs[0].w & 1))) return false;
+  if (!split_ok(x) || x->c != w->cin) return false;
+  if (stride == 2 && ((x->h & 1) || (x->w & 1))) return false;
   if (!aligned16(w->w_umma) || !aligned16(w->scale) || !aligned16(w->shift)) return false;
   return true;
 }
 
-// Fills geometry, tensor maps and the K loop.  `missing_tail_c` > 0: a ConvLSTM step whose state is None omits the
-// trailing prev_hidden source (clstm.py:26-37 materialises zeros); its K chunks exist in the packed weights and are
-// simply never multiplied.
-int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, int stride,
-          int pad, int missing_tail_c) {
+// Fills geometry, tensor maps and the K loop.
+int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w, int stride, int pad) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK) return g_init_status;
-  const rsis_tensor& x = srcs[0];
   p.N = x.n;
   p.Ho = x.h / stride;
   p.Wo = x.w / stride;
   p.Cout = w->cout;
-  p.BW = next_pow2(p.Wo) < kBM ? next_pow2(p.Wo) : kBM;
-  p.BH = next_pow2(p.Ho) < kBM / p.BW ? next_pow2(p.Ho) : kBM / p.BW;
-  p.BI = kBM / (p.BW * p.BH);
-  p.tiles_w = ceil_div(p.Wo, p.BW);
-  p.tiles_h = ceil_div(p.Ho, p.BH);
-  p.tiles_i = ceil_div(p.N, p.BI);
-  p.BN = w->cout <= 32 ? 32 : (w->cout <= 64 ? 64 : 128);
-  p.tiles_n = ceil_div(w->cout, p.BN);
-  const long long nt = (long long)p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
-  if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
-  p.num_tiles = (int)nt;
-  p.a_tx_bytes = (uint32_t)kABytes;
-  p.b_tx_bytes = (uint32_t)(2 * p.BN * 128);
-  p.stage_bytes = kABytes + 2 * p.BN * 128;
-  p.stages = (kDynSmem - 1024) / p.stage_bytes;
-  if (p.stages > 8) p.stages = 8;
   p.taps = w->kh * w->kw;
   p.ksize = w->kw;
   p.stride = stride;
   p.pad = pad;
+  p.halo = (g_halo_enabled && w->kh == 3 && stride == 1 && p.Wo % kHaloBW == 0 && p.Ho % kHaloBH == 0) ? 1 : 0;
+  if (p.halo) {
+    p.BW = kHaloBW;
+    p.BH = kHaloBH;
+    p.BI = 1;
+  } else {
+    p.BW = next_pow2(p.Wo) < kBM ? next_pow2(p.Wo) : kBM;
+    p.BH = next_pow2(p.Ho) < kBM / p.BW ? next_pow2(p.Ho) : kBM / p.BW;
+    p.BI = kBM / (p.BW * p.BH);
+  }
+  p.tiles_w = ceil_div(p.Wo, p.BW);
+  p.tiles_h = ceil_div(p.Ho, p.BH);
+  p.tiles_i = ceil_div(p.N, p.BI);
+  const long long mt = (long long)p.tiles_w * p.tiles_h * p.tiles_i;
+  // largest BN that still gives every SM a tile; small maps fall back to narrower tiles
+  p.BN = w->cout <= 32 ? 32 : (w->cout <= 64 ? 64 : 128);
+  while (p.BN > 32 && mt * ceil_div(w->cout, p.BN) < g_min_ctas) p.BN >>= 1;
+  p.tiles_n = ceil_div(w->cout, p.BN);
+  const long long nt = mt * p.tiles_n;
+  if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
+  p.num_tiles = (int)nt;
+  p.chunks = ceil_div(x.c, kBK);
+  p.last_ksteps = ceil_div(x.c - (p.chunks - 1) * kBK, 16);
+  const int a_rows = p.halo ? kHaloRows : kBM;
+  p.a_plane_bytes = a_rows * 128;
+  p.a_tx_bytes = (uint32_t)(2 * p.a_plane_bytes);
+  p.a_stage_bytes = round_up(2 * p.a_plane_bytes, 1024);
+  p.a_sbo = p.halo ? (uint32_t)(kHaloBW + 2) * 128u : 1024u;
+  p.base_off_mode = g_base_off_mode;
+  p.b_stage_bytes = 2 * p.BN * 128;
+  p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
+  const int budget = kDynSmem - 1024;
+  if (p.halo) {
+    p.a_stages = 2;
+    p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+    if (p.b_stages > kMaxStages) {
+      p.b_stages = kMaxStages;
+      p.a_stages = (budget - p.b_stages * p.b_stage_bytes) / p.a_stage_bytes;
+      if (p.a_stages > 3) p.a_stages = 3;
+    }
+  } else {
+    p.a_stages = budget / (p.a_stage_bytes + p.b_stage_bytes);
+    if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
+    p.b_stages = p.a_stages;
+  }
+  if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
   p.scale = w->scale;
   p.shift = w->shift;
-  int present = 0;
-  for (int s = 0; s < n_src; ++s) {
-    p.chunks[s] = ceil_div(srcs[s].c, kBK);
-    present += p.chunks[s];
-  }
-  p.n_src = n_src;
-  p.chunks_per_tap = present + (missing_tail_c > 0 ? ceil_div(missing_tail_c, kBK) : 0);
-  p.num_k = p.taps * present;
   const int cout_pad = round_up(w->cout, 16);
-  const int k_pad = p.taps * p.chunks_per_tap * kBK;
+  const int k_pad = p.taps * p.chunks * kBK;
   if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN)) return e;
   if (stride == 1) {
-    for (int s = 0; s < n_src; ++s)
-      if (int e = encode_act_map(&maps.a[s], srcs[s], 1, 0, 0, p.BW, p.BH, p.BI)) return e;
+    if (p.halo) {
+      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1)) return e;
+    } else {
+      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, p.BW, p.BH, p.BI)) return e;
+    }
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
-        if (int e = encode_act_map(&maps.a[ph * 2 + pw], srcs[0], 2, ph, pw, p.BW, p.BH, p.BI)) return e;
+        if (int e = encode_act_map(&maps.a[ph * 2 + pw], x, 2, ph, pw, p.BW, p.BH, p.BI)) return e;
   }
   return RSIS_OK;
 }
@@ -634,31 +725,36 @@ int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
 
 bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                            const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad) {
-  if (!common_supported(srcs, n_src, w, stride, pad, false) || w->gate_interleaved) return false;
-  if (!valid_tensor(y) || !aligned16(y->data)) return false;
-  if (y2 && (!valid_tensor(y2) || !aligned16(y2->data))) return false;
-  if (residual && (!valid_tensor(residual) || !aligned16(residual->data))) return false;
+  if (n_src != 1 || !common_supported(srcs, w, stride, pad) || w->gate_interleaved) return false;
+  if (!out_ok(y)) return false;
+  if (y2 && !out_ok(y2)) return false;
+  if (residual && !out_ok(residual)) return false;
   return true;
 }
 
 int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                 const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, cudaStream_t st) {
+  (void)n_src;
   UmmaMaps maps;
   UmmaParams p{};
-  if (int e = setup(maps, p, srcs, n_src, w, stride, pad, 0)) return e;
+  if (int e = setup(maps, p, srcs[0], w, stride, pad)) return e;
   if (y->n != p.N || y->h != p.Ho || y->w != p.Wo || y->c != p.Cout) return RSIS_ERR_BAD_ARG;
   p.y = y->data;
-  p.y_plane = numel(*y);
+  p.y_cs = pitch(*y);
+  p.y_plane = plane_elems(*y);
   p.y_fmt = y->fmt;
   if (y2) {
-    if (numel(*y2) != numel(*y) || y2->c != y->c) return RSIS_ERR_BAD_ARG;
+    if (y2->n != y->n || y2->h != y->h || y2->w != y->w || y2->c != y->c) return RSIS_ERR_BAD_ARG;
     p.y2 = y2->data;
-    p.y2_plane = numel(*y2);
+    p.y2_cs = pitch(*y2);
+    p.y2_plane = plane_elems(*y2);
     p.y2_fmt = y2->fmt;
   }
   if (residual) {
-    if (numel(*residual) != numel(*y) || residual->c != y->c) return RSIS_ERR_BAD_ARG;
+    if (residual->n != y->n || residual->h != y->h || residual->w != y->w || residual->c != y->c)
+      return RSIS_ERR_BAD_ARG;
     p.res = make_view(*residual);
+    p.res_cs = pitch(*residual);
     p.has_res = 1;
   }
   p.relu = relu ? 1 : 0;
@@ -666,32 +762,35 @@ int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
 }
 
 bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w) {
-  if (!w || !w->gate_interleaved || !common_supported(srcs, n_src, w, 1, w->kh / 2, true)) return false;
+  if (n_src != 1 || !w || !w->gate_interleaved || !common_supported(srcs, w, 1, w->kh / 2)) return false;
   return (w->cout / 4) % 8 == 0;  // the epilogue handles 8 hidden channels (32 gate columns) at a time
 }
 
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, cudaStream_t st) {
+  (void)n_src;
   UmmaMaps maps;
   UmmaParams p{};
-  int csum = 0;
-  for (int s = 0; s < n_src; ++s) csum += srcs[s].c;
-  if (csum != w->cin && (c_prev || w->cin - csum != w->cout / 4)) return RSIS_ERR_BAD_ARG;
-  if (int e = setup(maps, p, srcs, n_src, w, 1, w->kh / 2, w->cin - csum)) return e;
+  if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2)) return e;
   const int Ch = p.Cout / 4;
   auto ok = [&](const rsis_tensor* t, int fmt) {
     return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&
            aligned16(t->data);
   };
-  if (!ok(h_out, RSIS_FMT_F32) || !ok(c_out, RSIS_FMT_F32)) return RSIS_ERR_BAD_ARG;
-  if (h_split && !ok(h_split, RSIS_FMT_SPLIT_BF16)) return RSIS_ERR_BAD_ARG;
+  if (!ok(h_out, RSIS_FMT_F32) || !ok(c_out, RSIS_FMT_F32) || pitch(*h_out) != Ch || pitch(*c_out) != Ch)
+    return RSIS_ERR_BAD_ARG;
+  if (h_split && (!ok(h_split, RSIS_FMT_SPLIT_BF16) || pitch(*h_split) % 8 != 0)) return RSIS_ERR_BAD_ARG;
   if (side_max && (side_stride < side_offset + Ch || side_offset < 0)) return RSIS_ERR_BAD_ARG;
   if (c_prev && !aligned16(c_prev)) return RSIS_ERR_ALIGN;
   p.c_prev = c_prev;
   p.h_out = reinterpret_cast<float*>(h_out->data);
   p.c_out = reinterpret_cast<float*>(c_out->data);
-  p.h_split = h_split ? reinterpret_cast<__nv_bfloat16*>(h_split->data) : nullptr;
+  if (h_split) {
+    p.h_split = reinterpret_cast<__nv_bfloat16*>(h_split->data);
+    p.hs_cs = pitch(*h_split);
+    p.hs_plane = plane_elems(*h_split);
+  }
   p.side_max = side_max;
   p.side_stride = side_stride;
   p.side_offset = side_offset;

@@ -69,8 +69,8 @@ __global__ void maxpool3x3s2_kernel(View x, void* y, size_t y_plane, int y_fmt, 
 // nn.UpsamplingBilinear2d(size) == bilinear with align_corners=True -- /root/reference/src/modules/model.py:149-150,
 // 163-164.  Index arithmetic follows ATen's area_pixel_compute_source_index(align_corners=true): src = scale * dst with
 // scale = (in - 1) / (out - 1) evaluated in float.
-__global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_fmt, int N, int H, int W, int C,
-                                         int Ho, int Wo, float sh, float sw) {
+__global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_fmt, int y_cs, int N, int H, int W,
+                                         int C, int Ho, int Wo, float sh, float sw) {
   const int C4 = C >> 2;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -94,7 +94,7 @@ __global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       o[j] = h0l * (w0l * v00[j] + w1l * v01[j]) + h1l * (w0l * v10[j] + w1l * v11[j]);
-    store4v(y, y_plane, y_fmt, (((size_t)n * Ho + ho) * Wo + wo) * C + c, o);
+    store4v(y, y_plane, y_fmt, (((size_t)n * Ho + ho) * Wo + wo) * y_cs + c, o);
   }
 }
 
@@ -204,7 +204,7 @@ int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t 
   if (!valid_tensor(x) || !valid_tensor(y)) return RSIS_ERR_BAD_ARG;
   const int Ho = (x->h + 2 - 3) / 2 + 1, Wo = (x->w + 2 - 3) / 2 + 1;
   if (y->n != x->n || y->c != x->c || y->h != Ho || y->w != Wo) return RSIS_ERR_BAD_ARG;
-  if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
+  if (x->c % 4 != 0 || !is_dense(*x) || !is_dense(*y)) return RSIS_ERR_UNSUPPORTED;
   if (!aligned16(x->data) || !aligned16(y->data)) return RSIS_ERR_ALIGN;
   const size_t total = numel(*y) / 4;
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(make_view(*x), y->data, numel(*y), y->fmt,
@@ -215,13 +215,13 @@ int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t 
 
 int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
   if (!valid_tensor(x) || !valid_tensor(y) || y->n != x->n || y->c != x->c) return RSIS_ERR_BAD_ARG;
-  if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
+  if (x->c % 4 != 0 || !is_dense(*x) || pitch(*y) % 4 != 0) return RSIS_ERR_UNSUPPORTED;
   if (!aligned16(x->data) || !aligned16(y->data)) return RSIS_ERR_ALIGN;
   const float sh = y->h > 1 ? (float)(x->h - 1) / (float)(y->h - 1) : 0.f;
   const float sw = y->w > 1 ? (float)(x->w - 1) / (float)(y->w - 1) : 0.f;
   const size_t total = numel(*y) / 4;
   upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      make_view(*x), y->data, numel(*y), y->fmt, x->n, x->h, x->w, x->c, y->h, y->w, sh, sw);
+      make_view(*x), y->data, plane_elems(*y), y->fmt, pitch(*y), x->n, x->h, x->w, x->c, y->h, y->w, sh, sw);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }
@@ -229,7 +229,8 @@ int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stre
 int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias, int ksize, float* logits,
                    float* prob_out, int64_t prob_stride_n, rsis_stream_t stream) {
   if (!valid_tensor(x) || !w_oihw || (!logits && !prob_out)) return RSIS_ERR_BAD_ARG;
-  if (x->fmt != RSIS_FMT_F32 || x->c % 4 != 0 || x->c > 256 || (ksize != 1 && ksize != 3)) return RSIS_ERR_UNSUPPORTED;
+  if (x->fmt != RSIS_FMT_F32 || x->c % 4 != 0 || x->c > 256 || (ksize != 1 && ksize != 3) || !is_dense(*x))
+    return RSIS_ERR_UNSUPPORTED;
   if (!aligned16(x->data)) return RSIS_ERR_ALIGN;
   const size_t total = (size_t)x->n * x->h * x->w;
   const size_t smem = (size_t)ksize * ksize * x->c * sizeof(float);

@@ -23,16 +23,42 @@ def _mask_size(h: int, w: int) -> Tuple[int, int]:
     return 2 * ((h - 1) // 2 + 1), 2 * ((w - 1) // 2 + 1)
 
 
+def feature_sizes(h: int, w: int):
+    """Spatial sizes of the five decoder levels (x5 .. x1 of vision.py:11-21) for an h x w image: the stem conv
+    (k7 s2 p3), the max-pool (k3 s2 p1) and the three stride-2 3x3 convs (p1) each map n -> (n - 1) // 2 + 1."""
+    sizes = []
+    for _ in range(5):
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        sizes.append((h, w))
+    return sizes[::-1]
+
+
 def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: torch.Tensor,
-              out_classes: torch.Tensor, out_stops: torch.Tensor, feats_op=None):
-    """Encoder once + T decoder steps, writing into the stacked outputs. Pure kernel launches on the current stream."""
+              out_classes: torch.Tensor, out_stops: torch.Tensor, feats_op=None, ws=None):
+    """Encoder once + T decoder steps, writing into the stacked outputs. Pure kernel launches on the current stream.
+
+    tcgen05 kernel family: runs inside a `DecoderWorkspace` (`ws`, created when not given) -- the skip heads write
+    straight into the decoder's concatenated input buffers and every step is 13 launches with no allocation.
+    Returns the workspace (tcgen05) or the final state list (CUDA-core family)."""
     B, _, H, W = x.shape
     if _mask_size(H, W) != (H, W):
         raise NotImplementedError("rsis_b200.test: input height and width must be even (mask is produced at "
                                   "2*ceil(H/2) x 2*ceil(W/2); the resize of test.py:39-40 is not implemented)")
+    C = out_classes.shape[-1]
+    if ops.uses_tcgen05(impl):
+        if ws is None:
+            ws = decoder.workspace(B, feature_sizes(H, W), x.device)
+        if feats_op is None:
+            encoder.forward_act(x, impl, skip_out=ws.skip_views())
+        else:
+            ws.load_feats(feats_op)
+        ws.reset()
+        for t in range(T):
+            decoder.step_ws(ws, impl, None, out_classes[:, t], T * C, None, T, mask_prob=out_masks[:, t],
+                            mask_prob_stride=T * H * W, stop_prob=out_stops[:, t])
+        return ws
     if feats_op is None:
         _, feats_op = encoder.forward_act(x, impl)
-    C = out_classes.shape[-1]
     state = None
     for t in range(T):
         state = decoder.step_act(feats_op, state, impl, None, out_classes[:, t], T * C, None, T,
@@ -59,17 +85,21 @@ class InferenceSession:
         self.launches = 0
         encoder.eval()
         decoder.eval()
+        self.ws = None
+        if ops.uses_tcgen05(self.impl):
+            with torch.cuda.device(device):
+                self.ws = decoder.workspace(B, feature_sizes(H, W), device)
         # warm-up: builds the packed-weight caches and loads every kernel outside the capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side), torch.no_grad():
-            run_eager(encoder, decoder, self.x, self.T, self.impl, self.masks, self.classes, self.stops)
+            run_eager(encoder, decoder, self.x, self.T, self.impl, self.masks, self.classes, self.stops, ws=self.ws)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
         with torch.cuda.graph(g), torch.no_grad():
-            run_eager(encoder, decoder, self.x, self.T, self.impl, self.masks, self.classes, self.stops)
+            run_eager(encoder, decoder, self.x, self.T, self.impl, self.masks, self.classes, self.stops, ws=self.ws)
         self.launches = ops.launch_count() - n0
         self.graph = g
 

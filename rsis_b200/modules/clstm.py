@@ -46,7 +46,10 @@ class ConvLSTMCell(nn.Module):
         fmt = ops.activation_format(impl)
         have_state = prev_h is not None
         srcs = list(inputs) + ([prev_h] if have_state else [])
-        chans = [s.c for s in inputs] + [self.hidden_size]  # weight K layout always includes the hidden block
+        if fmt == ops.FMT_SPLIT_BF16:
+            chans = [self.input_size + self.hidden_size]  # the tcgen05 kernel reads ONE concatenated buffer
+        else:
+            chans = [s.c for s in inputs] + [self.hidden_size]  # weight K layout always includes the hidden block
         pc = self.packed(chans, want_umma=(fmt == ops.FMT_SPLIT_BF16))
         return ops.convlstm_cell(srcs, pc, prev_c if have_state else None, side_max, side_offset,
                                  want_split=(fmt == ops.FMT_SPLIT_BF16), impl=impl)

@@ -70,8 +70,13 @@ class FeatureExtractor(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False):
-        """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each."""
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, skip_out=None):
+        """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each.
+
+        skip_out (tcgen05 path only): five (view, view) pairs -- the skip-feature slices of the decoder's two
+        ping-pong input buffers (`DecoderWorkspace.skip_views()`).  The head convolutions then write their result
+        straight into those slices (the `torch.cat([hidden, skip], 1)` of model.py:153 never runs) and no float32
+        copy is produced; returns (None, None)."""
         impl = ops.default_impl() if impl is None else impl
         taps = self.base.forward_act(x, impl)
         if raw:
@@ -80,6 +85,12 @@ class FeatureExtractor(nn.Module):
             raise NotImplementedError("rsis_b200: train-mode BatchNorm is not implemented yet; call .eval()")
         fmt = ops.activation_format(impl)
         heads = self.packed_heads(want_umma=(fmt == ops.FMT_SPLIT_BF16))
+        if skip_out is not None:
+            if fmt != ops.FMT_SPLIT_BF16:
+                raise RuntimeError("skip_out needs the tcgen05 kernel family")
+            for tap, pc, (v0, v1) in zip(taps, heads, skip_out):
+                ops.conv2d([tap], pc, pad=self.padding, impl=impl, out=v0, out2=v1)
+            return None, None
         feats, feats_op = [], []
         for tap, pc in zip(taps, heads):
             if fmt == ops.FMT_F32:
@@ -105,6 +116,60 @@ class FeatureExtractor(nn.Module):
                 ops.attach_operand_copy(t, fo)  # lets the decoder skip re-deriving the split-bf16 copy
             outs.append(t)
         return tuple(outs)
+
+
+class DecoderWorkspace:
+    """Device buffers of the tcgen05 decoder for one (batch, feature-map sizes): per level l two ping-pong input
+    buffers X[l][p] = NHWC split-bf16 [up(h_{l-1}) | skip_l | h_prev_l] (level 0: [x5_skip | h_prev]) -- the
+    operand of the fused cell kernel, i.e. `torch.cat([hidden, skip], 1)` (model.py:153) and
+    `torch.cat((input_, prev_hidden), 1)` (clstm.py:43) laid out once; producers write their slice in place:
+      skip_l   by the encoder's skip head (or `load_feats`), once per batch, into both buffers;
+      up(h)    by the bilinear-upsample kernel of step t into X[l][t % 2];
+      h_prev   by the cell kernel's epilogue of step t into X[l][(t + 1) % 2] (a step reads its neighbours' h_prev
+               with a 3x3 halo, hence the ping-pong).
+    Plus float32 h / c per level (c is updated in place), the x2-upsampled last hidden for the mask head and the
+    side-feature max keys."""
+
+    def __init__(self, decoder: "RSIS", n: int, sizes, device):
+        self.n, self.sizes = n, [tuple(s) for s in sizes]
+        cells = decoder.clstm_list
+        self.hidden = [c.hidden_size for c in cells]
+        self.cin = [c.input_size + c.hidden_size for c in cells]
+        self.up_c = [0] + self.hidden[:-1]                              # channels of up(h_{l-1})
+        self.skip_c = [c.input_size - u for c, u in zip(cells, self.up_c)]
+        self.h_off = [c.input_size for c in cells]
+        F16 = ops.FMT_SPLIT_BF16
+        self.X = [[ops.Act.zeros(n, h, w, ct, F16, device) for _ in range(2)] for (h, w), ct in zip(self.sizes, self.cin)]
+        self.h = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
+        self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
+        hl, wl = self.sizes[-1]
+        self.up_last = ops.Act.empty(n, 2 * hl, 2 * wl, self.hidden[-1], ops.FMT_F32, device)
+        self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
+        self.t = 0
+        self.feats_key = None
+
+    def skip_views(self):
+        return [(self.X[l][0].slice(self.up_c[l], self.skip_c[l]), self.X[l][1].slice(self.up_c[l], self.skip_c[l]))
+                for l in range(len(self.X))]
+
+    def h_view(self, l: int, p: int) -> Act:
+        return self.X[l][p].slice(self.h_off[l], self.hidden[l])
+
+    def up_view(self, l: int, p: int) -> Act:
+        return self.X[l][p].slice(0, self.up_c[l])
+
+    def load_feats(self, feats: Sequence[Act]):
+        """Copies the five skip features (either element format, dense) into both ping-pong buffers."""
+        for (v0, v1), f in zip(self.skip_views(), feats):
+            ops.convert(f, ops.FMT_SPLIT_BF16, out=v0)
+            ops.convert(f, ops.FMT_SPLIT_BF16, out=v1)
+
+    def reset(self):
+        """New sequence: hidden state None == zeros (clstm.py:26-37)."""
+        for l in range(len(self.X)):
+            sl = slice(self.h_off[l], self.h_off[l] + self.hidden[l])
+            self.X[l][0].t[..., sl].zero_()
+        self.t = 0
 
 
 class RSIS(nn.Module):
@@ -136,6 +201,35 @@ class RSIS(nn.Module):
         self.fc_dim = sum(skip_dims_out)
         self.fc_class = nn.Linear(self.fc_dim, self.num_classes)
         self.fc_stop = nn.Linear(self.fc_dim, 1)
+
+    def workspace(self, n: int, sizes, device) -> DecoderWorkspace:
+        return DecoderWorkspace(self, n, sizes, device)
+
+    def step_ws(self, ws: DecoderWorkspace, impl: int, mask_logits: Optional[torch.Tensor],
+                class_probs: torch.Tensor, class_stride: int, stop_logit: Optional[torch.Tensor],
+                stop_stride: int, mask_prob: Optional[torch.Tensor] = None, mask_prob_stride: int = 0,
+                stop_prob: Optional[torch.Tensor] = None):
+        """One decoder time-step of the tcgen05 fast path, entirely inside `ws` (13 kernel launches, no allocation):
+        per level [upsample into the input buffer] + fused cell; then x2 upsample, mask head, class/stop heads."""
+        if self.fc_class.in_features != self.fc_dim:
+            raise RuntimeError("fc_class.in_features does not match the decoder's side-feature width")
+        p = ws.t & 1
+        ws.side.zero_()
+        off = 0
+        nlev = len(self.clstm_list)
+        for l, cell in enumerate(self.clstm_list):
+            x = ws.X[l][p]
+            if l > 0:
+                ops.upsample_bilinear(ws.h[l - 1], x.h, x.w, out=ws.up_view(l, p))
+            pc = cell.packed([cell.input_size + cell.hidden_size], want_umma=True)
+            ops.convlstm_cell_x(x, pc, ws.c[l].t if ws.t > 0 else None, ws.side, off, h_out=ws.h[l], c_out=ws.c[l],
+                                h16_out=ws.h_view(l, 1 - p), impl=impl)
+            off += cell.hidden_size
+        ops.upsample_bilinear(ws.h[nlev - 1], ws.up_last.h, ws.up_last.w, out=ws.up_last)
+        ops.mask_head(ws.up_last, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob, mask_prob_stride)
+        ops.class_stop_heads(ws.side, self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight, self.fc_stop.bias,
+                             class_probs, class_stride, stop_logit, stop_prob, stop_stride)
+        ws.t += 1
 
     def step_act(self, feats: Sequence[Act], prev, impl: int, mask_logits: torch.Tensor,
                  class_probs: torch.Tensor, class_stride: int, stop_logit: Optional[torch.Tensor],

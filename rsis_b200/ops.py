@@ -133,15 +133,16 @@ def _src_array(srcs: Sequence[Act]):
 
 def conv2d(srcs: Sequence[Act], pc: PackedConv, stride: int = 1, pad: int = 0, relu: bool = False,
            residual: Optional[Act] = None, out_fmt: int = FMT_F32, out2_fmt: Optional[int] = None,
-           impl: int = IMPL_AUTO, out: Optional[Act] = None):
-    """conv (+folded BN/bias) (+residual) (+ReLU); inputs concatenated along C. Returns y or (y, y2)."""
+           impl: int = IMPL_AUTO, out: Optional[Act] = None, out2: Optional[Act] = None):
+    """conv (+folded BN/bias) (+residual) (+ReLU); inputs concatenated along C. Returns y or (y, y2).
+    `out` / `out2` may be pitched channel-slice views (the result lands inside a wider NHWC buffer)."""
     lib = _lib.load()
     x = srcs[0]
     ho = (x.h + 2 * pad - pc.kh) // stride + 1
     wo = (x.w + 2 * pad - pc.kw) // stride + 1
     dev = x.t.device
     y = out if out is not None else Act.empty(x.n, ho, wo, pc.cout, out_fmt, dev)
-    y2 = Act.empty(x.n, ho, wo, pc.cout, out2_fmt, dev) if out2_fmt is not None else None
+    y2 = out2 if out2 is not None else (Act.empty(x.n, ho, wo, pc.cout, out2_fmt, dev) if out2_fmt is not None else None)
     check(lib.rsis_conv2d(_src_array(srcs), len(srcs), pc.ref(), residual.ref() if residual is not None else None,
                           y.ref(), y2.ref() if y2 is not None else None, stride, pad, int(relu), impl,
                           _lib.stream_ptr()), "conv2d")
@@ -168,23 +169,62 @@ def nchw_to_nhwc(x: torch.Tensor, fmt: int = FMT_F32) -> Act:
     return y
 
 
-def convert(x: Act, fmt: int) -> Act:
+def convert(x: Act, fmt: int, out: Optional[Act] = None) -> Act:
+    """Element-format conversion and/or channel-slice copy (`out` may be a pitched view of a wider buffer)."""
     lib = _lib.load()
-    y = Act.empty(x.n, x.h, x.w, x.c, fmt, x.t.device)
+    y = out if out is not None else Act.empty(x.n, x.h, x.w, x.c, fmt, x.t.device)
     check(lib.rsis_convert(x.ref(), y.ref(), _lib.stream_ptr()), "convert")
     _lib.count_launch(1)
     return y
+
+
+def uses_tcgen05(impl: int) -> bool:
+    return activation_format(impl) == FMT_SPLIT_BF16
+
+
+def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
+                    side_offset: int = 0, h_out: Optional[Act] = None, c_out: Optional[Act] = None,
+                    h16_out: Optional[Act] = None, impl: int = IMPL_AUTO):
+    """One fused ConvLSTM step on the already-concatenated input buffer `x` = [input_ | prev_hidden] (split-bf16,
+    all w.cin channels; the prev_hidden slice is zeros when the state is None).  `h16_out` (optional, may be a
+    pitched view) receives the new hidden state in the operand format, e.g. the prev_hidden slice of the next
+    step's input buffer.  c_out may alias c_prev.  Returns (h Act f32, c Act f32)."""
+    lib = _lib.load()
+    ch = pc.cout // 4
+    dev = x.t.device
+    h = h_out if h_out is not None else Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
+    c = c_out if c_out is not None else Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
+    stride = side_max.shape[1] if side_max is not None else 0
+    srcs = _src_array([x])
+    check(lib.rsis_convlstm_cell(srcs, 1, pc.ref(), _ptr(c_prev), h.ref(), h16_out.ref() if h16_out else None,
+                                 c.ref(), _ptr(side_max), stride, side_offset, impl, _lib.stream_ptr()),
+          "convlstm_cell")
+    _lib.count_launch(1)
+    return h, c
 
 
 def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
                   side_offset: int = 0, want_split: bool = False, impl: int = IMPL_AUTO):
     """One fused ConvLSTM step. `srcs` = [input_ parts..., prev_hidden] (prev_hidden omitted when the state is None).
 
-    Returns (h Act f32, c Act f32, h_split Act or None). side_max: int32/uint32-viewed [N, F] key buffer (zeroed)."""
+    Returns (h Act f32, c Act f32, h_split Act or None). side_max: int32/uint32-viewed [N, F] key buffer (zeroed).
+    The CUDA-core kernel reads the parts directly; the tcgen05 kernel takes one concatenated buffer, so the parts
+    are first copied into their channel slices of it (general-purpose entry; the decoder's fast path writes those
+    slices in place instead)."""
     lib = _lib.load()
     x = srcs[0]
     ch = pc.cout // 4
     dev = x.t.device
+    if uses_tcgen05(impl) and all(s.fmt == FMT_SPLIT_BF16 for s in srcs):
+        have = sum(s.c for s in srcs)
+        buf = (Act.zeros if have < pc.cin else Act.empty)(x.n, x.h, x.w, pc.cin, FMT_SPLIT_BF16, dev)
+        off = 0
+        for s_ in srcs:
+            convert(s_, FMT_SPLIT_BF16, out=buf.slice(off, s_.c))
+            off += s_.c
+        hs = Act.empty(x.n, x.h, x.w, ch, FMT_SPLIT_BF16, dev) if want_split else None
+        h, c = convlstm_cell_x(buf, pc, c_prev, side_max, side_offset, h16_out=hs, impl=impl)
+        return h, c, hs
     h = Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
     c = Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
     hs = Act.empty(x.n, x.h, x.w, ch, FMT_SPLIT_BF16, dev) if want_split else None
@@ -196,9 +236,9 @@ def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Te
     return h, c, hs
 
 
-def upsample_bilinear(x: Act, ho: int, wo: int, fmt: int = FMT_F32) -> Act:
+def upsample_bilinear(x: Act, ho: int, wo: int, fmt: int = FMT_F32, out: Optional[Act] = None) -> Act:
     lib = _lib.load()
-    y = Act.empty(x.n, ho, wo, x.c, fmt, x.t.device)
+    y = out if out is not None else Act.empty(x.n, ho, wo, x.c, fmt, x.t.device)
     check(lib.rsis_upsample_bilinear(x.ref(), y.ref(), _lib.stream_ptr()), "upsample_bilinear")
     _lib.count_launch(1)
     return y

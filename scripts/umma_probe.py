@@ -18,7 +18,11 @@ CASES = {
     "3x3_s2": (2, [128], 16, 16, 128, 3, 2, True, False),
     "1x1_s2": (2, [256], 16, 16, 512, 1, 2, False, False),
     "3x3_c40_n24": (1, [40], 5, 5, 24, 3, 1, False, False),
-    "3x3_cat": (2, [64, 32, 16], 12, 12, 48, 3, 1, False, False),
+    "3x3_c112_ragged": (2, [112], 12, 12, 48, 3, 1, False, False),
+    "3x3_halo_c40_n32": (2, [40], 32, 24, 32, 3, 1, False, False),
+    "3x3_halo_c96_n40": (2, [96], 32, 24, 40, 3, 1, True, True),
+    "3x3_halo_c256_n256": (8, [256], 16, 16, 256, 3, 1, True, False),
+    "3x3_halo_c320_n512": (4, [320], 16, 16, 512, 3, 1, False, False),
     "3x3_small_img": (8, [128], 8, 8, 128, 3, 1, False, False),
     "3x3_wide": (2, [64], 4, 256, 16, 3, 1, False, False),
     "sk5": (2, [2048], 8, 8, 128, 3, 1, False, False),
@@ -59,16 +63,29 @@ def run_case(name):
               "bad rows(h):", sorted(set(bad.nonzero()[:, 2].tolist()))[:16], flush=True)
 
 
+MODES = {  # environment knobs of conv_umma.cu
+    "halo": {"RSIS_B200_HALO": "1", "RSIS_B200_HALO_BASEOFF": "0"},
+    "halo+baseoff": {"RSIS_B200_HALO": "1", "RSIS_B200_HALO_BASEOFF": "1"},
+    "tap": {"RSIS_B200_HALO": "0"},
+}
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] in CASES:
         run_case(sys.argv[1])
     else:
-        for name in CASES:
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=120, capture_output=True,
-                                   text=True)
-                out = (r.stdout + r.stderr).strip().splitlines()
-                keep = [l for l in out if l.startswith(name) or "first bad" in l or "rror" in l or "timed out" in l]
-                print("\n".join(keep[-6:]) if keep else f"{name}: no output rc={r.returncode}", flush=True)
-            except subprocess.TimeoutExpired:
-                print(f"{name}: TIMEOUT", flush=True)
+        modes = sys.argv[1:] or list(MODES)
+        for mode in modes:
+            print(f"== mode {mode}", flush=True)
+            for name in CASES:
+                if mode != "halo" and "3x3" not in name:
+                    continue
+                env = dict(os.environ)
+                env.update(MODES[mode])
+                try:
+                    r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=120,
+                                       capture_output=True, text=True, env=env)
+                    out = (r.stdout + r.stderr).strip().splitlines()
+                    keep = [l for l in out if l.startswith(name) or "first bad" in l or "rror" in l or "timed out" in l]
+                    print("\n".join(keep[-6:]) if keep else f"{name}: no output rc={r.returncode}", flush=True)
+                except subprocess.TimeoutExpired:
+                    print(f"{name}: TIMEOUT", flush=True)

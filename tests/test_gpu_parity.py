@@ -92,6 +92,9 @@ CONV_CASES = [
     (1, 2048, 4, 4, 128, 3, 1, 1, True, True, False, False),   # sk5, K = 18432
     (1, 40, 5, 5, 24, 3, 1, 1, True, False, False, False),     # odd channel counts (multiples of 4)
     (2, 512, 8, 8, 128, 1, 1, 0, True, True, False, False),    # kernel_size=1 heads (args.kernel_size=1)
+    (2, 96, 32, 24, 40, 3, 1, 1, True, True, True, True),      # halo-staged 3x3 (W % 8 == 0, H % 16 == 0), 1.5 chunks
+    (8, 256, 16, 16, 256, 3, 1, 1, False, True, True, False),  # layer3 conv2 at batch 8: 16 pixel tiles, narrow BN
+    (2, 40, 32, 32, 32, 3, 1, 1, True, False, False, False),   # level-4-like: 40 channels = 3 K steps of one chunk
 ]
 
 
@@ -158,6 +161,36 @@ def test_conv2d_concat_sources(R, impl):
     srcs = [ops.act_from_nchw(t.cuda(), fmt) for t in (a, b, c)]
     y = ops.conv2d(srcs, pc, pad=1, impl=which)
     assert rel(y.nchw(), ref) < _tol(impl)
+
+
+def test_conv2d_on_channel_slices(R):
+    """tcgen05 convolution reading a pitched channel slice of a wider NHWC buffer and writing its result into slices
+    of two other buffers -- how the decoder's concatenated cell inputs are filled in place (rsis_tensor.cstride)."""
+    ops = R.ops
+    if not ops.has_tcgen05():
+        pytest.skip("library built without tcgen05 kernels")
+    g = torch.Generator().manual_seed(21)
+    wide = torch.rand((2, 104, 16, 24), generator=g) * 2 - 1
+    w = (torch.rand((32, 64, 3, 3), generator=g) - 0.5) * 0.1
+    b = torch.rand(32, generator=g) - 0.5
+    ref = F.conv2d(wide[:, 24:88], w, b, padding=1)
+    src = ops.act_from_nchw(wide.cuda(), ops.FMT_SPLIT_BF16).slice(24, 64)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), None, want_umma=True)
+    dst0 = ops.Act.zeros(2, 16, 24, 80, ops.FMT_SPLIT_BF16, "cuda")
+    dst1 = ops.Act.zeros(2, 16, 24, 40, ops.FMT_F32, "cuda")
+    ops.conv2d([src], pc, pad=1, impl=ops.IMPL_TCGEN05, out=dst0.slice(16, 32), out2=dst1.slice(8, 32))
+    got0 = dst0.float().permute(0, 3, 1, 2)
+    got1 = dst1.float().permute(0, 3, 1, 2)
+    assert rel(got0[:, 16:48], ref) < TOL and rel(got1[:, 8:40], ref) < TOL
+    assert float(got0[:, :16].abs().max()) == 0.0 and float(got0[:, 48:].abs().max()) == 0.0  # neighbours untouched
+    assert float(got1[:, :8].abs().max()) == 0.0
+    # upsample into a slice
+    x = torch.rand((2, 16, 8, 12), generator=g)
+    up = ops.Act.zeros(2, 16, 24, 40, ops.FMT_SPLIT_BF16, "cuda")
+    ops.upsample_bilinear(ops.act_from_nchw(x.cuda(), ops.FMT_F32), 16, 24, out=up.slice(8, 16))
+    refu = F.interpolate(x, size=(16, 24), mode="bilinear", align_corners=True)
+    gu = up.float().permute(0, 3, 1, 2)
+    assert rel(gu[:, 8:24], refu) < 2e-5 and float(gu[:, :8].abs().max()) == 0.0 and float(gu[:, 24:].abs().max()) == 0.0
 
 
 def test_maxpool_and_upsample(R):
