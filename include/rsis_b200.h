@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 2
+#define RSIS_ABI_VERSION 3
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -106,6 +106,14 @@ int rsis_nchw_to_nhwc(const float* src_nchw, const rsis_tensor* dst, rsis_stream
 /* NHWC tensor -> NHWC tensor of the other element format (same shape). */
 int rsis_convert(const rsis_tensor* src, const rsis_tensor* dst, rsis_stream_t stream);
 
+/* ---- workspace ------------------------------------------------------------------------------------------------ */
+/* The tcgen05 convolution splits K across co-resident CTAs when a launch has fewer output tiles than SMs; the
+ * partial accumulators are exchanged through a caller-owned device buffer of rsis_conv_workspace_bytes() bytes
+ * (a fixed size, ~19.4 MB).  It must be zero-filled ONCE after allocation (the kernels leave its counters at zero),
+ * 16-byte aligned, and must not be shared by launches that can run concurrently (one per stream).  Passing
+ * workspace = NULL is allowed: split-K is then not used. */
+size_t rsis_conv_workspace_bytes(void);
+
 /* ---- encoder primitives ----------------------------------------------------------------------------------- */
 /* conv (+folded BN/bias) (+residual) (+ReLU).  Replaces nn.Conv2d + nn.BatchNorm2d (+ReLU, + `out += identity`)
  * of vision.py:12-19 / torchvision Bottleneck.forward and the skip heads model.py:59-63.
@@ -113,7 +121,7 @@ int rsis_convert(const rsis_tensor* src, const rsis_tensor* dst, rsis_stream_t s
  * result in another element format (e.g. float32 for the API-visible feature + split-bf16 for the decoder). */
 int rsis_conv2d(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                 const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, int impl,
-                rsis_stream_t stream);
+                void* workspace, size_t workspace_bytes, rsis_stream_t stream);
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of vision.py:15. */
 int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
 
@@ -131,7 +139,8 @@ int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t 
  *             Must be zero-filled before the step (key 0 sorts below every float). */
 int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
-                       uint32_t* side_max, int side_stride, int side_offset, int impl, rsis_stream_t stream);
+                       uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
+                       size_t workspace_bytes, rsis_stream_t stream);
 /* nn.UpsamplingBilinear2d(size=(y.h, y.w)) == bilinear, align_corners=True (model.py:149-150,163-164). */
 int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
 /* conv_out (model.py:167): ksize x ksize (1 or 3), Cin -> 1, on an NHWC float32 input; writes logits [N,H,W] float32 (when

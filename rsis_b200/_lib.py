@@ -17,7 +17,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Tensor(C.Structure):
@@ -54,9 +54,10 @@ SIGNATURES = {
     "rsis_conv_pack_umma": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _P, _P]),
     "rsis_nchw_to_nhwc": (_I, [_P, _TP, _P]),
     "rsis_convert": (_I, [_TP, _TP, _P]),
-    "rsis_conv2d": (_I, [_TP, _I, _WP, _TP, _TP, _TP, _I, _I, _I, _I, _P]),
+    "rsis_conv_workspace_bytes": (C.c_size_t, []),
+    "rsis_conv2d": (_I, [_TP, _I, _WP, _TP, _TP, _TP, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_maxpool3x3s2": (_I, [_TP, _TP, _P]),
-    "rsis_convlstm_cell": (_I, [_TP, _I, _WP, _P, _TP, _TP, _TP, _P, _I, _I, _I, _P]),
+    "rsis_convlstm_cell": (_I, [_TP, _I, _WP, _P, _TP, _TP, _TP, _P, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_upsample_bilinear": (_I, [_TP, _TP, _P]),
     "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),
     "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
@@ -111,6 +112,24 @@ def check(status: int, what: str):
 
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_workspaces = {}
+
+
+def workspace():
+    """(pointer, bytes) of the current device's split-K exchange buffer: allocated and zero-filled once; the kernels
+    leave its counters at zero.  This package issues all its launches of a device in one stream order (eager stream or
+    one captured graph at a time); callers that run rsis_b200 kernels concurrently on several streams of one device
+    must give each stream its own buffer through the C ABI."""
+    dev = torch.cuda.current_device()
+    key = dev
+    ws = _workspaces.get(key)
+    if ws is None:
+        n = load().rsis_conv_workspace_bytes()
+        ws = torch.zeros(n, dtype=torch.uint8, device=torch.device("cuda", dev))
+        _workspaces[key] = ws
+    return ws.data_ptr(), ws.numel()
 
 
 class Act:

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librsis_b200.so")
 SOURCES = ["api.cu", "pack.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "decoder_ops.cu", "dispatch.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = (["-DRSIS_DEBUG_TIMING"] if os.environ.get("RSIS_B200_BUILD_DEBUG_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:

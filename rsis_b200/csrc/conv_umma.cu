@@ -45,9 +45,10 @@ namespace {
 
 constexpr int kBM = 128;          // rows (output pixels) per tile == TMEM lanes
 constexpr int kBK = 64;           // bf16 channels per K chunk == one 128-byte swizzle row
-constexpr int kMaxBN = 128;       // accumulator columns per TMEM stage
+constexpr int kMaxBN = 256;       // widest output-channel tile
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kMaxBN * kAccStages;  // 256, power of two
+constexpr int kStageCols = 256;   // accumulator columns per TMEM stage (BN, or 2*BN when the weight planes are stacked)
+constexpr int kTmemCols = kStageCols * kAccStages;  // 512: the whole TMEM (one CTA per SM)
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsUmma = kEpiThreads + 64;
@@ -64,7 +65,12 @@ struct UmmaParams {
   // tile geometry
   int BW, BH, BI;          // output-pixel box: width x height x images, product 128
   int tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
-  int BN;                  // output channels per tile (32 / 64 / 128)
+  int BN;                  // output channels per tile (32 / 64 / 128 / 256)
+  int stacked;             // 1: one MMA multiplies by [W_hi | W_lo] (N = 2*BN), 2 MMAs per K step; 0: 3 MMAs, N = BN
+  int pw;                  // epilogue piece width in accumulator columns (32, or 16 so that BN = 32 keeps all 8 warps busy)
+  int ksplit;              // K slices per tile (split-K across co-resident CTAs, reduced through `scratch`)
+  float* scratch;          // [num_tiles * ksplit][128][ncols] fp32 partial accumulators
+  unsigned* counters;      // [num_tiles][2] arrival / completion counters (zero between launches)
   int halo;                // 1: HALO staging, 0: TAP staging
   int a_stages, b_stages;
   int a_plane_bytes;       // bytes of one bf16 plane of an A stage (rows * 128)
@@ -156,6 +162,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of a fully converged warp; the compiler keeps the elected region's operands in uniform registers, so
+// UTMALDG / UTCHMMA issue back to back (an `if (lane == 0)` region makes it wrap every one in a uniformisation loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -186,6 +204,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int PW>
+__device__ __forceinline__ void tmem_ld_piece(uint32_t taddr, uint32_t (&r)[PW]) {
+  if constexpr (PW == 32)
+    tmem_ld32(taddr, r);
+  else
+    tmem_ld16(taddr, r);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row core matrices `sbo` bytes apart.
@@ -203,125 +237,419 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo,
 }
 
 // ---- epilogues --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store8(void* p, size_t plane, int fmt, size_t idx, const float* v) {
+// The accumulator comes out of TMEM with thread = row (pixel) and registers = columns (channels), but NHWC memory
+// wants consecutive lanes on consecutive channels.  Every 32-row x PW-column piece is therefore transposed through a
+// per-warp shared-memory tile (pitch 33 floats: conflict-free both ways) and then finished with lane = channel:
+// residual / c_prev loads and all stores are contiguous runs per pixel instead of one small piece per lane at a
+// pixel-sized stride (which costs one LSU wavefront per lane and made the epilogue the slowest stage of the kernel).
+constexpr int kStagePitch = 33;
+constexpr int kStageFloats = 32 * kStagePitch;             // per epilogue warp
+constexpr int kStageBytes = kEpiWarps * kStageFloats * 4;  // 33792
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void store4(void* ptr, size_t plane, int fmt, size_t idx, const float (&v)[4]) {
   if (fmt == RSIS_FMT_F32) {
-    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx);
-    q[0] = make_float4(v[0], v[1], v[2], v[3]);
-    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + idx) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    __nv_bfloat16 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_bf16(v[j], hi[j], lo[j]);
-    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(p);
-    *reinterpret_cast<uint4*>(b + idx) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(b + idx + plane) = *reinterpret_cast<const uint4*>(lo);
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ptr);
+    *reinterpret_cast<uint2*>(q + idx) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(q + idx + plane) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
   }
 }
-__device__ __forceinline__ void store4u(void* p, size_t plane, int fmt, size_t idx, const float* v) {
-  if (fmt == RSIS_FMT_F32) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    __align__(8) __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
-    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(p);
-    *reinterpret_cast<uint2*>(b + idx) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(b + idx + plane) = *reinterpret_cast<const uint2*>(lo);
-  }
-}
-__device__ __forceinline__ void load4r(const View& v, size_t idx, float* out) {
+__device__ __forceinline__ void load4(const View& v, size_t idx, float (&out)[4]) {
   if (v.fmt == RSIS_FMT_F32) {
     const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.p) + idx);
     out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
   } else {
-    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(v.p);
-    const uint2 h = *reinterpret_cast<const uint2*>(b + idx);
-    const uint2 l = *reinterpret_cast<const uint2*>(b + idx + v.plane);
-    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&h);
-    const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&l);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
+    const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(v.p);
+    const uint2 h = *reinterpret_cast<const uint2*>(q + idx);
+    const uint2 l = *reinterpret_cast<const uint2*>(q + idx + v.plane);
+    out[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+    out[1] = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+    out[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+    out[3] = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
   }
 }
 
-// One 32-column chunk of one accumulator row -> folded BN/bias (+residual) (+ReLU) -> y (and y2).
-__device__ __forceinline__ void conv_epilogue_chunk(const UmmaParams& p, const uint32_t (&r)[32], bool row_ok,
-                                                    size_t pix, int col0) {
-  if (!row_ok) return;
+// Finishes one staged piece of a plain convolution: folded BN/bias (+residual) (+ReLU) -> y (and y2).
+// stage[row * 33 + c] holds accumulator (row, c); mypix is this lane's row's pixel index (0xffffffff = outside).
+// Lane = (row within the iteration, group of 4 adjacent channels): a pixel's PW channels are one contiguous run.
+template <int PW>
+__device__ __forceinline__ void conv_finish_piece(const UmmaParams& p, const float* stage, int lane, uint32_t mypix,
+                                                  int col0) {
+  constexpr int LPR = PW / 4;    // lanes per row, four adjacent columns each
+  constexpr int RPI = 32 / LPR;  // rows per iteration
+  const int c = 4 * (lane % LPR);
+  const int col = col0 + c;
+  const bool col_ok = col < p.Cout;  // Cout % 4 == 0
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+  if (col_ok) {
+    sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+    sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+  }
+  const float* srow = stage + (lane / LPR) * kStagePitch + c;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int col = col0 + 4 * q;
-    if (col >= p.Cout) break;
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const int row = it * RPI + lane / LPR;
+    const uint32_t pix = __shfl_sync(0xffffffffu, mypix, row);
+    const float* sp = srow + it * RPI * kStagePitch;
     float v[4];
-    v[0] = fmaf(__uint_as_float(r[4 * q + 0]), sc.x, sh.x);
-    v[1] = fmaf(__uint_as_float(r[4 * q + 1]), sc.y, sh.y);
-    v[2] = fmaf(__uint_as_float(r[4 * q + 2]), sc.z, sh.z);
-    v[3] = fmaf(__uint_as_float(r[4 * q + 3]), sc.w, sh.w);
-    if (p.has_res) {
-      float t[4];
-      load4r(p.res, pix * p.res_cs + col, t);
+    v[0] = fmaf(sp[0], sc.x, sh.x);
+    v[1] = fmaf(sp[1], sc.y, sh.y);
+    v[2] = fmaf(sp[2], sc.z, sh.z);
+    v[3] = fmaf(sp[3], sc.w, sh.w);
+    if (pix != 0xffffffffu && col_ok) {
+      if (p.has_res) {
+        float t[4];
+        load4(p.res, (size_t)pix * p.res_cs + col, t);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] += t[j];
-    }
-    if (p.relu) {
+        for (int j = 0; j < 4; ++j) v[j] += t[j];
+      }
+      if (p.relu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      store4(p.y, p.y_plane, p.y_fmt, (size_t)pix * p.y_cs + col, v);
+      if (p.y2) store4(p.y2, p.y2_plane, p.y2_fmt, (size_t)pix * p.y2_cs + col, v);
     }
-    store4u(p.y, p.y_plane, p.y_fmt, pix * p.y_cs + col, v);
-    if (p.y2) store4u(p.y2, p.y2_plane, p.y2_fmt, pix * p.y2_cs + col, v);
   }
 }
 
-// One 32-column chunk = 8 hidden channels x (in, remember, out, cell) of one pixel -> ConvLSTM update (clstm.py:50-58).
-// seg = number of consecutive rows (lanes) that belong to the same image (power of two, <= 32) for the side max.
-__device__ __forceinline__ void cell_epilogue_chunk(const UmmaParams& p, const uint32_t (&r)[32], bool row_ok,
-                                                    size_t pix, int img, int col0, int seg) {
+// ConvLSTM cell pieces (clstm.py:50-58): PW gate columns = PW/4 hidden channels x (in, remember, out, cell).
+// Lane = (row within the iteration, hidden channel).  c_prev is fetched BEFORE the accumulator is waited for /
+// staged, so its DRAM latency overlaps the MMAs and the TMEM read instead of stalling every iteration.
+template <int PW>
+struct CellPiece {
+  static constexpr int CPP = PW / 4;    // hidden channels in the piece
+  static constexpr int RPI = 32 / CPP;  // rows per iteration
+  static constexpr int NIT = 32 / RPI;  // iterations
+  uint32_t pix[NIT];
+  float cp[NIT];
+};
+
+template <int PW>
+__device__ __forceinline__ void cell_prefetch(const UmmaParams& p, CellPiece<PW>& cpz, int lane, uint32_t mypix,
+                                              int col0) {
+  using CP = CellPiece<PW>;
   const int Ch = p.Cout >> 2;
-  const int ch0 = col0 >> 2;
-  if (ch0 >= Ch) return;  // uniform across the warp
-  float hval[8];
-  if (row_ok) {
-    const size_t idx = pix * Ch + ch0;
-    float cp[8];
-    if (p.c_prev) {
-      const float4 a = *reinterpret_cast<const float4*>(p.c_prev + idx);
-      const float4 b = *reinterpret_cast<const float4*>(p.c_prev + idx + 4);
-      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-    } else {
+  const int chg = (col0 >> 2) + lane % CP::CPP;
+  const bool ch_ok = chg < Ch;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cp[j] = 0.f;
-    }
-    float cval[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
-      const float gi = sigmoidf_acc(fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x));
-      const float gf = sigmoidf_acc(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y));
-      const float go = sigmoidf_acc(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z));
-      const float gg = tanhf(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w));
-      const float c = gf * cp[j] + gi * gg;
-      cval[j] = c;
-      hval[j] = go * tanhf(c);
-    }
-    store8(p.c_out, 0, RSIS_FMT_F32, idx, cval);
-    store8(p.h_out, 0, RSIS_FMT_F32, idx, hval);
-    if (p.h_split) store8(p.h_split, p.hs_plane, RSIS_FMT_SPLIT_BF16, pix * p.hs_cs + ch0, hval);
+  for (int it = 0; it < CP::NIT; ++it) {
+    const int row = it * CP::RPI + lane / CP::CPP;
+    const uint32_t pix = __shfl_sync(0xffffffffu, mypix, row);
+    cpz.pix[it] = ch_ok ? pix : 0xffffffffu;
+    cpz.cp[it] = (p.c_prev && cpz.pix[it] != 0xffffffffu) ? __ldg(p.c_prev + (size_t)pix * Ch + chg) : 0.f;
   }
-  if (p.side_max) {
-    // global nn.MaxPool2d (model.py:143): max over the rows of this warp that belong to the same image, then one
-    // atomicMax per (image segment, channel).  Key 0 sorts below every float.
+}
+
+// The side feature (global nn.MaxPool2d of model.py:143) is a running max per lane, merged across the lanes of a
+// channel at the end.
+template <int PW>
+__device__ __forceinline__ void cell_finish_piece(const UmmaParams& p, const float* stage, int lane,
+                                                  const CellPiece<PW>& cpz, int myimg, int col0, int seg) {
+  using CP = CellPiece<PW>;
+  const int Ch = p.Cout >> 2;
+  const int ch = lane % CP::CPP;
+  const int chg = (col0 >> 2) + ch;
+  const bool ch_ok = chg < Ch;
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+  if (ch_ok) {
+    sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * ch));
+    sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * ch));
+  }
+  uint32_t best = 0u;  // key 0 sorts below every float
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint32_t key = row_ok ? float_to_key(hval[j]) : 0u;
-      for (int s = 1; s < seg; s <<= 1) {
-        const uint32_t o = __shfl_xor_sync(0xffffffffu, key, s);
-        key = o > key ? o : key;
+  for (int it = 0; it < CP::NIT; ++it) {
+    const int row = it * CP::RPI + lane / CP::CPP;
+    const uint32_t pix = cpz.pix[it];
+    const float* g = stage + row * kStagePitch + 4 * ch;
+    const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x));
+    const float gf = fast_sigmoid(fmaf(g[1], sc.y, sh.y));
+    const float go = fast_sigmoid(fmaf(g[2], sc.z, sh.z));
+    const float gg = fast_tanh(fmaf(g[3], sc.w, sh.w));
+    const float cv = fmaf(gf, cpz.cp[it], gi * gg);
+    const float hv = go * fast_tanh(cv);
+    if (pix == 0xffffffffu) continue;
+    const size_t idx = (size_t)pix * Ch + chg;
+    p.c_out[idx] = cv;
+    p.h_out[idx] = hv;
+    if (p.h_split) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(hv, hi, lo);
+      const size_t k = (size_t)pix * p.hs_cs + chg;
+      p.h_split[k] = hi;
+      p.h_split[k + p.hs_plane] = lo;
+    }
+    if (p.side_max) {
+      const uint32_t key = float_to_key(hv);
+      if (seg == 32) {
+        best = key > best ? key : best;
+      } else {  // maps smaller than a warp's 32 rows: rows of several images share the warp
+        const int img = (int)(pix / (uint32_t)(p.Ho * p.Wo));
+        atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg, key);
       }
-      if ((threadIdx.x & (seg - 1)) == 0 && key != 0u)
-        atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + ch0 + j, key);
+    }
+  }
+  if (p.side_max && seg == 32) {
+#pragma unroll
+    for (int s = CP::CPP; s < 32; s <<= 1) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, best, s);
+      best = o > best ? o : best;
+    }
+    const int img0 = __shfl_sync(0xffffffffu, myimg, 0);
+    if (lane < CP::CPP && ch_ok && best != 0u)
+      atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg, best);
+  }
+}
+
+// Row (= TMEM lane = output pixel of the tile) -> pixel geometry.
+struct RowGeom {
+  bool ok;
+  size_t pix;
+  int img;
+};
+__device__ __forceinline__ RowGeom row_geom(const UmmaParams& p, int row, int tw, int th, int ti) {
+  const int wl = row % p.BW;
+  const int hl = (row / p.BW) % p.BH;
+  const int il = row / (p.BW * p.BH);
+  const int wo = tw * p.BW + wl, ho = th * p.BH + hl, img = ti * p.BI + il;
+  RowGeom g;
+  g.ok = wo < p.Wo && ho < p.Ho && img < p.N;
+  g.pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+  g.img = img;
+  return g;
+}
+
+#ifdef RSIS_DEBUG_TIMING
+__device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
+  if (blockIdx.x == 0 && p.counters) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(p.counters)[256 + slot] = t;
+  }
+}
+#define STAMP(slot) stamp(p, slot)
+#else
+#define STAMP(slot)
+#endif
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// Epilogue warps: accumulator pieces (32 rows x PW columns) -> staged transpose -> finish.  With split-K the CTA first
+// parks its partial accumulator in the L2-resident scratch (TMEM-native order: for a fixed column the 32 lanes of a
+// warp write 32 consecutive floats), waits for the other K slices of its tile, then reduces and finishes its share.
+template <bool CELL, int PW>
+__device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, float* stage, int warp, int lane) {
+  const int quarter = warp & 3;       // TMEM lane quarter this warp may read
+  const int half = warp >> 2;         // which pieces (even / odd) of the quarter this warp handles
+  const int rows_per_img = p.BW * p.BH;
+  const int seg = rows_per_img < 32 ? rows_per_img : 32;
+  const int npc = p.BN / PW;          // output pieces per row quarter
+  const int ncols = p.stacked ? 2 * p.BN : p.BN;
+  const int num_work = p.num_tiles * p.ksplit;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+    const int nt = tile % p.tiles_n;
+    int mt = tile / p.tiles_n;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const int th = mt % p.tiles_h;
+    const int ti = mt / p.tiles_h;
+    const RowGeom g = row_geom(p, quarter * 32 + lane, tw, th, ti);
+    const uint32_t mypix = g.ok ? (uint32_t)g.pix : 0xffffffffu;
+    CellPiece<PW> cpz0;
+    if constexpr (CELL) {
+      if (p.ksplit == 1 && half < npc) cell_prefetch<PW>(p, cpz0, lane, mypix, nt * p.BN + PW * half);
+    }
+    mbar_wait(tfull0 + 8 * acc, acc_phase);
+    tc_fence_after();
+    if (threadIdx.x == 0) STAMP(7);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
+    if (p.ksplit == 1) {
+      for (int j = half; j < npc; j += 2) {
+        const int col0 = nt * p.BN + PW * j;
+        if (col0 >= p.Cout) break;
+        CellPiece<PW> cpz;
+        if constexpr (CELL) {
+          if (j != half) cell_prefetch<PW>(p, cpz, lane, mypix, col0);
+          else cpz = cpz0;
+        }
+        uint32_t r[PW];
+        tmem_ld_piece<PW>(taddr + PW * j, r);
+        tmem_ld_wait();
+        if (p.stacked) {
+          uint32_t r2[PW];
+          tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+        }
+#pragma unroll
+        for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
+        __syncwarp();
+        if constexpr (CELL)
+          cell_finish_piece<PW>(p, stage, lane, cpz, g.img, col0, seg);
+        else
+          conv_finish_piece<PW>(p, stage, lane, mypix, col0);
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+    } else {
+      // ---- split-K (1): park this CTA's partial accumulator in the scratch as [row][column] (staged transpose,
+      // so each row's 32 columns are one 128-byte store)
+      {
+        float* dst = p.scratch + ((size_t)work * kBM + quarter * 32) * ncols;
+        for (int j = half; j < (ncols >> 5); j += 2) {
+          uint32_t r[32];
+          tmem_ld32(taddr + 32 * j, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
+          __syncwarp();
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) __stcg(dst + (size_t)rr * ncols + 32 * j + lane, stage[rr * kStagePitch + lane]);
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+      if (threadIdx.x == 0) STAMP(8);
+      // ---- (2) wait until all K slices of the tile are parked
+      __threadfence();
+      epi_bar();
+      if (threadIdx.x == 0) {
+        atomicAdd(p.counters + 2 * tile, 1u);
+        unsigned seen;
+        const long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + 2 * tile) : "memory");
+          if (clock64() - t0 > 4000000000LL) {
+            printf("rsis_b200 conv_umma: split-K wait timed out (block %d tile %d seen %u of %d)\n", blockIdx.x, tile,
+                   seen, p.ksplit);
+            __trap();
+          }
+        } while (seen < (unsigned)p.ksplit);
+        STAMP(9);
+      }
+      epi_bar();
+      // ---- (3) reduce + finish.  Unit = 4 rows x 32 columns: lane = (row, 4 adjacent columns), every load and
+      // store is a 128-byte (or per-pixel contiguous) run.  Units are dealt round-robin to the 8 * ksplit warps.
+      {
+        const int ncg = p.BN >> 5;
+        const int units = (kBM / 4) * ncg;
+        const int Ch = p.Cout >> 2;
+        for (int u = ks * kEpiWarps + warp; u < units; u += kEpiWarps * p.ksplit) {
+          const int cg = u % ncg;
+          const int row = 4 * (u / ncg) + (lane >> 3);
+          const int c4 = lane & 7;
+          const int col = nt * p.BN + 32 * cg + 4 * c4;
+          const RowGeom g2 = row_geom(p, row, tw, th, ti);
+          const bool ok = g2.ok && col < p.Cout;
+          float cprev = 0.f;
+          if constexpr (CELL) {
+            if (ok && p.c_prev) cprev = __ldg(p.c_prev + g2.pix * Ch + (col >> 2));
+          }
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float* src = p.scratch + ((size_t)(tile * p.ksplit) * kBM + row) * ncols + 32 * cg + 4 * c4;
+          const size_t sstride = (size_t)kBM * ncols;
+#pragma unroll 4
+          for (int s2 = 0; s2 < p.ksplit; ++s2) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            if (p.stacked) {
+              const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride + p.BN));
+              v.x += t2.x; v.y += t2.y; v.z += t2.z; v.w += t2.w;
+            }
+          }
+          float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+          if (col < p.Cout) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
+            sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+          }
+          if constexpr (CELL) {
+            const int chg = col >> 2;
+            const float gi = fast_sigmoid(fmaf(v.x, sc.x, sh.x));
+            const float gf = fast_sigmoid(fmaf(v.y, sc.y, sh.y));
+            const float go = fast_sigmoid(fmaf(v.z, sc.z, sh.z));
+            const float gg = fast_tanh(fmaf(v.w, sc.w, sh.w));
+            const float cv = fmaf(gf, cprev, gi * gg);
+            const float hv = go * fast_tanh(cv);
+            uint32_t key = 0u;
+            if (ok) {
+              const size_t idx = g2.pix * Ch + chg;
+              p.c_out[idx] = cv;
+              p.h_out[idx] = hv;
+              if (p.h_split) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(hv, hi, lo);
+                const size_t k = g2.pix * p.hs_cs + chg;
+                p.h_split[k] = hi;
+                p.h_split[k + p.hs_plane] = lo;
+              }
+              key = float_to_key(hv);
+            }
+            if (p.side_max) {
+              if ((rows_per_img & 3) == 0) {  // the unit's 4 rows belong to one image: merge them first
+                uint32_t o = __shfl_xor_sync(0xffffffffu, key, 8);
+                key = o > key ? o : key;
+                o = __shfl_xor_sync(0xffffffffu, key, 16);
+                key = o > key ? o : key;
+                const int img0 = __shfl_sync(0xffffffffu, g2.img, 0);
+                if (lane < 8 && key != 0u)
+                  atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg, key);
+              } else if (key != 0u) {
+                atomicMax(p.side_max + (size_t)g2.img * p.side_stride + p.side_offset + chg, key);
+              }
+            }
+          } else {
+            float o[4];
+            o[0] = fmaf(v.x, sc.x, sh.x);
+            o[1] = fmaf(v.y, sc.y, sh.y);
+            o[2] = fmaf(v.z, sc.z, sh.z);
+            o[3] = fmaf(v.w, sc.w, sh.w);
+            if (ok) {
+              if (p.has_res) {
+                float t[4];
+                load4(p.res, g2.pix * p.res_cs + col, t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] += t[e];
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+              }
+              store4(p.y, p.y_plane, p.y_fmt, g2.pix * p.y_cs + col, o);
+              if (p.y2) store4(p.y2, p.y2_plane, p.y2_fmt, g2.pix * p.y2_cs + col, o);
+            }
+          }
+        }
+      }
+      epi_bar();
+      if (threadIdx.x == 0) STAMP(10);
+      if (threadIdx.x == 0) {
+        // the last CTA of the tile to finish re-arms the counters for the next launch that uses this scratch
+        if (atomicAdd(p.counters + 2 * tile + 1, 1u) == (unsigned)p.ksplit - 1u) {
+          p.counters[2 * tile] = 0u;
+          p.counters[2 * tile + 1] = 0u;
+        }
+      }
+    }
+    if (++acc == kAccStages) {
+      acc = 0;
+      acc_phase ^= 1u;
     }
   }
 }
@@ -333,9 +661,12 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages];
   __shared__ uint32_t tmem_slot;
 
+  if (threadIdx.x == 0) STAMP(0);
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_b = smem_a + p.a_stages * p.a_stage_bytes;
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (smem_a - smem_u32(smem_raw)) + p.a_stages * p.a_stage_bytes +
+                                               p.b_stages * p.b_stage_bytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t afull0 = smem_u32(&bars[0]);
@@ -377,170 +708,163 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) STAMP(1);
 
   // A "items" per tile: HALO -> one per chunk (nine B items each); TAP -> one per (tap, chunk) (one B item each).
+  // A work unit is (tile, K slice): slice ks of `ksplit` covers items [ks * a_items / ksplit, (ks + 1) * ...).
   const int b_per_a = p.halo ? p.taps : 1;
   const int a_items = p.halo ? p.chunks : p.taps * p.chunks;
+  const int num_work = p.num_tiles * p.ksplit;
 
   if (warp == kEpiWarps) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int mt = tile / p.tiles_n;
-        const int tw = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int ti = mt / p.tiles_h;
-        const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
-        for (int ai = 0; ai < a_items; ++ai) {
-          const int cc = p.halo ? ai : ai % p.chunks;
-          const int tap0 = p.halo ? 0 : ai / p.chunks;
-          mbar_wait(aempty0 + 8 * as, aph ^ 1u);
-          {
-            const uint32_t sa = smem_a + as * p.a_stage_bytes;
-            const uint32_t bar = afull0 + 8 * as;
-            mbar_arrive_expect_tx(bar, p.a_tx_bytes);
-            if (p.halo) {
-              tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
-            } else {
-              const int kh = tap0 / p.ksize, kw = tap0 - kh * p.ksize;
-              if (p.stride == 1) {
-                tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
-              } else {
-                // input pixel = 2*out + k - pad: parity (k - pad) & 1, sub-grid index out + floor((k - pad) / 2)
-                const int dh = kh - p.pad, dw = kw - p.pad;
-                const int ph = dh & 1, pw = dw & 1;
-                tma_load_5d(sa, &maps.a[ph * 2 + pw], bar, cc * kBK, w0 + ((dw - pw) >> 1), h0 + ((dh - ph) >> 1), i0,
-                            0);
-              }
-            }
-          }
-          if (++as == p.a_stages) {
-            as = 0;
-            aph ^= 1u;
-          }
-          for (int bi = 0; bi < b_per_a; ++bi) {
-            const int tap = tap0 + bi;
-            mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
-            const uint32_t bar = bfull0 + 8 * bs;
-            mbar_arrive_expect_tx(bar, p.b_tx_bytes);
-            tma_load_3d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, (tap * p.chunks + cc) * kBK, nt * p.BN, 0);
-            if (++bs == p.b_stages) {
-              bs = 0;
-              bph ^= 1u;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == kEpiWarps + 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((kBM >> 4) << 24);
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d = tmem_base + acc * kMaxBN;
-        uint32_t accumulate = 0;
-        for (int ai = 0; ai < a_items; ++ai) {
-          const int cc = p.halo ? ai : ai % p.chunks;
-          const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
-          mbar_wait(afull0 + 8 * as, aph);
-          tc_fence_after();
-          const uint32_t sa = smem_a + as * p.a_stage_bytes;
-          for (int bi = 0; bi < b_per_a; ++bi) {
-            mbar_wait(bfull0 + 8 * bs, bph);
-            tc_fence_after();
-            const uint32_t sb = smem_b + bs * p.b_stage_bytes;
-            uint32_t sat = sa;
-            if (p.halo) {
-              const int kh = bi / 3, kw = bi - kh * 3;
-              sat += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
-            }
-            const uint64_t a_hi = make_smem_desc(sat, p.a_sbo, p.base_off_mode);
-            const uint64_t a_lo = make_smem_desc(sat + p.a_plane_bytes, p.a_sbo, p.base_off_mode);
-            const uint64_t b_hi = make_smem_desc(sb, 1024, 0), b_lo = make_smem_desc(sb + p.BN * 128, 1024, 0);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
-              umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
-              umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
-              umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
-              accumulate = 1u;
-            }
-            umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
-            if (++bs == p.b_stages) {
-              bs = 0;
-              bph ^= 1u;
-            }
-          }
-          umma_commit(aempty0 + 8 * as);  // activation slot free
-          if (++as == p.a_stages) {
-            as = 0;
-            aph ^= 1u;
-          }
-        }
-        umma_commit(tfull0 + 8 * acc);  // accumulator complete
-        if (++acc == kAccStages) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
-      }
-    }
-  } else {
-    // =============================== epilogue (warps 0-7) ===============================
-    const int quarter = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = warp >> 2;         // which 32-column chunks (even / odd) this warp handles
-    const int row = quarter * 32 + lane;  // accumulator row == TMEM lane
-    const int wl = row % p.BW;
-    const int hl = (row / p.BW) % p.BH;
-    const int il = row / (p.BW * p.BH);
-    const int rows_per_img = p.BW * p.BH;
-    const int seg = rows_per_img < 32 ? rows_per_img : 32;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
       const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
       const int tw = mt % p.tiles_w;
       mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int ti = mt / p.tiles_h;
-      const int wo = tw * p.BW + wl, ho = th * p.BH + hl, img = ti * p.BI + il;
-      const bool row_ok = wo < p.Wo && ho < p.Ho && img < p.N;
-      const size_t pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kMaxBN;
-      for (int c32 = half * 32; c32 < p.BN; c32 += 64) {
-        const int col0 = nt * p.BN + c32;
-        if (col0 >= p.Cout) break;
-        uint32_t r[32];
-        tmem_ld32(taddr + c32, r);
-        tmem_ld_wait();
-        if constexpr (CELL)
-          cell_epilogue_chunk(p, r, row_ok, pix, img, col0, seg);
-        else
-          conv_epilogue_chunk(p, r, row_ok, pix, col0);
+      const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
+      for (int ai = item0; ai < item1; ++ai) {
+        const int cc = p.halo ? ai : ai % p.chunks;
+        const int tap0 = p.halo ? 0 : ai / p.chunks;
+        mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+        if (elect_one()) {
+          const uint32_t sa = smem_a + as * p.a_stage_bytes;
+          const uint32_t bar = afull0 + 8 * as;
+          mbar_arrive_expect_tx(bar, p.a_tx_bytes);
+          if (p.halo) {
+            tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
+          } else {
+            const int kh = tap0 / p.ksize, kw = tap0 - kh * p.ksize;
+            if (p.stride == 1) {
+              tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
+            } else {
+              // input pixel = 2*out + k - pad: parity (k - pad) & 1, sub-grid index out + floor((k - pad) / 2)
+              const int dh = kh - p.pad, dw = kw - p.pad;
+              const int ph = dh & 1, pw = dw & 1;
+              tma_load_5d(sa, &maps.a[ph * 2 + pw], bar, cc * kBK, w0 + ((dw - pw) >> 1), h0 + ((dh - ph) >> 1), i0, 0);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && ai == item0) STAMP(2);
+        if (++as == p.a_stages) {
+          as = 0;
+          aph ^= 1u;
+        }
+        for (int bi = 0; bi < b_per_a; ++bi) {
+          const int tap = tap0 + bi;
+          mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
+          if (elect_one()) {
+            const uint32_t bar = bfull0 + 8 * bs;
+            mbar_arrive_expect_tx(bar, p.b_tx_bytes);
+            tma_load_3d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, (tap * p.chunks + cc) * kBK, nt * p.BN, 0);
+          }
+          __syncwarp();
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1u;
+          }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) STAMP(3);
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // =============================== MMA issuer ===============================
+    // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128.
+    // STACKED (BN <= 128): the weight stage holds [W_hi (BN rows) | W_lo (BN rows)] contiguously, so ONE MMA with
+    // N = 2*BN multiplies an activation plane by both weight planes (columns [0,BN) and [BN,2BN) of the
+    // accumulator, added in the epilogue): 2 MMAs per K step (x_hi, x_lo) give all four partial products.
+    // An SS-mode MMA costs ~128 cycles of A-operand reads whatever N is, so wide N is what makes it efficient.
+    const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
+      mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * kStageCols;
+      uint32_t accumulate = 0;
+      for (int ai = item0; ai < item1; ++ai) {
+        const int cc = p.halo ? ai : ai % p.chunks;
+        const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+        mbar_wait(afull0 + 8 * as, aph);
+        tc_fence_after();
+        if (lane == 0 && ai == item0) STAMP(4);
+        const uint32_t sa = smem_a + as * p.a_stage_bytes;
+        for (int bi = 0; bi < b_per_a; ++bi) {
+          mbar_wait(bfull0 + 8 * bs, bph);
+          tc_fence_after();
+          if (lane == 0 && ai == item0 && bi == 0) STAMP(5);
+          const uint32_t sb = smem_b + bs * p.b_stage_bytes;
+          uint32_t sat = sa;
+          if (p.halo) {
+            const int kh = bi / 3, kw = bi - kh * 3;
+            sat += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
+          }
+          const uint64_t a_hi = make_smem_desc(sat, p.a_sbo, p.base_off_mode);
+          const uint64_t a_lo = make_smem_desc(sat + p.a_plane_bytes, p.a_sbo, p.base_off_mode);
+          const uint64_t b_hi = make_smem_desc(sb, 1024, 0), b_lo = make_smem_desc(sb + p.BN * 128, 1024, 0);
+          if (elect_one()) {
+            if (p.stacked) {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
+                umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
+                umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+                accumulate = 1u;
+              }
+            } else {
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
+                umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+                accumulate = 1u;
+              }
+            }
+            umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+            if (bi == b_per_a - 1) umma_commit(aempty0 + 8 * as);  // activation slot free
+            if (bi == b_per_a - 1 && ai == item1 - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+          }
+          __syncwarp();
+          accumulate = 1u;
+          if (++bs == p.b_stages) {
+            bs = 0;
+            bph ^= 1u;
+          }
+        }
+        if (++as == p.a_stages) {
+          as = 0;
+          aph ^= 1u;
+        }
+      }
+      if (lane == 0) STAMP(6);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
+  } else {
+    // =============================== epilogue (warps 0-7) ===============================
+    if (p.pw == 32)
+      epilogue_role<CELL, 32>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
+    else
+      epilogue_role<CELL, 16>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) STAMP(11);
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -557,7 +881,8 @@ int g_num_sms = 0;
 int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
 int g_base_off_mode = 0;   // RSIS_B200_HALO_BASEOFF=1 sets the descriptor base-offset field (debug)
-int g_min_ctas = 120;      // BN is shrunk until a launch has at least this many tiles (RSIS_B200_MIN_CTAS)
+int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
+int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
 std::once_flag g_once;
 
 constexpr int kSmemLimit = 227 * 1024;
@@ -566,7 +891,9 @@ constexpr int kDynSmem = kSmemLimit - 1024;  // static barriers live beside it
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_HALO_BASEOFF")) g_base_off_mode = atoi(e) != 0;
-  if (const char* e = getenv("RSIS_B200_MIN_CTAS")) g_min_ctas = atoi(e);
+  if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
+
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -636,8 +963,62 @@ bool common_supported(const rsis_tensor* x, const rsis_conv_weights* w, int stri
   return true;
 }
 
+constexpr size_t kScratchFloats = (size_t)148 * kBM * kStageCols;   // one partial accumulator per SM
+constexpr size_t kCounterBytes = 4096;
+constexpr size_t kWorkspaceBytes = kCounterBytes + kScratchFloats * sizeof(float);
+
+// Tile-shape planner.  An SS-mode tcgen05.mma costs ~128 cycles of A-operand (activation) reads whatever its N, so the
+// time of a launch is (MMAs per CTA) x 128 cycles: pick the output-channel width BN (stacking the hi|lo weight planes
+// along N when 2*BN <= 256) and, when a launch has fewer work units than SMs, a K split that minimises it.
+struct Plan {
+  int BN, stacked, ksplit, halo;
+  long long cost;
+};
+
+Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
+               bool can_split) {
+  const long long ksteps_tile = (long long)taps * ((chunks - 1) * (kBK / 16) + last_ksteps);
+  Plan best{0, 0, 1, 0, -1};
+  int cands[2], nc = 0;
+  if (cout > 128) {
+    cands[nc++] = 256;
+    cands[nc++] = 128;
+  } else {
+    cands[nc++] = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  }
+  for (int ci = 0; ci < nc; ++ci) {
+    const int BN = cands[ci];
+    if (g_force_bn && BN != g_force_bn && nc > 1) continue;
+    const int stacked = BN <= 128 ? 1 : 0;
+    const int mpk = stacked ? 2 : 3;
+    const int tiles_n = ceil_div(cout, BN);
+    // (a) no split: persistent CTAs, HALO staging when eligible
+    {
+      const long long tiles = (long long)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
+      const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
+      const long long cost = waves * ksteps_tile * mpk * 128 + 3000;
+      if (best.cost < 0 || cost < best.cost) best = Plan{BN, stacked, 1, halo_ok ? 1 : 0, cost};
+    }
+    // (b) split-K over (tap, chunk) items, TAP staging, single wave
+    if (can_split && g_split_k) {
+      const long long tiles = (long long)m_tiles_tap * tiles_n;
+      const int items = taps * chunks;
+      int S = (int)(g_num_sms / tiles);
+      if (S > items) S = items;
+      if (S > 32) S = 32;
+      if (tiles <= g_num_sms && S >= 2) {
+        const long long per = (long long)ceil_div(items, S) * (kBK / 16) * mpk * 128;
+        const long long cost = per + 3000 + 2500 + 40LL * S * (stacked ? 2 : 1);  // + park, wait, reduce
+        if (cost < best.cost) best = Plan{BN, stacked, S, 0, cost};
+      }
+    }
+  }
+  return best;
+}
+
 // Fills geometry, tensor maps and the K loop.
-int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w, int stride, int pad) {
+int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w, int stride, int pad,
+          void* workspace, size_t workspace_bytes) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK) return g_init_status;
   p.N = x.n;
@@ -648,29 +1029,42 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.ksize = w->kw;
   p.stride = stride;
   p.pad = pad;
-  p.halo = (g_halo_enabled && w->kh == 3 && stride == 1 && p.Wo % kHaloBW == 0 && p.Ho % kHaloBH == 0) ? 1 : 0;
+  p.chunks = ceil_div(x.c, kBK);
+  p.last_ksteps = ceil_div(x.c - (p.chunks - 1) * kBK, 16);
+  const bool halo_ok = g_halo_enabled && w->kh == 3 && stride == 1 && p.Wo % kHaloBW == 0 && p.Ho % kHaloBH == 0;
+  // TAP-mode pixel box
+  const int tBW = next_pow2(p.Wo) < kBM ? next_pow2(p.Wo) : kBM;
+  const int tBH = next_pow2(p.Ho) < kBM / tBW ? next_pow2(p.Ho) : kBM / tBW;
+  const int tBI = kBM / (tBW * tBH);
+  const long long mt_tap = (long long)ceil_div(p.Wo, tBW) * ceil_div(p.Ho, tBH) * ceil_div(p.N, tBI);
+  const long long mt_halo = (long long)(p.Wo / kHaloBW) * (p.Ho / kHaloBH) * p.N;
+  if (mt_tap > 0x3fffffLL || mt_halo > 0x3fffffLL) return RSIS_ERR_UNSUPPORTED;
+  const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
+  const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split);
+  p.BN = plan.BN;
+  p.stacked = plan.stacked;
+  p.ksplit = plan.ksplit;
+  p.halo = plan.halo;
   if (p.halo) {
     p.BW = kHaloBW;
     p.BH = kHaloBH;
     p.BI = 1;
   } else {
-    p.BW = next_pow2(p.Wo) < kBM ? next_pow2(p.Wo) : kBM;
-    p.BH = next_pow2(p.Ho) < kBM / p.BW ? next_pow2(p.Ho) : kBM / p.BW;
-    p.BI = kBM / (p.BW * p.BH);
+    p.BW = tBW;
+    p.BH = tBH;
+    p.BI = tBI;
   }
   p.tiles_w = ceil_div(p.Wo, p.BW);
   p.tiles_h = ceil_div(p.Ho, p.BH);
   p.tiles_i = ceil_div(p.N, p.BI);
-  const long long mt = (long long)p.tiles_w * p.tiles_h * p.tiles_i;
-  // largest BN that still gives every SM a tile; small maps fall back to narrower tiles
-  p.BN = w->cout <= 32 ? 32 : (w->cout <= 64 ? 64 : 128);
-  while (p.BN > 32 && mt * ceil_div(w->cout, p.BN) < g_min_ctas) p.BN >>= 1;
   p.tiles_n = ceil_div(w->cout, p.BN);
-  const long long nt = mt * p.tiles_n;
-  if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
+  const long long nt = (long long)p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
+  if (nt * p.ksplit > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
   p.num_tiles = (int)nt;
-  p.chunks = ceil_div(x.c, kBK);
-  p.last_ksteps = ceil_div(x.c - (p.chunks - 1) * kBK, 16);
+  if (p.ksplit > 1 || (can_split && getenv("RSIS_B200_DEBUG_TIMING"))) {
+    p.counters = reinterpret_cast<unsigned*>(workspace);
+    p.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
+  }
   const int a_rows = p.halo ? kHaloRows : kBM;
   p.a_plane_bytes = a_rows * 128;
   p.a_tx_bytes = (uint32_t)(2 * p.a_plane_bytes);
@@ -679,7 +1073,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.base_off_mode = g_base_off_mode;
   p.b_stage_bytes = 2 * p.BN * 128;
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
-  const int budget = kDynSmem - 1024;
+  p.pw = p.BN >= 64 ? 32 : 16;
+  const int budget = kDynSmem - 1023 - kStageBytes;
   if (p.halo) {
     p.a_stages = 2;
     p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
@@ -715,7 +1110,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
 
 template <bool CELL>
 int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int work = p.num_tiles * p.ksplit;
+  const int grid = work < g_num_sms ? work : g_num_sms;
   conv_umma_kernel<CELL><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
@@ -732,12 +1128,15 @@ bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_w
   return true;
 }
 
+size_t conv_umma_workspace_bytes() { return kWorkspaceBytes; }
+
 int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
-                const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, cudaStream_t st) {
+                const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, void* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
   (void)n_src;
   UmmaMaps maps;
   UmmaParams p{};
-  if (int e = setup(maps, p, srcs[0], w, stride, pad)) return e;
+  if (int e = setup(maps, p, srcs[0], w, stride, pad, workspace, workspace_bytes)) return e;
   if (y->n != p.N || y->h != p.Ho || y->w != p.Wo || y->c != p.Cout) return RSIS_ERR_BAD_ARG;
   p.y = y->data;
   p.y_cs = pitch(*y);
@@ -768,11 +1167,12 @@ bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis
 
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
-                       uint32_t* side_max, int side_stride, int side_offset, cudaStream_t st) {
+                       uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st) {
   (void)n_src;
   UmmaMaps maps;
   UmmaParams p{};
-  if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2)) return e;
+  if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2, workspace, workspace_bytes)) return e;
   const int Ch = p.Cout / 4;
   auto ok = [&](const rsis_tensor* t, int fmt) {
     return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&

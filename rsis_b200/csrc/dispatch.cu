@@ -11,45 +11,53 @@ int convlstm_cell_simt(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
 bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                            const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad);
 int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
-                const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, cudaStream_t st);
+                const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, void* workspace,
+                size_t workspace_bytes, cudaStream_t st);
+size_t conv_umma_workspace_bytes();
 bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w);
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
-                       uint32_t* side_max, int side_stride, int side_offset, cudaStream_t st);
+                       uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
 }  // namespace rsis
 
 using namespace rsis;
 
 extern "C" {
 
+size_t rsis_conv_workspace_bytes(void) { return conv_umma_workspace_bytes(); }
+
 int rsis_conv2d(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                 const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad, int relu, int impl,
-                rsis_stream_t stream) {
+                void* workspace, size_t workspace_bytes, rsis_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == RSIS_IMPL_SIMT) return conv2d_simt(srcs, n_src, w, residual, y, y2, stride, pad, relu, st);
   const bool ok = srcs && w && y && conv2d_umma_supported(srcs, n_src, w, residual, y, y2, stride, pad);
   if (impl == RSIS_IMPL_TCGEN05) {
     if (!ok) return RSIS_ERR_UNSUPPORTED;
-    return conv2d_umma(srcs, n_src, w, residual, y, y2, stride, pad, relu, st);
+    return conv2d_umma(srcs, n_src, w, residual, y, y2, stride, pad, relu, workspace, workspace_bytes, st);
   }
   if (impl != RSIS_IMPL_AUTO) return RSIS_ERR_BAD_ARG;
-  return ok ? conv2d_umma(srcs, n_src, w, residual, y, y2, stride, pad, relu, st)
+  return ok ? conv2d_umma(srcs, n_src, w, residual, y, y2, stride, pad, relu, workspace, workspace_bytes, st)
             : conv2d_simt(srcs, n_src, w, residual, y, y2, stride, pad, relu, st);
 }
 
 int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
-                       uint32_t* side_max, int side_stride, int side_offset, int impl, rsis_stream_t stream) {
+                       uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
+                       size_t workspace_bytes, rsis_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == RSIS_IMPL_SIMT)
     return convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset, st);
   const bool ok = srcs && w && convlstm_cell_umma_supported(srcs, n_src, w);
   if (impl == RSIS_IMPL_TCGEN05) {
     if (!ok) return RSIS_ERR_UNSUPPORTED;
-    return convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset, st);
+    return convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
+                              workspace, workspace_bytes, st);
   }
   if (impl != RSIS_IMPL_AUTO) return RSIS_ERR_BAD_ARG;
-  return ok ? convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset, st)
+  return ok ? convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
+                                 workspace, workspace_bytes, st)
             : convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  st);
 }

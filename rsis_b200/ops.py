@@ -145,7 +145,7 @@ def conv2d(srcs: Sequence[Act], pc: PackedConv, stride: int = 1, pad: int = 0, r
     y2 = out2 if out2 is not None else (Act.empty(x.n, ho, wo, pc.cout, out2_fmt, dev) if out2_fmt is not None else None)
     check(lib.rsis_conv2d(_src_array(srcs), len(srcs), pc.ref(), residual.ref() if residual is not None else None,
                           y.ref(), y2.ref() if y2 is not None else None, stride, pad, int(relu), impl,
-                          _lib.stream_ptr()), "conv2d")
+                          *_lib.workspace(), _lib.stream_ptr()), "conv2d")
     _lib.count_launch(1)
     return (y, y2) if y2 is not None else y
 
@@ -197,7 +197,8 @@ def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side
     stride = side_max.shape[1] if side_max is not None else 0
     srcs = _src_array([x])
     check(lib.rsis_convlstm_cell(srcs, 1, pc.ref(), _ptr(c_prev), h.ref(), h16_out.ref() if h16_out else None,
-                                 c.ref(), _ptr(side_max), stride, side_offset, impl, _lib.stream_ptr()),
+                                 c.ref(), _ptr(side_max), stride, side_offset, impl, *_lib.workspace(),
+                                 _lib.stream_ptr()),
           "convlstm_cell")
     _lib.count_launch(1)
     return h, c
@@ -230,7 +231,8 @@ def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Te
     hs = Act.empty(x.n, x.h, x.w, ch, FMT_SPLIT_BF16, dev) if want_split else None
     stride = side_max.shape[1] if side_max is not None else 0
     check(lib.rsis_convlstm_cell(_src_array(srcs), len(srcs), pc.ref(), _ptr(c_prev), h.ref(), hs.ref() if hs else None,
-                                 c.ref(), _ptr(side_max), stride, side_offset, impl, _lib.stream_ptr()),
+                                 c.ref(), _ptr(side_max), stride, side_offset, impl, *_lib.workspace(),
+                                 _lib.stream_ptr()),
           "convlstm_cell")
     _lib.count_launch(1)
     return h, c, hs

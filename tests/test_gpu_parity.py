@@ -406,8 +406,11 @@ def test_encoder_raw_taps(R, O, sw, impl):
 # size-independent properties at BASELINE.json's full sizes
 # ---------------------------------------------------------------------------------------------------------
 def test_batch_sharding_is_exact_cfg2(R, sw, impl):
-    """The path shards per image: running a batch of 8 in one piece or as two shards of 4 gives
-    bit-identical results, and a run is deterministic (the only atomics are order-independent maxima)."""
+    """The path shards per image: a run is deterministic bit for bit (the only atomics are
+    order-independent maxima; split-K partials are summed in a fixed order), and running a batch of 8 in one piece
+    or as two shards of 4 gives the same images.  The CUDA-core family is bit-identical across shardings; the
+    tcgen05 family picks its tile width / K split from the batch size, which reorders fp32 sums, so there the
+    shards agree to fp32 rounding (5e-5 tensor-relative, 20x below the parity tolerance)."""
     args, enc, dec = _models(R, sw, 21, 10)
     args.cuda_graph = False
     x = sw.synthetic_images(123, 8, 256, 256).cuda()
@@ -417,7 +420,11 @@ def test_batch_sharding_is_exact_cfg2(R, sw, impl):
         assert torch.equal(a, b)
     parts = [R.test(args, enc, dec, x[i:i + 4].contiguous()) for i in (0, 4)]
     for k in range(3):
-        assert torch.equal(full[k], torch.cat([parts[0][k], parts[1][k]], 0))
+        joined = torch.cat([parts[0][k], parts[1][k]], 0)
+        if impl == "simt":
+            assert torch.equal(full[k], joined)
+        else:
+            assert rel(joined, full[k]) < 5e-5
     masks, classes, stops = full
     assert float(masks.min()) >= 0.0 and float(masks.max()) <= 1.0
     assert float((classes.sum(-1) - 1).abs().max()) < 1e-5  # Softmax rows
