@@ -25,10 +25,10 @@
 //   budget (single-pass fp16/bf16/tf32 operands do not: DESIGN.md "precision").
 //   K steps that only cover zero padding (channels beyond C in the last chunk) are not issued.
 //
-// Persistent, warp-specialised CTA (320 threads, one per SM): warps 0-7 epilogue (TMEM lane quarter = warp % 4,
-// column half = warp / 4), warp 8 TMA producer, warp 9 MMA issuer; mbarrier full/empty rings for A and B, TMEM
-// full/empty between MMA and epilogue.  BN (32/64/128) is chosen so that small maps still spread over the 148 SMs.
-// Every mbarrier wait is bounded (trap instead of hang).
+// Persistent, warp-specialised CTA (352 threads, one per SM): warps 0-7 epilogue (TMEM lane quarter = warp % 4,
+// column half = warp / 4), warp 8 activation-TMA producer, warp 9 MMA issuer, warp 10 weight-TMA producer; mbarrier
+// full/empty rings for A and B, TMEM full/empty between MMA and epilogue.  A host-side planner picks the
+// output-channel width BN (32..256) and a K split per launch.  Every mbarrier wait is bounded (trap, not hang).
 #include <cuda.h>
 
 #include <cstdio>
@@ -51,7 +51,7 @@ constexpr int kStageCols = 256;   // accumulator columns per TMEM stage (BN, or 
 constexpr int kTmemCols = kStageCols * kAccStages;  // 512: the whole TMEM (one CTA per SM)
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreadsUmma = kEpiThreads + 64;
+constexpr int kThreadsUmma = kEpiThreads + 96;  // + A producer, MMA issuer, B producer
 constexpr int kMaxStages = 8;
 constexpr int kHaloBW = 8, kHaloBH = 16;
 constexpr int kHaloRows = (kHaloBW + 2) * (kHaloBH + 2);  // 180 pixels
@@ -256,12 +256,17 @@ __device__ __forceinline__ void store4(void* ptr, size_t plane, int fmt, size_t 
   if (fmt == RSIS_FMT_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + idx) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+    // hi = rn(v) two at a time (cvt.rn.bf16x2.f32), lo = rn(v - hi)
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+    const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - __uint_as_float(u01 << 16),
+                                                     v[1] - __uint_as_float(u01 & 0xffff0000u));
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - __uint_as_float(u23 << 16),
+                                                     v[3] - __uint_as_float(u23 & 0xffff0000u));
     __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(ptr);
-    *reinterpret_cast<uint2*>(q + idx) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    *reinterpret_cast<uint2*>(q + idx + plane) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    *reinterpret_cast<uint2*>(q + idx) = make_uint2(u01, u23);
+    *reinterpret_cast<uint2*>(q + idx + plane) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
   }
 }
 __device__ __forceinline__ void load4(const View& v, size_t idx, float (&out)[4]) {
@@ -551,29 +556,43 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
         const int ncg = p.BN >> 5;
         const int units = (kBM / 4) * ncg;
         const int Ch = p.Cout >> 2;
-        for (int u = ks * kEpiWarps + warp; u < units; u += kEpiWarps * p.ksplit) {
+        struct Unit {
+          RowGeom g;
+          int col;
+          bool ok;
+          float cprev;
+          float4 v;
+        };
+        // loads of one unit: issued for two units before either is finished, so their L2 / DRAM latencies overlap
+        auto unit_load = [&](int u) {
+          Unit t;
           const int cg = u % ncg;
           const int row = 4 * (u / ncg) + (lane >> 3);
           const int c4 = lane & 7;
-          const int col = nt * p.BN + 32 * cg + 4 * c4;
-          const RowGeom g2 = row_geom(p, row, tw, th, ti);
-          const bool ok = g2.ok && col < p.Cout;
-          float cprev = 0.f;
+          t.col = nt * p.BN + 32 * cg + 4 * c4;
+          t.g = row_geom(p, row, tw, th, ti);
+          t.ok = t.g.ok && t.col < p.Cout;
+          t.cprev = 0.f;
           if constexpr (CELL) {
-            if (ok && p.c_prev) cprev = __ldg(p.c_prev + g2.pix * Ch + (col >> 2));
+            if (t.ok && p.c_prev) t.cprev = __ldg(p.c_prev + t.g.pix * Ch + (t.col >> 2));
           }
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          t.v = make_float4(0.f, 0.f, 0.f, 0.f);
           const float* src = p.scratch + ((size_t)(tile * p.ksplit) * kBM + row) * ncols + 32 * cg + 4 * c4;
           const size_t sstride = (size_t)kBM * ncols;
 #pragma unroll 4
           for (int s2 = 0; s2 < p.ksplit; ++s2) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride));
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            const float4 a4 = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride));
+            t.v.x += a4.x; t.v.y += a4.y; t.v.z += a4.z; t.v.w += a4.w;
             if (p.stacked) {
-              const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride + p.BN));
-              v.x += t2.x; v.y += t2.y; v.z += t2.z; v.w += t2.w;
+              const float4 b4 = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride + p.BN));
+              t.v.x += b4.x; t.v.y += b4.y; t.v.z += b4.z; t.v.w += b4.w;
             }
           }
+          return t;
+        };
+        auto unit_finish = [&](const Unit& t) {
+          const int col = t.col;
+          const float4 v = t.v;
           float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
           if (col < p.Cout) {
             sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
@@ -585,17 +604,17 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             const float gf = fast_sigmoid(fmaf(v.y, sc.y, sh.y));
             const float go = fast_sigmoid(fmaf(v.z, sc.z, sh.z));
             const float gg = fast_tanh(fmaf(v.w, sc.w, sh.w));
-            const float cv = fmaf(gf, cprev, gi * gg);
+            const float cv = fmaf(gf, t.cprev, gi * gg);
             const float hv = go * fast_tanh(cv);
             uint32_t key = 0u;
-            if (ok) {
-              const size_t idx = g2.pix * Ch + chg;
+            if (t.ok) {
+              const size_t idx = t.g.pix * Ch + chg;
               p.c_out[idx] = cv;
               p.h_out[idx] = hv;
               if (p.h_split) {
                 __nv_bfloat16 hi, lo;
                 split_bf16(hv, hi, lo);
-                const size_t k = g2.pix * p.hs_cs + chg;
+                const size_t k = t.g.pix * p.hs_cs + chg;
                 p.h_split[k] = hi;
                 p.h_split[k + p.hs_plane] = lo;
               }
@@ -607,11 +626,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
                 key = o > key ? o : key;
                 o = __shfl_xor_sync(0xffffffffu, key, 16);
                 key = o > key ? o : key;
-                const int img0 = __shfl_sync(0xffffffffu, g2.img, 0);
+                const int img0 = __shfl_sync(0xffffffffu, t.g.img, 0);
                 if (lane < 8 && key != 0u)
                   atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg, key);
               } else if (key != 0u) {
-                atomicMax(p.side_max + (size_t)g2.img * p.side_stride + p.side_offset + chg, key);
+                atomicMax(p.side_max + (size_t)t.g.img * p.side_stride + p.side_offset + chg, key);
               }
             }
           } else {
@@ -620,20 +639,31 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             o[1] = fmaf(v.y, sc.y, sh.y);
             o[2] = fmaf(v.z, sc.z, sh.z);
             o[3] = fmaf(v.w, sc.w, sh.w);
-            if (ok) {
+            if (t.ok) {
               if (p.has_res) {
-                float t[4];
-                load4(p.res, g2.pix * p.res_cs + col, t);
+                float r4[4];
+                load4(p.res, t.g.pix * p.res_cs + col, r4);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] += t[e];
+                for (int e = 0; e < 4; ++e) o[e] += r4[e];
               }
               if (p.relu) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
               }
-              store4(p.y, p.y_plane, p.y_fmt, g2.pix * p.y_cs + col, o);
-              if (p.y2) store4(p.y2, p.y2_plane, p.y2_fmt, g2.pix * p.y2_cs + col, o);
+              store4(p.y, p.y_plane, p.y_fmt, t.g.pix * p.y_cs + col, o);
+              if (p.y2) store4(p.y2, p.y2_plane, p.y2_fmt, t.g.pix * p.y2_cs + col, o);
             }
+          }
+        };
+        const int ustride = kEpiWarps * p.ksplit;
+        for (int u = ks * kEpiWarps + warp; u < units; u += 2 * ustride) {
+          const Unit t0 = unit_load(u);
+          if (u + ustride < units) {
+            const Unit t1 = unit_load(u + ustride);
+            unit_finish(t0);
+            unit_finish(t1);
+          } else {
+            unit_finish(t0);
           }
         }
       }
@@ -717,13 +747,12 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   const int num_work = p.num_tiles * p.ksplit;
 
   if (warp == kEpiWarps) {
-    // =============================== TMA producer ===============================
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
+    // =============================== TMA producer: activations (A ring) ===============================
+    int as = 0;
+    uint32_t aph = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
       const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
-      const int nt = tile % p.tiles_n;
       int mt = tile / p.tiles_n;
       const int tw = mt % p.tiles_w;
       mt /= p.tiles_w;
@@ -758,6 +787,21 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
           as = 0;
           aph ^= 1u;
         }
+      }
+      if (lane == 0) STAMP(3);
+    }
+  } else if (warp == kEpiWarps + 2) {
+    // =============================== TMA producer: weights (B ring) ===============================
+    // Its own warp, so that activation tiles run a_stages items ahead no matter how far the weight ring is.
+    int bs = 0;
+    uint32_t bph = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
+      const int nt = tile % p.tiles_n;
+      for (int ai = item0; ai < item1; ++ai) {
+        const int cc = p.halo ? ai : ai % p.chunks;
+        const int tap0 = p.halo ? 0 : ai / p.chunks;
         for (int bi = 0; bi < b_per_a; ++bi) {
           const int tap = tap0 + bi;
           mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
@@ -773,7 +817,6 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
           }
         }
       }
-      if (lane == 0) STAMP(3);
     }
   } else if (warp == kEpiWarps + 1) {
     // =============================== MMA issuer ===============================
@@ -854,7 +897,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         acc_phase ^= 1u;
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // =============================== epilogue (warps 0-7) ===============================
     if (p.pw == 32)
       epilogue_role<CELL, 32>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
@@ -976,7 +1019,12 @@ struct Plan {
 };
 
 Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
-               bool can_split) {
+               bool can_split, bool cell) {
+  // Cost model in nanoseconds, calibrated with in-kernel %globaltimer stamps on B200 (scripts/stamp_probe.py):
+  //   launch -> first MMA and exit: ~3000; one tcgen05.mma instruction: ~70 whatever its N;
+  //   finishing one 32 x 32 accumulator piece on one epilogue warp: ~900 (conv) / ~1300 (cell), 8 warps per CTA;
+  //   split-K hand-over (park the partial, wait for the slowest slice, reduce): ~4500 + 110 per (unit, slice).
+  const long long kFixed = 3000, kMma = 70, kPiece = cell ? 1300 : 900;
   const long long ksteps_tile = (long long)taps * ((chunks - 1) * (kBK / 16) + last_ksteps);
   Plan best{0, 0, 1, 0, -1};
   int cands[2], nc = 0;
@@ -992,11 +1040,15 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     const int stacked = BN <= 128 ? 1 : 0;
     const int mpk = stacked ? 2 : 3;
     const int tiles_n = ceil_div(cout, BN);
-    // (a) no split: persistent CTAs, HALO staging when eligible
-    {
+    const long long pieces_per_warp = ceil_div(4 * ceil_div(BN, 32), kEpiWarps);
+    const long long epi_tile = pieces_per_warp * kPiece;
+    // (a) no split: persistent CTAs, HALO staging when eligible; MMAs of tile i+1 overlap the epilogue of tile i
+    if (!(halo_ok && BN == 256)) {  // a HALO stage + 64 KB weight stages do not leave room for a pipeline
       const long long tiles = (long long)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
-      const long long waves = (tiles + g_num_sms - 1) / g_num_sms;
-      const long long cost = waves * ksteps_tile * mpk * 128 + 3000;
+      const long long per_cta = (tiles + g_num_sms - 1) / g_num_sms;
+      const long long mma_tile = ksteps_tile * mpk * kMma;
+      const long long slow = mma_tile > epi_tile ? mma_tile : epi_tile, fast = mma_tile + epi_tile - slow;
+      const long long cost = kFixed + per_cta * slow + fast;
       if (best.cost < 0 || cost < best.cost) best = Plan{BN, stacked, 1, halo_ok ? 1 : 0, cost};
     }
     // (b) split-K over (tap, chunk) items, TAP staging, single wave
@@ -1007,8 +1059,9 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
       if (S > items) S = items;
       if (S > 32) S = 32;
       if (tiles <= g_num_sms && S >= 2) {
-        const long long per = (long long)ceil_div(items, S) * (kBK / 16) * mpk * 128;
-        const long long cost = per + 3000 + 2500 + 40LL * S * (stacked ? 2 : 1);  // + park, wait, reduce
+        const long long mma = (long long)ceil_div(items, S) * (kBK / 16) * mpk * kMma;
+        const long long units_per_warp = ceil_div((kBM / 4) * ceil_div(BN, 32), kEpiWarps * S);
+        const long long cost = kFixed + mma + 4500 + units_per_warp * (300 + 110LL * S * (stacked ? 2 : 1));
         if (cost < best.cost) best = Plan{BN, stacked, S, 0, cost};
       }
     }
@@ -1040,7 +1093,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const long long mt_halo = (long long)(p.Wo / kHaloBW) * (p.Ho / kHaloBH) * p.N;
   if (mt_tap > 0x3fffffLL || mt_halo > 0x3fffffLL) return RSIS_ERR_UNSUPPORTED;
   const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
-  const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split);
+  const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
+                              w->gate_interleaved != 0);
   p.BN = plan.BN;
   p.stacked = plan.stacked;
   p.ksplit = plan.ksplit;
