@@ -341,6 +341,7 @@ def run_ours(a):
         }
         print(json.dumps(line))
     rdist.barrier()
+    rdist.shutdown()
     return 0
 
 
