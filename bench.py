@@ -168,8 +168,8 @@ def run_reference(a):
 # --------------------------------------------------------------------------------------------------------------
 def time_cells(rsis_b200, dec, ws, impl, iters=20):
     """CUDA-event time of the five fused ConvLSTM cell launches of one decoder step, per level, on the real state a
-    2-step run left in the decoder workspace `ws` (inputs = its concatenated [up(h) | skip | h_prev] buffers,
-    c_prev = its cell state; outputs go to scratch).  Between iterations a 512 MiB buffer is written to flush L2."""
+    2-step run left in the decoder workspace `ws` (inputs = its concatenated [up(h) | h_prev] buffers + the hoisted
+    skip share of the gates, c_prev = its cell state; outputs go to scratch).  Between iterations a 512 MiB buffer is written to flush L2."""
     ops = rsis_b200.ops
     dev = ws.side.device
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -181,7 +181,7 @@ def time_cells(rsis_b200, dec, ws, impl, iters=20):
         scratch.append((ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_F32, dev),
                         ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_F32, dev),
                         ops.Act.empty(x.n, x.h, x.w, cell.hidden_size, ops.FMT_SPLIT_BF16, dev),
-                        cell.packed([cell.input_size + cell.hidden_size], want_umma=True)))
+                        ws.packs(dec, l)[1]))
     per_level = [[] for _ in dec.clstm_list]
     # One (flush, event, cell, event) group per launch: the ~150 us flush kernel lets the host enqueue the cell
     # and both events before the GPU reaches them, so the interval is kernel time, not host launch latency.
@@ -191,7 +191,8 @@ def time_cells(rsis_b200, dec, ws, impl, iters=20):
             flush.fill_(it & 0xFF)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.convlstm_cell_x(ws.X[l][p], pc, ws.c[l].t, side, 0, h_out=h, c_out=c, h16_out=h16, impl=impl)
+            ops.convlstm_cell_x(ws.X[l][p], pc, ws.c[l].t, side, 0, h_out=h, c_out=c, h16_out=h16, impl=impl,
+                                gate_preact=ws.P[l])
             e1.record()
             if it >= 3:
                 per_level[l].append((e0, e1))

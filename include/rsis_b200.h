@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 3
+#define RSIS_ABI_VERSION 4
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -132,13 +132,18 @@ int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t 
  *             be omitted (n_src excludes it) when the state is None (clstm.py:26-37: zeros) -- then c_prev=NULL
  *   w         packed with gate_interleave=1
  *   c_prev    float32 NHWC [N,H,W,Ch] or NULL (zero state)
+ *   gate_preact  optional float32 [N,H,W,4*Ch] in (hidden channel, gate) order, added to the gate pre-activations:
+ *             the contribution of TIME-INVARIANT input channels (the skip feature of model.py:153 and level 0's
+ *             x5_skip are the same at every step t), computed once per image by rsis_conv2d with the matching
+ *             column block of the gate weights (packed with gate_interleave) and the gate bias -- the per-step
+ *             kernel then only contracts over [upsampled hidden | prev_hidden].  tcgen05 kernel family only.
  *   h_out     float32 NHWC; h_split (optional) the same values as split-bf16 for the next consumer
  *   c_out     float32 NHWC
  *   side_max  optional: per-(image, channel) running max of h, as order-preserving uint32 keys, at
  *             side_max[n*side_stride + side_offset + ch] -- the global nn.MaxPool2d of model.py:143.
  *             Must be zero-filled before the step (key 0 sorts below every float). */
 int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
-                       const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
+                       const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
                        size_t workspace_bytes, rsis_stream_t stream);
 /* nn.UpsamplingBilinear2d(size=(y.h, y.w)) == bilinear, align_corners=True (model.py:149-150,163-164). */

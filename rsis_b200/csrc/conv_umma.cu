@@ -52,7 +52,7 @@ constexpr int kTmemCols = kStageCols * kAccStages;  // 512: the whole TMEM (one 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsUmma = kEpiThreads + 96;  // + A producer, MMA issuer, B producer
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 9;  // 9 = all taps of a one-chunk 3x3 weight set resident (b_resident)
 constexpr int kHaloBW = 8, kHaloBH = 16;
 constexpr int kHaloRows = (kHaloBW + 2) * (kHaloBH + 2);  // 180 pixels
 
@@ -73,6 +73,7 @@ struct UmmaParams {
   unsigned* counters;      // [num_tiles][2] arrival / completion counters (zero between launches)
   int halo;                // 1: HALO staging, 0: TAP staging
   int a_stages, b_stages;
+  int b_resident;          // 1: the tile's whole weight set stays in the B ring for the CTA's lifetime (loaded once)
   int a_plane_bytes;       // bytes of one bf16 plane of an A stage (rows * 128)
   int a_stage_bytes;       // both planes, rounded up to 1024
   int b_stage_bytes;       // 2 * BN * 128
@@ -99,6 +100,7 @@ struct UmmaParams {
   int y2_fmt, y2_cs;
   // cell epilogue
   const float* c_prev;
+  const float* preact;     // optional [N][H][W][4*Ch] fp32, (channel, gate) order: time-invariant part of the gates
   float* h_out;
   float* c_out;
   __nv_bfloat16* h_split;
@@ -338,6 +340,7 @@ struct CellPiece {
   static constexpr int NIT = 32 / RPI;  // iterations
   uint32_t pix[NIT];
   float cp[NIT];
+  float4 pre[NIT];
 };
 
 template <int PW>
@@ -353,6 +356,9 @@ __device__ __forceinline__ void cell_prefetch(const UmmaParams& p, CellPiece<PW>
     const uint32_t pix = __shfl_sync(0xffffffffu, mypix, row);
     cpz.pix[it] = ch_ok ? pix : 0xffffffffu;
     cpz.cp[it] = (p.c_prev && cpz.pix[it] != 0xffffffffu) ? __ldg(p.c_prev + (size_t)pix * Ch + chg) : 0.f;
+    cpz.pre[it] = (p.preact && cpz.pix[it] != 0xffffffffu)
+                      ? __ldg(reinterpret_cast<const float4*>(p.preact + ((size_t)pix * Ch + chg) * 4))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -377,10 +383,10 @@ __device__ __forceinline__ void cell_finish_piece(const UmmaParams& p, const flo
     const int row = it * CP::RPI + lane / CP::CPP;
     const uint32_t pix = cpz.pix[it];
     const float* g = stage + row * kStagePitch + 4 * ch;
-    const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x));
-    const float gf = fast_sigmoid(fmaf(g[1], sc.y, sh.y));
-    const float go = fast_sigmoid(fmaf(g[2], sc.z, sh.z));
-    const float gg = fast_tanh(fmaf(g[3], sc.w, sh.w));
+    const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x) + cpz.pre[it].x);
+    const float gf = fast_sigmoid(fmaf(g[1], sc.y, sh.y) + cpz.pre[it].y);
+    const float go = fast_sigmoid(fmaf(g[2], sc.z, sh.z) + cpz.pre[it].z);
+    const float gg = fast_tanh(fmaf(g[3], sc.w, sh.w) + cpz.pre[it].w);
     const float cv = fmaf(gf, cpz.cp[it], gi * gg);
     const float hv = go * fast_tanh(cv);
     if (pix == 0xffffffffu) continue;
@@ -443,8 +449,12 @@ __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   }
 }
 #define STAMP(slot) stamp(p, slot)
+// per-tile timeline of block 0: role 0 = A issued, 1 = MMA sees A, 2 = MMAs issued, 3 = epilogue sees accumulator,
+// 4 = epilogue released the accumulator; up to 16 tiles each
+#define STAMP_T(role, iter) do { if ((iter) < 16) stamp(p, 16 + (role) * 16 + (iter)); } while (0)
 #else
 #define STAMP(slot)
+#define STAMP_T(role, iter)
 #endif
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
@@ -452,7 +462,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // Epilogue warps: accumulator pieces (32 rows x PW columns) -> staged transpose -> finish.  With split-K the CTA first
 // parks its partial accumulator in the L2-resident scratch (TMEM-native order: for a fixed column the 32 lanes of a
 // warp write 32 consecutive floats), waits for the other K slices of its tile, then reduces and finishes its share.
-template <bool CELL, int PW>
+template <bool CELL, int PW, bool SPLIT>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, float* stage, int warp, int lane) {
   const int quarter = warp & 3;       // TMEM lane quarter this warp may read
@@ -464,6 +474,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   const int num_work = p.num_tiles * p.ksplit;
   int acc = 0;
   uint32_t acc_phase = 0;
+  CellPiece<PW> cpz_cur;
   for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
     const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
     const int nt = tile % p.tiles_n;
@@ -474,22 +485,34 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
     const int ti = mt / p.tiles_h;
     const RowGeom g = row_geom(p, quarter * 32 + lane, tw, th, ti);
     const uint32_t mypix = g.ok ? (uint32_t)g.pix : 0xffffffffu;
-    CellPiece<PW> cpz0;
-    if constexpr (CELL) {
-      if (p.ksplit == 1 && half < npc) cell_prefetch<PW>(p, cpz0, lane, mypix, nt * p.BN + PW * half);
+    if constexpr (CELL && !SPLIT) {
+      // the very first piece of this warp; afterwards every piece's c_prev / hoisted-gate loads are issued one piece
+      // ahead (rolling, across tiles), so their DRAM latency hides behind the previous piece instead of stalling it
+      if (work == (int)blockIdx.x && half < npc) cell_prefetch<PW>(p, cpz_cur, lane, mypix, nt * p.BN + PW * half);
     }
     mbar_wait(tfull0 + 8 * acc, acc_phase);
     tc_fence_after();
     if (threadIdx.x == 0) STAMP(7);
+    if (threadIdx.x == 0) STAMP_T(3, (work - (int)blockIdx.x) / (int)gridDim.x);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
-    if (p.ksplit == 1) {
+    if constexpr (!SPLIT) {
       for (int j = half; j < npc; j += 2) {
         const int col0 = nt * p.BN + PW * j;
         if (col0 >= p.Cout) break;
-        CellPiece<PW> cpz;
+        CellPiece<PW> cpz_next;
         if constexpr (CELL) {
-          if (j != half) cell_prefetch<PW>(p, cpz, lane, mypix, col0);
-          else cpz = cpz0;
+          const int coln = col0 + 2 * PW;
+          if (j + 2 < npc && coln < p.Cout) {
+            cell_prefetch<PW>(p, cpz_next, lane, mypix, coln);
+          } else if (work + (int)gridDim.x < num_work) {
+            const int tile2 = (work + (int)gridDim.x) / p.ksplit;
+            const int nt2 = tile2 % p.tiles_n;
+            int mt2 = tile2 / p.tiles_n;
+            const int tw2 = mt2 % p.tiles_w;
+            mt2 /= p.tiles_w;
+            const RowGeom g2 = row_geom(p, quarter * 32 + lane, tw2, mt2 % p.tiles_h, mt2 / p.tiles_h);
+            cell_prefetch<PW>(p, cpz_next, lane, g2.ok ? (uint32_t)g2.pix : 0xffffffffu, nt2 * p.BN + PW * half);
+          }
         }
         uint32_t r[PW];
         tmem_ld_piece<PW>(taddr + PW * j, r);
@@ -504,14 +527,17 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
 #pragma unroll
         for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
         __syncwarp();
-        if constexpr (CELL)
-          cell_finish_piece<PW>(p, stage, lane, cpz, g.img, col0, seg);
-        else
+        if constexpr (CELL) {
+          cell_finish_piece<PW>(p, stage, lane, cpz_cur, g.img, col0, seg);
+          cpz_cur = cpz_next;
+        } else {
           conv_finish_piece<PW>(p, stage, lane, mypix, col0);
+        }
         __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * acc);
+      if (threadIdx.x == 0) STAMP_T(4, (work - (int)blockIdx.x) / (int)gridDim.x);
     } else {
       // ---- split-K (1): park this CTA's partial accumulator in the scratch as [row][column] (staged transpose,
       // so each row's 32 columns are one 128-byte store)
@@ -561,6 +587,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           int col;
           bool ok;
           float cprev;
+          float4 pre;
           float4 v;
         };
         // loads of one unit: issued for two units before either is finished, so their L2 / DRAM latencies overlap
@@ -575,11 +602,13 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           t.cprev = 0.f;
           if constexpr (CELL) {
             if (t.ok && p.c_prev) t.cprev = __ldg(p.c_prev + t.g.pix * Ch + (t.col >> 2));
+            t.pre = (t.ok && p.preact) ? __ldg(reinterpret_cast<const float4*>(p.preact + t.g.pix * p.Cout + t.col))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           t.v = make_float4(0.f, 0.f, 0.f, 0.f);
           const float* src = p.scratch + ((size_t)(tile * p.ksplit) * kBM + row) * ncols + 32 * cg + 4 * c4;
           const size_t sstride = (size_t)kBM * ncols;
-#pragma unroll 4
+#pragma unroll 8
           for (int s2 = 0; s2 < p.ksplit; ++s2) {
             const float4 a4 = __ldcg(reinterpret_cast<const float4*>(src + s2 * sstride));
             t.v.x += a4.x; t.v.y += a4.y; t.v.z += a4.z; t.v.w += a4.w;
@@ -600,10 +629,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           }
           if constexpr (CELL) {
             const int chg = col >> 2;
-            const float gi = fast_sigmoid(fmaf(v.x, sc.x, sh.x));
-            const float gf = fast_sigmoid(fmaf(v.y, sc.y, sh.y));
-            const float go = fast_sigmoid(fmaf(v.z, sc.z, sh.z));
-            const float gg = fast_tanh(fmaf(v.w, sc.w, sh.w));
+            const float gi = fast_sigmoid(fmaf(v.x, sc.x, sh.x) + t.pre.x);
+            const float gf = fast_sigmoid(fmaf(v.y, sc.y, sh.y) + t.pre.y);
+            const float go = fast_sigmoid(fmaf(v.z, sc.z, sh.z) + t.pre.z);
+            const float gg = fast_tanh(fmaf(v.w, sc.w, sh.w) + t.pre.w);
             const float cv = fmaf(gf, t.cprev, gi * gg);
             const float hv = go * fast_tanh(cv);
             uint32_t key = 0u;
@@ -684,7 +713,9 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   }
 }
 
-template <bool CELL>
+// One instantiation per (epilogue kind, piece width, split-K or not): each carries a single epilogue variant, which
+// keeps the 11 differently-specialised warps of a CTA inside the instruction cache.
+template <bool CELL, int PW, bool SPLIT>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
 conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -783,6 +814,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         }
         __syncwarp();
         if (lane == 0 && ai == item0) STAMP(2);
+        if (lane == 0 && ai == item0) STAMP_T(0, (work - (int)blockIdx.x) / (int)gridDim.x);
         if (++as == p.a_stages) {
           as = 0;
           aph ^= 1u;
@@ -796,6 +828,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     int bs = 0;
     uint32_t bph = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      if (p.b_resident && work != (int)blockIdx.x) break;  // resident weights: loaded for the first tile only
       const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
       const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
       const int nt = tile % p.tiles_n;
@@ -844,8 +877,13 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         mbar_wait(afull0 + 8 * as, aph);
         tc_fence_after();
         if (lane == 0 && ai == item0) STAMP(4);
+        if (lane == 0 && ai == item0) STAMP_T(1, (work - (int)blockIdx.x) / (int)gridDim.x);
         const uint32_t sa = smem_a + as * p.a_stage_bytes;
         for (int bi = 0; bi < b_per_a; ++bi) {
+          if (p.b_resident) {
+            bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
+            bph = 0;
+          }
           mbar_wait(bfull0 + 8 * bs, bph);
           tc_fence_after();
           if (lane == 0 && ai == item0 && bi == 0) STAMP(5);
@@ -875,13 +913,13 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
                 accumulate = 1u;
               }
             }
-            umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+            if (!p.b_resident) umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
             if (bi == b_per_a - 1) umma_commit(aempty0 + 8 * as);  // activation slot free
             if (bi == b_per_a - 1 && ai == item1 - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
           }
           __syncwarp();
           accumulate = 1u;
-          if (++bs == p.b_stages) {
+          if (!p.b_resident && ++bs == p.b_stages) {
             bs = 0;
             bph ^= 1u;
           }
@@ -892,6 +930,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         }
       }
       if (lane == 0) STAMP(6);
+      if (lane == 0) STAMP_T(2, (work - (int)blockIdx.x) / (int)gridDim.x);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
@@ -899,10 +938,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     }
   } else if (warp < kEpiWarps) {
     // =============================== epilogue (warps 0-7) ===============================
-    if (p.pw == 32)
-      epilogue_role<CELL, 32>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
-    else
-      epilogue_role<CELL, 16>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
+    epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
   }
 
   tc_fence_before();
@@ -926,16 +962,23 @@ int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-
 int g_base_off_mode = 0;   // RSIS_B200_HALO_BASEOFF=1 sets the descriptor base-offset field (debug)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
+int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
 std::once_flag g_once;
 
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kDynSmem = kSmemLimit - 1024;  // static barriers live beside it
+
+template <bool CELL, int PW, bool SPLIT>
+cudaError_t set_smem_attr() {
+  return cudaFuncSetAttribute(conv_umma_kernel<CELL, PW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
+}
 
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_HALO_BASEOFF")) g_base_off_mode = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
+  if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -949,10 +992,10 @@ void init_once() {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
-          cudaSuccess ||
-      (e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
-          cudaSuccess) {
+      (e = set_smem_attr<false, 32, false>()) != cudaSuccess || (e = set_smem_attr<false, 32, true>()) != cudaSuccess ||
+      (e = set_smem_attr<false, 16, false>()) != cudaSuccess || (e = set_smem_attr<false, 16, true>()) != cudaSuccess ||
+      (e = set_smem_attr<true, 32, false>()) != cudaSuccess || (e = set_smem_attr<true, 32, true>()) != cudaSuccess ||
+      (e = set_smem_attr<true, 16, false>()) != cudaSuccess || (e = set_smem_attr<true, 16, true>()) != cudaSuccess) {
     set_cuda_error(e);
     g_init_status = RSIS_ERR_CUDA;
   }
@@ -1142,6 +1185,19 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
     p.b_stages = p.a_stages;
   }
+  {
+    // Weight residency: a persistent CTA that walks several pixel tiles of ONE output-channel tile re-reads the same
+    // taps x chunks weight boxes for every tile; when they all fit next to two activation stages, load them once.
+    const int items_b = p.taps * p.chunks;
+    const bool many_tiles = p.num_tiles >= 2 * g_num_sms;
+    if (g_b_resident && p.ksplit == 1 && p.tiles_n == 1 && many_tiles && items_b <= kMaxStages &&
+        2 * p.a_stage_bytes + items_b * p.b_stage_bytes <= budget) {
+      p.b_resident = 1;
+      p.b_stages = items_b;
+      p.a_stages = (budget - items_b * p.b_stage_bytes) / p.a_stage_bytes;
+      if (p.a_stages > 4) p.a_stages = 4;
+    }
+  }
   if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
   p.scale = w->scale;
   p.shift = w->shift;
@@ -1166,7 +1222,17 @@ template <bool CELL>
 int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   const int work = p.num_tiles * p.ksplit;
   const int grid = work < g_num_sms ? work : g_num_sms;
-  conv_umma_kernel<CELL><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
+  if (p.ksplit > 1) {
+    if (p.pw == 32)
+      conv_umma_kernel<CELL, 32, true><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
+    else
+      conv_umma_kernel<CELL, 16, true><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
+  } else {
+    if (p.pw == 32)
+      conv_umma_kernel<CELL, 32, false><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
+    else
+      conv_umma_kernel<CELL, 16, false><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
+  }
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }
@@ -1175,7 +1241,7 @@ int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
 
 bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                            const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad) {
-  if (n_src != 1 || !common_supported(srcs, w, stride, pad) || w->gate_interleaved) return false;
+  if (n_src != 1 || !common_supported(srcs, w, stride, pad)) return false;
   if (!out_ok(y)) return false;
   if (y2 && !out_ok(y2)) return false;
   if (residual && !out_ok(residual)) return false;
@@ -1220,7 +1286,7 @@ bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis
 }
 
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
-                       const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
+                       const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
                        cudaStream_t st) {
   (void)n_src;
@@ -1236,8 +1302,9 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
     return RSIS_ERR_BAD_ARG;
   if (h_split && (!ok(h_split, RSIS_FMT_SPLIT_BF16) || pitch(*h_split) % 8 != 0)) return RSIS_ERR_BAD_ARG;
   if (side_max && (side_stride < side_offset + Ch || side_offset < 0)) return RSIS_ERR_BAD_ARG;
-  if (c_prev && !aligned16(c_prev)) return RSIS_ERR_ALIGN;
+  if ((c_prev && !aligned16(c_prev)) || (gate_preact && !aligned16(gate_preact))) return RSIS_ERR_ALIGN;
   p.c_prev = c_prev;
+  p.preact = gate_preact;
   p.h_out = reinterpret_cast<float*>(h_out->data);
   p.c_out = reinterpret_cast<float*>(c_out->data);
   if (h_split) {

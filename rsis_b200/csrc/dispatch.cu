@@ -16,7 +16,7 @@ int conv2d_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
 size_t conv_umma_workspace_bytes();
 bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w);
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
-                       const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
+                       const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
 }  // namespace rsis
@@ -43,20 +43,22 @@ int rsis_conv2d(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
 }
 
 int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
-                       const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
+                       const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
                        size_t workspace_bytes, rsis_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (gate_preact && (impl == RSIS_IMPL_SIMT || !(srcs && w && convlstm_cell_umma_supported(srcs, n_src, w))))
+    return RSIS_ERR_UNSUPPORTED;  // the hoisted-gates form exists in the tcgen05 kernel only
   if (impl == RSIS_IMPL_SIMT)
     return convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset, st);
   const bool ok = srcs && w && convlstm_cell_umma_supported(srcs, n_src, w);
   if (impl == RSIS_IMPL_TCGEN05) {
     if (!ok) return RSIS_ERR_UNSUPPORTED;
-    return convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
+    return convlstm_cell_umma(srcs, n_src, w, c_prev, gate_preact, h_out, h_split, c_out, side_max, side_stride, side_offset,
                               workspace, workspace_bytes, st);
   }
   if (impl != RSIS_IMPL_AUTO) return RSIS_ERR_BAD_ARG;
-  return ok ? convlstm_cell_umma(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
+  return ok ? convlstm_cell_umma(srcs, n_src, w, c_prev, gate_preact, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  workspace, workspace_bytes, st)
             : convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  st);

@@ -37,8 +37,8 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
               out_classes: torch.Tensor, out_stops: torch.Tensor, feats_op=None, ws=None):
     """Encoder once + T decoder steps, writing into the stacked outputs. Pure kernel launches on the current stream.
 
-    tcgen05 kernel family: runs inside a `DecoderWorkspace` (`ws`, created when not given) -- the skip heads write
-    straight into the decoder's concatenated input buffers and every step is 13 launches with no allocation.
+    tcgen05 kernel family: runs inside a `DecoderWorkspace` (`ws`, created when not given) -- the time-invariant
+    share of every level's gates is computed once, and every step is 13 launches with no allocation.
     Returns the workspace (tcgen05) or the final state list (CUDA-core family)."""
     B, _, H, W = x.shape
     if _mask_size(H, W) != (H, W):
@@ -49,9 +49,8 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
         if ws is None:
             ws = decoder.workspace(B, feature_sizes(H, W), x.device)
         if feats_op is None:
-            encoder.forward_act(x, impl, skip_out=ws.skip_views())
-        else:
-            ws.load_feats(feats_op)
+            _, feats_op = encoder.forward_act(x, impl, operand_only=True)
+        ws.load_feats(decoder, feats_op, impl)
         ws.reset()
         for t in range(T):
             decoder.step_ws(ws, impl, None, out_classes[:, t], T * C, None, T, mask_prob=out_masks[:, t],

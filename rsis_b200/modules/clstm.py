@@ -40,6 +40,28 @@ class ConvLSTMCell(nn.Module):
             self._packed[key] = hit
         return hit[1]
 
+    def packed_hoisted(self, up_c: int, skip_c: int):
+        """Packs for the hoisted form of the step (tcgen05 family): `input_ = [up(h_below) (up_c) | skip (skip_c)]`
+        where the skip channels are the same at every time-step, so their share of the gate convolution (plus the
+        bias) is computed once per image.  Returns (pc_skip, pc_step): a plain convolution pack over the skip
+        channels (gate-interleaved output order, bias folded) and the per-step cell pack over
+        `[up(h_below) | prev_hidden]` without bias."""
+        w, b = self.Gates.weight, self.Gates.bias
+        assert up_c + skip_c == self.input_size
+        key = ("hoisted", up_c, skip_c)
+        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            wd = w.detach()
+            w_skip = wd[:, up_c:up_c + skip_c].contiguous()
+            w_step = torch.cat([wd[:, :up_c], wd[:, up_c + skip_c:]], 1).contiguous()
+            pc_skip = PackedConv(w_skip, b, None, gate_interleave=True, src_channels=[skip_c], want_umma=True)
+            pc_step = PackedConv(w_step, None, None, gate_interleave=True, src_channels=[up_c + self.hidden_size],
+                                 want_umma=True)
+            hit = (ver, (pc_skip, pc_step))
+            self._packed[key] = hit
+        return hit[1]
+
     def step_act(self, inputs: Sequence[Act], prev_h: Optional[Act], prev_c: Optional[torch.Tensor],
                  side_max: Optional[torch.Tensor], side_offset: int, impl: int = ops.IMPL_AUTO):
         """NHWC-level step used by the decoder. `inputs` are the parts of `input_` (concatenated along C)."""

@@ -70,13 +70,11 @@ class FeatureExtractor(nn.Module):
             self._packed_key = key
         return self._packed
 
-    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, skip_out=None):
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, operand_only: bool = False):
         """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each.
 
-        skip_out (tcgen05 path only): five (view, view) pairs -- the skip-feature slices of the decoder's two
-        ping-pong input buffers (`DecoderWorkspace.skip_views()`).  The head convolutions then write their result
-        straight into those slices (the `torch.cat([hidden, skip], 1)` of model.py:153 never runs) and no float32
-        copy is produced; returns (None, None)."""
+        operand_only (tcgen05 family): skip the float32 copy of the features (the decoder's fast path consumes the
+        split-bf16 operand copy only); returns (None, feats_op)."""
         impl = ops.default_impl() if impl is None else impl
         taps = self.base.forward_act(x, impl)
         if raw:
@@ -85,12 +83,8 @@ class FeatureExtractor(nn.Module):
             raise NotImplementedError("rsis_b200: train-mode BatchNorm is not implemented yet; call .eval()")
         fmt = ops.activation_format(impl)
         heads = self.packed_heads(want_umma=(fmt == ops.FMT_SPLIT_BF16))
-        if skip_out is not None:
-            if fmt != ops.FMT_SPLIT_BF16:
-                raise RuntimeError("skip_out needs the tcgen05 kernel family")
-            for tap, pc, (v0, v1) in zip(taps, heads, skip_out):
-                ops.conv2d([tap], pc, pad=self.padding, impl=impl, out=v0, out2=v1)
-            return None, None
+        if operand_only and fmt == ops.FMT_SPLIT_BF16:
+            return None, [ops.conv2d([tap], pc, pad=self.padding, out_fmt=fmt, impl=impl) for tap, pc in zip(taps, heads)]
         feats, feats_op = [], []
         for tap, pc in zip(taps, heads):
             if fmt == ops.FMT_F32:
@@ -119,14 +113,15 @@ class FeatureExtractor(nn.Module):
 
 
 class DecoderWorkspace:
-    """Device buffers of the tcgen05 decoder for one (batch, feature-map sizes): per level l two ping-pong input
-    buffers X[l][p] = NHWC split-bf16 [up(h_{l-1}) | skip_l | h_prev_l] (level 0: [x5_skip | h_prev]) -- the
-    operand of the fused cell kernel, i.e. `torch.cat([hidden, skip], 1)` (model.py:153) and
-    `torch.cat((input_, prev_hidden), 1)` (clstm.py:43) laid out once; producers write their slice in place:
-      skip_l   by the encoder's skip head (or `load_feats`), once per batch, into both buffers;
-      up(h)    by the bilinear-upsample kernel of step t into X[l][t % 2];
-      h_prev   by the cell kernel's epilogue of step t into X[l][(t + 1) % 2] (a step reads its neighbours' h_prev
-               with a 3x3 halo, hence the ping-pong).
+    """Device buffers of the tcgen05 decoder for one (batch, feature-map sizes).
+
+    The gate convolution of level l contracts over `[up(h_{l-1}) | skip_l | h_prev_l]` (`torch.cat([hidden, skip], 1)`
+    model.py:153 and `torch.cat((input_, prev_hidden), 1)` clstm.py:43).  skip_l (level 0: x5_skip) does not depend on
+    the time-step, so its share of the gates (+ bias) is hoisted: `P[l]` = fp32 `[N,H,W,4*Ch]`, computed once per batch
+    by `load_feats`.  Per step the fused cell kernel contracts over the ping-pong input buffer
+    `X[l][p] = [up(h_{l-1}) | h_prev_l]` (split-bf16) and adds `P[l]` in its epilogue.  Producers write their slice of
+    X in place: the bilinear-upsample kernel of step t into `X[l][t % 2]`, the cell epilogue of step t (new hidden
+    state) into `X[l][(t + 1) % 2]` (a step reads its neighbours' h_prev with a 3x3 halo, hence the ping-pong).
     Plus float32 h / c per level (c is updated in place), the x2-upsampled last hidden for the mask head and the
     side-feature max keys."""
 
@@ -134,40 +129,40 @@ class DecoderWorkspace:
         self.n, self.sizes = n, [tuple(s) for s in sizes]
         cells = decoder.clstm_list
         self.hidden = [c.hidden_size for c in cells]
-        self.cin = [c.input_size + c.hidden_size for c in cells]
         self.up_c = [0] + self.hidden[:-1]                              # channels of up(h_{l-1})
         self.skip_c = [c.input_size - u for c, u in zip(cells, self.up_c)]
-        self.h_off = [c.input_size for c in cells]
+        self.cin = [u + h for u, h in zip(self.up_c, self.hidden)]      # channels of X[l]
         F16 = ops.FMT_SPLIT_BF16
         self.X = [[ops.Act.zeros(n, h, w, ct, F16, device) for _ in range(2)] for (h, w), ct in zip(self.sizes, self.cin)]
+        self.P = [ops.Act.empty(n, h, w, 4 * ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.h = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         hl, wl = self.sizes[-1]
         self.up_last = ops.Act.empty(n, 2 * hl, 2 * wl, self.hidden[-1], ops.FMT_F32, device)
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
         self.t = 0
-        self.feats_key = None
 
-    def skip_views(self):
-        return [(self.X[l][0].slice(self.up_c[l], self.skip_c[l]), self.X[l][1].slice(self.up_c[l], self.skip_c[l]))
-                for l in range(len(self.X))]
+    def packs(self, decoder: "RSIS", l: int):
+        return decoder.clstm_list[l].packed_hoisted(self.up_c[l], self.skip_c[l])
 
     def h_view(self, l: int, p: int) -> Act:
-        return self.X[l][p].slice(self.h_off[l], self.hidden[l])
+        return self.X[l][p].slice(self.up_c[l], self.hidden[l])
 
     def up_view(self, l: int, p: int) -> Act:
         return self.X[l][p].slice(0, self.up_c[l])
 
-    def load_feats(self, feats: Sequence[Act]):
-        """Copies the five skip features (either element format, dense) into both ping-pong buffers."""
-        for (v0, v1), f in zip(self.skip_views(), feats):
-            ops.convert(f, ops.FMT_SPLIT_BF16, out=v0)
-            ops.convert(f, ops.FMT_SPLIT_BF16, out=v1)
+    def load_feats(self, decoder: "RSIS", feats: Sequence[Act], impl: int):
+        """Hoisted, time-invariant part of the gates: P[l] = conv(skip_l, W_gates[:, skip channels]) + bias."""
+        for l, f in enumerate(feats):
+            if f.fmt != ops.FMT_SPLIT_BF16:
+                f = ops.convert(f, ops.FMT_SPLIT_BF16)
+            pc_skip, _ = self.packs(decoder, l)
+            ops.conv2d([f], pc_skip, pad=pc_skip.kh // 2, impl=impl, out=self.P[l])
 
     def reset(self):
         """New sequence: hidden state None == zeros (clstm.py:26-37)."""
         for l in range(len(self.X)):
-            sl = slice(self.h_off[l], self.h_off[l] + self.hidden[l])
+            sl = slice(self.up_c[l], self.up_c[l] + self.hidden[l])
             self.X[l][0].t[..., sl].zero_()
         self.t = 0
 
@@ -221,9 +216,9 @@ class RSIS(nn.Module):
             x = ws.X[l][p]
             if l > 0:
                 ops.upsample_bilinear(ws.h[l - 1], x.h, x.w, out=ws.up_view(l, p))
-            pc = cell.packed([cell.input_size + cell.hidden_size], want_umma=True)
+            _, pc = ws.packs(self, l)
             ops.convlstm_cell_x(x, pc, ws.c[l].t if ws.t > 0 else None, ws.side, off, h_out=ws.h[l], c_out=ws.c[l],
-                                h16_out=ws.h_view(l, 1 - p), impl=impl)
+                                h16_out=ws.h_view(l, 1 - p), impl=impl, gate_preact=ws.P[l])
             off += cell.hidden_size
         ops.upsample_bilinear(ws.h[nlev - 1], ws.up_last.h, ws.up_last.w, out=ws.up_last)
         ops.mask_head(ws.up_last, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob, mask_prob_stride)

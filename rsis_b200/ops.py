@@ -184,7 +184,7 @@ def uses_tcgen05(impl: int) -> bool:
 
 def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
                     side_offset: int = 0, h_out: Optional[Act] = None, c_out: Optional[Act] = None,
-                    h16_out: Optional[Act] = None, impl: int = IMPL_AUTO):
+                    h16_out: Optional[Act] = None, impl: int = IMPL_AUTO, gate_preact: Optional[Act] = None):
     """One fused ConvLSTM step on the already-concatenated input buffer `x` = [input_ | prev_hidden] (split-bf16,
     all w.cin channels; the prev_hidden slice is zeros when the state is None).  `h16_out` (optional, may be a
     pitched view) receives the new hidden state in the operand format, e.g. the prev_hidden slice of the next
@@ -196,7 +196,11 @@ def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side
     c = c_out if c_out is not None else Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
     stride = side_max.shape[1] if side_max is not None else 0
     srcs = _src_array([x])
-    check(lib.rsis_convlstm_cell(srcs, 1, pc.ref(), _ptr(c_prev), h.ref(), h16_out.ref() if h16_out else None,
+    pre = None
+    if gate_preact is not None:
+        assert gate_preact.fmt == FMT_F32 and gate_preact.dense and gate_preact.c == pc.cout
+        pre = gate_preact.t.data_ptr()
+    check(lib.rsis_convlstm_cell(srcs, 1, pc.ref(), _ptr(c_prev), pre, h.ref(), h16_out.ref() if h16_out else None,
                                  c.ref(), _ptr(side_max), stride, side_offset, impl, *_lib.workspace(),
                                  _lib.stream_ptr()),
           "convlstm_cell")
@@ -230,7 +234,8 @@ def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Te
     c = Act.empty(x.n, x.h, x.w, ch, FMT_F32, dev)
     hs = Act.empty(x.n, x.h, x.w, ch, FMT_SPLIT_BF16, dev) if want_split else None
     stride = side_max.shape[1] if side_max is not None else 0
-    check(lib.rsis_convlstm_cell(_src_array(srcs), len(srcs), pc.ref(), _ptr(c_prev), h.ref(), hs.ref() if hs else None,
+    check(lib.rsis_convlstm_cell(_src_array(srcs), len(srcs), pc.ref(), _ptr(c_prev), None, h.ref(),
+                                 hs.ref() if hs else None,
                                  c.ref(), _ptr(side_max), stride, side_offset, impl, *_lib.workspace(),
                                  _lib.stream_ptr()),
           "convlstm_cell")

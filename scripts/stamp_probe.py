@@ -54,4 +54,9 @@ for name, (N, Ct, Ch, H, W) in CELLS.items():
     st = ws[2048:2048 + 8 * 12].view(torch.int64).cpu().tolist()
     t0 = st[0]
     print(f"{name}: event {e0.elapsed_time(e1)*1e3:.1f} us; " + "; ".join(f"{n} {(t - t0)/1e3:.2f}" for n, t in zip(NAMES, st) if t >= t0))
-    ws[2048:2048 + 96].zero_()
+    tl = ws[2048 + 8 * 16:2048 + 8 * 96].view(torch.int64).cpu().view(5, 16)
+    for role, rn in enumerate(["A issued", "MMA sees A", "MMAs issued", "epi sees acc", "epi released"]):
+        vals = [f"{(int(t) - t0)/1e3:.1f}" for t in tl[role].tolist() if int(t) >= t0]
+        if vals:
+            print(f"      {rn:13s}: " + " ".join(vals))
+    ws[2048:2048 + 8 * 96].zero_()

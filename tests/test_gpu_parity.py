@@ -307,6 +307,37 @@ def test_convlstm_cell_matches_oracle_ragged(R, O, impl, shape):
     assert int(side[:, :3].abs().sum()) == 0 and int(side[:, 3 + ch:].abs().sum()) == 0
 
 
+def test_convlstm_cell_hoisted_gates(R, O):
+    """The decoder's fast path computes the time-invariant skip share of the gates once (rsis_conv2d with the skip
+    columns of Gates.weight, gate-interleaved, + bias) and feeds it to the cell kernel as `gate_preact`; the step then
+    contracts over [up(h_below) | prev_hidden] only.  Must equal the reference cell on cat([up, skip]) (model.py:153)."""
+    ops = R.ops
+    if not ops.has_tcgen05():
+        pytest.skip("library built without tcgen05 kernels")
+    g = torch.Generator().manual_seed(77)
+    B, up_c, skip_c, ch, H, W = 3, 32, 32, 16, 16, 24
+    up = torch.rand((B, up_c, H, W), generator=g) * 2 - 1
+    skip = torch.rand((B, skip_c, H, W), generator=g) * 4 - 2
+    hp = torch.rand((B, ch, H, W), generator=g) * 2 - 1
+    cp = torch.rand((B, ch, H, W), generator=g) * 4 - 2
+    w = (torch.rand((4 * ch, up_c + skip_c + ch, 3, 3), generator=g) * 2 - 1) * 0.08
+    b = torch.rand(4 * ch, generator=g) - 0.5
+    href, cref = O.convlstm_cell(w, b, torch.cat([up, skip], 1), (hp, cp))
+    cell = R.ConvLSTMCell(_args(), up_c + skip_c, ch, 3, 1)
+    cell.load_state_dict({"Gates.weight": w, "Gates.bias": b})
+    cell.cuda()
+    pc_skip, pc_step = cell.packed_hoisted(up_c, skip_c)
+    F16 = ops.FMT_SPLIT_BF16
+    pre = ops.conv2d([ops.act_from_nchw(skip.cuda(), F16)], pc_skip, pad=1, impl=ops.IMPL_TCGEN05)
+    x = ops.Act.zeros(B, H, W, up_c + ch, F16, "cuda")
+    ops.convert(ops.act_from_nchw(up.cuda(), F16), F16, out=x.slice(0, up_c))
+    ops.convert(ops.act_from_nchw(hp.cuda(), F16), F16, out=x.slice(up_c, ch))
+    side = torch.zeros((B, ch), dtype=torch.int32, device="cuda")
+    h, c = ops.convlstm_cell_x(x, pc_step, ops.act_from_nchw(cp.cuda(), ops.FMT_F32).t, side, 0,
+                               impl=ops.IMPL_TCGEN05, gate_preact=pre)
+    assert rel(h.nchw(), href) < TOL_FP32 * 5 and rel(c.nchw(), cref) < TOL_FP32 * 5
+
+
 # ---------------------------------------------------------------------------------------------------------
 # module surface: encoder features, decoder step, test() end to end -- against reference-generated goldens
 # ---------------------------------------------------------------------------------------------------------
