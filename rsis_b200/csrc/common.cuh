@@ -78,6 +78,12 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Programmatic dependent launch (PDL).  `pdl_trigger` lets the NEXT kernel of the stream begin launching its CTAs
+// (prologue only) while this one is still running; a kernel launched with the programmatic-serialization attribute
+// calls `pdl_wait` before it touches anything an earlier kernel produced.  Both are no-ops in plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace rsis

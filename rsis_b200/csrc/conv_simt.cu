@@ -66,6 +66,7 @@ __device__ __forceinline__ void store4(void* p, size_t plane, int fmt, size_t id
 
 template <int BM, int BN, bool CELL>
 __global__ void __launch_bounds__(kThreads) conv_simt_kernel(const ConvParams p) {
+  pdl_trigger();
   constexpr int TX = BN / 4;        // threads along N, 4 columns each
   constexpr int TY = kThreads / TX; // threads along M
   constexpr int RM = BM / TY;       // rows per thread

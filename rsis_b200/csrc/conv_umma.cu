@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -79,7 +80,6 @@ struct UmmaParams {
   int b_stage_bytes;       // 2 * BN * 128
   uint32_t a_tx_bytes, b_tx_bytes;
   uint32_t a_sbo;          // bytes between 8-row core matrices of A
-  int base_off_mode;       // debug knob: put (addr >> 7) & 7 into the descriptor's base-offset field
   // K loop
   int taps, ksize, stride, pad;
   int chunks;              // 64-channel chunks of the source
@@ -227,13 +227,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row core matrices `sbo` bytes apart.
 // The swizzle XOR acts on absolute smem address bits, so a start address shifted by whole rows (HALO taps) or by
 // 32 bytes (K step inside the row) addresses the same TMA-written tile.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, int base_off_mode) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major; canonical 1)
   d |= (uint64_t)(sbo >> 4) << 32;             // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
-  if (base_off_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;
 }
@@ -769,6 +768,10 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; from here on
+  // we read what it produced.  Our own dependents may start their prologue right away.
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x == 0) STAMP(1);
 
   // A "items" per tile: HALO -> one per chunk (nine B items each); TAP -> one per (tap, chunk) (one B item each).
@@ -858,6 +861,9 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     // N = 2*BN multiplies an activation plane by both weight planes (columns [0,BN) and [BN,2BN) of the
     // accumulator, added in the epilogue): 2 MMAs per K step (x_hi, x_lo) give all four partial products.
     // An SS-mode MMA costs ~128 cycles of A-operand reads whatever N is, so wide N is what makes it efficient.
+    // descriptors are linear in the smem address (a 14-bit field of 16-byte units): build one per ring, then add offsets
+    const uint64_t adesc0 = make_smem_desc(smem_a, p.a_sbo);
+    const uint64_t bdesc0 = make_smem_desc(smem_b, 1024);
     const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
     int as = 0, bs = 0;
@@ -878,24 +884,25 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         tc_fence_after();
         if (lane == 0 && ai == item0) STAMP(4);
         if (lane == 0 && ai == item0) STAMP_T(1, (work - (int)blockIdx.x) / (int)gridDim.x);
-        const uint32_t sa = smem_a + as * p.a_stage_bytes;
         for (int bi = 0; bi < b_per_a; ++bi) {
           if (p.b_resident) {
             bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
             bph = 0;
           }
-          mbar_wait(bfull0 + 8 * bs, bph);
-          tc_fence_after();
+          if (!(p.b_resident && work != (int)blockIdx.x)) {
+            mbar_wait(bfull0 + 8 * bs, bph);
+            tc_fence_after();
+          }
           if (lane == 0 && ai == item0 && bi == 0) STAMP(5);
-          const uint32_t sb = smem_b + bs * p.b_stage_bytes;
-          uint32_t sat = sa;
+          uint32_t aoff = (uint32_t)(as * p.a_stage_bytes);
           if (p.halo) {
             const int kh = bi / 3, kw = bi - kh * 3;
-            sat += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
+            aoff += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
           }
-          const uint64_t a_hi = make_smem_desc(sat, p.a_sbo, p.base_off_mode);
-          const uint64_t a_lo = make_smem_desc(sat + p.a_plane_bytes, p.a_sbo, p.base_off_mode);
-          const uint64_t b_hi = make_smem_desc(sb, 1024, 0), b_lo = make_smem_desc(sb + p.BN * 128, 1024, 0);
+          const uint64_t a_hi = adesc0 + (uint64_t)(aoff >> 4);
+          const uint64_t a_lo = a_hi + (uint64_t)(p.a_plane_bytes >> 4);
+          const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)(bs * p.b_stage_bytes) >> 4);
+          const uint64_t b_lo = b_hi + (uint64_t)((uint32_t)(p.BN * 128) >> 4);
           if (elect_one()) {
             if (p.stacked) {
               for (int k = 0; k < ksteps; ++k) {
@@ -959,9 +966,10 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
-int g_base_off_mode = 0;   // RSIS_B200_HALO_BASEOFF=1 sets the descriptor base-offset field (debug)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
+int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
+int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
 int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
 std::once_flag g_once;
 
@@ -975,10 +983,11 @@ cudaError_t set_smem_attr() {
 
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
-  if (const char* e = getenv("RSIS_B200_HALO_BASEOFF")) g_base_off_mode = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_PRINT_PLAN")) g_print_plan = atoi(e) != 0;
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1063,49 +1072,56 @@ struct Plan {
 
 Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
                bool can_split, bool cell) {
-  // Cost model in nanoseconds, calibrated with in-kernel %globaltimer stamps on B200 (scripts/stamp_probe.py):
-  //   launch -> first MMA and exit: ~3000; one tcgen05.mma instruction: ~70 whatever its N;
+  // Cost model in nanoseconds, calibrated on B200 with in-kernel %globaltimer stamps and graph-replay timings
+  // (scripts/stamp_probe.py, scripts/gap_probe.py):
+  //   launch -> first MMA and exit: ~3000;  one tcgen05.mma instruction: ~70 whatever its N;
+  //   TMA ingest of one SM: ~80 bytes/ns, of the whole chip (L2 -> SMs): ~12000 bytes/ns;
   //   finishing one 32 x 32 accumulator piece on one epilogue warp: ~900 (conv) / ~1300 (cell), 8 warps per CTA;
   //   split-K hand-over (park the partial, wait for the slowest slice, reduce): ~4500 + 110 per (unit, slice).
-  const long long kFixed = 3000, kMma = 70, kPiece = cell ? 1300 : 900;
-  const long long ksteps_tile = (long long)taps * ((chunks - 1) * (kBK / 16) + last_ksteps);
+  const double kFixed = 3000, kMma = 70, kPiece = cell ? 1300 : 900, kSmBw = 80, kChipBw = 12000;
+  const double ksteps_tile = (double)taps * ((chunks - 1) * (kBK / 16) + last_ksteps);
+  const int items = taps * chunks;
   Plan best{0, 0, 1, 0, -1};
-  int cands[2], nc = 0;
-  if (cout > 128) {
-    cands[nc++] = 256;
-    cands[nc++] = 128;
-  } else {
-    cands[nc++] = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
-  }
-  for (int ci = 0; ci < nc; ++ci) {
-    const int BN = cands[ci];
-    if (g_force_bn && BN != g_force_bn && nc > 1) continue;
+  const int all[4] = {256, 128, 64, 32};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int BN = all[ci];
+    if (BN >= 2 * cout && BN > 32) continue;              // wider than the layer: nothing but padding
+    if (cout <= 128 && BN > 128) continue;
+    if (g_force_bn && BN != g_force_bn) continue;
     const int stacked = BN <= 128 ? 1 : 0;
-    const int mpk = stacked ? 2 : 3;
+    const double mpk = stacked ? 2 : 3;
     const int tiles_n = ceil_div(cout, BN);
-    const long long pieces_per_warp = ceil_div(4 * ceil_div(BN, 32), kEpiWarps);
-    const long long epi_tile = pieces_per_warp * kPiece;
+    const double b_item = 2.0 * BN * 128;
+    const double pieces_per_warp = BN >= 64 ? ceil_div(4 * (BN / 32), kEpiWarps) : 0.6;
+    const double epi_tile = pieces_per_warp * kPiece;
     // (a) no split: persistent CTAs, HALO staging when eligible; MMAs of tile i+1 overlap the epilogue of tile i
     if (!(halo_ok && BN == 256)) {  // a HALO stage + 64 KB weight stages do not leave room for a pipeline
-      const long long tiles = (long long)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
-      const long long per_cta = (tiles + g_num_sms - 1) / g_num_sms;
-      const long long mma_tile = ksteps_tile * mpk * kMma;
-      const long long slow = mma_tile > epi_tile ? mma_tile : epi_tile, fast = mma_tile + epi_tile - slow;
-      const long long cost = kFixed + per_cta * slow + fast;
-      if (best.cost < 0 || cost < best.cost) best = Plan{BN, stacked, 1, halo_ok ? 1 : 0, cost};
+      const double tiles = (double)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
+      const double per_cta = ceil(tiles / g_num_sms);
+      const double bytes_tile = (halo_ok ? chunks * 2.0 * kHaloRows * 128 : items * 32768.0) + items * b_item;
+      const double mma_tile = ksteps_tile * mpk * kMma;
+      double tile_t = mma_tile > epi_tile ? mma_tile : epi_tile;
+      if (bytes_tile / kSmBw > tile_t) tile_t = bytes_tile / kSmBw;
+      double cost = kFixed + per_cta * tile_t + epi_tile;
+      const double chip = kFixed + tiles * bytes_tile / kChipBw;
+      if (chip > cost) cost = chip;
+      if (best.cost < 0 || cost < best.cost) best = Plan{BN, stacked, 1, halo_ok ? 1 : 0, (long long)cost};
     }
     // (b) split-K over (tap, chunk) items, TAP staging, single wave
     if (can_split && g_split_k) {
-      const long long tiles = (long long)m_tiles_tap * tiles_n;
-      const int items = taps * chunks;
+      const double tiles = (double)m_tiles_tap * tiles_n;
       int S = (int)(g_num_sms / tiles);
       if (S > items) S = items;
       if (S > 32) S = 32;
       if (tiles <= g_num_sms && S >= 2) {
-        const long long mma = (long long)ceil_div(items, S) * (kBK / 16) * mpk * kMma;
-        const long long units_per_warp = ceil_div((kBM / 4) * ceil_div(BN, 32), kEpiWarps * S);
-        const long long cost = kFixed + mma + 4500 + units_per_warp * (300 + 110LL * S * (stacked ? 2 : 1));
-        if (cost < best.cost) best = Plan{BN, stacked, S, 0, cost};
+        const double items_s = ceil_div(items, S);
+        const double mma = items_s * (kBK / 16) * mpk * kMma;
+        const double load = items_s * (32768.0 + b_item) / kSmBw;
+        const double units_per_warp = ceil_div((kBM / 4) * ceil_div(BN, 32), kEpiWarps * S);
+        double cost = kFixed + (mma > load ? mma : load) + 4500 + units_per_warp * (300 + 110.0 * S * (stacked ? 2 : 1));
+        const double chip = kFixed + tiles * items * (32768.0 + b_item) / kChipBw;
+        if (chip > cost) cost = chip;
+        if (cost < best.cost) best = Plan{BN, stacked, S, 0, (long long)cost};
       }
     }
   }
@@ -1138,6 +1154,10 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
   const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
                               w->gate_interleaved != 0);
+  if (g_print_plan)
+    fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d halo=%d est %lld ns\n",
+            x.n, x.h, x.w, x.c, w->cout, w->kh, stride, w->gate_interleaved ? " cell/gates" : "", plan.BN, plan.stacked,
+            plan.ksplit, plan.halo, plan.cost);
   p.BN = plan.BN;
   p.stacked = plan.stacked;
   p.ksplit = plan.ksplit;
@@ -1167,7 +1187,6 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.a_tx_bytes = (uint32_t)(2 * p.a_plane_bytes);
   p.a_stage_bytes = round_up(2 * p.a_plane_bytes, 1024);
   p.a_sbo = p.halo ? (uint32_t)(kHaloBW + 2) * 128u : 1024u;
-  p.base_off_mode = g_base_off_mode;
   p.b_stage_bytes = 2 * p.BN * 128;
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   p.pw = p.BN >= 64 ? 32 : 16;
@@ -1218,21 +1237,31 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   return RSIS_OK;
 }
 
+template <bool CELL, int PW, bool SPLIT>
+cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsUmma);
+  cfg.dynamicSmemBytes = kDynSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CELL, PW, SPLIT>, maps, p);
+}
+
 template <bool CELL>
 int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   const int work = p.num_tiles * p.ksplit;
   const int grid = work < g_num_sms ? work : g_num_sms;
-  if (p.ksplit > 1) {
-    if (p.pw == 32)
-      conv_umma_kernel<CELL, 32, true><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
-    else
-      conv_umma_kernel<CELL, 16, true><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
-  } else {
-    if (p.pw == 32)
-      conv_umma_kernel<CELL, 32, false><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
-    else
-      conv_umma_kernel<CELL, 16, false><<<grid, kThreadsUmma, kDynSmem, st>>>(maps, p);
-  }
+  cudaError_t e;
+  if (p.ksplit > 1)
+    e = p.pw == 32 ? launch_one<CELL, 32, true>(maps, p, grid, st) : launch_one<CELL, 16, true>(maps, p, grid, st);
+  else
+    e = p.pw == 32 ? launch_one<CELL, 32, false>(maps, p, grid, st) : launch_one<CELL, 16, false>(maps, p, grid, st);
+  RSIS_CUDA_TRY(e);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

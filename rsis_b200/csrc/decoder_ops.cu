@@ -38,6 +38,7 @@ __device__ __forceinline__ void store4v(void* p, size_t plane, int fmt, size_t i
 // nn.MaxPool2d(kernel_size=3, stride=2, padding=1) -- /root/reference/src/modules/vision.py:15
 __global__ void maxpool3x3s2_kernel(View x, void* y, size_t y_plane, int y_fmt, int N, int H, int W, int C, int Ho,
                                     int Wo) {
+  pdl_trigger();
   const int C4 = C >> 2;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -71,6 +72,7 @@ __global__ void maxpool3x3s2_kernel(View x, void* y, size_t y_plane, int y_fmt, 
 // scale = (in - 1) / (out - 1) evaluated in float.
 __global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_fmt, int y_cs, int N, int H, int W,
                                          int C, int Ho, int Wo, float sh, float sw) {
+  pdl_trigger();
   const int C4 = C >> 2;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -104,6 +106,7 @@ __global__ void mask_head_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ bias, float* __restrict__ logits,
                                  float* __restrict__ prob_out, long long prob_stride_n, int N, int H, int W, int C,
                                  int ks) {
+  pdl_trigger();
   extern __shared__ float sw[];
   const int taps = ks * ks;
   for (int i = threadIdx.x; i < taps * C; i += blockDim.x) {
@@ -150,6 +153,7 @@ __global__ void class_stop_heads_kernel(const uint32_t* __restrict__ side_max, i
                                         float* __restrict__ feat_out, float* __restrict__ class_probs,
                                         long long class_stride, float* __restrict__ stop_logit,
                                         float* __restrict__ stop_prob, long long stop_stride) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* feat = sm;            // [F]
   float* logit = sm + F;       // [num_classes + 1]; the last entry is the stop logit

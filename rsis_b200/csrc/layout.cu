@@ -8,6 +8,7 @@ namespace rsis {
 // (/root/reference/src/test.py:35 `encoder(x)`), where the strided NCHW reads hit three planes only.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* dst, size_t plane, int fmt, int C,
                                     size_t HW, size_t total) {
+  pdl_trigger();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const size_t np = i / C;
@@ -18,6 +19,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, void* dst, si
 
 // Format conversion / channel-slice copy: src and dst may both be pitched views (pixel pitch scs / dcs elements).
 __global__ void convert_kernel(View src, int scs, void* dst, size_t plane, int fmt, int dcs, int C, size_t total) {
+  pdl_trigger();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t pix = i / C;
     const int c = (int)(i - pix * C);
