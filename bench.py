@@ -31,6 +31,19 @@ METRIC = "masks/sec (images x T) at 256x256 T=10"
 UNIT = "masks/s"
 B, H, W, T, NUM_CLASSES = 8, 256, 256, 10, 21
 WORKLOAD = "BASELINE.json configs[1]: Pascal VOC inference, batch 8 per GPU, 256x256, T=10, ResNet-101 encoder"
+# Other BASELINE.json configs can be timed with --workload (extra data points; the default is the headline config).
+WORKLOADS = {
+    "cfg2": (8, 256, 256, 10, 21, WORKLOAD),
+    "cfg3": (4, 512, 1024, 20, 9, "BASELINE.json configs[2]: Cityscapes inference, batch 4, 512x1024, T=20, 9 classes"),
+    "cfg5": (32, 512, 512, 16, 21, "BASELINE.json configs[4] per-rank shard at 8 GPUs: batch 32, 512x512, T=16"),
+}
+
+
+def set_workload(name):
+    global B, H, W, T, NUM_CLASSES, WORKLOAD, METRIC
+    B, H, W, T, NUM_CLASSES, WORKLOAD = WORKLOADS[name]
+    if name != "cfg2":
+        METRIC = f"masks/sec (images x T) at {H}x{W} T={T}"
 
 
 def peaks():
@@ -354,7 +367,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-passes", type=int, default=5, help="timed CPU test() passes for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     a = ap.parse_args()
+    set_workload(a.workload)
     if a.impl == "reference":
         return run_reference(a)
     return run_ours(a)

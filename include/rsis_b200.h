@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 4
+#define RSIS_ABI_VERSION 5
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -152,6 +152,11 @@ int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stre
  * logits != NULL) and, when prob_out != NULL, sigmoid(logit) at prob_out[n*prob_stride_n + pixel] (the stacking + sigmoid of test.py:46,50). */
 int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias, int ksize, float* logits,
                    float* prob_out, int64_t prob_stride_n, rsis_stream_t stream);
+/* The same result as rsis_upsample_bilinear(h -> out_h x out_w) followed by rsis_mask_head, in one kernel that never
+ * writes the upsampled tensor (model.py:163-167: `upsample_match_clstm5` then `conv_out`).  h: float32 dense NHWC with
+ * C % 4 == 0 and C <= 16 (RSIS_ERR_UNSUPPORTED otherwise -- use the two-call form). */
+int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
+                            int out_w, float* logits, float* prob_out, int64_t prob_stride_n, rsis_stream_t stream);
 /* fc_class + Softmax + fc_stop on the side features (model.py:169-182).  side_max holds the uint32 keys written by
  * rsis_convlstm_cell; feat_out (optional) receives the decoded float features [N, F].  Outputs: class_probs [N,C]
  * written at class_probs[n*class_stride + c], stop logit at stop_logit[n*stop_stride], and optional sigmoid(stop)

@@ -17,7 +17,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Tensor(C.Structure):
@@ -60,6 +60,7 @@ SIGNATURES = {
     "rsis_convlstm_cell": (_I, [_TP, _I, _WP, _P, _P, _TP, _TP, _TP, _P, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_upsample_bilinear": (_I, [_TP, _TP, _P]),
     "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),
+    "rsis_upsample_mask_head": (_I, [_TP, _P, _P, _I, _I, _I, _P, _P, C.c_int64, _P]),
     "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
 }
 

@@ -146,6 +146,86 @@ __global__ void mask_head_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// Fused tail of the decoder step (model.py:163-167): x2 align-corners bilinear upsampling of the last hidden state
+// followed by conv_out (k x k, C -> 1) (+ the sigmoid / stacking of test.py:46-50).  A 32 x 32 output tile's
+// (32 + 2*pad)^2 x C window of the UPSAMPLED map is built in shared memory straight from the low-resolution hidden
+// state (which stays L2/L1 resident), so the upsampled tensor -- 4x the hidden state -- never exists in HBM.
+// Interpolation and accumulation orders equal upsample_bilinear_kernel + mask_head_kernel: bit-identical results.
+constexpr int kMaskTile = 32;
+__global__ void __launch_bounds__(256)
+upsample_mask_head_kernel(const float* __restrict__ h, const float* __restrict__ w_oihw, const float* __restrict__ bias,
+                          float* __restrict__ logits, float* __restrict__ prob_out, long long prob_stride_n, int H,
+                          int W, int C, int Ho, int Wo, int ks, float sh, float sw) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float smem_mask[];
+  const int pad = ks / 2;
+  const int TW = kMaskTile + 2 * pad;
+  float* up = smem_mask;                 // [TW][TW][C]
+  float* sw_ = smem_mask + TW * TW * C;  // [tap][C]
+  const int taps = ks * ks;
+  const int n = blockIdx.z;
+  const int oy0 = blockIdx.y * kMaskTile, ox0 = blockIdx.x * kMaskTile;
+  for (int i = threadIdx.x; i < taps * C; i += blockDim.x) {
+    const int tap = i / C, c = i % C;
+    sw_[i] = w_oihw[c * taps + tap];
+  }
+  const int C4 = C >> 2;
+  const float* hn = h + (size_t)n * H * W * C;
+  for (int i = threadIdx.x; i < TW * TW * C4; i += blockDim.x) {
+    const int c = (i % C4) * 4;
+    const int t = i / C4;
+    const int tx = t % TW, ty = t / TW;
+    const int oy = oy0 + ty - pad, ox = ox0 + tx - pad;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);  // conv_out's zero padding outside the upsampled map
+    if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+      const float fh = sh * oy, fw = sw * ox;
+      const int h1 = min((int)fh, H - 1), w1 = min((int)fw, W - 1);
+      const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
+      const float h1l = fminf(fmaxf(fh - h1, 0.f), 1.f), h0l = 1.f - h1l;
+      const float w1l = fminf(fmaxf(fw - w1, 0.f), 1.f), w0l = 1.f - w1l;
+      const float* b = hn + ((size_t)h1 * W + w1) * C + c;
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(b));
+      const float4 v01 = __ldg(reinterpret_cast<const float4*>(b + (size_t)w1p * C));
+      const float4 v10 = __ldg(reinterpret_cast<const float4*>(b + (size_t)h1p * W * C));
+      const float4 v11 = __ldg(reinterpret_cast<const float4*>(b + (size_t)h1p * W * C + (size_t)w1p * C));
+      o.x = h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x);
+      o.y = h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y);
+      o.z = h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z);
+      o.w = h0l * (w0l * v00.w + w1l * v01.w) + h1l * (w0l * v10.w + w1l * v11.w);
+    }
+    *reinterpret_cast<float4*>(up + (size_t)t * C + c) = o;
+  }
+  __syncthreads();
+  const float bs = bias ? bias[0] : 0.f;
+  const int px = threadIdx.x % kMaskTile;
+  for (int py = threadIdx.x / kMaskTile; py < kMaskTile; py += 256 / kMaskTile) {
+    const int oy = oy0 + py, ox = ox0 + px;
+    if (oy >= Ho || ox >= Wo) continue;
+    float acc = 0.f;
+    for (int kh = 0; kh < ks; ++kh) {
+      const int hi = oy - pad + kh;
+      if (hi < 0 || hi >= Ho) continue;  // same skipping (hence summation order) as mask_head_kernel
+      for (int kw = 0; kw < ks; ++kw) {
+        const int wi = ox - pad + kw;
+        if (wi < 0 || wi >= Wo) continue;
+        const float* pxl = up + ((size_t)(py + kh) * TW + (px + kw)) * C;
+        const float* pw = sw_ + (kh * ks + kw) * C;
+        for (int c = 0; c < C; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(pxl + c);
+          acc = fmaf(v.x, pw[c], acc);
+          acc = fmaf(v.y, pw[c + 1], acc);
+          acc = fmaf(v.z, pw[c + 2], acc);
+          acc = fmaf(v.w, pw[c + 3], acc);
+        }
+      }
+    }
+    acc += bs;
+    const size_t pix = (size_t)oy * Wo + ox;
+    if (logits) logits[(size_t)n * Ho * Wo + pix] = acc;
+    if (prob_out) prob_out[(size_t)n * prob_stride_n + pix] = sigmoidf_acc(acc);
+  }
+}
+
 // fc_class + Softmax + fc_stop on the max-pooled side features (model.py:169-182). One CTA per image.
 __global__ void class_stop_heads_kernel(const uint32_t* __restrict__ side_max, int F, const float* __restrict__ w_class,
                                         const float* __restrict__ b_class, int num_classes,
@@ -241,6 +321,31 @@ int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias,
   mask_head_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const float*>(x->data), w_oihw, bias, logits, prob_out, (long long)prob_stride_n, x->n, x->h,
       x->w, x->c, ksize);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
+                            int out_w, float* logits, float* prob_out, int64_t prob_stride_n, rsis_stream_t stream) {
+  if (!valid_tensor(h) || !w_oihw || (!logits && !prob_out) || out_h < 1 || out_w < 1) return RSIS_ERR_BAD_ARG;
+  if (h->fmt != RSIS_FMT_F32 || !is_dense(*h) || h->c % 4 != 0 || h->c > 16 || (ksize != 1 && ksize != 3))
+    return RSIS_ERR_UNSUPPORTED;
+  if (!aligned16(h->data)) return RSIS_ERR_ALIGN;
+  const int pad = ksize / 2, TW = kMaskTile + 2 * pad;
+  const size_t smem = (size_t)(TW * TW * h->c + ksize * ksize * h->c) * sizeof(float);
+  static bool attr_set = false;  // idempotent; a race only repeats the call
+  if (!attr_set) {
+    RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (34 * 34 * 16 + 9 * 16) * (int)sizeof(float)));
+    attr_set = true;
+  }
+  const float sh = out_h > 1 ? (float)(h->h - 1) / (float)(out_h - 1) : 0.f;
+  const float sw = out_w > 1 ? (float)(h->w - 1) / (float)(out_w - 1) : 0.f;
+  const dim3 grid(ceil_div(out_w, kMaskTile), ceil_div(out_h, kMaskTile), h->n);
+  if (grid.y > 65535 || grid.z > 65535) return RSIS_ERR_UNSUPPORTED;
+  upsample_mask_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(h->data), w_oihw, bias, logits, prob_out, (long long)prob_stride_n, h->h, h->w,
+      h->c, out_h, out_w, ksize, sh, sw);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

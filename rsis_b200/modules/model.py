@@ -137,8 +137,7 @@ class DecoderWorkspace:
         self.P = [ops.Act.empty(n, h, w, 4 * ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.h = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
-        hl, wl = self.sizes[-1]
-        self.up_last = ops.Act.empty(n, 2 * hl, 2 * wl, self.hidden[-1], ops.FMT_F32, device)
+        self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
         self.t = 0
 
@@ -204,7 +203,7 @@ class RSIS(nn.Module):
                 class_probs: torch.Tensor, class_stride: int, stop_logit: Optional[torch.Tensor],
                 stop_stride: int, mask_prob: Optional[torch.Tensor] = None, mask_prob_stride: int = 0,
                 stop_prob: Optional[torch.Tensor] = None):
-        """One decoder time-step of the tcgen05 fast path, entirely inside `ws` (13 kernel launches, no allocation):
+        """One decoder time-step of the tcgen05 fast path, entirely inside `ws` (12 kernel launches, no allocation):
         per level [upsample into the input buffer] + fused cell; then x2 upsample, mask head, class/stop heads."""
         if self.fc_class.in_features != self.fc_dim:
             raise RuntimeError("fc_class.in_features does not match the decoder's side-feature width")
@@ -220,8 +219,16 @@ class RSIS(nn.Module):
             ops.convlstm_cell_x(x, pc, ws.c[l].t if ws.t > 0 else None, ws.side, off, h_out=ws.h[l], c_out=ws.c[l],
                                 h16_out=ws.h_view(l, 1 - p), impl=impl, gate_preact=ws.P[l])
             off += cell.hidden_size
-        ops.upsample_bilinear(ws.h[nlev - 1], ws.up_last.h, ws.up_last.w, out=ws.up_last)
-        ops.mask_head(ws.up_last, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob, mask_prob_stride)
+        hl = ws.h[nlev - 1]
+        if hl.c % 4 == 0 and hl.c <= 16:
+            ops.upsample_mask_head(hl, 2 * hl.h, 2 * hl.w, self.conv_out.weight, self.conv_out.bias, mask_logits,
+                                   mask_prob, mask_prob_stride)
+        else:  # wide hidden sizes: two kernels through an upsampled buffer
+            if ws.up_last is None:
+                ws.up_last = ops.Act.empty(hl.n, 2 * hl.h, 2 * hl.w, hl.c, ops.FMT_F32, hl.t.device)
+            ops.upsample_bilinear(hl, ws.up_last.h, ws.up_last.w, out=ws.up_last)
+            ops.mask_head(ws.up_last, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob,
+                          mask_prob_stride)
         ops.class_stop_heads(ws.side, self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight, self.fc_stop.bias,
                              class_probs, class_stride, stop_logit, stop_prob, stop_stride)
         ws.t += 1

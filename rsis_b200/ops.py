@@ -261,6 +261,16 @@ def mask_head(x: Act, weight: torch.Tensor, bias: Optional[torch.Tensor], logits
     _lib.count_launch(1)
 
 
+def upsample_mask_head(h: Act, out_h: int, out_w: int, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                       logits: Optional[torch.Tensor], prob_out: Optional[torch.Tensor] = None, prob_stride_n: int = 0):
+    """upsample_bilinear(h -> out_h x out_w) + conv_out in one launch; the upsampled tensor never exists."""
+    lib = _lib.load()
+    ks = weight.shape[-1]
+    check(lib.rsis_upsample_mask_head(h.ref(), weight.data_ptr(), _ptr(bias), ks, out_h, out_w, _ptr(logits),
+                                      _ptr(prob_out), prob_stride_n, _lib.stream_ptr()), "upsample_mask_head")
+    _lib.count_launch(1)
+
+
 def class_stop_heads(side_max: torch.Tensor, w_class, b_class, w_stop, b_stop, class_probs: torch.Tensor,
                      class_stride: int, stop_logit: Optional[torch.Tensor], stop_prob: Optional[torch.Tensor],
                      stop_stride: int, feat_out: Optional[torch.Tensor] = None):

@@ -228,6 +228,29 @@ def test_mask_head(R, ks):
     assert float(probs[:, 0].abs().max()) == 0.0 and float(probs[:, 3].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("ks", [3, 1])
+def test_fused_upsample_mask_head(R, ks):
+    """model.py:163-167 in one launch: equals UpsamplingBilinear2d + conv_out, and is bit-identical to the two-kernel
+    form (same interpolation and accumulation order)."""
+    ops = R.ops
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand((3, 8, 20, 28), generator=g) * 2 - 1
+    w = torch.rand((1, 8, ks, ks), generator=g) - 0.5
+    b = torch.rand(1, generator=g)
+    up = F.interpolate(x, size=(40, 56), mode="bilinear", align_corners=True)
+    ref = F.conv2d(up, w, b, padding=ks // 2)
+    xa = ops.act_from_nchw(x.cuda(), ops.FMT_F32)
+    T = 3
+    logits = torch.empty((3, 1, 40, 56), device="cuda")
+    probs = torch.zeros((3, T, 40, 56), device="cuda")
+    ops.upsample_mask_head(xa, 40, 56, w.cuda(), b.cuda(), logits, probs[:, 1], T * 40 * 56)
+    assert rel(logits, ref) < TOL_FP32 and rel(probs[:, 1], torch.sigmoid(ref[:, 0])) < TOL_FP32
+    assert float(probs[:, 0].abs().max()) == 0.0 and float(probs[:, 2].abs().max()) == 0.0
+    two = torch.empty_like(logits)
+    ops.mask_head(ops.upsample_bilinear(xa, 40, 56, ops.FMT_F32), w.cuda(), b.cuda(), two)
+    assert torch.equal(two, logits)
+
+
 def test_class_stop_heads_and_side_keys(R, sw):
     """fc_class + Softmax + fc_stop (model.py:169-182) on max-pooled features delivered as order-preserving keys."""
     ops = R.ops
