@@ -271,32 +271,47 @@ def run_ours(a):
     launches = sess.launches * a.steps
 
     # ---- e2e: public API call with HOST buffers (pinned); H2D + graph + D2H inside the timed region ----
-    masks_h = torch.empty((B, T, H, W), dtype=torch.float32).pin_memory()
-    classes_h = torch.empty((B, T, NUM_CLASSES), dtype=torch.float32).pin_memory()
-    stops_h = torch.empty((B, T, 1), dtype=torch.float32).pin_memory()
+    # Results are read back on a copy stream into two alternating pinned buffers, so the D2H of pass i overlaps the
+    # H2D + compute of pass i+1 (every pass still pays its own H2D and D2H inside the timed region).
+    nbuf = 2
+    masks_h = [torch.empty((B, T, H, W), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    classes_h = [torch.empty((B, T, NUM_CLASSES), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    stops_h = [torch.empty((B, T, 1), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event() for _ in range(nbuf)]
 
-    def e2e_step():
+    def e2e_step(i):
+        k = i % nbuf
         xd = x_host.to(dev, non_blocking=True)
-        m, c, s = rsis_b200.test(args, enc, dec, xd)
-        masks_h.copy_(m, non_blocking=True)
-        classes_h.copy_(c, non_blocking=True)
-        stops_h.copy_(s, non_blocking=True)
+        m, c, s = rsis_b200.test(args, enc, dec, xd)          # fresh result tensors (clones of the session outputs)
+        done = torch.cuda.Event()
+        done.record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            masks_h[k].copy_(m, non_blocking=True)
+            classes_h[k].copy_(c, non_blocking=True)
+            stops_h[k].copy_(s, non_blocking=True)
+            copied[k].record(copy_stream)
+        for t in (m, c, s):
+            t.record_stream(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
+    for i in range(3):
+        e2e_step(i)
     torch.cuda.synchronize(dev)
     rdist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
-        e2e_step()
+    for i in range(a.steps):
+        e2e_step(i)
+    main_stream.wait_stream(copy_stream)   # the timed region ends when the last result has reached host memory
     e1.record()
     torch.cuda.synchronize(dev)
     rdist.barrier()
     e2e_s = rdist.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     e2e_value = world * B * T * a.steps / e2e_s
     h2d = x_host.numel() * 4
-    d2h = (masks_h.numel() + classes_h.numel() + stops_h.numel()) * 4
+    d2h = (masks_h[0].numel() + classes_h[0].numel() + stops_h[0].numel()) * 4
 
     # ---- roofline of the fused ConvLSTM cell kernel (the kernel BASELINE.json's metric names), rank 0 ----
     roof = None
