@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 5
+#define RSIS_ABI_VERSION 6
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -70,6 +70,11 @@ typedef struct rsis_conv_weights {
   const float* shift; /* [cout_pad] */
   int32_t cout, cin, kh, kw;
   int32_t gate_interleaved; /* 1: output channel order is (hidden channel, gate) -- ConvLSTM packs */
+  const void* w_umma_il;    /* optional: the tcgen05 pack with its two planes interleaved per output channel,
+                             * [cout_pad16][2 planes][k_pad] bfloat16 (same values as w_umma).  When given for a
+                             * ConvLSTM pack with cout = 32 or 64 and <= 64 input channels, rsis_convlstm_cell uses its
+                             * swapped-operand kernel (weights as the M operand, 256 pixels as N) on maps whose width is
+                             * a multiple of 8 and height a multiple of 32.  May be NULL. */
 } rsis_conv_weights;
 
 /* ---- library -------------------------------------------------------------------------------------------- */

@@ -17,7 +17,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Tensor(C.Structure):
@@ -30,7 +30,7 @@ class ConvWeights(C.Structure):
     """`rsis_conv_weights`."""
     _fields_ = [("w_kc", C.c_void_p), ("w_umma", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
-                ("gate_interleaved", C.c_int32)]
+                ("gate_interleaved", C.c_int32), ("w_umma_il", C.c_void_p)]
 
 
 _P = C.c_void_p

@@ -957,6 +957,285 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   }
 }
 
+// ===================================================================================================================
+// Swapped-operand ConvLSTM cell for the narrow, high-resolution decoder levels (4*Ch = 32 or 64 gate columns, at most
+// 64 input channels once the skip share is hoisted; levels 3-4 of the reference decoder).
+//
+// An SS-mode tcgen05.mma costs about the same whatever its N, so 128 pixels x 64 gate columns per instruction leaves
+// the tensor pipe mostly idle.  Here the roles are swapped: D[gate rows][256 pixels] = W[gate rows][K] * X[pixels][K]^T.
+//   A = weights of one tap: rows (gate column r, plane) -> 2r + plane, i.e. hi and lo bf16 planes of a gate column in
+//       ADJACENT accumulator lanes (64 or 128 rows; one TMA box {64 k, 2 planes, 4*Ch} of the same packed tensor);
+//   B = activations: the 8 x 32 output tile's 10 x 34 input halo, staged ONCE per tile (one TMA box); tap (kh, kw) is
+//       the descriptor shifted by kh*10 + kw rows, N = 256 = 32 core-matrix groups 1280 bytes apart;
+//   two MMAs per K step (x_hi, x_lo): lanes 2r / 2r+1 accumulate (W_hi + ...)(x_hi + x_lo) and (W_lo ...)(...), added
+//   with one lane shuffle in the epilogue -> all four partial products for half the instructions per pixel.
+// Epilogue: accumulator lanes are gate columns and columns are pixels; a warp owns 4 hidden channels x 128 pixels,
+// transposes 32-pixel chunks through shared memory and finishes with lane = (pixel, channel).
+constexpr int kSwTileH = 32;
+constexpr int kSwHaloRows = (kHaloBW + 2) * (kSwTileH + 2);  // 340
+constexpr int kSwActPlaneBytes = kSwHaloRows * 128;           // 43520
+constexpr int kSwActBytes = 2 * kSwActPlaneBytes;             // 87040 = 85 KB (1024-byte multiple)
+
+struct SwapPrefetch {
+  float cp[4];
+  float4 pre[4];
+};
+
+__device__ __forceinline__ size_t swap_pix(const UmmaParams& p, int img, int h0, int w0, int n) {
+  return ((size_t)img * p.Ho + h0 + (n >> 3)) * p.Wo + w0 + (n & 7);
+}
+__device__ __forceinline__ void swap_prefetch(const UmmaParams& p, SwapPrefetch& f, int lane, int img, int h0, int w0,
+                                              int col0, int chg, int Ch) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const size_t pix = swap_pix(p, img, h0, w0, col0 + it * 8 + (lane >> 2));
+    f.cp[it] = p.c_prev ? __ldg(p.c_prev + pix * Ch + chg) : 0.f;
+    f.pre[it] = p.preact ? __ldg(reinterpret_cast<const float4*>(p.preact + (pix * Ch + chg) * 4))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 + 2 * kMaxStages + 2 * kAccStages];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_x = (smem_u32(smem_raw) + 1023u) & ~1023u;  // activation halo tile (one stage)
+  const uint32_t smem_w = smem_x + kSwActBytes;                    // weight ring / resident weight set
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (smem_x - smem_u32(smem_raw)) + kSwActBytes +
+                                               p.b_stages * p.b_stage_bytes);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t xfull = smem_u32(&bars[0]);
+  const uint32_t xempty = smem_u32(&bars[1]);
+  const uint32_t wfull0 = smem_u32(&bars[2]);
+  const uint32_t wempty0 = smem_u32(&bars[2 + kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[2 + 2 * kMaxStages]);
+  const uint32_t tempty0 = smem_u32(&bars[2 + 2 * kMaxStages + kAccStages]);
+
+  if (warp == kEpiWarps && lane == 0) {
+    prefetch_tmap(&maps.a[0]);
+    prefetch_tmap(&maps.b);
+  }
+  if (warp == kEpiWarps + 1 && lane == 0) {
+    mbar_init(xfull, 1);
+    mbar_init(xempty, 1);
+    for (int s2 = 0; s2 < kMaxStages; ++s2) {
+      mbar_init(wfull0 + 8 * s2, 1);
+      mbar_init(wempty0 + 8 * s2, 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, kEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int ksteps = p.last_ksteps;  // one channel chunk only
+
+  if (warp == kEpiWarps) {
+    // ---- activation producer: one halo box per tile
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+      const int w0 = (r % p.tiles_w) * kHaloBW, h0 = (r / p.tiles_w) * kSwTileH;
+      mbar_wait(xempty, ph ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(xfull, (uint32_t)kSwActBytes);
+        tma_load_5d(smem_x, &maps.a[0], xfull, 0, w0 - 1, h0 - 1, img, 0);
+      }
+      __syncwarp();
+      ph ^= 1u;
+    }
+  } else if (warp == kEpiWarps + 2) {
+    // ---- weight producer: nine tap boxes per tile, or once per CTA when they stay resident
+    int ws = 0;
+    uint32_t wph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      if (p.b_resident && tile != (int)blockIdx.x) break;
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_wait(wempty0 + 8 * ws, wph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(wfull0 + 8 * ws, p.b_tx_bytes);
+          tma_load_3d(smem_w + ws * p.b_stage_bytes, &maps.b, wfull0 + 8 * ws, tap * kBK, 0, 0);
+        }
+        __syncwarp();
+        if (++ws == p.b_stages) {
+          ws = 0;
+          wph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
+    // ---- MMA issuer: M = 128 (weight rows; only 2 * 4*Ch of them are meaningful), N = 256 pixels
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((kBM >> 4) << 24);
+    const uint64_t wdesc0 = make_smem_desc(smem_w, 1024);
+    const uint64_t xdesc0 = make_smem_desc(smem_x, (kHaloBW + 2) * 128);
+    int ws = 0;
+    uint32_t wph = 0, xph = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      mbar_wait(xfull, xph);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * kStageCols;
+      uint32_t accumulate = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        if (p.b_resident) {
+          ws = tap;
+          wph = 0;
+        }
+        if (!(p.b_resident && tile != (int)blockIdx.x)) {
+          mbar_wait(wfull0 + 8 * ws, wph);
+          tc_fence_after();
+        }
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const uint64_t a = wdesc0 + (uint64_t)((uint32_t)(ws * p.b_stage_bytes) >> 4);
+        const uint64_t b_hi = xdesc0 + (uint64_t)((uint32_t)((kh * (kHaloBW + 2) + kw) * 128) >> 4);
+        const uint64_t b_lo = b_hi + (uint64_t)(kSwActPlaneBytes >> 4);
+        if (elect_one()) {
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_bf16(d, a + adv, b_hi + adv, idesc, accumulate);
+            umma_bf16(d, a + adv, b_lo + adv, idesc, 1u);
+            accumulate = 1u;
+          }
+          if (!p.b_resident) umma_commit(wempty0 + 8 * ws);
+          if (tap == 8) {
+            umma_commit(xempty);
+            umma_commit(tfull0 + 8 * acc);
+          }
+        }
+        __syncwarp();
+        accumulate = 1u;
+        if (!p.b_resident && ++ws == p.b_stages) {
+          ws = 0;
+          wph ^= 1u;
+        }
+      }
+      xph ^= 1u;
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < kEpiWarps) {
+    // ---- epilogue: warp = (lane quarter q -> hidden channels 4q..4q+3, pixel half)
+    const int q = warp & 3, half = warp >> 2;
+    const bool active = 32 * q < 2 * p.Cout;
+    const int Ch = p.Cout >> 2;
+    const int c = lane & 3;
+    const int chg = 4 * q + c;
+    float* stage = stage_base + warp * kStageFloats;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+      sc = __ldg(reinterpret_cast<const float4*>(p.scale + 4 * chg));
+      sh = __ldg(reinterpret_cast<const float4*>(p.shift + 4 * chg));
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    SwapPrefetch cur;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+      const int w0 = (r % p.tiles_w) * kHaloBW, h0 = (r / p.tiles_w) * kSwTileH;
+      if (active && first) swap_prefetch(p, cur, lane, img, h0, w0, 128 * half, chg, Ch);
+      first = false;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kStageCols;
+      uint32_t best = 0u;
+      if (active) {
+        for (int j = 0; j < 4; ++j) {
+          const int col0 = 128 * half + 32 * j;
+          SwapPrefetch nxt;
+          if (j < 3) {
+            swap_prefetch(p, nxt, lane, img, h0, w0, col0 + 32, chg, Ch);
+          } else if (tile + (int)gridDim.x < p.num_tiles) {
+            const int t2 = tile + (int)gridDim.x;
+            const int img2 = t2 / tiles_per_img, r2 = t2 - img2 * tiles_per_img;
+            swap_prefetch(p, nxt, lane, img2, (r2 / p.tiles_w) * kSwTileH, (r2 % p.tiles_w) * kHaloBW, 128 * half, chg, Ch);
+          }
+          uint32_t rr[32];
+          tmem_ld32(taddr + col0, rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            // lanes 2r / 2r+1 hold the hi- / lo-weight-plane partial sums of gate column r
+            const float v = __uint_as_float(rr[e]);
+            stage[e * kStagePitch + lane] = v + __shfl_xor_sync(0xffffffffu, v, 1);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int px = it * 8 + (lane >> 2);
+            const float* g = stage + px * kStagePitch + 8 * c;
+            const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x) + cur.pre[it].x);
+            const float gf = fast_sigmoid(fmaf(g[2], sc.y, sh.y) + cur.pre[it].y);
+            const float go = fast_sigmoid(fmaf(g[4], sc.z, sh.z) + cur.pre[it].z);
+            const float gg = fast_tanh(fmaf(g[6], sc.w, sh.w) + cur.pre[it].w);
+            const float cv = fmaf(gf, cur.cp[it], gi * gg);
+            const float hv = go * fast_tanh(cv);
+            const size_t pix = swap_pix(p, img, h0, w0, col0 + px);
+            const size_t idx = pix * Ch + chg;
+            p.c_out[idx] = cv;
+            p.h_out[idx] = hv;
+            if (p.h_split) {
+              __nv_bfloat16 hi, lo;
+              split_bf16(hv, hi, lo);
+              const size_t k2 = pix * p.hs_cs + chg;
+              p.h_split[k2] = hi;
+              p.h_split[k2 + p.hs_plane] = lo;
+            }
+            const uint32_t key = float_to_key(hv);
+            best = key > best ? key : best;
+          }
+          __syncwarp();
+          cur = nxt;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+      if (active && p.side_max) {
+        // global nn.MaxPool2d (model.py:143): lanes with the same lane % 4 hold the same channel
+#pragma unroll
+        for (int s2 = 4; s2 < 32; s2 <<= 1) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, best, s2);
+          best = o > best ? o : best;
+        }
+        if (lane < 4) atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg, best);
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -968,6 +1247,7 @@ int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
+int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
 int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
@@ -988,6 +1268,7 @@ void init_once() {
   if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PRINT_PLAN")) g_print_plan = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_SWAP")) g_swap = atoi(e) != 0;
 
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1004,7 +1285,9 @@ void init_once() {
       (e = set_smem_attr<false, 32, false>()) != cudaSuccess || (e = set_smem_attr<false, 32, true>()) != cudaSuccess ||
       (e = set_smem_attr<false, 16, false>()) != cudaSuccess || (e = set_smem_attr<false, 16, true>()) != cudaSuccess ||
       (e = set_smem_attr<true, 32, false>()) != cudaSuccess || (e = set_smem_attr<true, 32, true>()) != cudaSuccess ||
-      (e = set_smem_attr<true, 16, false>()) != cudaSuccess || (e = set_smem_attr<true, 16, true>()) != cudaSuccess) {
+      (e = set_smem_attr<true, 16, false>()) != cudaSuccess || (e = set_smem_attr<true, 16, true>()) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(cell_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
+          cudaSuccess) {
     set_cuda_error(e);
     g_init_status = RSIS_ERR_CUDA;
   }
@@ -1266,6 +1549,81 @@ int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   return RSIS_OK;
 }
 
+// Weight tensor map for the swapped cell: the plane-interleaved pack [cout_pad][2 planes][k_pad] (rsis_conv_weights::
+// w_umma_il) as {k, 2 * cout_pad rows}: one box {64, 2 * rows} lands as smem rows (gate column r, plane) -> 2r + plane.
+int encode_weight_map_swapped(CUtensorMap* m, const void* w, int cout_pad, int k_pad, int rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)2 * cout_pad, 1};
+  cuuint64_t strides[2] = {(cuuint64_t)k_pad * 2, (cuuint64_t)2 * cout_pad * k_pad * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)(2 * rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
+}
+
+bool swap_eligible(const rsis_tensor& x, const rsis_conv_weights* w) {
+  std::call_once(g_once, init_once);
+  return g_swap && g_init_status == RSIS_OK && w->w_umma_il && aligned16(w->w_umma_il) && w->kh == 3 &&
+         (w->cout == 32 || w->cout == 64) && x.c <= kBK &&
+         x.w % kHaloBW == 0 && x.h % kSwTileH == 0;
+}
+
+int setup_swap(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w) {
+  p.N = x.n;
+  p.Ho = x.h;
+  p.Wo = x.w;
+  p.Cout = w->cout;
+  p.BN = w->cout;
+  p.BW = kHaloBW;
+  p.BH = kSwTileH;
+  p.BI = 1;
+  p.tiles_w = x.w / kHaloBW;
+  p.tiles_h = x.h / kSwTileH;
+  p.tiles_i = x.n;
+  p.tiles_n = 1;
+  const long long nt = (long long)p.tiles_w * p.tiles_h * p.tiles_i;
+  if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
+  p.num_tiles = (int)nt;
+  p.ksplit = 1;
+  p.chunks = 1;
+  p.taps = 9;
+  p.last_ksteps = ceil_div(x.c, 16);
+  p.b_stage_bytes = 2 * p.BN * 128;
+  p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
+  // the M = 128 descriptor of a 64-row weight slot also reads the 64 rows behind it (ignored lanes): keep one slot
+  // of slack behind the ring (the epilogue staging area follows, so the read stays inside this CTA's shared memory)
+  const int budget = kDynSmem - 1023 - kStageBytes - kSwActBytes;
+  p.b_stages = budget / p.b_stage_bytes;
+  if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
+  p.b_resident = (g_b_resident && p.b_stages >= 9 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
+  if (p.b_resident) p.b_stages = 9;
+  if (p.b_stages < 2) return RSIS_ERR_UNSUPPORTED;
+  p.scale = w->scale;
+  p.shift = w->shift;
+  const int cout_pad = round_up(w->cout, 16);
+  const int k_pad = 9 * kBK;
+  if (int e = encode_weight_map_swapped(&maps.b, w->w_umma_il, cout_pad, k_pad, p.BN)) return e;
+  if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kSwTileH + 2, 1)) return e;
+  return RSIS_OK;
+}
+
+int launch_swap(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms);
+  cfg.blockDim = dim3(kThreadsUmma);
+  cfg.dynamicSmemBytes = kDynSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  RSIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, cell_swap_kernel, maps, p));
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
 }  // namespace
 
 bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
@@ -1321,7 +1679,12 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   (void)n_src;
   UmmaMaps maps;
   UmmaParams p{};
-  if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2, workspace, workspace_bytes)) return e;
+  const bool swapped = swap_eligible(srcs[0], w);
+  if (swapped) {
+    if (int e = setup_swap(maps, p, srcs[0], w)) return e;
+  } else {
+    if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2, workspace, workspace_bytes)) return e;
+  }
   const int Ch = p.Cout / 4;
   auto ok = [&](const rsis_tensor* t, int fmt) {
     return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&
@@ -1344,6 +1707,7 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   p.side_max = side_max;
   p.side_stride = side_stride;
   p.side_offset = side_offset;
+  if (swapped) return launch_swap(maps, p, st);
   return launch<true>(maps, p, st);
 }
 

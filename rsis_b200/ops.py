@@ -117,8 +117,14 @@ class PackedConv:
             check(lib.rsis_conv_pack_umma(_ptr(w), cout, cin, kh, kw, len(self.src_channels), sc,
                                           int(self.gate_interleave), _ptr(self.w_umma), st), "conv_pack_umma")
         _lib.count_launch(1)
+        # plane-interleaved copy [cout_pad][2][k_pad] for the swapped-operand cell kernel of the narrow decoder levels
+        self.w_umma_il = None
+        if (self.w_umma is not None and self.gate_interleave and cout in (32, 64) and len(self.src_channels) == 1
+                and cin <= 64 and kh == 3 and kw == 3):
+            cp = lib.rsis_conv_umma_coutpad(cout)
+            self.w_umma_il = self.w_umma.view(2, cp, self.k_pad).permute(1, 0, 2).contiguous()
         self.desc = _lib.ConvWeights(_ptr(self.w_kc), _ptr(self.w_umma), _ptr(self.scale), _ptr(self.shift), cout, cin,
-                                     kh, kw, int(self.gate_interleave))
+                                     kh, kw, int(self.gate_interleave), _ptr(self.w_umma_il))
 
     def ref(self):
         return C.byref(self.desc)

@@ -330,7 +330,11 @@ def test_convlstm_cell_matches_oracle_ragged(R, O, impl, shape):
     assert int(side[:, :3].abs().sum()) == 0 and int(side[:, 3 + ch:].abs().sum()) == 0
 
 
-def test_convlstm_cell_hoisted_gates(R, O):
+@pytest.mark.parametrize("shape", [(3, 32, 32, 16, 16, 24),    # pixels-as-M kernel (map height not a multiple of 32)
+                                   (2, 16, 16, 8, 32, 16),     # level-4-like: 32 gate columns -> swapped-operand kernel
+                                   (2, 32, 32, 16, 64, 24),    # level-3-like: 64 gate columns -> swapped-operand kernel
+                                   (5, 16, 16, 8, 96, 40)])    # several tiles per CTA, resident weights
+def test_convlstm_cell_hoisted_gates(R, O, shape):
     """The decoder's fast path computes the time-invariant skip share of the gates once (rsis_conv2d with the skip
     columns of Gates.weight, gate-interleaved, + bias) and feeds it to the cell kernel as `gate_preact`; the step then
     contracts over [up(h_below) | prev_hidden] only.  Must equal the reference cell on cat([up, skip]) (model.py:153)."""
@@ -338,7 +342,7 @@ def test_convlstm_cell_hoisted_gates(R, O):
     if not ops.has_tcgen05():
         pytest.skip("library built without tcgen05 kernels")
     g = torch.Generator().manual_seed(77)
-    B, up_c, skip_c, ch, H, W = 3, 32, 32, 16, 16, 24
+    B, up_c, skip_c, ch, H, W = shape
     up = torch.rand((B, up_c, H, W), generator=g) * 2 - 1
     skip = torch.rand((B, skip_c, H, W), generator=g) * 4 - 2
     hp = torch.rand((B, ch, H, W), generator=g) * 2 - 1
@@ -356,9 +360,15 @@ def test_convlstm_cell_hoisted_gates(R, O):
     ops.convert(ops.act_from_nchw(up.cuda(), F16), F16, out=x.slice(0, up_c))
     ops.convert(ops.act_from_nchw(hp.cuda(), F16), F16, out=x.slice(up_c, ch))
     side = torch.zeros((B, ch), dtype=torch.int32, device="cuda")
+    h16 = ops.Act.zeros(B, H, W, ch + 8, F16, "cuda")
     h, c = ops.convlstm_cell_x(x, pc_step, ops.act_from_nchw(cp.cuda(), ops.FMT_F32).t, side, 0,
-                               impl=ops.IMPL_TCGEN05, gate_preact=pre)
+                               h16_out=h16.slice(8, ch), impl=ops.IMPL_TCGEN05, gate_preact=pre)
     assert rel(h.nchw(), href) < TOL_FP32 * 5 and rel(c.nchw(), cref) < TOL_FP32 * 5
+    # the operand-format copy of h (next step's input slice) and the global max-pool side feature
+    assert rel(h16.float()[..., 8:].permute(0, 3, 1, 2), href) < 2e-5 and float(h16.float()[..., :8].abs().max()) == 0.0
+    k = side.cpu()
+    dec = torch.where(k < 0, k & 0x7FFFFFFF, ~k).view(torch.float32)
+    assert torch.equal(dec, h.nchw().amax(dim=(2, 3)).cpu())
 
 
 # ---------------------------------------------------------------------------------------------------------
