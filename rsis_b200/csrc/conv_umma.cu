@@ -976,51 +976,163 @@ constexpr int kSwHaloRows = (kHaloBW + 2) * (kSwTileH + 2);  // 340
 constexpr int kSwActPlaneBytes = kSwHaloRows * 128;           // 43520
 constexpr int kSwActBytes = 2 * kSwActPlaneBytes;             // 87040 = 85 KB (1024-byte multiple)
 
-struct SwapPrefetch {
-  float cp[4];
-  float4 pre[4];
-};
-
 __device__ __forceinline__ size_t swap_pix(const UmmaParams& p, int img, int h0, int w0, int n) {
   return ((size_t)img * p.Ho + h0 + (n >> 3)) * p.Wo + w0 + (n & 7);
 }
-__device__ __forceinline__ void swap_prefetch(const UmmaParams& p, SwapPrefetch& f, int lane, int img, int h0, int w0,
-                                              int col0, int chg, int Ch) {
+// Epilogue of the swapped cell.  warp = (lane quarter q, pixel half).  The accumulator lanes of quarter q are hidden
+// channels 4q..4q+3.  With 64 gate columns all four quarters carry data (PAIR = false); with 32 only quarters 0-1 do,
+// so the warps of quarters 2-3 (which cannot read those TMEM lanes) pair up with warp q-2 (PAIR = true): the reader
+// stages a 32-pixel chunk in shared memory and both warps finish 16 pixels of it.
+template <bool PAIR>
+__device__ __forceinline__ void swap_epilogue(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, float* stage_base, int warp, int lane) {
+  constexpr int NIT = PAIR ? 2 : 4;  // 8-pixel iterations of a 32-pixel chunk this warp finishes
+  const int q = warp & 3, half = warp >> 2;
+  const int qr = PAIR ? (q & 1) : q;
+  const bool reader = !PAIR || q < 2;
+  const int it0 = (PAIR && q >= 2) ? 2 : 0;
+  const int slot = PAIR ? half * 2 + qr : warp;
+  const int Ch = p.Cout >> 2;
+  const int c = lane & 3;
+  const int chg = 4 * qr + c;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  float* stage = stage_base + slot * kStageFloats;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + 4 * chg));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + 4 * chg));
+  struct Pre {
+    float cp[NIT];
+    float4 pre[NIT];
+  };
+  auto pair_sync = [&]() {
+    if constexpr (PAIR) {
+      // one named barrier per (reader, helper) pair: ids 2..5
+      if (slot == 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+      else if (slot == 1) asm volatile("bar.sync 3, 64;" ::: "memory");
+      else if (slot == 2) asm volatile("bar.sync 4, 64;" ::: "memory");
+      else asm volatile("bar.sync 5, 64;" ::: "memory");
+    } else {
+      __syncwarp();
+    }
+  };
+  auto prefetch = [&](Pre& f, int img, int h0, int w0, int col0) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const size_t pix = swap_pix(p, img, h0, w0, col0 + it * 8 + (lane >> 2));
-    f.cp[it] = p.c_prev ? __ldg(p.c_prev + pix * Ch + chg) : 0.f;
-    f.pre[it] = p.preact ? __ldg(reinterpret_cast<const float4*>(p.preact + (pix * Ch + chg) * 4))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NIT; ++i) {
+      const size_t pix = swap_pix(p, img, h0, w0, col0 + (it0 + i) * 8 + (lane >> 2));
+      f.cp[i] = p.c_prev ? __ldg(p.c_prev + pix * Ch + chg) : 0.f;
+      f.pre[i] = p.preact ? __ldg(reinterpret_cast<const float4*>(p.preact + (pix * Ch + chg) * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  Pre cur;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
+    const int w0 = (r % p.tiles_w) * kHaloBW, h0 = (r / p.tiles_w) * kSwTileH;
+    if (first) prefetch(cur, img, h0, w0, 128 * half);
+    first = false;
+    mbar_wait(tfull0 + 8 * acc, acc_phase);
+    tc_fence_after();
+    if (threadIdx.x == 0) STAMP_T(3, (tile - (int)blockIdx.x) / (int)gridDim.x);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kStageCols;
+    uint32_t best = 0u;
+    for (int j = 0; j < 4; ++j) {
+      const int col0 = 128 * half + 32 * j;
+      Pre nxt;
+      if (j < 3) {
+        prefetch(nxt, img, h0, w0, col0 + 32);
+      } else if (tile + (int)gridDim.x < p.num_tiles) {
+        const int t2 = tile + (int)gridDim.x;
+        const int img2 = t2 / tiles_per_img, r2 = t2 - img2 * tiles_per_img;
+        prefetch(nxt, img2, (r2 / p.tiles_w) * kSwTileH, (r2 % p.tiles_w) * kHaloBW, 128 * half);
+      }
+      if (reader) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + col0, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          // lanes 2r / 2r+1 hold the hi- / lo-weight-plane partial sums of gate column r
+          const float v = __uint_as_float(rr[e]);
+          stage[e * kStagePitch + lane] = v + __shfl_xor_sync(0xffffffffu, v, 1);
+        }
+      }
+      pair_sync();
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int px = (it0 + i) * 8 + (lane >> 2);
+        const float* g = stage + px * kStagePitch + 8 * c;
+        const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x) + cur.pre[i].x);
+        const float gf = fast_sigmoid(fmaf(g[2], sc.y, sh.y) + cur.pre[i].y);
+        const float go = fast_sigmoid(fmaf(g[4], sc.z, sh.z) + cur.pre[i].z);
+        const float gg = fast_tanh(fmaf(g[6], sc.w, sh.w) + cur.pre[i].w);
+        const float cv = fmaf(gf, cur.cp[i], gi * gg);
+        const float hv = go * fast_tanh(cv);
+        const size_t pix = swap_pix(p, img, h0, w0, col0 + px);
+        const size_t idx = pix * Ch + chg;
+        p.c_out[idx] = cv;
+        p.h_out[idx] = hv;
+        if (p.h_split) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(hv, hi, lo);
+          const size_t k2 = pix * p.hs_cs + chg;
+          p.h_split[k2] = hi;
+          p.h_split[k2 + p.hs_plane] = lo;
+        }
+        const uint32_t key = float_to_key(hv);
+        best = key > best ? key : best;
+      }
+      pair_sync();
+      cur = nxt;
+    }
+    tc_fence_before();
+    mbar_arrive(tempty0 + 8 * acc);
+    if (threadIdx.x == 0) STAMP_T(4, (tile - (int)blockIdx.x) / (int)gridDim.x);
+    if (p.side_max) {
+      // global nn.MaxPool2d (model.py:143): lanes with the same lane % 4 hold the same channel
+#pragma unroll
+      for (int s2 = 4; s2 < 32; s2 <<= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, best, s2);
+        best = o > best ? o : best;
+      }
+      if (lane < 4) atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg, best);
+    }
+    if (++acc == kAccStages) {
+      acc = 0;
+      acc_phase ^= 1u;
+    }
   }
 }
 
 __global__ void __launch_bounds__(kThreadsUmma, 1)
 cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 + 2 * kMaxStages + 2 * kAccStages];
+  __shared__ __align__(8) uint64_t bars[4 + 2 * kMaxStages + 2 * kAccStages];
   __shared__ uint32_t tmem_slot;
 
-  const uint32_t smem_x = (smem_u32(smem_raw) + 1023u) & ~1023u;  // activation halo tile (one stage)
-  const uint32_t smem_w = smem_x + kSwActBytes;                    // weight ring / resident weight set
-  float* stage_base = reinterpret_cast<float*>(smem_raw + (smem_x - smem_u32(smem_raw)) + kSwActBytes +
+  const uint32_t smem_x = (smem_u32(smem_raw) + 1023u) & ~1023u;  // activation halo tiles (a_stages of them)
+  const uint32_t smem_w = smem_x + p.a_stages * kSwActBytes;       // weight ring / resident weight set
+  float* stage_base = reinterpret_cast<float*>(smem_raw + (smem_x - smem_u32(smem_raw)) + p.a_stages * kSwActBytes +
                                                p.b_stages * p.b_stage_bytes);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t xfull = smem_u32(&bars[0]);
-  const uint32_t xempty = smem_u32(&bars[1]);
-  const uint32_t wfull0 = smem_u32(&bars[2]);
-  const uint32_t wempty0 = smem_u32(&bars[2 + kMaxStages]);
-  const uint32_t tfull0 = smem_u32(&bars[2 + 2 * kMaxStages]);
-  const uint32_t tempty0 = smem_u32(&bars[2 + 2 * kMaxStages + kAccStages]);
+  const uint32_t xfull0 = smem_u32(&bars[0]);
+  const uint32_t xempty0 = smem_u32(&bars[2]);
+  const uint32_t wfull0 = smem_u32(&bars[4]);
+  const uint32_t wempty0 = smem_u32(&bars[4 + kMaxStages]);
+  const uint32_t tfull0 = smem_u32(&bars[4 + 2 * kMaxStages]);
+  const uint32_t tempty0 = smem_u32(&bars[4 + 2 * kMaxStages + kAccStages]);
 
   if (warp == kEpiWarps && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     prefetch_tmap(&maps.b);
   }
   if (warp == kEpiWarps + 1 && lane == 0) {
-    mbar_init(xfull, 1);
-    mbar_init(xempty, 1);
+    for (int s2 = 0; s2 < 2; ++s2) {
+      mbar_init(xfull0 + 8 * s2, 1);
+      mbar_init(xempty0 + 8 * s2, 1);
+    }
     for (int s2 = 0; s2 < kMaxStages; ++s2) {
       mbar_init(wfull0 + 8 * s2, 1);
       mbar_init(wempty0 + 8 * s2, 1);
@@ -1043,6 +1155,7 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   const uint32_t tmem_base = tmem_slot;
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) STAMP(0);
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int ksteps = p.last_ksteps;  // one channel chunk only
@@ -1050,16 +1163,21 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
   if (warp == kEpiWarps) {
     // ---- activation producer: one halo box per tile
     uint32_t ph = 0;
+    int xs = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
       const int w0 = (r % p.tiles_w) * kHaloBW, h0 = (r / p.tiles_w) * kSwTileH;
-      mbar_wait(xempty, ph ^ 1u);
+      mbar_wait(xempty0 + 8 * xs, ph ^ 1u);
       if (elect_one()) {
-        mbar_arrive_expect_tx(xfull, (uint32_t)kSwActBytes);
-        tma_load_5d(smem_x, &maps.a[0], xfull, 0, w0 - 1, h0 - 1, img, 0);
+        mbar_arrive_expect_tx(xfull0 + 8 * xs, (uint32_t)kSwActBytes);
+        tma_load_5d(smem_x + xs * kSwActBytes, &maps.a[0], xfull0 + 8 * xs, 0, w0 - 1, h0 - 1, img, 0);
       }
       __syncwarp();
-      ph ^= 1u;
+      if (lane == 0) STAMP_T(0, (tile - (int)blockIdx.x) / (int)gridDim.x);
+      if (++xs == p.a_stages) {
+        xs = 0;
+        ph ^= 1u;
+      }
     }
   } else if (warp == kEpiWarps + 2) {
     // ---- weight producer: nine tap boxes per tile, or once per CTA when they stay resident
@@ -1085,15 +1203,16 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((kBM >> 4) << 24);
     const uint64_t wdesc0 = make_smem_desc(smem_w, 1024);
     const uint64_t xdesc0 = make_smem_desc(smem_x, (kHaloBW + 2) * 128);
-    int ws = 0;
+    int ws = 0, xs = 0;
     uint32_t wph = 0, xph = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
       tc_fence_after();
-      mbar_wait(xfull, xph);
+      mbar_wait(xfull0 + 8 * xs, xph);
       tc_fence_after();
+      if (lane == 0) STAMP_T(1, (tile - (int)blockIdx.x) / (int)gridDim.x);
       const uint32_t d = tmem_base + acc * kStageCols;
       uint32_t accumulate = 0;
       for (int tap = 0; tap < 9; ++tap) {
@@ -1107,7 +1226,7 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         }
         const int kh = tap / 3, kw = tap - kh * 3;
         const uint64_t a = wdesc0 + (uint64_t)((uint32_t)(ws * p.b_stage_bytes) >> 4);
-        const uint64_t b_hi = xdesc0 + (uint64_t)((uint32_t)((kh * (kHaloBW + 2) + kw) * 128) >> 4);
+        const uint64_t b_hi = xdesc0 + (uint64_t)((uint32_t)(xs * kSwActBytes + (kh * (kHaloBW + 2) + kw) * 128) >> 4);
         const uint64_t b_lo = b_hi + (uint64_t)(kSwActPlaneBytes >> 4);
         if (elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
@@ -1118,7 +1237,7 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
           }
           if (!p.b_resident) umma_commit(wempty0 + 8 * ws);
           if (tap == 8) {
-            umma_commit(xempty);
+            umma_commit(xempty0 + 8 * xs);
             umma_commit(tfull0 + 8 * acc);
           }
         }
@@ -1129,103 +1248,21 @@ cell_swap_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
           wph ^= 1u;
         }
       }
-      xph ^= 1u;
+      if (lane == 0) STAMP_T(2, (tile - (int)blockIdx.x) / (int)gridDim.x);
+      if (++xs == p.a_stages) {
+        xs = 0;
+        xph ^= 1u;
+      }
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
   } else if (warp < kEpiWarps) {
-    // ---- epilogue: warp = (lane quarter q -> hidden channels 4q..4q+3, pixel half)
-    const int q = warp & 3, half = warp >> 2;
-    const bool active = 32 * q < 2 * p.Cout;
-    const int Ch = p.Cout >> 2;
-    const int c = lane & 3;
-    const int chg = 4 * q + c;
-    float* stage = stage_base + warp * kStageFloats;
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-      sc = __ldg(reinterpret_cast<const float4*>(p.scale + 4 * chg));
-      sh = __ldg(reinterpret_cast<const float4*>(p.shift + 4 * chg));
-    }
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    SwapPrefetch cur;
-    bool first = true;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int img = tile / tiles_per_img, r = tile - img * tiles_per_img;
-      const int w0 = (r % p.tiles_w) * kHaloBW, h0 = (r / p.tiles_w) * kSwTileH;
-      if (active && first) swap_prefetch(p, cur, lane, img, h0, w0, 128 * half, chg, Ch);
-      first = false;
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kStageCols;
-      uint32_t best = 0u;
-      if (active) {
-        for (int j = 0; j < 4; ++j) {
-          const int col0 = 128 * half + 32 * j;
-          SwapPrefetch nxt;
-          if (j < 3) {
-            swap_prefetch(p, nxt, lane, img, h0, w0, col0 + 32, chg, Ch);
-          } else if (tile + (int)gridDim.x < p.num_tiles) {
-            const int t2 = tile + (int)gridDim.x;
-            const int img2 = t2 / tiles_per_img, r2 = t2 - img2 * tiles_per_img;
-            swap_prefetch(p, nxt, lane, img2, (r2 / p.tiles_w) * kSwTileH, (r2 % p.tiles_w) * kHaloBW, 128 * half, chg, Ch);
-          }
-          uint32_t rr[32];
-          tmem_ld32(taddr + col0, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            // lanes 2r / 2r+1 hold the hi- / lo-weight-plane partial sums of gate column r
-            const float v = __uint_as_float(rr[e]);
-            stage[e * kStagePitch + lane] = v + __shfl_xor_sync(0xffffffffu, v, 1);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int px = it * 8 + (lane >> 2);
-            const float* g = stage + px * kStagePitch + 8 * c;
-            const float gi = fast_sigmoid(fmaf(g[0], sc.x, sh.x) + cur.pre[it].x);
-            const float gf = fast_sigmoid(fmaf(g[2], sc.y, sh.y) + cur.pre[it].y);
-            const float go = fast_sigmoid(fmaf(g[4], sc.z, sh.z) + cur.pre[it].z);
-            const float gg = fast_tanh(fmaf(g[6], sc.w, sh.w) + cur.pre[it].w);
-            const float cv = fmaf(gf, cur.cp[it], gi * gg);
-            const float hv = go * fast_tanh(cv);
-            const size_t pix = swap_pix(p, img, h0, w0, col0 + px);
-            const size_t idx = pix * Ch + chg;
-            p.c_out[idx] = cv;
-            p.h_out[idx] = hv;
-            if (p.h_split) {
-              __nv_bfloat16 hi, lo;
-              split_bf16(hv, hi, lo);
-              const size_t k2 = pix * p.hs_cs + chg;
-              p.h_split[k2] = hi;
-              p.h_split[k2 + p.hs_plane] = lo;
-            }
-            const uint32_t key = float_to_key(hv);
-            best = key > best ? key : best;
-          }
-          __syncwarp();
-          cur = nxt;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
-      if (active && p.side_max) {
-        // global nn.MaxPool2d (model.py:143): lanes with the same lane % 4 hold the same channel
-#pragma unroll
-        for (int s2 = 4; s2 < 32; s2 <<= 1) {
-          const uint32_t o = __shfl_xor_sync(0xffffffffu, best, s2);
-          best = o > best ? o : best;
-        }
-        if (lane < 4) atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg, best);
-      }
-      if (++acc == kAccStages) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
-    }
+    if (2 * p.Cout < 128)
+      swap_epilogue<true>(p, tmem_base, tfull0, tempty0, stage_base, warp, lane);
+    else
+      swap_epilogue<false>(p, tmem_base, tfull0, tempty0, stage_base, warp, lane);
   }
 
   tc_fence_before();
@@ -1247,6 +1284,7 @@ int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
+unsigned* g_debug_counters = nullptr;  // set by the last non-swapped setup when RSIS_B200_DEBUG_TIMING is on
 int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
@@ -1461,6 +1499,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const long long nt = (long long)p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
   if (nt * p.ksplit > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
   p.num_tiles = (int)nt;
+  if (can_split && getenv("RSIS_B200_DEBUG_TIMING")) g_debug_counters = reinterpret_cast<unsigned*>(workspace);
   if (p.ksplit > 1 || (can_split && getenv("RSIS_B200_DEBUG_TIMING"))) {
     p.counters = reinterpret_cast<unsigned*>(workspace);
     p.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
@@ -1593,7 +1632,12 @@ int setup_swap(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_c
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   // the M = 128 descriptor of a 64-row weight slot also reads the 64 rows behind it (ignored lanes): keep one slot
   // of slack behind the ring (the epilogue staging area follows, so the read stays inside this CTA's shared memory)
-  const int budget = kDynSmem - 1023 - kStageBytes - kSwActBytes;
+  // Shared memory: activation halo stages (85 KB each) + weight ring + epilogue staging (one slot per ACTIVE warp).
+  // 32 gate columns: two activation stages (the next tile's halo loads under this tile's MMAs) and streamed weights;
+  // 64 gate columns: one activation stage, as many weight stages as fit.
+  const int stage_slots = 2 * p.BN >= 128 ? kEpiWarps : kEpiWarps / 2;
+  p.a_stages = (p.BN == 32 && p.num_tiles > g_num_sms) ? 2 : 1;
+  const int budget = kDynSmem - 1023 - stage_slots * kStageFloats * 4 - p.a_stages * kSwActBytes;
   p.b_stages = budget / p.b_stage_bytes;
   if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
   p.b_resident = (g_b_resident && p.b_stages >= 9 && p.num_tiles >= 2 * g_num_sms) ? 1 : 0;
@@ -1604,6 +1648,7 @@ int setup_swap(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_c
   const int cout_pad = round_up(w->cout, 16);
   const int k_pad = 9 * kBK;
   if (int e = encode_weight_map_swapped(&maps.b, w->w_umma_il, cout_pad, k_pad, p.BN)) return e;
+  p.counters = g_debug_counters;
   if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kSwTileH + 2, 1)) return e;
   return RSIS_OK;
 }
