@@ -337,8 +337,14 @@ def run_ours(a):
                               "GBps": nb / s / 1e9, "TFLOPs": nf / s / 1e12})
         step_s = sum(lv_s)
         ach = tot_b / step_s / 1e9
+        traffic = None  # ncu dram__bytes_read.sum + dram__bytes_write.sum of the five cell launches (one --set full capture)
+        tpath = os.path.join(ROOT, "profiles", "cell_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if tj.get("workload") == a.workload:
+                traffic = tj.get("dram_bytes_per_step")
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"] + " (burst copy figure; kernel timed alone, L2 flushed)",
+                "traffic": traffic, "peak_source": pk["source"] + " (burst copy figure; kernel timed alone, L2 flushed)",
                 "kernel": "fused ConvLSTM cell (5 launches = one decoder step, levels 0-4), CUDA-event timed live",
                 "alg_bytes_per_step": tot_b, "alg_flops_per_step": tot_f, "step_us": step_s * 1e6,
                 "tensor": {"achieved_TFLOPs": tot_f / step_s / 1e12, "peak_bf16_TFLOPs": pk["bf16_tflops"],

@@ -17,7 +17,7 @@ if [ "$2" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-      -k 'regex:conv_umma_kernel<\(bool\)1>' -s 20 -c 5 -o $OUT/prof_cell -f \
+      -k 'regex:conv_umma_kernel<\(bool\)1|cell_swap_kernel' -s 20 -c 5 -o $OUT/prof_cell -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_cell.log 2>&1
   ls -la $OUT
 fi
