@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 6
+#define RSIS_ABI_VERSION 7
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -129,6 +129,26 @@ int rsis_conv2d(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, 
                 void* workspace, size_t workspace_bytes, rsis_stream_t stream);
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of vision.py:15. */
 int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
+
+/* ---- train-mode BatchNorm (encoder.train(), train.py:71-77) -------------------------------------------------- */
+/* nn.BatchNorm2d in training mode = statistics of THIS batch, so it cannot be folded into the convolution that
+ * produces its input.  Pipeline: rsis_conv2d with a pack WITHOUT BatchNorm (raw float32 output) ->
+ * rsis_bn_train_stats -> rsis_affine_act.
+ * rsis_bn_train_stats: x float32 dense NHWC [N,H,W,C], C % 4 == 0.  Computes the biased batch variance / mean over
+ * N*H*W, writes scale = weight / sqrt(var + eps) and shift = bias - mean * scale (weight/bias may be NULL = 1/0), and
+ * updates running_mean / running_var (unbiased variance) / num_batches_tracked exactly as nn.BatchNorm2d does
+ * (momentum < 0 = cumulative average, i.e. momentum=None; running_* may both be NULL).  batch_mean / batch_invstd
+ * (optional) receive the batch statistics.  workspace: rsis_bn_workspace_bytes(C) bytes of device memory, zero-filled
+ * once (the call leaves it zeroed). */
+size_t rsis_bn_workspace_bytes(int channels);
+int rsis_bn_train_stats(const rsis_tensor* x, const float* weight, const float* bias, float eps, float momentum,
+                        float* running_mean, float* running_var, int64_t* num_batches_tracked, double* workspace,
+                        float* scale, float* shift, float* batch_mean, float* batch_invstd, rsis_stream_t stream);
+/* y = [relu](x * scale[c] + shift[c] [+ residual]); dense NHWC tensors of one shape, any element formats; y2
+ * (optional) receives a second copy in another format.  Replaces the normalisation + ReLU + `out += identity` of a
+ * train-mode Bottleneck (torchvision Bottleneck.forward) and the train-mode skip heads (model.py:59-63). */
+int rsis_affine_act(const rsis_tensor* x, const float* scale, const float* shift, const rsis_tensor* residual, int relu,
+                    const rsis_tensor* y, const rsis_tensor* y2, rsis_stream_t stream);
 
 /* ---- decoder primitives ----------------------------------------------------------------------------------- */
 /* One fused ConvLSTM cell step (clstm.py:19-62): gates = conv3x3(cat(srcs)) + bias; i,f,o = sigmoid, g = tanh;

@@ -17,7 +17,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class Tensor(C.Structure):
@@ -57,6 +57,9 @@ SIGNATURES = {
     "rsis_conv_workspace_bytes": (C.c_size_t, []),
     "rsis_conv2d": (_I, [_TP, _I, _WP, _TP, _TP, _TP, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_maxpool3x3s2": (_I, [_TP, _TP, _P]),
+    "rsis_bn_workspace_bytes": (C.c_size_t, [_I]),
+    "rsis_bn_train_stats": (_I, [_TP, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rsis_affine_act": (_I, [_TP, _P, _P, _TP, _I, _TP, _TP, _P]),
     "rsis_convlstm_cell": (_I, [_TP, _I, _WP, _P, _P, _TP, _TP, _TP, _P, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_upsample_bilinear": (_I, [_TP, _TP, _P]),
     "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),

@@ -70,6 +70,14 @@ class FeatureExtractor(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_heads_train(self, want_umma: bool):
+        """Skip-head packs without BatchNorm (bias only), for the training-mode forward."""
+        key = (tuple((sk.weight.data_ptr(), sk.weight._version, sk.bias._version) for sk, _ in self._heads()), want_umma)
+        if getattr(self, "_packed_tr", None) is None or self._packed_tr_key != key:
+            self._packed_tr = [PackedConv(sk.weight, sk.bias, None, want_umma=want_umma) for sk, _ in self._heads()]
+            self._packed_tr_key = key
+        return self._packed_tr
+
     def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, operand_only: bool = False):
         """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each.
 
@@ -79,9 +87,22 @@ class FeatureExtractor(nn.Module):
         taps = self.base.forward_act(x, impl)
         if raw:
             return taps, None
-        if self.training:
-            raise NotImplementedError("rsis_b200: train-mode BatchNorm is not implemented yet; call .eval()")
         fmt = ops.activation_format(impl)
+        if self.training:
+            # train-mode skip heads (model.py:59-63): conv + bias, then BatchNorm2d with this batch's statistics
+            feats, feats_op = [], []
+            for tap, pc, (sk, bn) in zip(taps, self.packed_heads_train(want_umma=(fmt == ops.FMT_SPLIT_BF16)),
+                                         self._heads()):
+                raw = ops.conv2d([tap], pc, pad=self.padding, out_fmt=ops.FMT_F32, impl=impl)
+                scale, shift = ops.bn_train_stats(raw, bn)
+                if fmt == ops.FMT_F32:
+                    y = ops.affine_act(raw, scale, shift, out_fmt=ops.FMT_F32)
+                    y2 = y
+                else:
+                    y, y2 = ops.affine_act(raw, scale, shift, out_fmt=ops.FMT_F32, out2_fmt=fmt)
+                feats.append(y)
+                feats_op.append(y2)
+            return feats, feats_op
         heads = self.packed_heads(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         if operand_only and fmt == ops.FMT_SPLIT_BF16:
             return None, [ops.conv2d([tap], pc, pad=self.padding, out_fmt=fmt, impl=impl) for tap, pc in zip(taps, heads)]

@@ -90,13 +90,61 @@ class ResNet101(nn.Module):
             self._packed, self._packed_key = pk, key
         return self._packed
 
+    def packed_train(self, want_umma: bool):
+        """Packs WITHOUT BatchNorm (raw convolution output): in training mode the statistics are those of the batch
+        and are applied after the convolution (ops.bn_train_stats + ops.affine_act)."""
+        convs = [self.conv1] + [m for li in range(1, 5) for blk in getattr(self, f"layer{li}")
+                                for m in ([blk.conv1, blk.conv2, blk.conv3] +
+                                          ([blk.downsample[0]] if blk.downsample is not None else []))]
+        key = (tuple((c.weight.data_ptr(), c.weight._version) for c in convs), want_umma)
+        if getattr(self, "_packed_tr", None) is None or self._packed_tr_key != key:
+            pk = {"stem": PackedConv(self.conv1.weight, None, None)}
+            for li in range(1, 5):
+                for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                    p = f"layer{li}.{bi}"
+                    pk[p + ".conv1"] = PackedConv(blk.conv1.weight, None, None, want_umma=want_umma)
+                    pk[p + ".conv2"] = PackedConv(blk.conv2.weight, None, None, want_umma=want_umma)
+                    pk[p + ".conv3"] = PackedConv(blk.conv3.weight, None, None, want_umma=want_umma)
+                    if blk.downsample is not None:
+                        pk[p + ".down"] = PackedConv(blk.downsample[0].weight, None, None, want_umma=want_umma)
+            self._packed_tr, self._packed_tr_key = pk, key
+        return self._packed_tr
+
+    def _forward_act_train(self, x: torch.Tensor, impl: int) -> List[Act]:
+        """Training-mode forward (train.py:71-77): every BatchNorm2d uses the statistics of this batch and updates its
+        running statistics; conv -> bn_train_stats -> affine_act (+residual, +ReLU)."""
+        fmt = ops.activation_format(impl)
+        pk = self.packed_train(want_umma=(fmt == ops.FMT_SPLIT_BF16))
+        F32 = ops.FMT_F32
+
+        def conv_bn(src, pc, bn, stride=1, pad=0, relu=True, residual=None, which=impl):
+            raw = ops.conv2d([src], pc, stride=stride, pad=pad, out_fmt=F32, impl=which)
+            scale, shift = ops.bn_train_stats(raw, bn)
+            return ops.affine_act(raw, scale, shift, residual=residual, relu=relu, out_fmt=fmt)
+
+        xa = ops.act_from_nchw(x, F32)
+        x1 = conv_bn(xa, pk["stem"], self.bn1, stride=2, pad=3, which=ops.IMPL_SIMT)
+        cur = ops.maxpool3x3s2(x1)
+        taps = []
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                p = f"layer{li}.{bi}"
+                out = conv_bn(cur, pk[p + ".conv1"], blk.bn1)
+                out = conv_bn(out, pk[p + ".conv2"], blk.bn2, stride=blk.stride, pad=1)
+                identity = cur
+                if blk.downsample is not None:
+                    identity = conv_bn(cur, pk[p + ".down"], blk.downsample[1], stride=blk.stride, relu=False)
+                cur = conv_bn(out, pk[p + ".conv3"], blk.bn3, residual=identity)
+            taps.append(cur)
+        x2, x3, x4, x5 = taps
+        return [x5, x4, x3, x2, x1]
+
     def forward_act(self, x: torch.Tensor, impl: Optional[int] = None) -> List[Act]:
         """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1]."""
         ops.require_cuda(x, "ResNet101")
         impl = ops.default_impl() if impl is None else impl
         if self.training:
-            raise NotImplementedError("rsis_b200: train-mode BatchNorm (batch statistics) is not implemented yet; "
-                                      "call .eval() (the inference path of /root/reference/src/test.py:29-30)")
+            return self._forward_act_train(x, impl)
         fmt = ops.activation_format(impl)
         pk = self.packed(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         xa = ops.act_from_nchw(x, ops.FMT_F32)

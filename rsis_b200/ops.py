@@ -184,6 +184,46 @@ def convert(x: Act, fmt: int, out: Optional[Act] = None) -> Act:
     return y
 
 
+_bn_workspaces = {}
+
+
+def bn_train_stats(x: Act, bn) -> "tuple[torch.Tensor, torch.Tensor]":
+    """Train-mode nn.BatchNorm2d statistics of `x` (float32 dense NHWC): returns this batch's (scale, shift) and
+    updates bn.running_mean / running_var / num_batches_tracked in place, like the module's own forward would."""
+    lib = _lib.load()
+    assert x.fmt == FMT_F32 and x.dense
+    dev = x.t.device
+    c = x.c
+    key = dev.index
+    ws = _bn_workspaces.get(key)
+    if ws is None or ws.numel() < 2 * c:
+        ws = torch.zeros(max(2 * c, 8192), dtype=torch.float64, device=dev)
+        _bn_workspaces[key] = ws
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = -1.0 if bn.momentum is None else float(bn.momentum)
+    check(lib.rsis_bn_train_stats(x.ref(), _ptr(bn.weight), _ptr(bn.bias), float(bn.eps), momentum,
+                                  _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
+                                  _ptr(bn.num_batches_tracked) if track else None, ws.data_ptr(), scale.data_ptr(),
+                                  shift.data_ptr(), None, None, _lib.stream_ptr()), "bn_train_stats")
+    _lib.count_launch(2)
+    return scale, shift
+
+
+def affine_act(x: Act, scale: torch.Tensor, shift: torch.Tensor, residual: Optional[Act] = None, relu: bool = False,
+               out_fmt: int = FMT_F32, out2_fmt: Optional[int] = None):
+    """y = [relu](x * scale[c] + shift[c] [+ residual]) -- the normalise/ReLU/residual tail of a train-mode block."""
+    lib = _lib.load()
+    dev = x.t.device
+    y = Act.empty(x.n, x.h, x.w, x.c, out_fmt, dev)
+    y2 = Act.empty(x.n, x.h, x.w, x.c, out2_fmt, dev) if out2_fmt is not None else None
+    check(lib.rsis_affine_act(x.ref(), scale.data_ptr(), shift.data_ptr(), residual.ref() if residual is not None else None,
+                              int(relu), y.ref(), y2.ref() if y2 is not None else None, _lib.stream_ptr()), "affine_act")
+    _lib.count_launch(1)
+    return (y, y2) if y2 is not None else y
+
+
 def uses_tcgen05(impl: int) -> bool:
     return activation_format(impl) == FMT_SPLIT_BF16
 

@@ -467,6 +467,65 @@ def test_encoder_raw_taps(R, O, sw, impl):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# training-mode forward (train.py:71-77): BatchNorm2d with batch statistics
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("momentum", [0.1, None])
+def test_bn_train_stats_and_affine(R, momentum):
+    ops = R.ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.rand((3, 64, 9, 13), generator=g) * 4 - 1.5
+    res = torch.rand((3, 64, 9, 13), generator=g) - 0.5
+    bn = torch.nn.BatchNorm2d(64, momentum=momentum)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(64, generator=g) + 0.5)
+        bn.bias.copy_(torch.rand(64, generator=g) - 0.5)
+        bn.running_mean.copy_(torch.rand(64, generator=g) - 0.5)
+        bn.running_var.copy_(torch.rand(64, generator=g) + 0.5)
+    import copy
+    ref_bn = copy.deepcopy(bn).train()
+    with torch.no_grad():
+        ref = F.relu(ref_bn(x) + res)
+        ref_bn(x * 0.5 + 1.0)  # a second batch: running statistics and num_batches_tracked advance again
+    bn = bn.cuda().train()
+    xa = ops.act_from_nchw(x.cuda(), ops.FMT_F32)
+    scale, shift = ops.bn_train_stats(xa, bn)
+    y, y2 = ops.affine_act(xa, scale, shift, residual=ops.act_from_nchw(res.cuda(), ops.FMT_SPLIT_BF16), relu=True,
+                           out_fmt=ops.FMT_F32, out2_fmt=ops.FMT_SPLIT_BF16)
+    assert rel(y.nchw(), ref) < TOL_FP32 and rel(y2.float().permute(0, 3, 1, 2), ref) < TOL_FP32
+    ops.bn_train_stats(ops.act_from_nchw((x * 0.5 + 1.0).cuda(), ops.FMT_F32), bn)
+    assert rel(bn.running_mean, ref_bn.running_mean) < 1e-5 and rel(bn.running_var, ref_bn.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 2
+
+
+def test_encoder_train_mode_forward(R, O, sw, impl):
+    """encoder.train(): every BatchNorm2d normalises with the statistics of the batch (oracle: F.batch_norm(training))
+    and advances its running statistics; the decoder has no BatchNorm (dropout 0), so runIter's forward
+    (train.py:71-115) is this + the same decoder steps.  Backward is not built."""
+    args, enc, dec = _models(R, sw)
+    x = sw.synthetic_images(7, 4, 64, 96)
+    esd = sw.encoder_state_dict(1)
+    with torch.no_grad():
+        ref = O.feature_extractor(esd, x, bn=O._bn_train)
+        conv1 = F.conv2d(x, esd["base.conv1.weight"], stride=2, padding=3)
+    enc.train()
+    dec.train()
+    rm0 = enc.base.bn1.running_mean.clone()
+    with torch.no_grad():
+        feats = enc(x.cuda())
+        m, c, s, hidden = dec(feats, None)
+    tol = _tol(impl) * (5 if impl == "simt" else 1)  # batch statistics amplify fp32 reassociation noise a little
+    for f, r in zip(feats, ref):
+        assert rel(f, r) < tol
+    rm = 0.9 * rm0.cpu() + 0.1 * conv1.mean(dim=(0, 2, 3))
+    assert rel(enc.base.bn1.running_mean, rm) < 1e-4 and int(enc.base.bn1.num_batches_tracked) == 1
+    with torch.no_grad():
+        rm_, rc_, rs_, _ = O.rsis_step(sw.decoder_state_dict(1), ref, None)
+    assert rel(m, rm_) < _tol(impl) * 5 and rel(c, rc_) < _tol(impl) * 5
+    enc.eval()
+    dec.eval()
+
+
+# ---------------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE.json's full sizes
 # ---------------------------------------------------------------------------------------------------------
 def test_batch_sharding_is_exact_cfg2(R, sw, impl):
