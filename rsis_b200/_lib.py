@@ -119,15 +119,32 @@ def stream_ptr() -> int:
 
 
 _workspaces = {}
+_lane = 0
+
+
+class lane:
+    """Context manager: launches issued inside use split-K exchange buffer number `n` of the device.  Launches that
+    may run concurrently (a forked side stream) must not share a buffer; everything else uses lane 0."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def __enter__(self):
+        global _lane
+        self.prev, _lane = _lane, self.n
+        return self
+
+    def __exit__(self, *exc):
+        global _lane
+        _lane = self.prev
+        return False
 
 
 def workspace():
-    """(pointer, bytes) of the current device's split-K exchange buffer: allocated and zero-filled once; the kernels
-    leave its counters at zero.  This package issues all its launches of a device in one stream order (eager stream or
-    one captured graph at a time); callers that run rsis_b200 kernels concurrently on several streams of one device
-    must give each stream its own buffer through the C ABI."""
+    """(pointer, bytes) of the split-K exchange buffer of the current (device, lane): allocated and zero-filled once;
+    the kernels leave its counters at zero.  All launches of a lane are issued in one stream order."""
     dev = torch.cuda.current_device()
-    key = dev
+    key = (dev, _lane)
     ws = _workspaces.get(key)
     if ws is None:
         n = load().rsis_conv_workspace_bytes()

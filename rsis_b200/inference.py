@@ -49,8 +49,9 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
         if ws is None:
             ws = decoder.workspace(B, feature_sizes(H, W), x.device)
         if feats_op is None:
-            _, feats_op = encoder.forward_act(x, impl, operand_only=True)
-        ws.load_feats(decoder, feats_op, impl)
+            keep = ws.encode_into(encoder, decoder, x, impl)  # noqa: F841 -- alive until the join is enqueued
+        else:
+            ws.load_feats(decoder, feats_op, impl)
         ws.reset()
         for t in range(T):
             decoder.step_ws(ws, impl, None, out_classes[:, t], T * C, None, T, mask_prob=out_masks[:, t],

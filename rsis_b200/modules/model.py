@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import _lib, ops
 from ..ops import Act, PackedConv
 from .clstm import ConvLSTMCell
 from .vision import ResNet101
@@ -160,6 +160,7 @@ class DecoderWorkspace:
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
+        self.side_stream = torch.cuda.Stream(device=device)  # forked work: skip heads, class/stop heads
         self.t = 0
 
     def packs(self, decoder: "RSIS", l: int):
@@ -170,6 +171,29 @@ class DecoderWorkspace:
 
     def up_view(self, l: int, p: int) -> Act:
         return self.X[l][p].slice(0, self.up_c[l])
+
+    def encode_into(self, encoder: "FeatureExtractor", decoder: "RSIS", x: torch.Tensor, impl: int):
+        """Encoder pass of the fast path.  Each skip head and its hoisted gate convolution only need one backbone tap,
+        so they are forked onto the side stream the moment that tap exists and run under the rest of the backbone
+        (their own split-K lane; joined before the first decoder step)."""
+        heads = encoder.packed_heads(want_umma=True)
+        main = torch.cuda.current_stream(x.device)
+        side = self.side_stream
+        keep = []
+
+        def on_tap(idx, tap):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side), _lib.lane(1):
+                side.wait_event(ev)
+                f = ops.conv2d([tap], heads[idx], pad=encoder.padding, out_fmt=ops.FMT_SPLIT_BF16, impl=impl)
+                pc_skip, _ = self.packs(decoder, idx)
+                ops.conv2d([f], pc_skip, pad=pc_skip.kh // 2, impl=impl, out=self.P[idx])
+                keep.append((tap, f))
+
+        taps = encoder.base.forward_act(x, impl, on_tap=on_tap)
+        main.wait_stream(side)
+        return taps, keep  # the caller holds these until the join is enqueued (allocator reuse safety)
 
     def load_feats(self, decoder: "RSIS", feats: Sequence[Act], impl: int):
         """Hoisted, time-invariant part of the gates: P[l] = conv(skip_l, W_gates[:, skip channels]) + bias."""
@@ -241,6 +265,12 @@ class RSIS(nn.Module):
                                 h16_out=ws.h_view(l, 1 - p), impl=impl, gate_preact=ws.P[l])
             off += cell.hidden_size
         hl = ws.h[nlev - 1]
+        # the class / stop heads only need the side features: fork them next to the mask head
+        main = torch.cuda.current_stream(hl.t.device)
+        ws.side_stream.wait_stream(main)
+        with torch.cuda.stream(ws.side_stream):
+            ops.class_stop_heads(ws.side, self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight,
+                                 self.fc_stop.bias, class_probs, class_stride, stop_logit, stop_prob, stop_stride)
         if hl.c % 4 == 0 and hl.c <= 16:
             ops.upsample_mask_head(hl, 2 * hl.h, 2 * hl.w, self.conv_out.weight, self.conv_out.bias, mask_logits,
                                    mask_prob, mask_prob_stride)
@@ -250,8 +280,7 @@ class RSIS(nn.Module):
             ops.upsample_bilinear(hl, ws.up_last.h, ws.up_last.w, out=ws.up_last)
             ops.mask_head(ws.up_last, self.conv_out.weight, self.conv_out.bias, mask_logits, mask_prob,
                           mask_prob_stride)
-        ops.class_stop_heads(ws.side, self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight, self.fc_stop.bias,
-                             class_probs, class_stride, stop_logit, stop_prob, stop_stride)
+        main.wait_stream(ws.side_stream)
         ws.t += 1
 
     def step_act(self, feats: Sequence[Act], prev, impl: int, mask_logits: torch.Tensor,

@@ -139,8 +139,10 @@ class ResNet101(nn.Module):
         x2, x3, x4, x5 = taps
         return [x5, x4, x3, x2, x1]
 
-    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None) -> List[Act]:
-        """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1]."""
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, on_tap=None) -> List[Act]:
+        """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1].
+        on_tap(index in that list, tap): called as soon as a tap exists (eval mode), so that work which only needs
+        that tap (its skip head) can be forked onto a side stream while the rest of the backbone runs."""
         ops.require_cuda(x, "ResNet101")
         impl = ops.default_impl() if impl is None else impl
         if self.training:
@@ -149,6 +151,8 @@ class ResNet101(nn.Module):
         pk = self.packed(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         xa = ops.act_from_nchw(x, ops.FMT_F32)
         x1 = ops.conv2d([xa], pk["stem"], stride=2, pad=3, relu=True, out_fmt=fmt, impl=ops.IMPL_SIMT)
+        if on_tap is not None:
+            on_tap(4, x1)
         cur = ops.maxpool3x3s2(x1)
         taps = []
         for li in range(1, 5):
@@ -161,6 +165,8 @@ class ResNet101(nn.Module):
                     identity = ops.conv2d([cur], pk[p + ".down"], stride=blk.stride, out_fmt=fmt, impl=impl)
                 cur = ops.conv2d([out], pk[p + ".conv3"], relu=True, residual=identity, out_fmt=fmt, impl=impl)
             taps.append(cur)
+            if on_tap is not None:
+                on_tap(4 - li, cur)
         x2, x3, x4, x5 = taps
         return [x5, x4, x3, x2, x1]
 

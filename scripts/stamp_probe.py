@@ -19,7 +19,7 @@ for name, (N, Cin, H, W, Cout, k) in CASES.items():
     xa = ops.act_from_nchw(x, ops.FMT_SPLIT_BF16)
     y = ops.Act.empty(N, H, W, Cout, ops.FMT_SPLIT_BF16, "cuda")
     ptr, nbytes = _lib.workspace()
-    ws = _lib._workspaces[torch.cuda.current_device()]
+    ws = _lib._workspaces[(torch.cuda.current_device(), 0)]
     for it in range(3):
         ops.conv2d([xa], pc, pad=k // 2, impl=ops.IMPL_TCGEN05, out=y)
     torch.cuda.synchronize()
@@ -43,7 +43,7 @@ for name, (N, Ct, Ch, H, W) in CELLS.items():
     side = torch.zeros((N, 248), dtype=torch.int32, device="cuda")
     h = ops.Act.empty(N, H, W, Ch, ops.FMT_F32, "cuda"); c = ops.Act.empty(N, H, W, Ch, ops.FMT_F32, "cuda")
     h16 = ops.Act.empty(N, H, W, Ch, ops.FMT_SPLIT_BF16, "cuda")
-    ws = _lib._workspaces[torch.cuda.current_device()]
+    ws = _lib._workspaces[(torch.cuda.current_device(), 0)]
     for it in range(3):
         ops.convlstm_cell_x(x, pc, cprev, side, 0, h_out=h, c_out=c, h16_out=h16, impl=ops.IMPL_TCGEN05)
     torch.cuda.synchronize()
