@@ -1428,6 +1428,20 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
       if (chip > cost) cost = chip;
       if (best.cost < 0 || cost < best.cost) best = Plan{BN, stacked, 1, halo_ok ? 1 : 0, (long long)cost};
     }
+    // (c) split-K over 64-channel chunks with HALO staging (each slice still stages its halo once per chunk)
+    if (can_split && g_split_k && halo_ok && BN != 256 && chunks >= 2) {
+      const double tiles = (double)m_tiles_halo * tiles_n;
+      int S = (int)(g_num_sms / tiles);
+      if (S > chunks) S = chunks;
+      if (tiles <= g_num_sms && S >= 2) {
+        const double chunks_s = ceil_div(chunks, S);
+        const double mma = chunks_s * taps * (kBK / 16) * mpk * kMma;
+        const double load = chunks_s * (2.0 * kHaloRows * 128 + taps * b_item) / kSmBw;
+        const double units_per_warp = ceil_div((kBM / 4) * ceil_div(BN, 32), kEpiWarps * S);
+        double cost = kFixed + (mma > load ? mma : load) + 4500 + units_per_warp * (300 + 110.0 * S * (stacked ? 2 : 1));
+        if (cost < best.cost) best = Plan{BN, stacked, S, 1, (long long)cost};
+      }
+    }
     // (b) split-K over (tap, chunk) items, TAP staging, single wave
     if (can_split && g_split_k) {
       const double tiles = (double)m_tiles_tap * tiles_n;
