@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 7
+#define RSIS_ABI_VERSION 8
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -190,6 +190,59 @@ int rsis_class_stop_heads(const uint32_t* side_max, int n, int f, const float* w
                           int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
                           float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
                           int64_t stop_stride, rsis_stream_t stream);
+
+/* ---- backward primitives: `loss.backward()` of train.py:184 through vision.py / model.py / clstm.py ----------- */
+/* All gradients are float32 NHWC.  The DATA gradient of a convolution is itself a forward convolution
+ * (rsis_conv2d) of dy with the weights rsis_conv_dgrad_weights produces -- stride 1: pad' = k - 1 - pad; stride 2:
+ * rsis_dilate2x(dy) first (3x3) or afterwards (1x1).  Replaces autograd's ConvolutionBackward for nn.Conv2d at
+ * vision.py:12, torchvision Bottleneck.conv1-3/downsample, model.py:43-47 (sk*), clstm.py:17 (Gates), model.py:107
+ * (conv_out). */
+/* out_oihw[ci - ci0][co][kh-1-i][kw-1-j] = w_oihw[co][ci][i][j] for the input channels [ci0, ci0 + nci). */
+int rsis_conv_dgrad_weights(const float* w_oihw, int cout, int cin, int kh, int kw, int ci0, int nci, float* out_oihw,
+                            rsis_stream_t stream);
+/* dw_oihw[co][ci][i][j] (+)= sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*stride - pad + i, wo*stride - pad + j, ci];
+ * dbias[co] (+)= sum dy.  x, dy: dense NHWC, either element format.  accumulate = 0 overwrites.  Either of
+ * dw_oihw / dbias may be NULL.  Partial sums are combined with float atomics (summation order is not fixed). */
+int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad, float* dw_oihw,
+                      float* dbias, int accumulate, rsis_stream_t stream);
+/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; y->h in {2*x->h - 1, 2*x->h} (same for w).  float32 dense. */
+int rsis_dilate2x(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
+/* Backward of train-mode nn.BatchNorm2d (+ the ReLU that follows it, + the residual branch of `out += identity`):
+ *   g = dy * (y_act > 0)  (y_act = the post-activation output; NULL: no ReLU);  dbias = sum g;  dweight = sum g*xhat;
+ *   dx = weight * invstd * (g - dbias/M - xhat * dweight/M);  dres (optional) = g.
+ * x_raw / dy float32 dense; mean / invstd = the batch statistics rsis_bn_train_stats returned; workspace as for
+ * rsis_bn_train_stats; dx either element format. */
+int rsis_bn_train_bwd(const rsis_tensor* x_raw, const rsis_tensor* y_act, const rsis_tensor* dy, const float* weight,
+                      const float* mean, const float* invstd, double* workspace, float* dweight, float* dbias,
+                      const rsis_tensor* dx, const rsis_tensor* dres, rsis_stream_t stream);
+/* Backward of nn.MaxPool2d(3, 2, 1) (vision.py:15): dy goes to the first maximum of each window. */
+int rsis_maxpool3x3s2_bwd(const rsis_tensor* x, const rsis_tensor* dy, const rsis_tensor* dx, rsis_stream_t stream);
+/* Training-mode ConvLSTM cell = rsis_conv2d (gate pre-activations, bias folded) + this kernel (clstm.py:47-58).
+ * gates: float32 [N,H,W,4*Ch], block order [in|remember|out|cell]; overwritten with the ACTIVATED gates, which the
+ * backward needs.  h_out2 (optional, may be a pitched slice, either format) receives a second copy of h. */
+int rsis_lstm_gates_fwd(const rsis_tensor* gates, const float* c_prev, const rsis_tensor* h_out, const rsis_tensor* h_out2,
+                        const rsis_tensor* c_out, rsis_stream_t stream);
+/* Backward of the above: dh = dh_a + dh_b (either may be NULL; float32, pitched slices allowed), dc_next (may be
+ * NULL) -> dgates (pre-activation gradients, same layout as gates, either element format) and dc_prev. */
+int rsis_lstm_gates_bwd(const rsis_tensor* gates, const float* c_prev, const float* c_new, const rsis_tensor* dh_a,
+                        const rsis_tensor* dh_b, const rsis_tensor* dc_next, const rsis_tensor* dgates, float* dc_prev,
+                        rsis_stream_t stream);
+/* Global nn.MaxPool2d of model.py:143 with its arg-max: keys (the format rsis_class_stop_heads reads) and pixel
+ * indices at [n*side_stride + side_offset + c]; first maximum wins. */
+int rsis_global_maxpool(const rsis_tensor* h, uint32_t* side_keys, int32_t* side_idx, int side_stride, int side_offset,
+                        rsis_stream_t stream);
+/* dh[n, idx, c] += dside[n*side_stride + side_offset + c]. */
+int rsis_global_maxpool_bwd(const float* dside, const int32_t* side_idx, int side_stride, int side_offset,
+                            const rsis_tensor* dh, rsis_stream_t stream);
+/* Adjoint of rsis_upsample_bilinear: dy float32 (may be a pitched slice) -> dx float32 dense (overwritten). */
+int rsis_upsample_bilinear_bwd(const rsis_tensor* dy, const rsis_tensor* dx, rsis_stream_t stream);
+/* Backward of rsis_class_stop_heads: feat [N,F] (its feat_out), class_probs [N,C] dense, dclass [N,C] / dstop [N]
+ * (either may be NULL = zero); writes dfeat [N,F] and ACCUMULATES dw_class [C,F], db_class [C], dw_stop [F],
+ * db_stop [1].  dlogit_scratch: N*(C+1) floats. */
+int rsis_class_stop_heads_bwd(const float* feat, const float* class_probs, const float* dclass, const float* dstop,
+                              int n, int f, const float* w_class, int num_classes, const float* w_stop,
+                              float* dlogit_scratch, float* dfeat, float* dw_class, float* db_class, float* dw_stop,
+                              float* db_stop, rsis_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from typing import Optional
 
 import torch
 
@@ -17,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class Tensor(C.Structure):
@@ -65,6 +66,18 @@ SIGNATURES = {
     "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),
     "rsis_upsample_mask_head": (_I, [_TP, _P, _P, _I, _I, _I, _P, _P, C.c_int64, _P]),
     "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
+    # backward primitives
+    "rsis_conv_dgrad_weights": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rsis_conv2d_wgrad": (_I, [_TP, _TP, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "rsis_dilate2x": (_I, [_TP, _TP, _P]),
+    "rsis_bn_train_bwd": (_I, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _TP, _TP, _P]),
+    "rsis_maxpool3x3s2_bwd": (_I, [_TP, _TP, _TP, _P]),
+    "rsis_lstm_gates_fwd": (_I, [_TP, _P, _TP, _TP, _TP, _P]),
+    "rsis_lstm_gates_bwd": (_I, [_TP, _P, _P, _TP, _TP, _TP, _TP, _P, _P]),
+    "rsis_global_maxpool": (_I, [_TP, _P, _P, _I, _I, _P]),
+    "rsis_global_maxpool_bwd": (_I, [_P, _P, _I, _I, _TP, _P]),
+    "rsis_upsample_bilinear_bwd": (_I, [_TP, _TP, _P]),
+    "rsis_class_stop_heads_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -198,6 +211,29 @@ class Act:
         if fmt == FMT_F32:
             return Act(torch.zeros((n, h, w, c), dtype=torch.float32, device=device), fmt)
         return Act(torch.zeros((2, n, h, w, c), dtype=torch.bfloat16, device=device), fmt)
+
+    @staticmethod
+    def strided_view(t: torch.Tensor) -> "Optional[Act]":
+        """Zero-copy Act over a logical [N,C,H,W] float32 tensor whose memory is NHWC with a pixel pitch >= C (a dense
+        channels-last tensor, or a channel slice of a wider NHWC buffer -- e.g. a gradient returned as a slice of a
+        concatenated gradient buffer).  Returns None when the strides do not have that form."""
+        if t.dim() != 4 or t.dtype != torch.float32:
+            return None
+        n, c, h, w = t.shape
+        sn, sc, sh, sw = t.stride()
+        pitch = sw if w > 1 else (sh if h > 1 else (sn // max(h * w, 1) if n > 1 else c))
+        if pitch < c or pitch % 4 != 0 or t.data_ptr() % 16 != 0:
+            return None
+        want = {"c": 1, "w": pitch, "h": w * pitch, "n": h * w * pitch}
+        if (c > 1 and sc != want["c"]) or (w > 1 and sw != want["w"]) or (h > 1 and sh != want["h"]) or \
+                (n > 1 and sn != want["n"]):
+            return None
+        a = object.__new__(Act)
+        a.t, a.fmt, a.n, a.h, a.w, a.c = t, FMT_F32, n, h, w, c
+        a.c0, a.pitch = 0, pitch
+        a.desc = Tensor(t.data_ptr(), FMT_F32, n, h, w, c, 0 if c == pitch else pitch)
+        a.source_key = None
+        return a
 
     @staticmethod
     def from_nchw_view(x: torch.Tensor) -> "Act":

@@ -40,6 +40,19 @@ class ConvLSTMCell(nn.Module):
             self._packed[key] = hit
         return hit[1]
 
+    def packed_plain(self, want_umma: bool) -> PackedConv:
+        """The gate convolution as a plain convolution pack (reference output-channel order [in|remember|out|cell],
+        bias folded): the training-mode step computes the pre-activations with rsis_conv2d and keeps the activated
+        gates for the backward (rsis_lstm_gates_fwd / _bwd)."""
+        w, b = self.Gates.weight, self.Gates.bias
+        key = ("plain", want_umma)
+        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, PackedConv(w, b, None, want_umma=want_umma))
+            self._packed[key] = hit
+        return hit[1]
+
     def packed_hoisted(self, up_c: int, skip_c: int):
         """Packs for the hoisted form of the step (tcgen05 family): `input_ = [up(h_below) (up_c) | skip (skip_c)]`
         where the skip channels are the same at every time-step, so their share of the gate convolution (plus the

@@ -78,23 +78,29 @@ class FeatureExtractor(nn.Module):
             self._packed_tr_key = key
         return self._packed_tr
 
-    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, operand_only: bool = False):
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, raw: bool = False, operand_only: bool = False,
+                    tape: Optional[dict] = None):
         """Returns (feats f32 Acts, feats in the kernels' operand format or None) -- five entries each.
 
         operand_only (tcgen05 family): skip the float32 copy of the features (the decoder's fast path consumes the
-        split-bf16 operand copy only); returns (None, feats_op)."""
+        split-bf16 operand copy only); returns (None, feats_op).
+        tape (training mode): dict that receives what the backward needs (see ResNet101._forward_act_train)."""
         impl = ops.default_impl() if impl is None else impl
-        taps = self.base.forward_act(x, impl)
+        taps = self.base.forward_act(x, impl, tape=tape)
         if raw:
             return taps, None
         fmt = ops.activation_format(impl)
         if self.training:
             # train-mode skip heads (model.py:59-63): conv + bias, then BatchNorm2d with this batch's statistics
             feats, feats_op = [], []
-            for tap, pc, (sk, bn) in zip(taps, self.packed_heads_train(want_umma=(fmt == ops.FMT_SPLIT_BF16)),
-                                         self._heads()):
+            for hi, (tap, pc, (sk, bn)) in enumerate(zip(taps, self.packed_heads_train(
+                    want_umma=(fmt == ops.FMT_SPLIT_BF16)), self._heads())):
                 raw = ops.conv2d([tap], pc, pad=self.padding, out_fmt=ops.FMT_F32, impl=impl)
-                scale, shift = ops.bn_train_stats(raw, bn)
+                if tape is None:
+                    scale, shift = ops.bn_train_stats(raw, bn)
+                else:
+                    scale, shift, mean, invstd = ops.bn_train_stats(raw, bn, want_stats=True)
+                    tape[f"head{hi}"] = (tap, raw, None, mean, invstd)
                 if fmt == ops.FMT_F32:
                     y = ops.affine_act(raw, scale, shift, out_fmt=ops.FMT_F32)
                     y2 = y
@@ -119,6 +125,11 @@ class FeatureExtractor(nn.Module):
         return feats, feats_op
 
     def forward(self, x, semseg=False, raw=False):
+        if self.training and torch.is_grad_enabled() and not (semseg or raw):
+            # train.py:71-77,184: the outputs carry an autograd node whose backward runs the CUDA backward kernels
+            from ..autograd import encoder_forward_train
+            ops.require_cuda(x, "FeatureExtractor")
+            return encoder_forward_train(self, x)
         if semseg or raw:
             taps, _ = self.forward_act(x, raw=True)
             outs = tuple(ops.act_to_nchw(a) for a in taps)
@@ -323,9 +334,12 @@ class RSIS(nn.Module):
         return new_state
 
     def forward(self, skip_feats, prev_hidden_list):
+        ops.require_cuda(skip_feats[0], "RSIS")
+        if self.training and torch.is_grad_enabled():
+            from ..autograd import decoder_forward_train
+            return decoder_forward_train(self, skip_feats, prev_hidden_list)
         impl = ops.default_impl()
         fmt = ops.activation_format(impl)
-        ops.require_cuda(skip_feats[0], "RSIS")
         feats = [ops.act_from_nchw(t, fmt) for t in skip_feats]
         prev = None
         if prev_hidden_list is not None:

@@ -110,43 +110,53 @@ class ResNet101(nn.Module):
             self._packed_tr, self._packed_tr_key = pk, key
         return self._packed_tr
 
-    def _forward_act_train(self, x: torch.Tensor, impl: int) -> List[Act]:
+    def _forward_act_train(self, x: torch.Tensor, impl: int, tape: Optional[dict] = None) -> List[Act]:
         """Training-mode forward (train.py:71-77): every BatchNorm2d uses the statistics of this batch and updates its
-        running statistics; conv -> bn_train_stats -> affine_act (+residual, +ReLU)."""
+        running statistics; conv -> bn_train_stats -> affine_act (+residual, +ReLU).
+        tape (optional dict): receives, per convolution, what `loss.backward()` needs -- (input, raw conv output,
+        post-activation output, batch mean, batch 1/std) -- consumed by rsis_b200.autograd.encoder_backward."""
         fmt = ops.activation_format(impl)
         pk = self.packed_train(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         F32 = ops.FMT_F32
 
-        def conv_bn(src, pc, bn, stride=1, pad=0, relu=True, residual=None, which=impl):
+        def conv_bn(tag, src, pc, bn, stride=1, pad=0, relu=True, residual=None, which=impl):
             raw = ops.conv2d([src], pc, stride=stride, pad=pad, out_fmt=F32, impl=which)
-            scale, shift = ops.bn_train_stats(raw, bn)
-            return ops.affine_act(raw, scale, shift, residual=residual, relu=relu, out_fmt=fmt)
+            if tape is None:
+                scale, shift = ops.bn_train_stats(raw, bn)
+                return ops.affine_act(raw, scale, shift, residual=residual, relu=relu, out_fmt=fmt)
+            scale, shift, mean, invstd = ops.bn_train_stats(raw, bn, want_stats=True)
+            y = ops.affine_act(raw, scale, shift, residual=residual, relu=relu, out_fmt=fmt)
+            tape[tag] = (src, raw, y, mean, invstd)
+            return y
 
         xa = ops.act_from_nchw(x, F32)
-        x1 = conv_bn(xa, pk["stem"], self.bn1, stride=2, pad=3, which=ops.IMPL_SIMT)
+        x1 = conv_bn("stem", xa, pk["stem"], self.bn1, stride=2, pad=3, which=ops.IMPL_SIMT)
         cur = ops.maxpool3x3s2(x1)
+        if tape is not None:
+            tape["pool"] = (x1, cur)
         taps = []
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self, f"layer{li}")):
                 p = f"layer{li}.{bi}"
-                out = conv_bn(cur, pk[p + ".conv1"], blk.bn1)
-                out = conv_bn(out, pk[p + ".conv2"], blk.bn2, stride=blk.stride, pad=1)
+                out = conv_bn(p + ".conv1", cur, pk[p + ".conv1"], blk.bn1)
+                out = conv_bn(p + ".conv2", out, pk[p + ".conv2"], blk.bn2, stride=blk.stride, pad=1)
                 identity = cur
                 if blk.downsample is not None:
-                    identity = conv_bn(cur, pk[p + ".down"], blk.downsample[1], stride=blk.stride, relu=False)
-                cur = conv_bn(out, pk[p + ".conv3"], blk.bn3, residual=identity)
+                    identity = conv_bn(p + ".down", cur, pk[p + ".down"], blk.downsample[1], stride=blk.stride,
+                                       relu=False)
+                cur = conv_bn(p + ".conv3", out, pk[p + ".conv3"], blk.bn3, residual=identity)
             taps.append(cur)
         x2, x3, x4, x5 = taps
         return [x5, x4, x3, x2, x1]
 
-    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, on_tap=None) -> List[Act]:
+    def forward_act(self, x: torch.Tensor, impl: Optional[int] = None, on_tap=None, tape: Optional[dict] = None) -> List[Act]:
         """x: float32 [N,3,H,W] (any memory format) -> the five taps as NHWC activations [x5, x4, x3, x2, x1].
         on_tap(index in that list, tap): called as soon as a tap exists (eval mode), so that work which only needs
         that tap (its skip head) can be forked onto a side stream while the rest of the backbone runs."""
         ops.require_cuda(x, "ResNet101")
         impl = ops.default_impl() if impl is None else impl
         if self.training:
-            return self._forward_act_train(x, impl)
+            return self._forward_act_train(x, impl, tape)
         fmt = ops.activation_format(impl)
         pk = self.packed(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         xa = ops.act_from_nchw(x, ops.FMT_F32)

@@ -187,28 +187,36 @@ def convert(x: Act, fmt: int, out: Optional[Act] = None) -> Act:
 _bn_workspaces = {}
 
 
-def bn_train_stats(x: Act, bn) -> "tuple[torch.Tensor, torch.Tensor]":
-    """Train-mode nn.BatchNorm2d statistics of `x` (float32 dense NHWC): returns this batch's (scale, shift) and
-    updates bn.running_mean / running_var / num_batches_tracked in place, like the module's own forward would."""
-    lib = _lib.load()
-    assert x.fmt == FMT_F32 and x.dense
-    dev = x.t.device
-    c = x.c
+def _bn_workspace(dev, c: int) -> torch.Tensor:
     key = dev.index
     ws = _bn_workspaces.get(key)
     if ws is None or ws.numel() < 2 * c:
         ws = torch.zeros(max(2 * c, 8192), dtype=torch.float64, device=dev)
         _bn_workspaces[key] = ws
+    return ws
+
+
+def bn_train_stats(x: Act, bn, want_stats: bool = False):
+    """Train-mode nn.BatchNorm2d statistics of `x` (float32 dense NHWC): returns this batch's (scale, shift) and
+    updates bn.running_mean / running_var / num_batches_tracked in place, like the module's own forward would.
+    want_stats: also return (batch mean, batch 1/sqrt(var + eps)) -- what the backward needs."""
+    lib = _lib.load()
+    assert x.fmt == FMT_F32 and x.dense
+    dev = x.t.device
+    c = x.c
+    ws = _bn_workspace(dev, c)
     scale = torch.empty(c, dtype=torch.float32, device=dev)
     shift = torch.empty(c, dtype=torch.float32, device=dev)
+    mean = torch.empty(c, dtype=torch.float32, device=dev) if want_stats else None
+    invstd = torch.empty(c, dtype=torch.float32, device=dev) if want_stats else None
     track = bn.track_running_stats and bn.running_mean is not None
     momentum = -1.0 if bn.momentum is None else float(bn.momentum)
     check(lib.rsis_bn_train_stats(x.ref(), _ptr(bn.weight), _ptr(bn.bias), float(bn.eps), momentum,
                                   _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
                                   _ptr(bn.num_batches_tracked) if track else None, ws.data_ptr(), scale.data_ptr(),
-                                  shift.data_ptr(), None, None, _lib.stream_ptr()), "bn_train_stats")
+                                  shift.data_ptr(), _ptr(mean), _ptr(invstd), _lib.stream_ptr()), "bn_train_stats")
     _lib.count_launch(2)
-    return scale, shift
+    return (scale, shift, mean, invstd) if want_stats else (scale, shift)
 
 
 def affine_act(x: Act, scale: torch.Tensor, shift: torch.Tensor, residual: Optional[Act] = None, relu: bool = False,
@@ -327,3 +335,135 @@ def class_stop_heads(side_max: torch.Tensor, w_class, b_class, w_stop, b_stop, c
                                     class_probs.data_ptr(), class_stride, _ptr(stop_logit), _ptr(stop_prob),
                                     stop_stride, _lib.stream_ptr()), "class_stop_heads")
     _lib.count_launch(1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward primitives (loss.backward() of train.py:184); see include/rsis_b200.h
+# ---------------------------------------------------------------------------------------------------------
+def dgrad_weights(weight: torch.Tensor, ci0: int = 0, nci: Optional[int] = None) -> torch.Tensor:
+    """OIHW weights of the convolution that computes the data gradient w.r.t. input channels [ci0, ci0 + nci)."""
+    lib = _lib.load()
+    w = weight.detach().contiguous().float()
+    cout, cin, kh, kw = w.shape
+    nci = cin - ci0 if nci is None else nci
+    out = torch.empty((nci, cout, kh, kw), dtype=torch.float32, device=w.device)
+    check(lib.rsis_conv_dgrad_weights(w.data_ptr(), cout, cin, kh, kw, ci0, nci, out.data_ptr(), _lib.stream_ptr()),
+          "conv_dgrad_weights")
+    _lib.count_launch(1)
+    return out
+
+
+def conv2d_wgrad(x: Act, dy: Act, kh: int, kw: int, stride: int, pad: int, dw: Optional[torch.Tensor],
+                 dbias: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """dw (OIHW, float32 contiguous) / dbias (+)= the weight / bias gradient of conv(x) given dy."""
+    lib = _lib.load()
+    if dw is not None:
+        assert dw.is_contiguous() and dw.dtype == torch.float32 and tuple(dw.shape) == (dy.c, x.c, kh, kw)
+    check(lib.rsis_conv2d_wgrad(x.ref(), dy.ref(), kh, kw, stride, pad, _ptr(dw), _ptr(dbias), int(accumulate),
+                                _lib.stream_ptr()), "conv2d_wgrad")
+    _lib.count_launch((1 if dw is not None else 0) + (1 if dbias is not None else 0))
+
+
+def dilate2x(x: Act, ho: int, wo: int) -> Act:
+    lib = _lib.load()
+    y = Act.empty(x.n, ho, wo, x.c, FMT_F32, x.t.device)
+    check(lib.rsis_dilate2x(x.ref(), y.ref(), _lib.stream_ptr()), "dilate2x")
+    _lib.count_launch(1)
+    return y
+
+
+def bn_train_bwd(raw: Act, y_act: Optional[Act], dy: Act, weight: Optional[torch.Tensor], mean: torch.Tensor,
+                 invstd: torch.Tensor, dx_fmt: int = FMT_F32, want_dres: bool = False):
+    """Backward of train-mode BatchNorm (+ReLU when y_act is given).  Returns (dx, dres or None, dweight, dbias)."""
+    lib = _lib.load()
+    dev = raw.t.device
+    c = raw.c
+    dx = Act.empty(raw.n, raw.h, raw.w, c, dx_fmt, dev)
+    dres = Act.empty(raw.n, raw.h, raw.w, c, FMT_F32, dev) if want_dres else None
+    dweight = torch.empty(c, dtype=torch.float32, device=dev)
+    dbias = torch.empty(c, dtype=torch.float32, device=dev)
+    check(lib.rsis_bn_train_bwd(raw.ref(), y_act.ref() if y_act is not None else None, dy.ref(), _ptr(weight),
+                                mean.data_ptr(), invstd.data_ptr(), _bn_workspace(dev, c).data_ptr(),
+                                dweight.data_ptr(), dbias.data_ptr(), dx.ref(), dres.ref() if dres is not None else None,
+                                _lib.stream_ptr()), "bn_train_bwd")
+    _lib.count_launch(3)
+    return dx, dres, dweight, dbias
+
+
+def maxpool3x3s2_bwd(x: Act, dy: Act) -> Act:
+    lib = _lib.load()
+    dx = Act.empty(x.n, x.h, x.w, x.c, FMT_F32, x.t.device)
+    check(lib.rsis_maxpool3x3s2_bwd(x.ref(), dy.ref(), dx.ref(), _lib.stream_ptr()), "maxpool3x3s2_bwd")
+    _lib.count_launch(1)
+    return dx
+
+
+def lstm_gates_fwd(gates: Act, c_prev: Optional[torch.Tensor], h_out2: Optional[Act] = None):
+    """gates (pre-activations, overwritten with the activated gates) -> (h Act f32, c Act f32)."""
+    lib = _lib.load()
+    ch = gates.c // 4
+    dev = gates.t.device
+    h = Act.empty(gates.n, gates.h, gates.w, ch, FMT_F32, dev)
+    c = Act.empty(gates.n, gates.h, gates.w, ch, FMT_F32, dev)
+    check(lib.rsis_lstm_gates_fwd(gates.ref(), _ptr(c_prev), h.ref(), h_out2.ref() if h_out2 is not None else None,
+                                  c.ref(), _lib.stream_ptr()), "lstm_gates_fwd")
+    _lib.count_launch(1)
+    return h, c
+
+
+def lstm_gates_bwd(gates: Act, c_prev: Optional[torch.Tensor], c_new: torch.Tensor, dh_a: Optional[Act],
+                   dh_b: Optional[Act], dc_next: Optional[Act], dg_fmt: int = FMT_F32):
+    """Returns (dgates Act [N,H,W,4Ch] in dg_fmt, dc_prev Act f32)."""
+    lib = _lib.load()
+    dev = gates.t.device
+    dg = Act.empty(gates.n, gates.h, gates.w, gates.c, dg_fmt, dev)
+    dcp = Act.empty(gates.n, gates.h, gates.w, gates.c // 4, FMT_F32, dev)
+    r = lambda a: a.ref() if a is not None else None  # noqa: E731
+    check(lib.rsis_lstm_gates_bwd(gates.ref(), _ptr(c_prev), c_new.data_ptr(), r(dh_a), r(dh_b), r(dc_next), dg.ref(),
+                                  dcp.t.data_ptr(), _lib.stream_ptr()), "lstm_gates_bwd")
+    _lib.count_launch(1)
+    return dg, dcp
+
+
+def global_maxpool(h: Act, side_keys: torch.Tensor, side_idx: torch.Tensor, side_offset: int):
+    lib = _lib.load()
+    check(lib.rsis_global_maxpool(h.ref(), side_keys.data_ptr(), side_idx.data_ptr(), side_keys.shape[1], side_offset,
+                                  _lib.stream_ptr()), "global_maxpool")
+    _lib.count_launch(1)
+
+
+def global_maxpool_bwd(dside: torch.Tensor, side_idx: torch.Tensor, side_offset: int, dh: Act):
+    lib = _lib.load()
+    assert dside.is_contiguous() and dside.shape == side_idx.shape
+    check(lib.rsis_global_maxpool_bwd(dside.data_ptr(), side_idx.data_ptr(), side_idx.shape[1], side_offset, dh.ref(),
+                                      _lib.stream_ptr()), "global_maxpool_bwd")
+    _lib.count_launch(1)
+
+
+def upsample_bilinear_bwd(dy: Act, h: int, w: int) -> Act:
+    lib = _lib.load()
+    dx = Act.empty(dy.n, h, w, dy.c, FMT_F32, dy.t.device)
+    check(lib.rsis_upsample_bilinear_bwd(dy.ref(), dx.ref(), _lib.stream_ptr()), "upsample_bilinear_bwd")
+    _lib.count_launch(1)
+    return dx
+
+
+def class_stop_heads_bwd(feat: torch.Tensor, class_probs: torch.Tensor, dclass: Optional[torch.Tensor],
+                         dstop: Optional[torch.Tensor], w_class: torch.Tensor, w_stop: torch.Tensor):
+    """Returns (dfeat [N,F], dw_class, db_class, dw_stop, db_stop)."""
+    lib = _lib.load()
+    n, f = feat.shape
+    nc = w_class.shape[0]
+    dev = feat.device
+    dfeat = torch.empty((n, f), dtype=torch.float32, device=dev)
+    dwc = torch.zeros((nc, f), dtype=torch.float32, device=dev)
+    dbc = torch.zeros(nc, dtype=torch.float32, device=dev)
+    dws = torch.zeros((1, f), dtype=torch.float32, device=dev)
+    dbs = torch.zeros(1, dtype=torch.float32, device=dev)
+    scratch = torch.empty(n * (nc + 1), dtype=torch.float32, device=dev)
+    check(lib.rsis_class_stop_heads_bwd(feat.data_ptr(), class_probs.data_ptr(), _ptr(dclass), _ptr(dstop), n, f,
+                                        w_class.data_ptr(), nc, w_stop.data_ptr(), scratch.data_ptr(),
+                                        dfeat.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), dws.data_ptr(),
+                                        dbs.data_ptr(), _lib.stream_ptr()), "class_stop_heads_bwd")
+    _lib.count_launch(2)
+    return dfeat, dwc, dbc, dws, dbs
