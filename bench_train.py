@@ -1,0 +1,172 @@
+#!/usr/bin/env python
+"""Training-step benchmark of the RSIS hot path: BASELINE.json configs[3] per-rank shard -- 8 images 256x256, T=10,
+21 classes: train-mode encoder forward, T decoder steps, `loss.backward()` through both and
+the ONE data-parallel gradient all-reduce over a flat buffer (section 8e) when launched on N ranks.
+
+    python bench_train.py --steps K --warmup W                      # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N ... bench_train.py --gpus N
+
+Prints ONE JSON line: images/s of whole training steps (forward + backward + all-reduce; the optimiser step and the
+criteria / Hungarian matching of train.py:96-176 are outside the hot path), with the forward / backward / all-reduce
+split, and -- on rank 0, `--cpu-steps` > 0 -- the same step through autograd over the CPU oracle (the reference's
+own torch CPU primitives) as the reported CPU baseline.  This is an extra data point next to bench.py, whose metric
+(masks/s of the inference pass) is the one BASELINE.json names.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B, H, W, T, NUM_CLASSES = 8, 256, 256, 10, 21
+
+
+def loss_fn(masks, classes, stops):
+    """Stand-in for the criteria of train.py:159-176 (outside the hot path): touches every output of every step."""
+    loss = 0
+    for m, c, s in zip(masks, classes, stops):
+        loss = loss + (torch.sigmoid(m) ** 2).mean() + (c ** 2).sum(-1).mean() + (s ** 2).mean()
+    return loss
+
+
+def cpu_step_time(steps):
+    from oracle import rsis_oracle as O, synth_weights as sw
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    esd = {k: v.clone() for k, v in sw.encoder_state_dict(1).items()}
+    dsd = {k: v.clone() for k, v in sw.decoder_state_dict(1, num_classes=NUM_CLASSES).items()}
+    for sd in (esd, dsd):
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(True)
+    x = sw.synthetic_images(123, B, H, W)
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        feats = O.feature_extractor(esd, x, bn=O._bn_train)
+        hidden = None
+        masks, classes, stops = [], [], []
+        for _ in range(T):
+            m, c, s, hidden = O.rsis_step(dsd, feats, hidden)
+            masks.append(m)
+            classes.append(c)
+            stops.append(s)
+        loss_fn(masks, classes, stops).backward()
+        for sd in (esd, dsd):
+            for v in sd.values():
+                v.grad = None
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    return times, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=1)
+    a = ap.parse_args()
+
+    import rsis_b200
+    from rsis_b200 import dist as rdist, ops
+    from rsis_b200.autograd import GradBucket, backward_impl
+    from oracle import synth_weights as sw
+    from oracle import ref_shims as rs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_train.py: no CUDA device; the CUDA path has no CPU fallback")
+    rank, local_rank, world = rdist.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    args = rs.make_args(num_classes=NUM_CLASSES, maxseqlen=T)
+    args.hidden_size = int(args.hidden_size)
+    args.use_gpu = True
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1, num_classes=NUM_CLASSES))
+    enc.to(dev).train()
+    dec.to(dev).train()
+    x = sw.synthetic_images(123 + rank, B, H, W).to(dev)
+    bucket = GradBucket(list(enc.parameters()) + list(dec.parameters()))
+
+    def step(ev=None):
+        bucket.zero()
+        if ev:
+            ev[0].record()
+        feats = enc(x)
+        hidden = None
+        masks, classes, stops = [], [], []
+        for _ in range(T):
+            m, c, s, hidden = dec(feats, hidden)
+            masks.append(m)
+            classes.append(c)
+            stops.append(s)
+        loss = loss_fn(masks, classes, stops)
+        if ev:
+            ev[1].record()
+        loss.backward()
+        if ev:
+            ev[2].record()
+        bucket.all_reduce()
+        if ev:
+            ev[3].record()
+        return loss
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    n0 = ops.launch_count()
+    rdist.barrier()
+    evs = []
+    for _ in range(a.steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        step(ev)
+        evs.append(ev)
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    launches = ops.launch_count() - n0
+    tot = sum(e[0].elapsed_time(e[3]) for e in evs) * 1e-3
+    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) * 1e-3 / a.steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / a.steps
+    ar = sum(e[2].elapsed_time(e[3]) for e in evs) * 1e-3 / a.steps
+    total_s = rdist.max_over_ranks(tot)
+    value = world * B * a.steps / total_s
+    cpu = None
+    if rank == 0 and a.cpu_steps > 0:
+        times, threads = cpu_step_time(a.cpu_steps)
+        cpu = {"value": B * len(times) / sum(times), "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"{len(times)} training step(s) (forward + autograd backward) of the same shard after 1 warm-up, "
+                         f"torch CPU fp32, {threads} threads"}
+    if rank == 0:
+        impl = ops.default_impl()
+        print(json.dumps({
+            "metric": "training images/sec (forward + backward + gradient all-reduce) at 256x256 T=10",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": 1e3 * total_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[3] per-rank shard: Pascal VOC training step, batch 8 per GPU, "
+                                   "256x256, T=10 (fp32 gradients; split-bf16 tensor-core operands where tcgen05 is used)",
+                       "batch_per_gpu": B, "global_batch": B * world, "T": T, "num_classes": NUM_CLASSES,
+                       "parallelism": f"dp{world}: one flat-buffer gradient all-reduce per step ({bucket.flat.numel() * 4} bytes)",
+                       "forward_impl": "auto" if ops.uses_tcgen05(impl) else "simt",
+                       "backward_impl": "auto" if backward_impl(impl) != ops.IMPL_SIMT else "simt",
+                       "masks_per_s": value * T},
+            "split_ms": {"forward": 1e3 * fwd, "backward": 1e3 * bwd, "all_reduce": 1e3 * ar},
+            "gpu_launches": launches, "launches_per_step": launches / a.steps, "cpu_baseline": cpu,
+        }))
+    rdist.barrier()
+    rdist.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
