@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step only")
     a = ap.parse_args()
 
     import rsis_b200
@@ -96,12 +97,48 @@ def main():
     enc.to(dev).train()
     dec.to(dev).train()
     x = sw.synthetic_images(123 + rank, B, H, W).to(dev)
+    from rsis_b200.training import TrainStep
     bucket = GradBucket(list(enc.parameters()) + list(dec.parameters()))
 
-    def step(ev=None):
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize(dev)
+        n0 = ops.launch_count()
+        rdist.barrier()
+        evs = []
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        rdist.barrier()
+        tot = sum(s_.elapsed_time(e_) for s_, e_ in evs) * 1e-3
+        return rdist.max_over_ranks(tot), ops.launch_count() - n0
+
+    # ---- CUDA graph: pack + forward + loss + backward captured once, replayed; all-reduce after the replay ----
+    graph_s = None
+    graph_err = None
+    if not a.no_graph:
+        try:
+            graphed = TrainStep(enc, dec, T, loss_fn, bucket=bucket, cuda_graph=True)
+            graph_s, _ = timed(lambda: graphed(x), a.steps, max(a.warmup, 3))
+        except Exception as e:  # report, do not hide: the eager number stands
+            import traceback
+            traceback.print_exc()
+            graph_err = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.synchronize(dev)
+    # ---- eager: every kernel launched from Python each step (host-bound) ----
+    eager = TrainStep(enc, dec, T, loss_fn, bucket=bucket, cuda_graph=False)
+    eager_s, eager_launches = timed(lambda: eager(x), a.steps, max(a.warmup, 3))
+    # forward / backward split of the eager step (CUDA events around loss.backward())
+    split = None
+    if rank == 0:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         bucket.zero()
-        if ev:
-            ev[0].record()
+        ev[0].record()
         feats = enc(x)
         hidden = None
         masks, classes, stops = [], [], []
@@ -111,35 +148,15 @@ def main():
             classes.append(c)
             stops.append(s)
         loss = loss_fn(masks, classes, stops)
-        if ev:
-            ev[1].record()
+        ev[1].record()
         loss.backward()
-        if ev:
-            ev[2].record()
-        bucket.all_reduce()
-        if ev:
-            ev[3].record()
-        return loss
-
-    for _ in range(max(a.warmup, 3)):
-        step()
-    torch.cuda.synchronize(dev)
-    n0 = ops.launch_count()
-    rdist.barrier()
-    evs = []
-    for _ in range(a.steps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        step(ev)
-        evs.append(ev)
-    torch.cuda.synchronize(dev)
-    rdist.barrier()
-    launches = ops.launch_count() - n0
-    tot = sum(e[0].elapsed_time(e[3]) for e in evs) * 1e-3
-    fwd = sum(e[0].elapsed_time(e[1]) for e in evs) * 1e-3 / a.steps
-    bwd = sum(e[1].elapsed_time(e[2]) for e in evs) * 1e-3 / a.steps
-    ar = sum(e[2].elapsed_time(e[3]) for e in evs) * 1e-3 / a.steps
-    total_s = rdist.max_over_ranks(tot)
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        split = {"forward": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2])}
+        del feats, hidden, masks, classes, stops, loss
+    total_s = graph_s if graph_s is not None else eager_s
     value = world * B * a.steps / total_s
+    launches = eager_launches
     cpu = None
     if rank == 0 and a.cpu_steps > 0:
         times, threads = cpu_step_time(a.cpu_steps)
@@ -160,7 +177,10 @@ def main():
                        "forward_impl": "auto" if ops.uses_tcgen05(impl) else "simt",
                        "backward_impl": "auto" if backward_impl(impl) != ops.IMPL_SIMT else "simt",
                        "masks_per_s": value * T},
-            "split_ms": {"forward": 1e3 * fwd, "backward": 1e3 * bwd, "all_reduce": 1e3 * ar},
+            "mode": "cuda_graph" if graph_s is not None else "eager",
+            "eager_ms_per_step": 1e3 * eager_s / a.steps,
+            "graph_ms_per_step": None if graph_s is None else 1e3 * graph_s / a.steps, "graph_error": graph_err,
+            "eager_split_ms": split,
             "gpu_launches": launches, "launches_per_step": launches / a.steps, "cpu_baseline": cpu,
         }))
     rdist.barrier()

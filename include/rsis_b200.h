@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 8
+#define RSIS_ABI_VERSION 10
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -202,19 +202,29 @@ int rsis_conv_dgrad_weights(const float* w_oihw, int cout, int cin, int kh, int 
                             rsis_stream_t stream);
 /* dw_oihw[co][ci][i][j] (+)= sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*stride - pad + i, wo*stride - pad + j, ci];
  * dbias[co] (+)= sum dy.  x, dy: dense NHWC, either element format.  accumulate = 0 overwrites.  Either of
- * dw_oihw / dbias may be NULL.  Partial sums are combined with float atomics (summation order is not fixed). */
+ * dw_oihw / dbias may be NULL.  Partial sums are combined with float atomics (summation order is not fixed).
+ * impl: RSIS_IMPL_SIMT = fp32 CUDA cores (any shape); RSIS_IMPL_AUTO = the tcgen05 kernel (pixels as the contraction
+ * dimension, MN-major split-bf16 operands, three products per multiply) for stride-1 1x1 / 3x3 convolutions whose x
+ * and dy are both RSIS_FMT_SPLIT_BF16, CUDA cores otherwise; RSIS_IMPL_TCGEN05 = that kernel or RSIS_ERR_UNSUPPORTED.
+ * workspace: rsis_wgrad_workspace_bytes() bytes, 16-byte aligned, zero-filled ONCE after allocation (the call leaves it
+ * zeroed), not shared by launches that may run concurrently; NULL = CUDA cores only. */
+size_t rsis_wgrad_workspace_bytes(void);
 int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad, float* dw_oihw,
-                      float* dbias, int accumulate, rsis_stream_t stream);
-/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; y->h in {2*x->h - 1, 2*x->h} (same for w).  float32 dense. */
+                      float* dbias, int accumulate, int impl, void* workspace, size_t workspace_bytes,
+                      rsis_stream_t stream);
+/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; y->h in {2*x->h - 1, 2*x->h} (same for w).  x float32 dense, y dense in
+ * either element format. */
 int rsis_dilate2x(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
 /* Backward of train-mode nn.BatchNorm2d (+ the ReLU that follows it, + the residual branch of `out += identity`):
  *   g = dy * (y_act > 0)  (y_act = the post-activation output; NULL: no ReLU);  dbias = sum g;  dweight = sum g*xhat;
  *   dx = weight * invstd * (g - dbias/M - xhat * dweight/M);  dres (optional) = g.
  * x_raw / dy float32 dense; mean / invstd = the batch statistics rsis_bn_train_stats returned; workspace as for
- * rsis_bn_train_stats; dx either element format. */
+ * rsis_bn_train_stats; dx either element format.  dweight / dbias receive this call's sums (overwritten);
+ * dweight_acc / dbias_acc (optional) are additionally incremented by them (gradient accumulation buffers). */
 int rsis_bn_train_bwd(const rsis_tensor* x_raw, const rsis_tensor* y_act, const rsis_tensor* dy, const float* weight,
                       const float* mean, const float* invstd, double* workspace, float* dweight, float* dbias,
-                      const rsis_tensor* dx, const rsis_tensor* dres, rsis_stream_t stream);
+                      float* dweight_acc, float* dbias_acc, const rsis_tensor* dx, const rsis_tensor* dres,
+                      rsis_stream_t stream);
 /* Backward of nn.MaxPool2d(3, 2, 1) (vision.py:15): dy goes to the first maximum of each window. */
 int rsis_maxpool3x3s2_bwd(const rsis_tensor* x, const rsis_tensor* dy, const rsis_tensor* dx, rsis_stream_t stream);
 /* Training-mode ConvLSTM cell = rsis_conv2d (gate pre-activations, bias folded) + this kernel (clstm.py:47-58).
@@ -227,10 +237,14 @@ int rsis_lstm_gates_fwd(const rsis_tensor* gates, const float* c_prev, const rsi
 int rsis_lstm_gates_bwd(const rsis_tensor* gates, const float* c_prev, const float* c_new, const rsis_tensor* dh_a,
                         const rsis_tensor* dh_b, const rsis_tensor* dc_next, const rsis_tensor* dgates, float* dc_prev,
                         rsis_stream_t stream);
-/* Global nn.MaxPool2d of model.py:143 with its arg-max: keys (the format rsis_class_stop_heads reads) and pixel
- * indices at [n*side_stride + side_offset + c]; first maximum wins. */
-int rsis_global_maxpool(const rsis_tensor* h, uint32_t* side_keys, int32_t* side_idx, int side_stride, int side_offset,
+/* Global nn.MaxPool2d of model.py:143 with its arg-max.  rsis_global_maxpool folds h into side_packed
+ * [n*side_stride + side_offset + c] = max over pixels of (order-preserving key << 32 | ~pixel index) -- zero-filled
+ * before the step; the FIRST maximum wins ties.  After all levels rsis_global_maxpool_finish unpacks the n*side_stride
+ * entries into keys (the format rsis_class_stop_heads reads) and pixel indices. */
+int rsis_global_maxpool(const rsis_tensor* h, uint64_t* side_packed, int side_stride, int side_offset,
                         rsis_stream_t stream);
+int rsis_global_maxpool_finish(const uint64_t* side_packed, int n, int side_stride, uint32_t* side_keys,
+                               int32_t* side_idx, rsis_stream_t stream);
 /* dh[n, idx, c] += dside[n*side_stride + side_offset + c]. */
 int rsis_global_maxpool_bwd(const float* dside, const int32_t* side_idx, int side_stride, int side_offset,
                             const rsis_tensor* dh, rsis_stream_t stream);

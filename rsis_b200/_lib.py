@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 8
+ABI_VERSION = 10
 
 
 class Tensor(C.Structure):
@@ -68,13 +68,15 @@ SIGNATURES = {
     "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
     # backward primitives
     "rsis_conv_dgrad_weights": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "rsis_conv2d_wgrad": (_I, [_TP, _TP, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "rsis_wgrad_workspace_bytes": (C.c_size_t, []),
+    "rsis_conv2d_wgrad": (_I, [_TP, _TP, _I, _I, _I, _I, _P, _P, _I, _I, _P, C.c_size_t, _P]),
     "rsis_dilate2x": (_I, [_TP, _TP, _P]),
-    "rsis_bn_train_bwd": (_I, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _TP, _TP, _P]),
+    "rsis_bn_train_bwd": (_I, [_TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _P, _P, _TP, _TP, _P]),
     "rsis_maxpool3x3s2_bwd": (_I, [_TP, _TP, _TP, _P]),
     "rsis_lstm_gates_fwd": (_I, [_TP, _P, _TP, _TP, _TP, _P]),
     "rsis_lstm_gates_bwd": (_I, [_TP, _P, _P, _TP, _TP, _TP, _TP, _P, _P]),
-    "rsis_global_maxpool": (_I, [_TP, _P, _P, _I, _I, _P]),
+    "rsis_global_maxpool": (_I, [_TP, _P, _I, _I, _P]),
+    "rsis_global_maxpool_finish": (_I, [_P, _I, _I, _P, _P, _P]),
     "rsis_global_maxpool_bwd": (_I, [_P, _P, _I, _I, _TP, _P]),
     "rsis_upsample_bilinear_bwd": (_I, [_TP, _TP, _P]),
     "rsis_class_stop_heads_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -163,6 +165,20 @@ def workspace():
         n = load().rsis_conv_workspace_bytes()
         ws = torch.zeros(n, dtype=torch.uint8, device=torch.device("cuda", dev))
         _workspaces[key] = ws
+    return ws.data_ptr(), ws.numel()
+
+
+_wgrad_workspaces = {}
+
+
+def wgrad_workspace():
+    """(pointer, bytes) of the device's weight-gradient scratch (zero-filled once; the kernels leave it zeroed)."""
+    dev = torch.cuda.current_device()
+    ws = _wgrad_workspaces.get(dev)
+    if ws is None:
+        n = load().rsis_wgrad_workspace_bytes()
+        ws = torch.zeros(n, dtype=torch.uint8, device=torch.device("cuda", dev))
+        _wgrad_workspaces[dev] = ws
     return ws.data_ptr(), ws.numel()
 
 

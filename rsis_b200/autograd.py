@@ -12,8 +12,8 @@ output (ReLU mask) and the batch statistics.  Per decoder step and level: the co
 `[up(h_{l-1}) | skip_l | h_prev_l]`, the activated gates, c_prev, c and the arg-max of the side max-pool.
 
 Kernel family of the backward convolutions: env RSIS_B200_BWD_IMPL = simt (exact fp32 CUDA cores) | auto (data
-gradients on the tcgen05 convolution where its shape rules allow; weight gradients stay on CUDA cores).  Default: auto
-when the forward runs on tcgen05, simt otherwise.
+gradients on the tcgen05 convolution, weight gradients on the tcgen05 MN-major kernel, wherever their shape rules
+allow; gradients then travel as split-bf16 planes).  Default: auto when the forward runs on tcgen05, simt otherwise.
 """
 from __future__ import annotations
 
@@ -53,6 +53,18 @@ def grad_as_act(t: Optional[torch.Tensor]) -> Optional[Act]:
     if a is not None:
         return a
     return ops.nchw_to_nhwc(t, F32)
+
+
+def _grad_target(p: torch.Tensor):
+    """Where the gradient of parameter `p` is written.  When `p.grad` already exists as a float32 contiguous tensor
+    (GradBucket views, or gradients left by an earlier backward) the kernels ACCUMULATE into it directly and the
+    autograd node reports no gradient for `p` -- this removes one elementwise add per parameter and backward node
+    (autograd's AccumulateGrad).  Otherwise a fresh tensor is returned to autograd.
+    Returns (tensor, accumulate flag, direct flag)."""
+    g = p.grad
+    if g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape and g.device == p.device:
+        return g, True, True
+    return torch.empty_like(p, memory_format=torch.contiguous_format), False, False
 
 
 class _DgradCache:
@@ -97,7 +109,7 @@ def conv_dgrad(cache: _DgradCache, dy: Act, weight: torch.Tensor, stride: int, p
         return ops.dilate2x(low, in_h, in_w)
     if dy.fmt != F32:
         dy = ops.convert(dy, F32)
-    return ops.conv2d([ops.dilate2x(dy, in_h, in_w)], pc, pad=k - 1 - pad, out_fmt=F32, impl=bimpl)
+    return ops.conv2d([ops.dilate2x(dy, in_h, in_w, _grad_fmt(bimpl))], pc, pad=k - 1 - pad, out_fmt=F32, impl=bimpl)
 
 
 # =============================================================================================================
@@ -119,17 +131,26 @@ def encoder_backward(enc, tape: dict, dfeats: Sequence[Optional[torch.Tensor]], 
         """BatchNorm(+ReLU) backward, then the weight (and bias) gradient of the convolution feeding it.
         Returns (draw, dres)."""
         src, raw, y, mean, invstd = tape[tag]
+        gw, _, direct_w = _grad_target(bn.weight)
+        gb, _, direct_b = _grad_target(bn.bias)
         draw, dres, dw_bn, db_bn = ops.bn_train_bwd(raw, y if relu else None, dy, bn.weight, mean, invstd,
-                                                    dx_fmt=gfmt if dx_fmt is None else dx_fmt, want_dres=want_dres)
-        put(bn.weight, dw_bn)
-        put(bn.bias, db_bn)
+                                                    dx_fmt=gfmt if dx_fmt is None else dx_fmt, want_dres=want_dres,
+                                                    dweight_acc=gw if direct_w else None,
+                                                    dbias_acc=gb if direct_b else None)
+        if not direct_w:
+            put(bn.weight, dw_bn)
+        if not direct_b:
+            put(bn.bias, db_bn)
         k = conv.weight.shape[-1]
-        dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-        db = torch.empty_like(conv.bias) if conv.bias is not None else None
-        ops.conv2d_wgrad(src, draw, k, k, stride, pad, dw, db)
-        put(conv.weight, dw)
-        if db is not None:
-            put(conv.bias, db)
+        dw, acc_w, direct_cw = _grad_target(conv.weight)
+        ops.conv2d_wgrad(src, draw, k, k, stride, pad, dw, None, accumulate=acc_w)
+        if not direct_cw:
+            put(conv.weight, dw)
+        if conv.bias is not None:
+            db, acc_b, direct_cb = _grad_target(conv.bias)
+            ops.conv2d_wgrad(src, draw, k, k, stride, pad, None, db, accumulate=acc_b)
+            if not direct_cb:
+                put(conv.bias, db)
         return draw, dres, src
 
     # ---- skip heads (model.py:59-63): BatchNorm (no ReLU) + biased 3x3 convolution ----
@@ -220,8 +241,7 @@ def decoder_step_train(dec, feats: Sequence[Act], prev, impl: int):
     dev = feats[0].t.device
     if dec.fc_class.in_features != dec.fc_dim:
         raise RuntimeError("fc_class.in_features does not match the decoder's side-feature width")
-    keys = torch.zeros((n, dec.fc_dim), dtype=torch.int32, device=dev)
-    idx = torch.empty((n, dec.fc_dim), dtype=torch.int32, device=dev)
+    packed = torch.zeros((n, dec.fc_dim), dtype=torch.int64, device=dev)
     levels = []
     state = []
     h_below: Optional[Act] = None
@@ -247,7 +267,7 @@ def decoder_step_train(dec, feats: Sequence[Act], prev, impl: int):
         k = cell.Gates.weight.shape[-1]
         gates = ops.conv2d([X], pc, pad=k // 2, out_fmt=F32, impl=impl)
         h, c = ops.lstm_gates_fwd(gates, c_prev.t if c_prev is not None else None)
-        ops.global_maxpool(h, keys, idx, off)
+        ops.global_maxpool(h, packed, off)
         levels.append(dict(X=X, gates=gates, c_prev=c_prev, c=c, up_c=up_c, skip_c=skip_c, ch=ch, off=off,
                            hw_below=(h_below.h, h_below.w) if h_below is not None else None))
         state.append((h, c))
@@ -258,6 +278,7 @@ def decoder_step_train(dec, feats: Sequence[Act], prev, impl: int):
     class_probs = torch.empty((n, dec.num_classes), dtype=torch.float32, device=dev)
     stop = torch.empty((n, 1), dtype=torch.float32, device=dev)
     side = torch.empty((n, dec.fc_dim), dtype=torch.float32, device=dev)
+    keys, idx = ops.global_maxpool_finish(packed)
     ops.mask_head(up, dec.conv_out.weight, dec.conv_out.bias, out_mask)
     ops.class_stop_heads(keys, dec.fc_class.weight, dec.fc_class.bias, dec.fc_stop.weight, dec.fc_stop.bias,
                          class_probs, dec.num_classes, stop, None, 1, feat_out=side)
@@ -283,10 +304,14 @@ def decoder_step_backward(dec, saved: dict, dmask, dclass, dstop, dh_out: List[O
     if dclass is not None or dstop is not None:
         dc_ = dclass.reshape(n, -1).contiguous().float() if dclass is not None else None
         ds_ = dstop.reshape(n).contiguous().float() if dstop is not None else None
+        hp = [dec.fc_class.weight, dec.fc_class.bias, dec.fc_stop.weight, dec.fc_stop.bias]
+        tg = [_grad_target(p_) for p_ in hp]
+        direct = all(t_[2] for t_ in tg)
         dside, dwc, dbc, dws, dbs = ops.class_stop_heads_bwd(saved["side"], saved["class_probs"], dc_, ds_,
-                                                             dec.fc_class.weight, dec.fc_stop.weight)
-        G[id(dec.fc_class.weight)], G[id(dec.fc_class.bias)] = dwc, dbc
-        G[id(dec.fc_stop.weight)], G[id(dec.fc_stop.bias)] = dws, dbs
+                                                             dec.fc_class.weight, dec.fc_stop.weight,
+                                                             into=[t_[0] for t_ in tg] if direct else None)
+        if not direct:
+            G[id(hp[0])], G[id(hp[1])], G[id(hp[2])], G[id(hp[3])] = dwc, dbc, dws, dbs
 
     # ---- mask head (conv_out on the x2-upsampled last hidden state) ----
     h_l, w_l = saved["last_hw"]
@@ -296,10 +321,17 @@ def decoder_step_backward(dec, saved: dict, dmask, dclass, dstop, dh_out: List[O
         dm = dmask.contiguous().float().view(n, up.h, up.w, 1)  # C = 1: NCHW and NHWC coincide
         dm_act = Act(dm, F32)
         k = dec.conv_out.weight.shape[-1]
-        dw = torch.empty_like(dec.conv_out.weight, memory_format=torch.contiguous_format)
-        db = torch.empty_like(dec.conv_out.bias)
-        ops.conv2d_wgrad(up, dm_act, k, k, 1, k // 2, dw, db)
-        G[id(dec.conv_out.weight)], G[id(dec.conv_out.bias)] = dw, db
+        dw, acc_w, direct_w = _grad_target(dec.conv_out.weight)
+        db, acc_b, direct_b = _grad_target(dec.conv_out.bias)
+        if acc_w == acc_b:
+            ops.conv2d_wgrad(up, dm_act, k, k, 1, k // 2, dw, db, accumulate=acc_w)
+        else:
+            ops.conv2d_wgrad(up, dm_act, k, k, 1, k // 2, dw, None, accumulate=acc_w)
+            ops.conv2d_wgrad(up, dm_act, k, k, 1, k // 2, None, db, accumulate=acc_b)
+        if not direct_w:
+            G[id(dec.conv_out.weight)] = dw
+        if not direct_b:
+            G[id(dec.conv_out.bias)] = db
         d_up = conv_dgrad(cache, dm_act, dec.conv_out.weight, 1, k // 2, up.h, up.w, ops.IMPL_SIMT)
         dh_base = ops.upsample_bilinear_bwd(d_up, h_l, w_l)
 
@@ -322,10 +354,14 @@ def decoder_step_backward(dec, saved: dict, dmask, dclass, dstop, dh_out: List[O
                                          dh_base, dh_b, dc_n, dg_fmt=gfmt)
         w = cell.Gates.weight
         k = w.shape[-1]
-        dw = torch.empty_like(w, memory_format=torch.contiguous_format)
-        db = torch.empty_like(cell.Gates.bias)
-        ops.conv2d_wgrad(X, dgates, k, k, 1, k // 2, dw, db)
-        G[id(w)], G[id(cell.Gates.bias)] = dw, db
+        dw, acc_w, direct_w = _grad_target(w)
+        db, acc_b, direct_b = _grad_target(cell.Gates.bias)
+        ops.conv2d_wgrad(X, dgates, k, k, 1, k // 2, dw, None, accumulate=acc_w)
+        ops.conv2d_wgrad(X, dgates, k, k, 1, k // 2, None, db, accumulate=acc_b)
+        if not direct_w:
+            G[id(w)] = dw
+        if not direct_b:
+            G[id(cell.Gates.bias)] = db
         dX = conv_dgrad(cache, dgates, w, 1, k // 2, X.h, X.w, bimpl)
         up_c, skip_c, ch = lv["up_c"], lv["skip_c"], lv["ch"]
         dfeats[l] = dX.t[..., up_c:up_c + skip_c].permute(0, 3, 1, 2)

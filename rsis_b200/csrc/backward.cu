@@ -17,6 +17,41 @@
 
 namespace rsis {
 
+// tcgen05 weight gradient (conv_umma.cu)
+bool conv_wgrad_umma_supported(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad,
+                               size_t workspace_bytes);
+int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, float* dw_oihw, int accumulate,
+                    void* workspace, cudaStream_t st);
+size_t conv_wgrad_umma_workspace_bytes();
+
+__device__ __forceinline__ void bw_ld4(const View& v, size_t idx, float out[4]) {
+  if (v.fmt == RSIS_FMT_F32) {
+    const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.p) + idx);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else {
+    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(v.p);
+    const uint2 h = *reinterpret_cast<const uint2*>(b + idx);
+    const uint2 l = *reinterpret_cast<const uint2*>(b + idx + v.plane);
+    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&h);
+    const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&l);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
+  }
+}
+__device__ __forceinline__ void bw_st4(void* p, size_t plane, int fmt, size_t idx, const float v[4]) {
+  if (fmt == RSIS_FMT_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(p);
+    *reinterpret_cast<uint2*>(b + idx) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(b + idx + plane) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // conv weight gradient: dw[co][ci][kh][kw] += sum_{n,ho,wo} dy[n,ho,wo,co] * x[n, ho*s-pad+kh, wo*s-pad+kw, ci]
 // GEMM view: rows = co, columns k = (kh*KW+kw)*Cin + ci, reduction over the P = N*Ho*Wo output pixels.
@@ -138,6 +173,70 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams p) {
   }
 }
 
+// Weight (+ bias) gradient of a convolution with ONE output channel and few input channels (conv_out, model.py:107:
+// hidden/16 -> 1): every thread walks pixels with its CI*KS*KS partial sums in registers; warp shuffles + shared
+// memory combine a block, one atomicAdd per weight and block.  dw index = c * KS*KS + tap (OIHW with O = 1).
+template <int CI, int KS>
+__global__ void __launch_bounds__(256) wgrad_cout1_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dw, float* __restrict__ dbias, int N,
+                                                          int H, int W) {
+  constexpr int TAPS = KS * KS, NW = TAPS * CI, PAD = KS / 2;
+  float acc[NW];
+  float accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) acc[i] = 0.f;
+  const size_t total = (size_t)N * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(i % W);
+    const int hq = (int)((i / W) % H);
+    const size_t n = i / ((size_t)H * W);
+    const float g = dy[i];
+    accb += g;
+#pragma unroll
+    for (int kh = 0; kh < KS; ++kh) {
+      const int hi = hq - PAD + kh;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < KS; ++kw) {
+        const int wi = wq - PAD + kw;
+        if (wi < 0 || wi >= W) continue;
+        const float* px = x + ((n * H + hi) * W + wi) * CI;
+#pragma unroll
+        for (int c = 0; c < CI; c += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(px + c);
+          acc[(kh * KS + kw) * CI + c] = fmaf(g, v.x, acc[(kh * KS + kw) * CI + c]);
+          acc[(kh * KS + kw) * CI + c + 1] = fmaf(g, v.y, acc[(kh * KS + kw) * CI + c + 1]);
+          acc[(kh * KS + kw) * CI + c + 2] = fmaf(g, v.z, acc[(kh * KS + kw) * CI + c + 2]);
+          acc[(kh * KS + kw) * CI + c + 3] = fmaf(g, v.w, acc[(kh * KS + kw) * CI + c + 3]);
+        }
+      }
+    }
+  }
+  __shared__ float red[8][NW + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+    if (lane == 0) red[warp][i] = v;
+  }
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, sft);
+  if (lane == 0) red[warp][NW] = accb;
+  __syncthreads();
+  for (int i = threadIdx.x; i <= NW; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += red[w8][i];
+    if (i < NW) {
+      if (dw) atomicAdd(dw + (i % CI) * TAPS + i / CI, v);
+    } else if (dbias) {
+      atomicAdd(dbias, v);
+    }
+  }
+}
+
 // dbias[c] += sum over pixels of dy[p][c]  (float atomics across gridDim.x slices)
 __global__ void channel_sum_kernel(View dy, long long P, int C, float* __restrict__ out) {
   __shared__ float red[256];
@@ -148,8 +247,16 @@ __global__ void channel_sum_kernel(View dy, long long P, int C, float* __restric
   const long long p1 = p0 + per < P ? p0 + per : P;
   for (int c = threadIdx.x % lanes_c; c < C; c += lanes_c) {
     float s = 0.f;
-    if (threadIdx.x < rows * lanes_c)
-      for (long long q = p0 + threadIdx.x / lanes_c; q < p1; q += rows) s += load_elem(dy, (size_t)q * C + c);
+    if (threadIdx.x < rows * lanes_c) {
+      long long q = p0 + threadIdx.x / lanes_c;
+      for (; q + 3LL * rows < p1; q += 4LL * rows) {  // four independent loads in flight
+        const float v0 = load_elem(dy, (size_t)q * C + c), v1 = load_elem(dy, (size_t)(q + rows) * C + c);
+        const float v2 = load_elem(dy, (size_t)(q + 2LL * rows) * C + c);
+        const float v3 = load_elem(dy, (size_t)(q + 3LL * rows) * C + c);
+        s += (v0 + v1) + (v2 + v3);
+      }
+      for (; q < p1; q += rows) s += load_elem(dy, (size_t)q * C + c);
+    }
     red[threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.x < lanes_c) {
@@ -177,8 +284,8 @@ __global__ void dgrad_weights_kernel(const float* __restrict__ w, int cout, int 
 }
 
 // y[n, 2i, 2j, :] = x[n, i, j, :], every other element of y is zero.
-__global__ void dilate2x_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int Ho,
-                                int Wo) {
+__global__ void dilate2x_kernel(const float* __restrict__ x, void* y, size_t y_plane, int y_fmt, int N, int H, int W,
+                                int C, int Ho, int Wo) {
   const int C4 = C >> 2;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -191,7 +298,8 @@ __global__ void dilate2x_kernel(const float* __restrict__ x, float* __restrict__
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!(ho & 1) && !(wo & 1) && (ho >> 1) < H && (wo >> 1) < W)
       v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C + c);
-    *reinterpret_cast<float4*>(y + i * 4) = v;
+    const float o[4] = {v.x, v.y, v.z, v.w};
+    bw_st4(y, y_plane, y_fmt, i * 4, o);
   }
 }
 
@@ -201,33 +309,6 @@ __global__ void dilate2x_kernel(const float* __restrict__ x, float* __restrict__
 //   dbias = sum g, dweight = sum g * xhat, xhat = (x - mean) * invstd
 //   dx = weight * invstd * (g - dbias / M - xhat * dweight / M);   dres = g
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bw_ld4(const View& v, size_t idx, float out[4]) {
-  if (v.fmt == RSIS_FMT_F32) {
-    const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(v.p) + idx);
-    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
-  } else {
-    const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(v.p);
-    const uint2 h = *reinterpret_cast<const uint2*>(b + idx);
-    const uint2 l = *reinterpret_cast<const uint2*>(b + idx + v.plane);
-    const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(&h);
-    const __nv_bfloat16* lp = reinterpret_cast<const __nv_bfloat16*>(&l);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = __bfloat162float(hp[j]) + __bfloat162float(lp[j]);
-  }
-}
-__device__ __forceinline__ void bw_st4(void* p, size_t plane, int fmt, size_t idx, const float v[4]) {
-  if (fmt == RSIS_FMT_F32) {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + idx) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) split_bf16(v[j], hi[j], lo[j]);
-    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(p);
-    *reinterpret_cast<uint2*>(b + idx) = *reinterpret_cast<uint2*>(hi);
-    *reinterpret_cast<uint2*>(b + idx + plane) = *reinterpret_cast<uint2*>(lo);
-  }
-}
-
 // acc: [2][C] doubles (sum g, sum g*xhat), zero on entry
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, View y, int has_y, const float* __restrict__ dy,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, size_t M, int C,
@@ -245,6 +326,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, View y, int ha
     const float4 is = *reinterpret_cast<const float4*>(invstd + 4 * c4);
     const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
     if (threadIdx.x < rows_per_iter * lanes_c) {
+#pragma unroll 4
       for (size_t p = p0 + threadIdx.x / lanes_c; p < p1; p += rows_per_iter) {
         const size_t idx = p * C + 4 * c4;
         const float4 xv = *reinterpret_cast<const float4*>(x + idx);
@@ -292,10 +374,13 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, View y, int ha
 }
 
 __global__ void bn_bwd_finalize_kernel(double* __restrict__ acc, int C, float* __restrict__ dweight,
-                                       float* __restrict__ dbias) {
+                                       float* __restrict__ dbias, float* __restrict__ dweight_acc,
+                                       float* __restrict__ dbias_acc) {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     dbias[c] = (float)acc[c];
     dweight[c] = (float)acc[C + c];
+    if (dbias_acc) dbias_acc[c] += (float)acc[c];
+    if (dweight_acc) dweight_acc[c] += (float)acc[C + c];
     acc[c] = 0;
     acc[C + c] = 0;
   }
@@ -490,10 +575,12 @@ __global__ void lstm_gates_bwd_kernel(const float* __restrict__ gates, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// global max-pool with arg-max (model.py:143).  One CTA per (image, group of <= 32 channels); first maximum wins.
+// global max-pool with arg-max (model.py:143).  CTA = (image, group of <= 32 channels, slice of the pixels); the
+// slices are combined with a 64-bit atomicMax on (order-preserving key << 32 | ~pixel index), so the FIRST maximum
+// wins ties; a finishing kernel unpacks keys (what rsis_class_stop_heads reads) and pixel indices.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void global_maxpool_kernel(const float* __restrict__ h, int HW, int C, uint32_t* __restrict__ keys,
-                                      int32_t* __restrict__ idx_out, int side_stride, int side_offset) {
+__global__ void global_maxpool_kernel(const float* __restrict__ h, int HW, int C, unsigned long long* __restrict__ packed,
+                                      int side_stride, int side_offset) {
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
   const int CG = C < 32 ? C : 32;
@@ -501,11 +588,15 @@ __global__ void global_maxpool_kernel(const float* __restrict__ h, int HW, int C
   const int n = blockIdx.x;
   const int c = blockIdx.y * CG + threadIdx.x % CG;
   const int row = threadIdx.x / CG;
+  const int per = (HW + gridDim.z - 1) / gridDim.z;
+  const int p0 = blockIdx.z * per;
+  const int p1 = p0 + per < HW ? p0 + per : HW;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
   if (row < R && c < C) {
     const float* base = h + (size_t)n * HW * C + c;
-    for (int p = row; p < HW; p += R) {
+#pragma unroll 4
+    for (int p = p0 + row; p < p1; p += R) {
       const float v = base[(size_t)p * C];
       if (v > best || best_i == 0x7fffffff) {
         best = v;
@@ -522,14 +613,24 @@ __global__ void global_maxpool_kernel(const float* __restrict__ h, int HW, int C
     for (int r = 1; r < R; ++r) {
       const float v = s_val[r * CG + threadIdx.x];
       const int vi = s_idx[r * CG + threadIdx.x];
-      if (vi != 0x7fffffff && (v > b || (v == b && vi < bi))) {
+      if (vi != 0x7fffffff && (bi == 0x7fffffff || v > b || (v == b && vi < bi))) {
         b = v;
         bi = vi;
       }
     }
-    keys[(size_t)n * side_stride + side_offset + c] = float_to_key(b);
-    idx_out[(size_t)n * side_stride + side_offset + c] = bi;
+    if (bi != 0x7fffffff)
+      atomicMax(packed + (size_t)n * side_stride + side_offset + c,
+                ((unsigned long long)float_to_key(b) << 32) | (unsigned long long)(0xffffffffu - (unsigned)bi));
   }
+}
+
+__global__ void global_maxpool_finish_kernel(const unsigned long long* __restrict__ packed, int total,
+                                             uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned long long v = packed[i];
+  keys[i] = (uint32_t)(v >> 32);
+  idx[i] = (int32_t)(0xffffffffu - (uint32_t)(v & 0xffffffffu));
 }
 
 // dh[n, idx[n][c], c] += dside[n][c]
@@ -673,8 +774,11 @@ int rsis_conv_dgrad_weights(const float* w_oihw, int cout, int cin, int kh, int 
   return RSIS_OK;
 }
 
+size_t rsis_wgrad_workspace_bytes(void) { return conv_wgrad_umma_workspace_bytes(); }
+
 int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad, float* dw_oihw,
-                      float* dbias, int accumulate, rsis_stream_t stream) {
+                      float* dbias, int accumulate, int impl, void* workspace, size_t workspace_bytes,
+                      rsis_stream_t stream) {
   if (!valid_tensor(x) || !valid_tensor(dy) || (!dw_oihw && !dbias) || kh < 1 || kw < 1 || stride < 1 || pad < 0)
     return RSIS_ERR_BAD_ARG;
   if (!is_dense(*x) || !is_dense(*dy)) return RSIS_ERR_UNSUPPORTED;
@@ -682,7 +786,31 @@ int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int k
   if (dy->n != x->n || dy->h != Ho || dy->w != Wo) return RSIS_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long long P = (long long)x->n * Ho * Wo;
-  if (dw_oihw) {
+  if (impl != RSIS_IMPL_AUTO && impl != RSIS_IMPL_SIMT && impl != RSIS_IMPL_TCGEN05) return RSIS_ERR_BAD_ARG;
+  const bool umma_ok = dw_oihw && impl != RSIS_IMPL_SIMT && workspace && aligned16(workspace) &&
+                       conv_wgrad_umma_supported(x, dy, kh, kw, stride, pad, workspace_bytes);
+  if (impl == RSIS_IMPL_TCGEN05 && dw_oihw && !umma_ok) return RSIS_ERR_UNSUPPORTED;
+  if (dy->c == 1 && x->c == 8 && kh == kw && (kh == 1 || kh == 3) && stride == 1 && pad == kh / 2 &&
+      x->fmt == RSIS_FMT_F32 && dy->fmt == RSIS_FMT_F32 && aligned16(x->data)) {
+    // conv_out: both gradients in one pass over the pixels
+    if (!accumulate) {
+      if (dw_oihw) RSIS_CUDA_TRY(cudaMemsetAsync(dw_oihw, 0, (size_t)x->c * kh * kw * sizeof(float), st));
+      if (dbias) RSIS_CUDA_TRY(cudaMemsetAsync(dbias, 0, sizeof(float), st));
+    }
+    long long blocks = (P + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    const float* xp = reinterpret_cast<const float*>(x->data);
+    const float* gp = reinterpret_cast<const float*>(dy->data);
+    if (kh == 3)
+      wgrad_cout1_kernel<8, 3><<<(unsigned)blocks, 256, 0, st>>>(xp, gp, dw_oihw, dbias, x->n, x->h, x->w);
+    else
+      wgrad_cout1_kernel<8, 1><<<(unsigned)blocks, 256, 0, st>>>(xp, gp, dw_oihw, dbias, x->n, x->h, x->w);
+    RSIS_CHECK_LAUNCH();
+    return RSIS_OK;
+  }
+  if (umma_ok) {
+    if (int e = conv_wgrad_umma(x, dy, kh, dw_oihw, accumulate, workspace, st)) return e;
+  } else if (dw_oihw) {
     WgradParams p{};
     p.x = make_view(*x);
     p.dy = make_view(*dy);
@@ -708,8 +836,8 @@ int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int k
   }
   if (dbias) {
     if (!accumulate) RSIS_CUDA_TRY(cudaMemsetAsync(dbias, 0, (size_t)dy->c * sizeof(float), st));
-    long long blocks = (P + 255) / 256;
-    if (blocks > 296) blocks = 296;
+    long long blocks = (P + 63) / 64;
+    if (blocks > 1184) blocks = 1184;
     channel_sum_kernel<<<(unsigned)blocks, 256, 0, st>>>(make_view(*dy), P, dy->c, dbias);
     RSIS_CHECK_LAUNCH();
   }
@@ -717,19 +845,21 @@ int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int k
 }
 
 int rsis_dilate2x(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
-  if (!f32_dense(x) || !f32_dense(y) || x->n != y->n || x->c != y->c) return RSIS_ERR_BAD_ARG;
+  if (!f32_dense(x) || !valid_tensor(y) || !is_dense(*y) || !aligned16(y->data) || x->n != y->n || x->c != y->c)
+    return RSIS_ERR_BAD_ARG;
   if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
   if ((y->h + 1) / 2 != x->h || (y->w + 1) / 2 != x->w) return RSIS_ERR_BAD_ARG;
   const size_t total = numel(*y) / 4;
   dilate2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float*>(x->data), reinterpret_cast<float*>(y->data), x->n, x->h, x->w, x->c, y->h, y->w);
+      reinterpret_cast<const float*>(x->data), y->data, plane_elems(*y), y->fmt, x->n, x->h, x->w, x->c, y->h, y->w);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }
 
 int rsis_bn_train_bwd(const rsis_tensor* x_raw, const rsis_tensor* y_act, const rsis_tensor* dy, const float* weight,
                       const float* mean, const float* invstd, double* workspace, float* dweight, float* dbias,
-                      const rsis_tensor* dx, const rsis_tensor* dres, rsis_stream_t stream) {
+                      float* dweight_acc, float* dbias_acc, const rsis_tensor* dx, const rsis_tensor* dres,
+                      rsis_stream_t stream) {
   if (!f32_dense(x_raw) || !f32_dense(dy) || !valid_tensor(dx) || !mean || !invstd || !workspace || !dweight || !dbias)
     return RSIS_ERR_BAD_ARG;
   if (!same_shape(x_raw, dy) || !same_shape(x_raw, dx) || !is_dense(*dx) || !aligned16(dx->data)) return RSIS_ERR_BAD_ARG;
@@ -743,12 +873,12 @@ int rsis_bn_train_bwd(const rsis_tensor* x_raw, const rsis_tensor* y_act, const 
   const float* xp = reinterpret_cast<const float*>(x_raw->data);
   const float* gp = reinterpret_cast<const float*>(dy->data);
   View yv = y_act ? make_view(*y_act) : make_view(*x_raw);
-  int blocks = (int)((M + 63) / 64);
-  if (blocks > 296) blocks = 296;
+  int blocks = (int)((M + 15) / 16);
+  if (blocks > 592) blocks = 592;
   bn_bwd_reduce_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(xp, yv, y_act ? 1 : 0, gp, mean, invstd, M, C,
                                                                     workspace);
   RSIS_CHECK_LAUNCH();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 256), 256, 0, st>>>(workspace, C, dweight, dbias);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 256), 256, 0, st>>>(workspace, C, dweight, dbias, dweight_acc, dbias_acc);
   RSIS_CHECK_LAUNCH();
   const size_t total4 = M * C / 4;
   bn_bwd_apply_kernel<<<grid_for(total4, 256), 256, 0, st>>>(xp, yv, y_act ? 1 : 0, gp, weight, mean, invstd, dweight,
@@ -815,16 +945,32 @@ int rsis_lstm_gates_bwd(const rsis_tensor* gates, const float* c_prev, const flo
   return RSIS_OK;
 }
 
-int rsis_global_maxpool(const rsis_tensor* h, uint32_t* side_keys, int32_t* side_idx, int side_stride, int side_offset,
+int rsis_global_maxpool(const rsis_tensor* h, uint64_t* side_packed, int side_stride, int side_offset,
                         rsis_stream_t stream) {
-  if (!f32_dense(h) || !side_keys || !side_idx || side_offset < 0 || side_stride < side_offset + h->c)
-    return RSIS_ERR_BAD_ARG;
+  if (!f32_dense(h) || !side_packed || side_offset < 0 || side_stride < side_offset + h->c) return RSIS_ERR_BAD_ARG;
   const long long HW = (long long)h->h * h->w;
   if (HW > 0x7ffffff0LL) return RSIS_ERR_UNSUPPORTED;
   const int CG = h->c < 32 ? h->c : 32;
   if (256 % CG != 0) return RSIS_ERR_UNSUPPORTED;
-  global_maxpool_kernel<<<dim3(h->n, ceil_div(h->c, CG)), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float*>(h->data), (int)HW, h->c, side_keys, side_idx, side_stride, side_offset);
+  const int groups = ceil_div(h->c, CG);
+  long long split = 296 / ((long long)h->n * groups);
+  const long long max_split = (HW + 63) / 64;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  if (h->n > 65535 || groups > 65535) return RSIS_ERR_UNSUPPORTED;
+  global_maxpool_kernel<<<dim3(h->n, groups, (unsigned)split), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(h->data), (int)HW, h->c, reinterpret_cast<unsigned long long*>(side_packed),
+      side_stride, side_offset);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_global_maxpool_finish(const uint64_t* side_packed, int n, int side_stride, uint32_t* side_keys,
+                               int32_t* side_idx, rsis_stream_t stream) {
+  if (!side_packed || !side_keys || !side_idx || n < 1 || side_stride < 1) return RSIS_ERR_BAD_ARG;
+  const int total = n * side_stride;
+  global_maxpool_finish_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(side_packed), total, side_keys, side_idx);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

@@ -21,6 +21,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, size_t M, int C, do
   const size_t p1 = p0 + per_block < M ? p0 + per_block : M;
   for (int c4 = threadIdx.x % lanes_c; c4 < C4; c4 += lanes_c) {
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (size_t p = p0 + threadIdx.x / lanes_c; p < p1; p += rows_per_iter) {
       const float4 v = *reinterpret_cast<const float4*>(x + p * C + 4 * c4);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
@@ -162,8 +163,8 @@ int rsis_bn_train_stats(const rsis_tensor* x, const float* weight, const float* 
   if ((running_mean == nullptr) != (running_var == nullptr)) return RSIS_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t M = (size_t)x->n * x->h * x->w;
-  int blocks = (int)((M + 63) / 64);
-  if (blocks > 296) blocks = 296;
+  int blocks = (int)((M + 15) / 16);
+  if (blocks > 592) blocks = 592;
   bn_stats_kernel<<<blocks, 256, 256 * 8 * sizeof(float), st>>>(reinterpret_cast<const float*>(x->data), M, x->c,
                                                                workspace);
   RSIS_CHECK_LAUNCH();

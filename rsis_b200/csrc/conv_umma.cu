@@ -1683,7 +1683,296 @@ int launch_swap(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   return RSIS_OK;
 }
 
+
+// ===================================================================================================================
+// tcgen05 weight gradient (the backward of every stride-1 1x1 / 3x3 convolution; train.py:184).
+//   dW[tap][co][ci] = sum over output pixels p of dY[p][co] * X[p + tap offset][ci]
+// GEMM view: D[M = 128 output channels][N = up to 4 x 64 (tap, input-channel chunk) columns] += A * B with the
+// PIXELS as the contraction dimension.  NHWC activations have the channels contiguous, i.e. both operands are
+// "MN-major": the smem tile TMA writes (rows = pixels, 64 bf16 channels = one 128-byte swizzle row) is consumed with
+// the MN-major SWIZZLE_128B canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 64 channels per chunk
+// (chunks LBO bytes apart), K groups of 8 pixel rows (SBO = 1024 bytes apart); a_major = b_major = 1 in the
+// instruction descriptor.  One 64-pixel box (TW x TH, TW*TH = 64) per stage and per operand chunk:
+//   A  dY, split-bf16 planes: two boxes {64 co, TW, TH, 1, 2 planes} (co chunks 0/1 of the 128-row block);
+//   B  X : up to four boxes, slot j = (tap, ci chunk) pair number 4*unit + j, the box origin shifted by the tap
+//      offset (TMA zero-fills outside the map = the convolution's zero padding, and beyond the last channel).
+// Three kind::f16 MMAs (128 x N x 16) per 16 pixels: dY_hi*X_hi + dY_hi*X_lo + dY_lo*X_hi, fp32 accumulation in TMEM.
+// Grid: (N unit, co block, pixel split); the partial dW tiles of the pixel splits are combined with 16-byte vector
+// reductions (red.global.add.v4.f32) into a zero-initialised scratch [tap][co][ci_pad], which a finishing kernel
+// transposes into the reference's OIHW layout (and re-zeroes).
+// Warps: 0 TMA producer, 1 MMA issuer (+ TMEM allocation), 2-5 epilogue (TMEM lane quarter = warp % 4).
+// ===================================================================================================================
+constexpr int kWgTilePx = 64;
+constexpr int kWgPlaneBytes = kWgTilePx * 128;      // one bf16 plane of one 64-channel chunk: 8 KB
+constexpr int kWgChunkBytes = 2 * kWgPlaneBytes;    // hi|lo planes = one TMA box: 16 KB
+constexpr int kWgAStage = 2 * kWgChunkBytes;        // two co chunks
+constexpr int kWgBStage = 4 * kWgChunkBytes;        // four (tap, ci chunk) slots
+constexpr int kWgStageBytes = kWgAStage + kWgBStage;  // 96 KB
+constexpr int kWgStages = 2;
+constexpr int kWgThreads = 192;
+constexpr int kWgTmemCols = 256;
+constexpr int kWgDynSmem = kWgStages * kWgStageBytes + 1024;
+
+struct alignas(64) WgMaps {
+  CUtensorMap dy;
+  CUtensorMap x;
+};
+
+struct WgParams {
+  int TW, TH;
+  int tiles_w, tiles_h, num_tiles;
+  int tiles_per_cta, splits;
+  int units_n, co_blocks;
+  int pairs, chunks, ksize, pad;
+  int Cout, ci_pad;
+  float* scratch;
+};
+
+// MN-major SWIZZLE_128B shared-memory matrix descriptor (see the block comment above).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;   // bytes between 64-element chunks along M / N
+  d |= (uint64_t)(sbo >> 4) << 32;   // bytes between groups of 8 K rows (pixels)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kWgStages + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(wg_smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kWgStages]), done = smem_u32(&bars[2 * kWgStages]);
+
+  // CTA -> (pixel split, N unit, co block)
+  const int s = blockIdx.x % p.splits;
+  const int u = blockIdx.x / p.splits;
+  const int nu = u % p.units_n;
+  const int cb = u / p.units_n;
+  const int co0 = cb * 128;
+  const int n_co_chunks = (p.Cout - co0) > 64 ? 2 : 1;
+  const int pair0 = nu * 4;
+  const int n_slots = (p.pairs - pair0) < 4 ? (p.pairs - pair0) : 4;
+  const int t_begin = s * p.tiles_per_cta;
+  const int t_end = (t_begin + p.tiles_per_cta) < p.num_tiles ? (t_begin + p.tiles_per_cta) : p.num_tiles;
+  const int my_tiles = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.dy);
+    prefetch_tmap(&maps.x);
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "n"(kWgTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_trigger();
+  pdl_wait();
+
+  if (my_tiles > 0) {
+    if (warp == 0) {
+      // =============================== TMA producer ===============================
+      if (elect_one()) {
+        const uint32_t tx = (uint32_t)(n_co_chunks + n_slots) * kWgChunkBytes;
+        const int tiles_img = p.tiles_w * p.tiles_h;
+        for (int it = 0; it < my_tiles; ++it) {
+          const int st = it % kWgStages;
+          mbar_wait(empty0 + 8 * st, ((it / kWgStages) & 1) ^ 1);
+          const int t = t_begin + it;
+          const int n = t / tiles_img;
+          const int r = t - n * tiles_img;
+          const int ty = r / p.tiles_w, txi = r - ty * p.tiles_w;
+          const int y0 = ty * p.TH, x0 = txi * p.TW;
+          const uint32_t sa = smem0 + st * kWgStageBytes, sb = sa + kWgAStage;
+          mbar_arrive_expect_tx(full0 + 8 * st, tx);
+          for (int cc = 0; cc < n_co_chunks; ++cc)
+            tma_load_5d(sa + cc * kWgChunkBytes, &maps.dy, full0 + 8 * st, co0 + cc * 64, x0, y0, n, 0);
+          for (int j = 0; j < n_slots; ++j) {
+            const int pair = pair0 + j;
+            const int tap = pair / p.chunks, chunk = pair - tap * p.chunks;
+            const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+            tma_load_5d(sb + j * kWgChunkBytes, &maps.x, full0 + 8 * st, chunk * 64, x0 + kw - p.pad, y0 + kh - p.pad, n,
+                        0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // =============================== MMA issuer ===============================
+      if (elect_one()) {
+        const uint32_t n_mma = (uint32_t)n_slots * 64u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((n_mma >> 3) << 17) |
+                               ((128u >> 4) << 24);
+        for (int it = 0; it < my_tiles; ++it) {
+          const int st = it % kWgStages;
+          mbar_wait(full0 + 8 * st, (it / kWgStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem0 + st * kWgStageBytes, sb = sa + kWgAStage;
+          const uint64_t a_hi0 = make_smem_desc_mn(sa, kWgChunkBytes, 1024);
+          const uint64_t b_hi0 = make_smem_desc_mn(sb, kWgChunkBytes, 1024);
+#pragma unroll
+          for (int ks = 0; ks < kWgTilePx / 16; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 16 * 128) >> 4);  // 16 pixel rows of 128 bytes
+            const uint64_t a_hi = a_hi0 + adv, a_lo = a_hi + (kWgPlaneBytes >> 4);
+            const uint64_t b_hi = b_hi0 + adv, b_lo = b_hi + (kWgPlaneBytes >> 4);
+            umma_bf16(tmem_base, a_hi, b_hi, idesc, (it | ks) ? 1u : 0u);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
+          }
+          umma_commit(empty0 + 8 * st);  // the stage is free once these MMAs have read it
+        }
+        umma_commit(done);
+      }
+    } else {
+      // =============================== epilogue (warps 2-5) ===============================
+      const int q = warp & 3;
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int co = co0 + 32 * q + lane;
+      const bool row_ok = co < p.Cout;
+      if (32 * q < (n_co_chunks * 64)) {
+        for (int j = 0; j < n_slots; ++j) {
+          const int pair = pair0 + j;
+          const int tap = pair / p.chunks, chunk = pair - tap * p.chunks;
+          float* dst = p.scratch + ((size_t)tap * p.Cout + (row_ok ? co : 0)) * p.ci_pad + chunk * 64;
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(j * 64 + piece * 32), r);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                red_add_v4(dst + piece * 32 + 4 * v, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                           __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWgTmemCols) : "memory");
+  }
+}
+
+// scratch [taps][Cout][ci_pad] -> dw OIHW [Cout][Cin][taps] (overwrite or accumulate); leaves the scratch zeroed.
+// One block per (output channel, slice of the 64-channel chunks): a chunk's taps x 64 values are read as `taps`
+// contiguous 256-byte rows, transposed through shared memory and written as one contiguous run of the OIHW tensor.
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(float* __restrict__ scratch, float* __restrict__ dw, int taps,
+                                                           int Cout, int Cin, int ci_pad, int accumulate) {
+  __shared__ float tile[9 * 64];
+  const int co = blockIdx.x;
+  const int chunks = ci_pad / 64;
+  for (int ch = blockIdx.y; ch < chunks; ch += gridDim.y) {
+    const int c0 = ch * 64;
+    for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) {
+      const int tap = i >> 6, j = i & 63;
+      float* src = scratch + ((size_t)tap * Cout + co) * ci_pad + c0 + j;
+      tile[j * taps + tap] = *src;
+      *src = 0.f;
+    }
+    __syncthreads();
+    const int valid = (Cin - c0 < 64 ? Cin - c0 : 64) * taps;
+    float* dst = dw + ((size_t)co * Cin + c0) * taps;
+    for (int i = threadIdx.x; i < valid; i += blockDim.x) dst[i] = accumulate ? dst[i] + tile[i] : tile[i];
+    __syncthreads();
+  }
+}
+
 }  // namespace
+
+size_t conv_wgrad_umma_workspace_bytes() { return (size_t)4 * 1024 * 1024 * sizeof(float); }
+
+bool conv_wgrad_umma_supported(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad,
+                               size_t workspace_bytes) {
+  std::call_once(g_once, init_once);
+  if (g_init_status != RSIS_OK || !x || !dy) return false;
+  if (kh != kw || (kh != 1 && kh != 3) || stride != 1 || pad != kh / 2) return false;
+  if (!split_ok(x) || !split_ok(dy) || dy->c % 8 != 0) return false;
+  if (x->n != dy->n || x->h != dy->h || x->w != dy->w) return false;
+  const size_t need = (size_t)kh * kw * dy->c * round_up(x->c, 64) * sizeof(float);
+  return need <= workspace_bytes && need <= conv_wgrad_umma_workspace_bytes();
+}
+
+// dw_oihw (+)= wgrad(x, dy).  workspace: conv_wgrad_umma_workspace_bytes() bytes, zero-filled once by the caller (the
+// finishing kernel re-zeroes what it used).
+int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, float* dw_oihw, int accumulate,
+                    void* workspace, cudaStream_t st) {
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgDynSmem);
+  });
+  if (attr_err != cudaSuccess) {
+    set_cuda_error(attr_err);
+    return RSIS_ERR_CUDA;
+  }
+  WgMaps maps;
+  WgParams p{};
+  p.TW = x->w > 8 ? 16 : 8;
+  p.TH = kWgTilePx / p.TW;
+  p.tiles_w = ceil_div(x->w, p.TW);
+  p.tiles_h = ceil_div(x->h, p.TH);
+  const long long nt = (long long)x->n * p.tiles_w * p.tiles_h;
+  if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
+  p.num_tiles = (int)nt;
+  p.chunks = ceil_div(x->c, 64);
+  p.ksize = ksize;
+  p.pad = ksize / 2;
+  p.pairs = ksize * ksize * p.chunks;
+  p.units_n = ceil_div(p.pairs, 4);
+  p.co_blocks = ceil_div(dy->c, 128);
+  p.Cout = dy->c;
+  p.ci_pad = p.chunks * 64;
+  p.scratch = reinterpret_cast<float*>(workspace);
+  // 1x1 convolutions whose Cin is a multiple of 64: the scratch layout [co][ci] IS the OIHW tensor -- reduce straight
+  // into the gradient (no finishing pass)
+  const bool direct = ksize == 1 && x->c % 64 == 0 && aligned16(dw_oihw);
+  if (direct) {
+    p.scratch = dw_oihw;
+    if (!accumulate) RSIS_CUDA_TRY(cudaMemsetAsync(dw_oihw, 0, (size_t)p.Cout * x->c * sizeof(float), st));
+  }
+  const long long units = (long long)p.units_n * p.co_blocks;
+  long long splits = units >= g_num_sms ? 1 : (2LL * g_num_sms) / units;
+  if (splits > p.num_tiles) splits = p.num_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (int)((p.num_tiles + splits - 1) / splits);
+  p.splits = ceil_div(p.num_tiles, p.tiles_per_cta);
+  if (units * p.splits > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
+  if (int e = encode_act_map(&maps.dy, *dy, 1, 0, 0, p.TW, p.TH, 1)) return e;
+  if (int e = encode_act_map(&maps.x, *x, 1, 0, 0, p.TW, p.TH, 1)) return e;
+  wgrad_umma_kernel<<<(unsigned)(units * p.splits), kWgThreads, kWgDynSmem, st>>>(maps, p);
+  RSIS_CHECK_LAUNCH();
+  if (direct) return RSIS_OK;
+  // one block per (output channel, 64-channel chunk): a single load -> transpose -> store round trip per block
+  int ysplit = p.chunks < 65535 ? p.chunks : 65535;
+  wgrad_finish_kernel<<<dim3((unsigned)p.Cout, (unsigned)ysplit), 256, 0, st>>>(p.scratch, dw_oihw, ksize * ksize, p.Cout,
+                                                                              x->c, p.ci_pad, accumulate);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
 
 bool conv2d_umma_supported(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const rsis_tensor* residual,
                            const rsis_tensor* y, const rsis_tensor* y2, int stride, int pad) {

@@ -354,27 +354,32 @@ def dgrad_weights(weight: torch.Tensor, ci0: int = 0, nci: Optional[int] = None)
 
 
 def conv2d_wgrad(x: Act, dy: Act, kh: int, kw: int, stride: int, pad: int, dw: Optional[torch.Tensor],
-                 dbias: Optional[torch.Tensor] = None, accumulate: bool = False):
-    """dw (OIHW, float32 contiguous) / dbias (+)= the weight / bias gradient of conv(x) given dy."""
+                 dbias: Optional[torch.Tensor] = None, accumulate: bool = False, impl: int = IMPL_AUTO):
+    """dw (OIHW, float32 contiguous) / dbias (+)= the weight / bias gradient of conv(x) given dy.
+    impl AUTO: the tcgen05 kernel when x and dy are split-bf16 and the convolution is a stride-1 1x1 / 3x3."""
     lib = _lib.load()
     if dw is not None:
         assert dw.is_contiguous() and dw.dtype == torch.float32 and tuple(dw.shape) == (dy.c, x.c, kh, kw)
-    check(lib.rsis_conv2d_wgrad(x.ref(), dy.ref(), kh, kw, stride, pad, _ptr(dw), _ptr(dbias), int(accumulate),
-                                _lib.stream_ptr()), "conv2d_wgrad")
-    _lib.count_launch((1 if dw is not None else 0) + (1 if dbias is not None else 0))
+    ws = _lib.wgrad_workspace() if (impl != IMPL_SIMT and x.fmt == FMT_SPLIT_BF16 and dy.fmt == FMT_SPLIT_BF16) \
+        else (None, 0)
+    check(lib.rsis_conv2d_wgrad(x.ref(), dy.ref(), kh, kw, stride, pad, _ptr(dw), _ptr(dbias), int(accumulate), impl,
+                                ws[0], ws[1], _lib.stream_ptr()), "conv2d_wgrad")
+    _lib.count_launch((2 if dw is not None else 0) + (1 if dbias is not None else 0))
 
 
-def dilate2x(x: Act, ho: int, wo: int) -> Act:
+def dilate2x(x: Act, ho: int, wo: int, fmt: int = FMT_F32) -> Act:
     lib = _lib.load()
-    y = Act.empty(x.n, ho, wo, x.c, FMT_F32, x.t.device)
+    y = Act.empty(x.n, ho, wo, x.c, fmt, x.t.device)
     check(lib.rsis_dilate2x(x.ref(), y.ref(), _lib.stream_ptr()), "dilate2x")
     _lib.count_launch(1)
     return y
 
 
 def bn_train_bwd(raw: Act, y_act: Optional[Act], dy: Act, weight: Optional[torch.Tensor], mean: torch.Tensor,
-                 invstd: torch.Tensor, dx_fmt: int = FMT_F32, want_dres: bool = False):
-    """Backward of train-mode BatchNorm (+ReLU when y_act is given).  Returns (dx, dres or None, dweight, dbias)."""
+                 invstd: torch.Tensor, dx_fmt: int = FMT_F32, want_dres: bool = False,
+                 dweight_acc: Optional[torch.Tensor] = None, dbias_acc: Optional[torch.Tensor] = None):
+    """Backward of train-mode BatchNorm (+ReLU when y_act is given).  Returns (dx, dres or None, dweight, dbias);
+    dweight_acc / dbias_acc (optional) are incremented in place by this call's sums."""
     lib = _lib.load()
     dev = raw.t.device
     c = raw.c
@@ -384,8 +389,8 @@ def bn_train_bwd(raw: Act, y_act: Optional[Act], dy: Act, weight: Optional[torch
     dbias = torch.empty(c, dtype=torch.float32, device=dev)
     check(lib.rsis_bn_train_bwd(raw.ref(), y_act.ref() if y_act is not None else None, dy.ref(), _ptr(weight),
                                 mean.data_ptr(), invstd.data_ptr(), _bn_workspace(dev, c).data_ptr(),
-                                dweight.data_ptr(), dbias.data_ptr(), dx.ref(), dres.ref() if dres is not None else None,
-                                _lib.stream_ptr()), "bn_train_bwd")
+                                dweight.data_ptr(), dbias.data_ptr(), _ptr(dweight_acc), _ptr(dbias_acc), dx.ref(),
+                                dres.ref() if dres is not None else None, _lib.stream_ptr()), "bn_train_bwd")
     _lib.count_launch(3)
     return dx, dres, dweight, dbias
 
@@ -425,11 +430,25 @@ def lstm_gates_bwd(gates: Act, c_prev: Optional[torch.Tensor], c_new: torch.Tens
     return dg, dcp
 
 
-def global_maxpool(h: Act, side_keys: torch.Tensor, side_idx: torch.Tensor, side_offset: int):
+def global_maxpool(h: Act, side_packed: torch.Tensor, side_offset: int):
+    """Folds the per-(image, channel) maximum of h and its pixel index into side_packed (int64 [N, F], zeroed)."""
     lib = _lib.load()
-    check(lib.rsis_global_maxpool(h.ref(), side_keys.data_ptr(), side_idx.data_ptr(), side_keys.shape[1], side_offset,
+    assert side_packed.dtype == torch.int64 and side_packed.is_contiguous()
+    check(lib.rsis_global_maxpool(h.ref(), side_packed.data_ptr(), side_packed.shape[1], side_offset,
                                   _lib.stream_ptr()), "global_maxpool")
     _lib.count_launch(1)
+
+
+def global_maxpool_finish(side_packed: torch.Tensor):
+    """Unpacks side_packed into (keys int32 [N,F] -- the input of class_stop_heads --, pixel indices int32 [N,F])."""
+    lib = _lib.load()
+    n, f = side_packed.shape
+    keys = torch.empty((n, f), dtype=torch.int32, device=side_packed.device)
+    idx = torch.empty((n, f), dtype=torch.int32, device=side_packed.device)
+    check(lib.rsis_global_maxpool_finish(side_packed.data_ptr(), n, f, keys.data_ptr(), idx.data_ptr(),
+                                         _lib.stream_ptr()), "global_maxpool_finish")
+    _lib.count_launch(1)
+    return keys, idx
 
 
 def global_maxpool_bwd(dside: torch.Tensor, side_idx: torch.Tensor, side_offset: int, dh: Act):
@@ -449,17 +468,21 @@ def upsample_bilinear_bwd(dy: Act, h: int, w: int) -> Act:
 
 
 def class_stop_heads_bwd(feat: torch.Tensor, class_probs: torch.Tensor, dclass: Optional[torch.Tensor],
-                         dstop: Optional[torch.Tensor], w_class: torch.Tensor, w_stop: torch.Tensor):
-    """Returns (dfeat [N,F], dw_class, db_class, dw_stop, db_stop)."""
+                         dstop: Optional[torch.Tensor], w_class: torch.Tensor, w_stop: torch.Tensor, into=None):
+    """Returns (dfeat [N,F], dw_class, db_class, dw_stop, db_stop).  `into` (optional): four float32 contiguous
+    buffers (dw_class, db_class, dw_stop, db_stop) that are incremented in place instead of fresh zero tensors."""
     lib = _lib.load()
     n, f = feat.shape
     nc = w_class.shape[0]
     dev = feat.device
     dfeat = torch.empty((n, f), dtype=torch.float32, device=dev)
-    dwc = torch.zeros((nc, f), dtype=torch.float32, device=dev)
-    dbc = torch.zeros(nc, dtype=torch.float32, device=dev)
-    dws = torch.zeros((1, f), dtype=torch.float32, device=dev)
-    dbs = torch.zeros(1, dtype=torch.float32, device=dev)
+    if into is not None:
+        dwc, dbc, dws, dbs = into
+    else:
+        dwc = torch.zeros((nc, f), dtype=torch.float32, device=dev)
+        dbc = torch.zeros(nc, dtype=torch.float32, device=dev)
+        dws = torch.zeros((1, f), dtype=torch.float32, device=dev)
+        dbs = torch.zeros(1, dtype=torch.float32, device=dev)
     scratch = torch.empty(n * (nc + 1), dtype=torch.float32, device=dev)
     check(lib.rsis_class_stop_heads_bwd(feat.data_ptr(), class_probs.data_ptr(), _ptr(dclass), _ptr(dstop), n, f,
                                         w_class.data_ptr(), nc, w_stop.data_ptr(), scratch.data_ptr(),

@@ -242,7 +242,10 @@ class FakeLib:
         _buf(out, nci * cout * kh * kw).view(nci, cout, kh, kw).copy_(o)
         return 0
 
-    def rsis_conv2d_wgrad(self, x, dy, kh, kw, stride, pad, dw, dbias, accumulate, st):
+    def rsis_wgrad_workspace_bytes(self):
+        return 64
+
+    def rsis_conv2d_wgrad(self, x, dy, kh, kw, stride, pad, dw, dbias, accumulate, impl, ws, ws_bytes, st):
         xv, gv = _nchw(_view(x)), _nchw(_view(dy))
         cout, cin = gv.shape[1], xv.shape[1]
         if dw:
@@ -262,7 +265,8 @@ class FakeLib:
         yv[:, ::2, ::2, :] = _view(x)
         return 0
 
-    def rsis_bn_train_bwd(self, x_raw, y_act, dy, weight, mean, invstd, ws, dweight, dbias, dx, dres, st):
+    def rsis_bn_train_bwd(self, x_raw, y_act, dy, weight, mean, invstd, ws, dweight, dbias, dw_acc, db_acc, dx, dres,
+                          st):
         xv, g = _view(x_raw), _view(dy).clone()
         c = xv.shape[3]
         if y_act is not None:
@@ -276,6 +280,10 @@ class FakeLib:
         _view(dx).copy_(w * is_ * (g - db / m - xh * dw / m))
         _buf(dweight, c).copy_(dw)
         _buf(dbias, c).copy_(db)
+        if dw_acc:
+            _buf(dw_acc, c).add_(dw)
+        if db_acc:
+            _buf(db_acc, c).add_(db)
         if dres is not None:
             _view(dres).copy_(g)
         return 0
@@ -322,16 +330,27 @@ class FakeLib:
         _buf(dc_prev, i.numel()).view(i.shape).copy_(dc * f)
         return 0
 
-    def rsis_global_maxpool(self, h, keys, idx, stride, off, st):
+    def rsis_global_maxpool(self, h, packed, stride, off, st):
         v = _view(h)
         n, hh, ww, c = v.shape
         flat = v.reshape(n, hh * ww, c)
-        best, arg = flat.max(1)
-        # torch.max returns the first maximal index on CPU for ties
-        k = _buf(keys, n * stride, torch.int32).view(n, stride)
-        ix = _buf(idx, n * stride, torch.int32).view(n, stride)
-        k[:, off:off + c] = self._float_to_key(best)
-        ix[:, off:off + c] = arg.to(torch.int32)
+        best = flat.max(1)[0]
+        arg = (flat == best.unsqueeze(1)).float().argmax(1)  # first maximal index
+        pk = _buf(packed, n * stride, torch.int64).view(n, stride)
+        key = self._float_to_key(best).to(torch.int64) & 0xFFFFFFFF
+        val = (key << 32) | (0xFFFFFFFF - arg.to(torch.int64))
+        # int64 storage of an unsigned 64-bit value: reinterpret through numpy
+        import numpy as np
+        pk[:, off:off + c] = torch.from_numpy(val.numpy().astype(np.uint64).view(np.int64).copy())
+        return 0
+
+    def rsis_global_maxpool_finish(self, packed, n, stride, keys, idx, st):
+        import numpy as np
+        pk = _buf(packed, n * stride, torch.int64).numpy().view(np.uint64)
+        k = (pk >> np.uint64(32)).astype(np.uint32)
+        ix = (np.uint64(0xFFFFFFFF) - (pk & np.uint64(0xFFFFFFFF))).astype(np.int64)
+        _buf(keys, n * stride, torch.int32).copy_(torch.from_numpy(k.view(np.int32).copy()))
+        _buf(idx, n * stride, torch.int32).copy_(torch.from_numpy(ix.astype(np.int32)))
         return 0
 
     def rsis_global_maxpool_bwd(self, dside, idx, stride, off, dh, st):

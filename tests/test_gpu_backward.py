@@ -152,6 +152,11 @@ def test_bn_train_bwd(R, shape, relu):
         assert rel(db, bs.grad) <= 5e-5
         want_res = dy * (out.detach() > 0) if relu else dy
         assert rel(_nchw(dres), want_res) <= 1e-6
+    # accumulation targets (gradient buffers that already hold a value)
+    acc_w, acc_b = torch.ones(C, device="cuda"), torch.full((C,), 2.0, device="cuda")
+    ops.bn_train_bwd(raw, ya if relu else None, _act(R, dy), bn.weight, mean, invstd, dweight_acc=acc_w, dbias_acc=acc_b)
+    assert rel(acc_w, wt.grad + 1) <= 5e-5
+    assert rel(acc_b, bs.grad + 2) <= 5e-5
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 16, 16), (2, 8, 15, 11), (1, 4, 2, 2)])
@@ -229,20 +234,22 @@ def test_global_maxpool_argmax_and_scatter(R):
     sizes = [(2, 2), (4, 8), (32, 32)]
     N = 3
     F_ = sum(chans)
-    keys = torch.zeros((N, F_), dtype=torch.int32, device="cuda")
-    idx = torch.empty((N, F_), dtype=torch.int32, device="cuda")
+    packed = torch.zeros((N, F_), dtype=torch.int64, device="cuda")
     dside = torch.randn((N, F_), generator=g)
     off = 0
+    hs = []
     for C, (H, W) in zip(chans, sizes):
         h = torch.randint(-4, 5, (N, C, H, W), generator=g).float().requires_grad_(True)  # ties on purpose
         m = F.max_pool2d(h, (H, W))
         m.backward(dside[:, off:off + C].reshape(N, C, 1, 1))
-        ha = _act(R, h.detach())
-        ops.global_maxpool(ha, keys, idx, off)
+        ops.global_maxpool(_act(R, h.detach()), packed, off)
+        hs.append((h, off))
+        off += C
+    keys, idx = ops.global_maxpool_finish(packed)
+    for (h, off), C, (H, W) in zip(hs, chans, sizes):
         dh = R.ops.Act.zeros(N, H, W, C, 0, "cuda")
         ops.global_maxpool_bwd(dside.cuda(), idx, off, dh)
         assert rel(_nchw(dh), h.grad) <= 1e-6
-        off += C
     # the keys decode to the maxima (rsis_class_stop_heads reads them)
     feat = torch.empty((N, F_), device="cuda")
     probs = torch.empty((N, 3), device="cuda")
@@ -361,3 +368,41 @@ def test_train_step_cfg4_shard_shape(R, monkeypatch):
     assert n_with > 300
     assert int(enc.base.bn1.num_batches_tracked) == 2
     assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0])
+
+
+def test_train_step_cuda_graph_matches_eager(R):
+    """rsis_b200.training.TrainStep: the captured step (pack + forward + loss + backward in ONE CUDA graph) reproduces
+    the eager step, keeps doing so after an in-place parameter update (the packing kernels are inside the graph),
+    and advances the BatchNorm running statistics once per call."""
+    import rsis_b200
+    from rsis_b200.training import TrainStep
+    from oracle import synth_weights as sw
+    from train_parity import _args
+    args = _args(5, 3)
+
+    def make():
+        enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+        enc.load_state_dict(sw.encoder_state_dict(1))
+        dec.load_state_dict(sw.decoder_state_dict(1, num_classes=5))
+        return enc.cuda().train(), dec.cuda().train()
+
+    def loss_fn(masks, classes, stops):
+        return sum((torch.sigmoid(m) ** 2).mean() + (c ** 2).sum(-1).mean() + (s ** 2).mean()
+                   for m, c, s in zip(masks, classes, stops))
+
+    x = sw.synthetic_images(123, 4, 128, 128).cuda()
+    enc_e, dec_e = make()
+    enc_g, dec_g = make()
+    eager = TrainStep(enc_e, dec_e, 3, loss_fn, cuda_graph=False, all_reduce=False)
+    graph = TrainStep(enc_g, dec_g, 3, loss_fn, cuda_graph=True, all_reduce=False)
+    for it in range(3):
+        le, lg = float(eager(x)), float(graph(x))
+        assert abs(le - lg) <= 1e-5 * abs(le), (it, le, lg)
+        ge, gg = eager.bucket.flat, graph.bucket.flat
+        assert float((ge - gg).norm() / ge.norm()) <= 1e-3, it
+        with torch.no_grad():  # the same in-place "optimiser step" on both
+            for pe, pg in zip(eager.bucket.params, graph.bucket.params):
+                pe.add_(pe.grad, alpha=-1e-4)
+                pg.add_(pe.grad, alpha=-1e-4)
+    assert int(enc_g.base.bn1.num_batches_tracked) == int(enc_e.base.bn1.num_batches_tracked) == 3
+    assert float((enc_g.base.bn1.running_mean - enc_e.base.bn1.running_mean).abs().max()) <= 1e-5

@@ -54,3 +54,30 @@ def test_grad_bucket_views_receive_the_gradients(fake):
     ref = grads_through_oracle(batch=2, size=64, T=2, num_classes=5)
     compare_grads(res, ref, tol=1e-2, metric="l2")
     assert isinstance(res["bucket"], GradBucket)
+
+
+def test_train_step_object_eager_matches_manual_loop(fake):
+    """rsis_b200.training.TrainStep (eager mode) = the manual loop of train.py:71-115 + backward, gradients in the
+    bucket."""
+    import rsis_b200
+    from rsis_b200.training import TrainStep
+    from oracle import synth_weights as sw
+    from train_parity import _args
+    args = _args(5, 2)
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1, num_classes=5))
+    enc.train()
+    dec.train()
+    x = sw.synthetic_images(123, 2, 64, 64)
+
+    def loss_fn(masks, classes, stops):
+        return sum((m ** 2).mean() + (c ** 2).sum() + (s ** 2).sum() for m, c, s in zip(masks, classes, stops))
+
+    step = TrainStep(enc, dec, 2, loss_fn, cuda_graph=False, all_reduce=False)
+    l1 = float(step(x))
+    g1 = step.bucket.flat.clone()
+    l2 = float(step(x))   # bucket.zero() at the start of every step: gradients do not pile up
+    assert abs(l1 - l2) <= 1e-4 * abs(l1)  # running statistics move, the train-mode outputs do not
+    assert float((step.bucket.flat - g1).abs().max()) <= 1e-3 * float(g1.abs().max())
+    assert float(g1.abs().sum()) > 0
