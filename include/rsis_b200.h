@@ -204,7 +204,7 @@ int rsis_conv_dgrad_weights(const float* w_oihw, int cout, int cin, int kh, int 
  * dbias[co] (+)= sum dy.  x, dy: dense NHWC, either element format.  accumulate = 0 overwrites.  Either of
  * dw_oihw / dbias may be NULL.  Partial sums are combined with float atomics (summation order is not fixed).
  * impl: RSIS_IMPL_SIMT = fp32 CUDA cores (any shape); RSIS_IMPL_AUTO = the tcgen05 kernel (pixels as the contraction
- * dimension, MN-major split-bf16 operands, three products per multiply) for stride-1 1x1 / 3x3 convolutions whose x
+ * dimension, MN-major split-bf16 operands, three products per multiply) for stride-1/2 1x1 / 3x3 convolutions whose x
  * and dy are both RSIS_FMT_SPLIT_BF16, CUDA cores otherwise; RSIS_IMPL_TCGEN05 = that kernel or RSIS_ERR_UNSUPPORTED.
  * workspace: rsis_wgrad_workspace_bytes() bytes, 16-byte aligned, zero-filled ONCE after allocation (the call leaves it
  * zeroed), not shared by launches that may run concurrently; NULL = CUDA cores only. */
@@ -212,8 +212,8 @@ size_t rsis_wgrad_workspace_bytes(void);
 int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad, float* dw_oihw,
                       float* dbias, int accumulate, int impl, void* workspace, size_t workspace_bytes,
                       rsis_stream_t stream);
-/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; y->h in {2*x->h - 1, 2*x->h} (same for w).  x float32 dense, y dense in
- * either element format. */
+/* y[n, 2i, 2j, :] = x[n, i, j, :], zero elsewhere; y->h in {2*x->h - 1, 2*x->h} (same for w).  x, y dense, either element
+ * format. */
 int rsis_dilate2x(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
 /* Backward of train-mode nn.BatchNorm2d (+ the ReLU that follows it, + the residual branch of `out += identity`):
  *   g = dy * (y_act > 0)  (y_act = the post-activation output; NULL: no ReLU);  dbias = sum g;  dweight = sum g*xhat;

@@ -107,8 +107,6 @@ def conv_dgrad(cache: _DgradCache, dy: Act, weight: torch.Tensor, stride: int, p
     if k == 1:  # scatter of the low-resolution result onto the even grid
         low = ops.conv2d([dy], pc, pad=0, out_fmt=F32, impl=bimpl)
         return ops.dilate2x(low, in_h, in_w)
-    if dy.fmt != F32:
-        dy = ops.convert(dy, F32)
     return ops.conv2d([ops.dilate2x(dy, in_h, in_w, _grad_fmt(bimpl))], pc, pad=k - 1 - pad, out_fmt=F32, impl=bimpl)
 
 
@@ -181,8 +179,7 @@ def encoder_backward(enc, tape: dict, dfeats: Sequence[Optional[torch.Tensor]], 
             s = blk.stride
             draw3, dres, out2 = bn_conv_bwd(p + ".conv3", blk.conv3, blk.bn3, dcur, True, 1, 0, want_dres=True)
             dout2 = conv_dgrad(cache, draw3, blk.conv3.weight, 1, 0, out2.h, out2.w, bimpl)
-            draw2, _, out1 = bn_conv_bwd(p + ".conv2", blk.conv2, blk.bn2, dout2, True, s, 1,
-                                         dx_fmt=F32 if s == 2 else None)
+            draw2, _, out1 = bn_conv_bwd(p + ".conv2", blk.conv2, blk.bn2, dout2, True, s, 1)
             dout1 = conv_dgrad(cache, draw2, blk.conv2.weight, s, 1, out1.h, out1.w, bimpl)
             draw1, _, cur = bn_conv_bwd(p + ".conv1", blk.conv1, blk.bn1, dout1, True, 1, 0)
             if blk.downsample is not None:

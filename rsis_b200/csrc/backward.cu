@@ -20,7 +20,7 @@ namespace rsis {
 // tcgen05 weight gradient (conv_umma.cu)
 bool conv_wgrad_umma_supported(const rsis_tensor* x, const rsis_tensor* dy, int kh, int kw, int stride, int pad,
                                size_t workspace_bytes);
-int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, float* dw_oihw, int accumulate,
+int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, int stride, float* dw_oihw, int accumulate,
                     void* workspace, cudaStream_t st);
 size_t conv_wgrad_umma_workspace_bytes();
 
@@ -284,8 +284,8 @@ __global__ void dgrad_weights_kernel(const float* __restrict__ w, int cout, int 
 }
 
 // y[n, 2i, 2j, :] = x[n, i, j, :], every other element of y is zero.
-__global__ void dilate2x_kernel(const float* __restrict__ x, void* y, size_t y_plane, int y_fmt, int N, int H, int W,
-                                int C, int Ho, int Wo) {
+__global__ void dilate2x_kernel(View x, void* y, size_t y_plane, int y_fmt, int N, int H, int W, int C, int Ho,
+                                int Wo) {
   const int C4 = C >> 2;
   const size_t total = (size_t)N * Ho * Wo * C4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -295,10 +295,9 @@ __global__ void dilate2x_kernel(const float* __restrict__ x, void* y, size_t y_p
     r /= Wo;
     const int ho = (int)(r % Ho);
     const int n = (int)(r / Ho);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (!(ho & 1) && !(wo & 1) && (ho >> 1) < H && (wo >> 1) < W)
-      v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C + c);
-    const float o[4] = {v.x, v.y, v.z, v.w};
+      bw_ld4(x, (((size_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C + c, o);
     bw_st4(y, y_plane, y_fmt, i * 4, o);
   }
 }
@@ -809,7 +808,7 @@ int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int k
     return RSIS_OK;
   }
   if (umma_ok) {
-    if (int e = conv_wgrad_umma(x, dy, kh, dw_oihw, accumulate, workspace, st)) return e;
+    if (int e = conv_wgrad_umma(x, dy, kh, stride, dw_oihw, accumulate, workspace, st)) return e;
   } else if (dw_oihw) {
     WgradParams p{};
     p.x = make_view(*x);
@@ -845,13 +844,14 @@ int rsis_conv2d_wgrad(const rsis_tensor* x, const rsis_tensor* dy, int kh, int k
 }
 
 int rsis_dilate2x(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
-  if (!f32_dense(x) || !valid_tensor(y) || !is_dense(*y) || !aligned16(y->data) || x->n != y->n || x->c != y->c)
+  if (!valid_tensor(x) || !is_dense(*x) || !aligned16(x->data) || !valid_tensor(y) || !is_dense(*y) ||
+      !aligned16(y->data) || x->n != y->n || x->c != y->c)
     return RSIS_ERR_BAD_ARG;
   if (x->c % 4 != 0) return RSIS_ERR_UNSUPPORTED;
   if ((y->h + 1) / 2 != x->h || (y->w + 1) / 2 != x->w) return RSIS_ERR_BAD_ARG;
   const size_t total = numel(*y) / 4;
   dilate2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float*>(x->data), y->data, plane_elems(*y), y->fmt, x->n, x->h, x->w, x->c, y->h, y->w);
+      make_view(*x), y->data, plane_elems(*y), y->fmt, x->n, x->h, x->w, x->c, y->h, y->w);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

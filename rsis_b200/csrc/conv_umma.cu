@@ -1715,7 +1715,7 @@ constexpr int kWgDynSmem = kWgStages * kWgStageBytes + 1024;
 
 struct alignas(64) WgMaps {
   CUtensorMap dy;
-  CUtensorMap x;
+  CUtensorMap x[4];  // stride 1: x[0]; stride 2: one per (row parity, column parity) sub-grid of the input
 };
 
 struct WgParams {
@@ -1723,7 +1723,7 @@ struct WgParams {
   int tiles_w, tiles_h, num_tiles;
   int tiles_per_cta, splits;
   int units_n, co_blocks;
-  int pairs, chunks, ksize, pad;
+  int pairs, chunks, ksize, pad, stride;
   int Cout, ci_pad;
   float* scratch;
 };
@@ -1767,7 +1767,12 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&maps.dy);
-    prefetch_tmap(&maps.x);
+    prefetch_tmap(&maps.x[0]);
+    if (p.stride == 2) {
+      prefetch_tmap(&maps.x[1]);
+      prefetch_tmap(&maps.x[2]);
+      prefetch_tmap(&maps.x[3]);
+    }
     for (int i = 0; i < kWgStages; ++i) {
       mbar_init(full0 + 8 * i, 1);
       mbar_init(empty0 + 8 * i, 1);
@@ -1810,8 +1815,16 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             const int pair = pair0 + j;
             const int tap = pair / p.chunks, chunk = pair - tap * p.chunks;
             const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-            tma_load_5d(sb + j * kWgChunkBytes, &maps.x, full0 + 8 * st, chunk * 64, x0 + kw - p.pad, y0 + kh - p.pad, n,
-                        0);
+            // input pixel of output pixel (y, x) under this tap: (stride*y + kh - pad, stride*x + kw - pad).  Stride 2:
+            // that is pixel (y + sy, x + sx) of the (row parity, column parity) sub-grid map.
+            int oy = kh - p.pad, ox = kw - p.pad, mi = 0;
+            if (p.stride == 2) {
+              const int ph = oy & 1, pw = ox & 1;
+              oy = (oy - ph) >> 1;
+              ox = (ox - pw) >> 1;
+              mi = ph * 2 + pw;
+            }
+            tma_load_5d(sb + j * kWgChunkBytes, &maps.x[mi], full0 + 8 * st, chunk * 64, x0 + ox, y0 + oy, n, 0);
           }
         }
       }
@@ -1909,16 +1922,17 @@ bool conv_wgrad_umma_supported(const rsis_tensor* x, const rsis_tensor* dy, int 
                                size_t workspace_bytes) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK || !x || !dy) return false;
-  if (kh != kw || (kh != 1 && kh != 3) || stride != 1 || pad != kh / 2) return false;
+  if (kh != kw || (kh != 1 && kh != 3) || (stride != 1 && stride != 2) || pad != kh / 2) return false;
   if (!split_ok(x) || !split_ok(dy) || dy->c % 8 != 0) return false;
-  if (x->n != dy->n || x->h != dy->h || x->w != dy->w) return false;
+  if (stride == 2 && ((x->h & 1) || (x->w & 1))) return false;
+  if (x->n != dy->n || x->h != dy->h * stride || x->w != dy->w * stride) return false;
   const size_t need = (size_t)kh * kw * dy->c * round_up(x->c, 64) * sizeof(float);
   return need <= workspace_bytes && need <= conv_wgrad_umma_workspace_bytes();
 }
 
 // dw_oihw (+)= wgrad(x, dy).  workspace: conv_wgrad_umma_workspace_bytes() bytes, zero-filled once by the caller (the
 // finishing kernel re-zeroes what it used).
-int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, float* dw_oihw, int accumulate,
+int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, int stride, float* dw_oihw, int accumulate,
                     void* workspace, cudaStream_t st) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -1931,11 +1945,12 @@ int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, floa
   }
   WgMaps maps;
   WgParams p{};
-  p.TW = x->w > 8 ? 16 : 8;
+  p.TW = dy->w > 8 ? 16 : 8;   // tiles walk the OUTPUT pixels
   p.TH = kWgTilePx / p.TW;
-  p.tiles_w = ceil_div(x->w, p.TW);
-  p.tiles_h = ceil_div(x->h, p.TH);
-  const long long nt = (long long)x->n * p.tiles_w * p.tiles_h;
+  p.tiles_w = ceil_div(dy->w, p.TW);
+  p.tiles_h = ceil_div(dy->h, p.TH);
+  p.stride = stride;
+  const long long nt = (long long)dy->n * p.tiles_w * p.tiles_h;
   if (nt > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
   p.num_tiles = (int)nt;
   p.chunks = ceil_div(x->c, 64);
@@ -1955,14 +1970,21 @@ int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, floa
     if (!accumulate) RSIS_CUDA_TRY(cudaMemsetAsync(dw_oihw, 0, (size_t)p.Cout * x->c * sizeof(float), st));
   }
   const long long units = (long long)p.units_n * p.co_blocks;
-  long long splits = units >= g_num_sms ? 1 : (2LL * g_num_sms) / units;
+  // one CTA per SM (192 KB of operand stages): split the pixels so that the launch is ONE wave
+  long long splits = units >= g_num_sms ? 1 : g_num_sms / units;
   if (splits > p.num_tiles) splits = p.num_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (int)((p.num_tiles + splits - 1) / splits);
   p.splits = ceil_div(p.num_tiles, p.tiles_per_cta);
   if (units * p.splits > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
   if (int e = encode_act_map(&maps.dy, *dy, 1, 0, 0, p.TW, p.TH, 1)) return e;
-  if (int e = encode_act_map(&maps.x, *x, 1, 0, 0, p.TW, p.TH, 1)) return e;
+  if (stride == 1) {
+    if (int e = encode_act_map(&maps.x[0], *x, 1, 0, 0, p.TW, p.TH, 1)) return e;
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if (int e = encode_act_map(&maps.x[ph * 2 + pw], *x, 2, ph, pw, p.TW, p.TH, 1)) return e;
+  }
   wgrad_umma_kernel<<<(unsigned)(units * p.splits), kWgThreads, kWgDynSmem, st>>>(maps, p);
   RSIS_CHECK_LAUNCH();
   if (direct) return RSIS_OK;

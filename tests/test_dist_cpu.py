@@ -27,6 +27,25 @@ WORKER = textwrap.dedent("""
     assert rd.max_over_ranks(1.0 + rank, device="cpu") == 2.0
     assert rd.sum_over_ranks(float(e - b), device="cpu") == float(n)
     rd.barrier()
+    # training: ONE all-reduce over the flat gradient buffer every parameter's .grad is a view of (section 8e)
+    from rsis_b200.autograd import GradBucket
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)),
+              torch.nn.Parameter(torch.randn(2, 2, 3), requires_grad=False)]
+    bucket = GradBucket(params)
+    assert bucket.flat.numel() == 22 and params[2].grad is None
+    bucket.zero()
+    loss = sum(((rank + 1.0) * p * p).sum() for p in params[:2])   # rank-dependent gradients
+    loss.backward()                                                # autograd accumulates into the views in place
+    assert params[0].grad.data_ptr() == bucket.flat.data_ptr()
+    bucket.all_reduce()                                            # sum over ranks, / world
+    want = torch.cat([(2 * 1.5 * p.detach()).reshape(-1) for p in params[:2]])   # mean of 2*(rank+1)*p over ranks
+    assert torch.allclose(bucket.flat, want, atol=1e-6), (bucket.flat, want)
+    for p_ in params[:2]:
+        p_.grad = None                                            # an optimiser's zero_grad(set_to_none=True)
+    bucket.zero()                                                  # ... re-attaches the views
+    assert params[1].grad is not None and float(bucket.flat.abs().sum()) == 0.0
+    rd.barrier()
     print(f"rank {rank} ok [{b},{e})")
 """)
 
