@@ -157,6 +157,36 @@ def main():
     total_s = graph_s if graph_s is not None else eager_s
     value = world * B * a.steps / total_s
     launches = eager_launches
+    # ---- soft-IoU cost matrix of train.py:96-110 (section 8f rank 1): HBM-bound kernel, roofline live ----
+    iou = None
+    if rank == 0:
+        from rsis_b200 import objectives
+        G = 20                                            # gt_maxseqlen (args.py)
+        gen = torch.Generator().manual_seed(3)
+        logits = (torch.randn((B, H * W), generator=gen) * 2).to(dev)
+        y = (torch.rand((B, G, H * W), generator=gen) < 0.25).to(dev)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+        peak = 6650.0
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        src = "fallback (B200_PROFILING.md)"
+        if os.path.exists(pk):
+            peak, src = float(json.load(open(pk))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+        iou = {"peak_GBps": peak, "peak_source": src, "shape": {"B": B, "gtT": G, "HW": H * W}}
+        for name, gt, gbytes in (("f32_masks", y.float(), 4), ("u8_masks", y.to(torch.uint8), 1)):
+            out = torch.empty((B, G), device=dev)
+            evs = []
+            for it in range(13):
+                flush.fill_(it)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                objectives.soft_iou_cost_matrix(logits, gt, 1.0, out=out)
+                e1.record()
+                if it >= 3:
+                    evs.append((e0, e1))
+            torch.cuda.synchronize(dev)
+            t = sum(s_.elapsed_time(e_) for s_, e_ in evs) * 1e-3 / len(evs)
+            nbytes = 4 * B * H * W + gbytes * B * G * H * W
+            iou[name] = {"us": t * 1e6, "alg_bytes": nbytes, "GBps": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak}
     cpu = None
     if rank == 0 and a.cpu_steps > 0:
         times, threads = cpu_step_time(a.cpu_steps)
@@ -182,6 +212,7 @@ def main():
             "graph_ms_per_step": None if graph_s is None else 1e3 * graph_s / a.steps, "graph_error": graph_err,
             "eager_split_ms": split,
             "gpu_launches": launches, "launches_per_step": launches / a.steps, "cpu_baseline": cpu,
+            "soft_iou_cost": iou,
         }))
     rdist.barrier()
     rdist.shutdown()

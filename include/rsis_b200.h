@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 10
+#define RSIS_ABI_VERSION 11
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -257,6 +257,23 @@ int rsis_class_stop_heads_bwd(const float* feat, const float* class_probs, const
                               int n, int f, const float* w_class, int num_classes, const float* w_stop,
                               float* dlogit_scratch, float* dfeat, float* dw_class, float* db_class, float* dw_stop,
                               float* db_stop, rsis_stream_t stream);
+
+/* ---- soft-IoU cost / loss of the training loop --------------------------------------- */
+/* softIoU of utils/hungarian.py:64-90: s = sigmoid(logit); num = sum(s*y); den = sum(s + y - s*y) + eps;
+ * cost = weight * (1 - num/den).
+ * rsis_soft_iou_cost: logits float32 [b][hw] against the g ground-truth rows gt [b][g][hw] (float32, or uint8 when
+ * gt_is_u8) of the same image, in ONE pass over HBM -- the per-step cost matrix of train.py:96-110 (there:
+ * `y_pred_i.repeat`, softIoU, `.cpu()`); with g = 1 and b = rows it is the row-wise softIoU of softIoULoss
+ * (utils/objectives.py:27-34).  cost is written at cost[b*cost_stride_b + g*cost_stride_g] (e.g. straight into
+ * scores[:, :, t] of train.py:110).  num_out / den_out (optional, [b*g]) keep what rsis_soft_iou_bwd needs.
+ * workspace: rsis_soft_iou_workspace_bytes(b, g) bytes, zero-filled once (the call leaves it zeroed).  hw % 4 == 0. */
+size_t rsis_soft_iou_workspace_bytes(int b, int g);
+int rsis_soft_iou_cost(const float* logits, const void* gt, int gt_is_u8, int b, int g, int64_t hw, float eps,
+                       float weight, float* workspace, float* cost, int64_t cost_stride_b, int64_t cost_stride_g,
+                       float* num_out, float* den_out, rsis_stream_t stream);
+/* dlogits[r][p] = dcost[r] * d cost[r] / d logits[r][p] for row-wise softIoU (logits, gt: [rows][hw]). */
+int rsis_soft_iou_bwd(const float* logits, const void* gt, int gt_is_u8, int rows, int64_t hw, const float* num,
+                      const float* den, const float* dcost, float weight, float* dlogits, rsis_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,8 @@ What it restates (fp32, NCHW, state_dict in / tensors out, no nn.Module):
   * ConvLSTMCell           -- /root/reference/src/modules/clstm.py:19-62
   * RSIS decoder step      -- /root/reference/src/modules/model.py:122-184 (skip_mode='concat')
   * test() inference loop  -- /root/reference/src/test.py:16-50
+  * softIoU / cost matrix  -- /root/reference/src/utils/hungarian.py:64-90, src/train.py:96-110,
+                              src/utils/objectives.py:27-34
 
 Pinning: the reference holds no golden vectors or tests for this path (SURVEY.md
 section 4), so the oracle is pinned against outputs of the UNMODIFIED reference
@@ -159,6 +161,29 @@ def test_loop(enc_sd, dec_sd, x, T, conv=F.conv2d):
         classes = torch.stack(classes, 1)
         stops = torch.stack(stops, 1)
         return torch.sigmoid(masks), classes, torch.sigmoid(stops)
+
+
+def soft_iou(target, out, e=1e-6):
+    """utils/hungarian.py:64-90 `softIoU`: row-wise cost 1 - IoU(sigmoid(out), target) for [rows, N] tensors."""
+    out = torch.sigmoid(out)
+    num = (out * target).sum(1, True)
+    den = (out + target - out * target).sum(1, True) + e
+    return (1 - num / den).squeeze()
+
+
+def soft_iou_cost_matrix(out_mask, y_mask, iou_weight=1.0):
+    """train.py:96-110: the mask logits of one decoder step [B, HW] against all gtT ground-truth masks [B, gtT, HW]
+    -> `c.view(B, gtT)` (the reference repeats the prediction gtT times and calls softIoU on [B*gtT, HW])."""
+    b, g, hw = y_mask.shape
+    y_pred_i = out_mask.view(b, -1).unsqueeze(0).permute(1, 0, 2).repeat(1, g, 1).view(b * g, hw)
+    y_true_p = y_mask.reshape(b * g, hw)
+    return (iou_weight * soft_iou(y_true_p, y_pred_i)).view(b, -1)
+
+
+def soft_iou_loss(y_true, y_pred, sw):
+    """utils/objectives.py:27-34 `softIoULoss.forward`."""
+    costs = soft_iou(y_true, y_pred).view(-1, 1)
+    return torch.mean(torch.masked_select(costs, sw.bool()))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,105 @@
+"""Soft-IoU cost and loss -- counterparts of /root/reference/src/utils/hungarian.py:64-90 (`softIoU`),
+/root/reference/src/utils/objectives.py:27-34 (`softIoULoss`) and the per-step cost matrix of
+/root/reference/src/train.py:96-110 (the component right after the decoder step in the
+training loop).  One fused, HBM-bound CUDA kernel per call (`csrc/objectives.cu`) instead of the reference's
+`repeat` + ~8 elementwise / reduction kernels; ground-truth masks may stay uint8 on the device (4x fewer bytes).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import check
+
+_workspaces = {}
+
+
+def _workspace(dev, b: int, g: int) -> torch.Tensor:
+    n = _lib.load().rsis_soft_iou_workspace_bytes(b, g) // 4
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.zeros(max(n, 4096), dtype=torch.float32, device=dev)
+        _workspaces[key] = ws
+    return ws
+
+
+def _gt(t: torch.Tensor):
+    if t.dtype == torch.uint8 or t.dtype == torch.bool:
+        return t.contiguous().view(torch.uint8), 1
+    return t.contiguous().float(), 0
+
+
+def soft_iou_cost_matrix(out_mask: torch.Tensor, y_mask: torch.Tensor, iou_weight: float = 1.0, e: float = 1e-6,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """train.py:96-110 in one kernel: `c = iou_weight * softIoU(y_true_p, y_pred_i).view(B, gtT)` for the mask logits
+    of ONE decoder step `out_mask` [B, HW] (or [B,1,H,W]) against all ground-truth masks `y_mask` [B, gtT, HW]
+    (float 0/1 as in the reference, or uint8 / bool).  `out` may be a strided [B, gtT] view (e.g. `scores[:, :, t]` on
+    the device).  No autograd (the reference detaches it too: `c.cpu().data`)."""
+    ops.require_cuda(out_mask, "soft_iou_cost_matrix")
+    lib = _lib.load()
+    b = out_mask.shape[0]
+    logits = out_mask.detach().reshape(b, -1).contiguous().float()
+    hw = logits.shape[1]
+    g = y_mask.shape[1]
+    gt, is_u8 = _gt(y_mask.detach().reshape(b, g, hw))
+    if out is None:
+        out = torch.empty((b, g), dtype=torch.float32, device=logits.device)
+    assert out.shape == (b, g) and out.dtype == torch.float32 and out.device == logits.device
+    ws = _workspace(logits.device, b, g)
+    check(lib.rsis_soft_iou_cost(logits.data_ptr(), gt.data_ptr(), is_u8, b, g, hw, float(e), float(iou_weight),
+                                 ws.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1), None, None,
+                                 _lib.stream_ptr()), "soft_iou_cost")
+    _lib.count_launch(3)
+    return out
+
+
+class _SoftIoURows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, target, out, e):
+        lib = _lib.load()
+        rows = out.shape[0]
+        logits = out.detach().reshape(rows, -1).contiguous().float()
+        hw = logits.shape[1]
+        gt, is_u8 = _gt(target.detach().reshape(rows, hw))
+        dev = logits.device
+        cost = torch.empty(rows, dtype=torch.float32, device=dev)
+        num = torch.empty(rows, dtype=torch.float32, device=dev)
+        den = torch.empty(rows, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, rows, 1)
+        check(lib.rsis_soft_iou_cost(logits.data_ptr(), gt.data_ptr(), is_u8, rows, 1, hw, float(e), 1.0, ws.data_ptr(),
+                                     cost.data_ptr(), 1, 1, num.data_ptr(), den.data_ptr(), _lib.stream_ptr()),
+              "soft_iou_cost")
+        _lib.count_launch(3)
+        ctx.saved = (logits, gt, is_u8, num, den, tuple(out.shape))
+        return cost
+
+    @staticmethod
+    def backward(ctx, dcost):
+        lib = _lib.load()
+        logits, gt, is_u8, num, den, shape = ctx.saved
+        rows, hw = logits.shape
+        d = torch.empty_like(logits)
+        dc = dcost.contiguous().float()
+        check(lib.rsis_soft_iou_bwd(logits.data_ptr(), gt.data_ptr(), is_u8, rows, hw, num.data_ptr(), den.data_ptr(),
+                                    dc.data_ptr(), 1.0, d.data_ptr(), _lib.stream_ptr()), "soft_iou_bwd")
+        _lib.count_launch(1)
+        return None, d.view(shape), None
+
+
+def softIoU(target: torch.Tensor, out: torch.Tensor, e: float = 1e-6) -> torch.Tensor:
+    """utils/hungarian.py:64-90: row-wise `1 - IoU(sigmoid(out), target)` for [rows, N] logits / binary targets;
+    differentiable w.r.t. `out` (one forward kernel pass, one backward kernel)."""
+    ops.require_cuda(out, "softIoU")
+    return _SoftIoURows.apply(target, out, e)
+
+
+class softIoULoss(nn.Module):
+    """utils/objectives.py:27-34: mean of the soft-IoU cost over the rows selected by `sw`."""
+
+    def forward(self, y_true, y_pred, sw):
+        costs = softIoU(y_true, y_pred).view(-1, 1)
+        return torch.mean(torch.masked_select(costs, sw.bool()))

@@ -84,3 +84,22 @@ def test_reference_state_dict_keys_match():
         assert v.shape == esd[k].shape and v.dtype == esd[k].dtype, k
     for k, v in dec.state_dict().items():
         assert v.shape == dsd[k].shape, k
+
+
+def test_soft_iou_oracle_matches_reference_golden(golden_dir):
+    """oracle.soft_iou / soft_iou_cost_matrix / soft_iou_loss == the unmodified utils/hungarian.py:64-90,
+    train.py:96-110 and utils/objectives.py:27-34 run in the build container (oracle/make_golden.py)."""
+    import numpy as np
+    import torch
+    from oracle import rsis_oracle as O
+    from oracle.make_golden import soft_iou_inputs
+    g = np.load(os.path.join(golden_dir, "soft_iou.npz"))
+    logits, y_mask, sw = soft_iou_inputs()
+    b, gt, hw = y_mask.shape
+    cost = O.soft_iou_cost_matrix(logits, y_mask, 1.0)
+    assert np.abs(cost.numpy() - g["cost"]).max() <= 1e-6
+    pred = logits.unsqueeze(1).repeat(1, gt, 1).view(b * gt, hw).clone().requires_grad_(True)
+    loss = O.soft_iou_loss(y_mask.view(b * gt, hw), pred, sw)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6
+    assert np.abs(pred.grad.numpy()[:, ::16] - g["grad"]).max() <= 1e-9 + 1e-5 * np.abs(g["grad"]).max()
