@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 11
+#define RSIS_ABI_VERSION 12
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -274,6 +274,15 @@ int rsis_soft_iou_cost(const float* logits, const void* gt, int gt_is_u8, int b,
 /* dlogits[r][p] = dcost[r] * d cost[r] / d logits[r][p] for row-wise softIoU (logits, gt: [rows][hw]). */
 int rsis_soft_iou_bwd(const float* logits, const void* gt, int gt_is_u8, int rows, int64_t hw, const float* num,
                       const float* den, const float* dcost, float weight, float* dlogits, rsis_stream_t stream);
+
+/* Hungarian matching on the device (replaces `Munkres().compute` per image on the host,
+ * utils/hungarian.py:91-125, train.py:137).  cost: float32 [b][rows][cols] with element strides (rows = ground-truth
+ * objects, cols = predictions; both <= 32).  perm[b][col] = row matched to column col for col < min(rows, cols), 0
+ * elsewhere (perm_len entries per image; the reference's `permute_indices`); total_cost (optional) [b] = the optimal
+ * assignment cost.  Minimum-cost assignment of the smaller side, i.e. what Munkres returns for the zero-padded
+ * square matrix; when several assignments are optimal (equal costs) any one of them is returned. */
+int rsis_hungarian_match(const float* cost, int64_t stride_b, int64_t stride_r, int64_t stride_c, int b, int rows,
+                         int cols, int32_t* perm, int perm_len, float* total_cost, rsis_stream_t stream);
 
 #ifdef __cplusplus
 }

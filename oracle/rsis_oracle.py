@@ -186,6 +186,32 @@ def soft_iou_loss(y_true, y_pred, sw):
     return torch.mean(torch.masked_select(costs, sw.bool()))
 
 
+def match(t_mask, t_class, overlaps):
+    """utils/hungarian.py:91-125 `match`: per image, the minimum-cost assignment of the [gtT, T] cost matrix
+    `overlaps[b]`, then `permute_indices[b, column] = row` and the ground-truth masks / classes gathered by it.
+    The reference calls `munkres.Munkres().compute` (munkres==1.0.12 in requirements.txt: a third-party dependency that
+    is NOT in /root/reference and not installed in this image); `scipy.optimize.linear_sum_assignment` solves the same
+    problem -- Munkres pads a rectangular matrix with zeros to a square one, whose optimum restricted to the original
+    entries is the rectangular optimum -- but may pick a different optimal assignment when costs tie.
+    Returns (t_mask_perm, t_class_perm, permute_indices [B, gtT] int64, total cost [B])."""
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    b, r, _ = overlaps.shape
+    perm = np.zeros((b, r), dtype=np.int64)
+    total = np.zeros(b, dtype=np.float64)
+    for i in range(b):
+        cost = overlaps[i].detach().double().numpy()
+        rows, cols = linear_sum_assignment(cost)
+        total[i] = cost[rows, cols].sum()
+        for row, col in zip(rows, cols):
+            if col < r:
+                perm[i, col] = row
+    idx = torch.from_numpy(perm)
+    t_mask_perm = torch.stack([t_mask[i, idx[i]] for i in range(b)])
+    t_class_perm = torch.stack([t_class[i, idx[i]] for i in range(b)])
+    return t_mask_perm, t_class_perm, idx, torch.from_numpy(total)
+
+
 # ----------------------------------------------------------------------------------------------
 # precision emulators (design aids; not part of any parity claim)
 # ----------------------------------------------------------------------------------------------

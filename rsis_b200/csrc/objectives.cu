@@ -16,7 +16,8 @@
 
 namespace rsis {
 
-constexpr int kIouMaxG = 32;  // ground-truth rows walked per pass (gt_maxseqlen is 20 in the reference, args.py)
+constexpr int kIouMaxG = 8;  // ground-truth rows per CTA: 16 accumulators keep the kernel at 4 CTAs per SM (one wave); the
+                              // logits (1/gtT of the bytes) are re-read by each group of 8 rows
 
 __device__ __forceinline__ void load_gt4(const float* p, float out[4]) {
   const float4 t = *reinterpret_cast<const float4*>(p);
@@ -27,12 +28,26 @@ __device__ __forceinline__ void load_gt4(const uint8_t* p, float out[4]) {
   out[0] = (float)t.x; out[1] = (float)t.y; out[2] = (float)t.z; out[3] = (float)t.w;
 }
 
-// acc: [B][G][2] (num, sum y) followed by [B] (sum sigmoid); zero on entry.  grid = (pixel slices, B).
+// acc: [B][G][2] (num, sum y) followed by [B] (sum sigmoid); zero on entry.
+// grid = (pixel slices, B, groups of kIouMaxG ground-truth rows).
+struct IouFinish {
+  float eps, weight;
+  float* cost;
+  long long sb, sg;
+  float* num_out;
+  float* den_out;
+};
+
+// The LAST CTA to arrive (ticket counter behind the sums) turns the sums into costs and re-zeroes the workspace, so
+// one call is one launch.
 template <typename GT>
-__global__ void __launch_bounds__(256) soft_iou_partial_kernel(const float* __restrict__ logits, const GT* __restrict__ gt,
-                                                               int G, int g0, long long HW, float* __restrict__ acc,
-                                                               int B, int Gtot) {
+__global__ void __launch_bounds__(256, 4) soft_iou_partial_kernel(const float* __restrict__ logits,
+                                                                  const GT* __restrict__ gt, long long HW,
+                                                                  float* __restrict__ acc, int B, int Gtot,
+                                                                  const IouFinish fin) {
   const int b = blockIdx.y;
+  const int g0 = blockIdx.z * kIouMaxG;
+  const int G = Gtot - g0 < kIouMaxG ? Gtot - g0 : kIouMaxG;
   const long long per = ((HW / 4 + gridDim.x - 1) / gridDim.x) * 4;
   const long long p0 = (long long)blockIdx.x * per;
   const long long p1 = p0 + per < HW ? p0 + per : HW;
@@ -84,33 +99,37 @@ __global__ void __launch_bounds__(256) soft_iou_partial_kernel(const float* __re
     for (int w = 0; w < 8; ++w) v += red[w][i];
     atomicAdd(acc + ((size_t)b * Gtot + g0) * 2 + i, v);
   }
-  if (threadIdx.x == 0 && g0 == 0) {
+  if (threadIdx.x == 0 && blockIdx.z == 0) {
     float v = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) v += red[w][2 * kIouMaxG];
     atomicAdd(acc + (size_t)B * Gtot * 2 + b, v);
   }
-}
-
-// cost[b*sb + g*sg] = weight * (1 - num / den), den = sum(s) + sum(y) - num + eps; re-zeroes acc.
-__global__ void soft_iou_finish_kernel(float* __restrict__ acc, int B, int G, float eps, float weight,
-                                       float* __restrict__ cost, long long sb, long long sg, float* __restrict__ num_out,
-                                       float* __restrict__ den_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * G) return;
-  const int b = i / G, g = i - b * G;
-  const float num = acc[2 * (size_t)i], sy = acc[2 * (size_t)i + 1];
-  const float ssig = acc[(size_t)B * G * 2 + b];
-  const float den = ssig + sy - num + eps;
-  cost[b * sb + g * sg] = weight * (1.f - num / den);
-  if (num_out) num_out[i] = num;
-  if (den_out) den_out[i] = den;
-  acc[2 * (size_t)i] = 0.f;
-  acc[2 * (size_t)i + 1] = 0.f;
-}
-__global__ void soft_iou_zero_sig_kernel(float* __restrict__ acc, int B, int G) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) acc[(size_t)B * G * 2 + b] = 0.f;
+  // ---- last CTA: costs + workspace reset ----
+  __shared__ unsigned s_last;
+  __threadfence();
+  __syncthreads();
+  unsigned* counter = reinterpret_cast<unsigned*>(acc + (size_t)B * Gtot * 2 + B);
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    s_last = atomicAdd(counter, 1u) == total - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int n = B * Gtot;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int bb = i / Gtot, g = i - bb * Gtot;
+    const float nm = __ldcg(acc + 2 * (size_t)i), sy_ = __ldcg(acc + 2 * (size_t)i + 1);
+    const float ss = __ldcg(acc + (size_t)n * 2 + bb);
+    const float den = ss + sy_ - nm + fin.eps;
+    fin.cost[bb * fin.sb + g * fin.sg] = fin.weight * (1.f - nm / den);
+    if (fin.num_out) fin.num_out[i] = nm;
+    if (fin.den_out) fin.den_out[i] = den;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * n + B; i += blockDim.x) acc[i] = 0.f;
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 // d cost / d logit = -weight * (y*den - num*(1-y)) / den^2 * s*(1-s), times the incoming dcost of the row.
@@ -138,6 +157,92 @@ __global__ void soft_iou_bwd_kernel(const float* __restrict__ logits, const GT* 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hungarian matching on the device: utils/hungarian.py:91-125 runs `Munkres().compute`
+// per image on the HOST over the [gtT, T] cost matrix (after a D2H copy of the costs AND of all ground-truth masks).
+// Here: one CTA per image; the cost matrix is staged in shared memory and one thread runs the O(n^2 m) shortest
+// augmenting path algorithm with dual potentials (Kuhn-Munkres, rectangular form) in double precision.  The problem is
+// tiny (<= 32 x 32, gt_maxseqlen = 20, maxseqlen = 10): what matters is that nothing leaves the device.
+// Output convention = the reference's `permute_indices`: perm[b][column] = the row assigned to that column for
+// column < min(rows, cols); every other entry stays 0 (np.zeros initialisation of hungarian.py:113).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHungMax = 32;
+
+__global__ void hungarian_kernel(const float* __restrict__ cost, long long sb, long long sr, long long sc, int R, int C,
+                                 int32_t* __restrict__ perm, int perm_len, float* __restrict__ total_out) {
+  __shared__ double a[kHungMax][kHungMax + 1];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    a[r][c] = (double)cost[b * sb + r * sr + c * sc];
+  }
+  for (int i = threadIdx.x; i < perm_len; i += blockDim.x) perm[(size_t)b * perm_len + i] = 0;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  // assign every index of the SMALLER side to a distinct index of the larger side: n "workers" x m "jobs", n <= m
+  const bool cols_are_workers = C <= R;
+  const int n = cols_are_workers ? C : R, m = cols_are_workers ? R : C;
+  auto w = [&](int i, int j) { return cols_are_workers ? a[j][i] : a[i][j]; };  // cost of worker i doing job j
+  double u[kHungMax + 1], v[kHungMax + 1], minv[kHungMax + 1];
+  int p[kHungMax + 1], way[kHungMax + 1];
+  bool used[kHungMax + 1];
+  for (int j = 0; j <= m; ++j) {
+    v[j] = 0;
+    p[j] = 0;
+  }
+  for (int i = 0; i <= n; ++i) u[i] = 0;
+  for (int i = 1; i <= n; ++i) {
+    p[0] = i;
+    int j0 = 0;
+    for (int j = 0; j <= m; ++j) {
+      minv[j] = 1e300;
+      used[j] = false;
+    }
+    do {
+      used[j0] = true;
+      const int i0 = p[j0];
+      double delta = 1e300;
+      int j1 = 0;
+      for (int j = 1; j <= m; ++j) {
+        if (used[j]) continue;
+        const double cur = w(i0 - 1, j - 1) - u[i0] - v[j];
+        if (cur < minv[j]) {
+          minv[j] = cur;
+          way[j] = j0;
+        }
+        if (minv[j] < delta) {
+          delta = minv[j];
+          j1 = j;
+        }
+      }
+      for (int j = 0; j <= m; ++j) {
+        if (used[j]) {
+          u[p[j]] += delta;
+          v[j] -= delta;
+        } else {
+          minv[j] -= delta;
+        }
+      }
+      j0 = j1;
+    } while (p[j0] != 0);
+    do {
+      const int j1 = way[j0];
+      p[j0] = p[j1];
+      j0 = j1;
+    } while (j0);
+  }
+  double total = 0;
+  for (int j = 1; j <= m; ++j) {
+    if (p[j] == 0) continue;
+    const int worker = p[j] - 1, job = j - 1;
+    const int row = cols_are_workers ? job : worker, col = cols_are_workers ? worker : job;
+    total += a[row][col];
+    if (col < perm_len) perm[(size_t)b * perm_len + col] = row;
+  }
+  if (total_out) total_out[b] = (float)total;
+}
+
 }  // namespace rsis
 
 using namespace rsis;
@@ -145,7 +250,7 @@ using namespace rsis;
 extern "C" {
 
 size_t rsis_soft_iou_workspace_bytes(int b, int g) {
-  return (b > 0 && g > 0) ? ((size_t)b * g * 2 + b) * sizeof(float) : 0;
+  return (b > 0 && g > 0) ? ((size_t)b * g * 2 + b + 1) * sizeof(float) : 0;  // sums + one ticket counter
 }
 
 int rsis_soft_iou_cost(const float* logits, const void* gt, int gt_is_u8, int b, int g, int64_t hw, float eps,
@@ -157,26 +262,21 @@ int rsis_soft_iou_cost(const float* logits, const void* gt, int gt_is_u8, int b,
     return RSIS_ERR_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   // pixel slices: ~4 CTAs per SM, at least 1024 pixels (one float4 per thread) each
-  long long slices = (4LL * 148 + b - 1) / b;
+  // ONE wave: 4 CTAs per SM over (pixel slices x images x row groups), at least 1024 pixels per slice
+  const int groups = ceil_div(g, kIouMaxG);
+  if (groups > 65535) return RSIS_ERR_UNSUPPORTED;
+  long long slices = (4LL * 148) / ((long long)b * groups);
   const long long max_slices = (hw + 1023) / 1024;
   if (slices > max_slices) slices = max_slices;
   if (slices < 1) slices = 1;
-  for (int g0 = 0; g0 < g; g0 += kIouMaxG) {
-    const int gn = g - g0 < kIouMaxG ? g - g0 : kIouMaxG;
-    const dim3 grid((unsigned)slices, (unsigned)b);
-    if (gt_is_u8)
-      soft_iou_partial_kernel<uint8_t><<<grid, 256, 0, st>>>(logits, reinterpret_cast<const uint8_t*>(gt), gn, g0,
-                                                            (long long)hw, workspace, b, g);
-    else
-      soft_iou_partial_kernel<float><<<grid, 256, 0, st>>>(logits, reinterpret_cast<const float*>(gt), gn, g0,
-                                                          (long long)hw, workspace, b, g);
-    RSIS_CHECK_LAUNCH();
-  }
-  soft_iou_finish_kernel<<<ceil_div(b * g, 256), 256, 0, st>>>(workspace, b, g, eps, weight, cost,
-                                                               (long long)cost_stride_b, (long long)cost_stride_g,
-                                                               num_out, den_out);
-  RSIS_CHECK_LAUNCH();
-  soft_iou_zero_sig_kernel<<<ceil_div(b, 256), 256, 0, st>>>(workspace, b, g);
+  const dim3 grid((unsigned)slices, (unsigned)b, (unsigned)groups);
+  const IouFinish fin{eps, weight, cost, (long long)cost_stride_b, (long long)cost_stride_g, num_out, den_out};
+  if (gt_is_u8)
+    soft_iou_partial_kernel<uint8_t><<<grid, 256, 0, st>>>(logits, reinterpret_cast<const uint8_t*>(gt), (long long)hw,
+                                                          workspace, b, g, fin);
+  else
+    soft_iou_partial_kernel<float><<<grid, 256, 0, st>>>(logits, reinterpret_cast<const float*>(gt), (long long)hw,
+                                                        workspace, b, g, fin);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }
@@ -196,6 +296,16 @@ int rsis_soft_iou_bwd(const float* logits, const void* gt, int gt_is_u8, int row
   else
     soft_iou_bwd_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         logits, reinterpret_cast<const float*>(gt), (long long)hw, num, den, dcost, weight, dlogits, total4);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_hungarian_match(const float* cost, int64_t stride_b, int64_t stride_r, int64_t stride_c, int b, int rows,
+                         int cols, int32_t* perm, int perm_len, float* total_cost, rsis_stream_t stream) {
+  if (!cost || !perm || b < 1 || rows < 1 || cols < 1 || perm_len < 1) return RSIS_ERR_BAD_ARG;
+  if (rows > kHungMax || cols > kHungMax) return RSIS_ERR_UNSUPPORTED;
+  hungarian_kernel<<<b, 32, 0, (cudaStream_t)stream>>>(cost, (long long)stride_b, (long long)stride_r,
+                                                      (long long)stride_c, rows, cols, perm, perm_len, total_cost);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

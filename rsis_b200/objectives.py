@@ -53,7 +53,7 @@ def soft_iou_cost_matrix(out_mask: torch.Tensor, y_mask: torch.Tensor, iou_weigh
     check(lib.rsis_soft_iou_cost(logits.data_ptr(), gt.data_ptr(), is_u8, b, g, hw, float(e), float(iou_weight),
                                  ws.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1), None, None,
                                  _lib.stream_ptr()), "soft_iou_cost")
-    _lib.count_launch(3)
+    _lib.count_launch(1)
     return out
 
 
@@ -73,7 +73,7 @@ class _SoftIoURows(torch.autograd.Function):
         check(lib.rsis_soft_iou_cost(logits.data_ptr(), gt.data_ptr(), is_u8, rows, 1, hw, float(e), 1.0, ws.data_ptr(),
                                      cost.data_ptr(), 1, 1, num.data_ptr(), den.data_ptr(), _lib.stream_ptr()),
               "soft_iou_cost")
-        _lib.count_launch(3)
+        _lib.count_launch(1)
         ctx.saved = (logits, gt, is_u8, num, den, tuple(out.shape))
         return cost
 
@@ -103,3 +103,32 @@ class softIoULoss(nn.Module):
     def forward(self, y_true, y_pred, sw):
         costs = softIoU(y_true, y_pred).view(-1, 1)
         return torch.mean(torch.masked_select(costs, sw.bool()))
+
+
+def hungarian_match(overlaps: torch.Tensor):
+    """Minimum-cost matching per image on the device.  overlaps: float32 [B, gtT, T] costs (any strides).
+    Returns (permute_indices int32 [B, gtT] -- `permute_indices[b, t] = ground-truth row matched to prediction t` for
+    t < min(gtT, T), 0 elsewhere, the convention of utils/hungarian.py:113-121 --, total cost [B])."""
+    ops.require_cuda(overlaps, "hungarian_match")
+    lib = _lib.load()
+    c = overlaps.detach().float()
+    b, r, t = c.shape
+    perm = torch.empty((b, r), dtype=torch.int32, device=c.device)
+    total = torch.empty(b, dtype=torch.float32, device=c.device)
+    check(lib.rsis_hungarian_match(c.data_ptr(), c.stride(0), c.stride(1), c.stride(2), b, r, t, perm.data_ptr(), r,
+                                   total.data_ptr(), _lib.stream_ptr()), "hungarian_match")
+    _lib.count_launch(1)
+    return perm, total
+
+
+def match(masks, classes, overlaps):
+    """utils/hungarian.py:91-125 with everything left on the device: the ground-truth masks [B, gtT, N] and classes
+    [B, gtT] permuted by the minimum-cost matching of `overlaps` [B, gtT, T].  Returns (t_mask, t_class,
+    permute_indices) as device tensors (the reference returns numpy arrays after a D2H copy of all masks)."""
+    t_mask, _p_mask = masks
+    t_class, _p_class = classes
+    perm, _ = hungarian_match(overlaps)
+    idx = perm.long()
+    t_mask_perm = torch.gather(t_mask, 1, idx.unsqueeze(-1).expand(-1, -1, t_mask.shape[2]))
+    t_class_perm = torch.gather(t_class, 1, idx if t_class.dim() == 2 else idx.unsqueeze(-1).expand_as(t_class))
+    return t_mask_perm, t_class_perm, perm

@@ -81,3 +81,47 @@ def test_soft_iou_loss_forward_backward(OBJ, u8, golden_dir):
     p3 = pred.clone().requires_grad_(True)
     (O.soft_iou(y_rows, p3) * w).sum().backward()
     assert rel(p2.grad, p3.grad) <= 1e-5
+
+
+def test_hungarian_match_matches_reference_golden(OBJ, golden_dir):
+    from oracle.make_golden import match_inputs
+    g = np.load(os.path.join(golden_dir, "match.npz"))
+    t_mask, t_class, overlaps = match_inputs()
+    pm, pc, perm = OBJ.match([t_mask.cuda(), None], [t_class.cuda(), None], overlaps.cuda())
+    assert (perm.cpu().numpy() == g["perm"]).all()
+    assert (pc.cpu().numpy() == g["t_class"]).all()
+    assert np.abs(pm.sum(-1).cpu().numpy() - g["t_mask_sum"]).max() == 0
+
+
+@pytest.mark.parametrize("shape", [(8, 20, 10), (3, 10, 20), (5, 7, 7), (2, 1, 1), (4, 32, 32), (6, 20, 1)])
+def test_hungarian_match_matches_oracle(OBJ, shape):
+    from oracle import rsis_oracle as O
+    b, r, t = shape
+    gen = torch.Generator().manual_seed(r * 37 + t)
+    big = torch.rand((b, r, t + 3), generator=gen)
+    overlaps = big[:, :, 1:t + 1]                      # a strided view, like scores[B, gtT, T] slices
+    t_mask = torch.rand((b, r, 16), generator=gen)
+    t_class = torch.randint(0, 21, (b, r), generator=gen)
+    _, _, want_perm, want_total = O.match(t_mask, t_class, overlaps)
+    perm, total = OBJ.hungarian_match(big.cuda()[:, :, 1:t + 1])
+    assert (perm.cpu().long() == want_perm).all()
+    assert float((total.cpu().double() - want_total).abs().max()) <= 1e-5
+
+
+def test_hungarian_match_with_ties_is_optimal(OBJ):
+    """train.py:125: masked-out pairs all cost 10 -> many optimal assignments; the total must be the optimum."""
+    from oracle import rsis_oracle as O
+    gen = torch.Generator().manual_seed(4)
+    b, r, t = 8, 20, 10
+    scores = torch.rand((b, r, t), generator=gen)
+    n_obj = torch.randint(1, 12, (b,), generator=gen)
+    for i in range(b):
+        scores[i, int(n_obj[i]):, :] = 10.0
+        scores[i, :, int(n_obj[i]):] = 10.0
+    _, _, _, want_total = O.match(torch.zeros(b, r, 1), torch.zeros(b, r, dtype=torch.long), scores)
+    perm, total = OBJ.hungarian_match(scores.cuda())
+    assert float((total.cpu().double() - want_total).abs().max()) <= 1e-4
+    p = perm.cpu().long()
+    for i in range(b):   # a valid assignment: the first T entries are distinct rows, the tail is zero
+        assert len(set(p[i, :t].tolist())) == t and int(p[i, t:].abs().sum()) == 0
+        assert abs(float(scores[i, p[i, :t], torch.arange(t)].sum()) - float(want_total[i])) <= 1e-4

@@ -103,3 +103,18 @@ def test_soft_iou_oracle_matches_reference_golden(golden_dir):
     loss.backward()
     assert abs(float(loss) - float(g["loss"])) <= 1e-6
     assert np.abs(pred.grad.numpy()[:, ::16] - g["grad"]).max() <= 1e-9 + 1e-5 * np.abs(g["grad"]).max()
+
+
+def test_match_oracle_matches_reference_golden(golden_dir):
+    """oracle.match == the unmodified utils/hungarian.py:91-125 `match` (its Munkres stubbed by scipy: see
+    oracle/make_golden.py::golden_match) -- pins the permutation / gather conventions."""
+    import numpy as np
+    from oracle import rsis_oracle as O
+    from oracle.make_golden import match_inputs
+    g = np.load(os.path.join(golden_dir, "match.npz"))
+    t_mask, t_class, overlaps = match_inputs()
+    pm, pc, perm, total = O.match(t_mask, t_class, overlaps)
+    assert (perm.numpy() == g["perm"]).all()
+    assert (pc.numpy() == g["t_class"]).all()
+    assert np.abs(pm.sum(-1).numpy() - g["t_mask_sum"]).max() == 0
+    assert (perm[:, overlaps.shape[2]:] == 0).all()   # the zero-initialised tail of permute_indices
