@@ -47,6 +47,10 @@ typedef enum rsis_status {
 
 enum { RSIS_FMT_F32 = 0, RSIS_FMT_SPLIT_BF16 = 1 };
 enum { RSIS_IMPL_AUTO = 0, RSIS_IMPL_SIMT = 1, RSIS_IMPL_TCGEN05 = 2 };
+/* rsis_convlstm_cell only: `impl | RSIS_IMPL_CTA_CAP(n)` limits the persistent tcgen05 kernel to n CTAs (n SMs), so that
+ * the cells of different decoder levels -- independent along the (level, step) wavefront -- share the chip side by side
+ * instead of each launch taking every SM in turn.  Ignored by launches that split K across CTAs. */
+#define RSIS_IMPL_CTA_CAP(n) (((n) & 0xffff) << 8)
 
 /* NHWC activation view.  `cstride` is the pixel pitch in elements (0 means dense, = c): a view with
  * cstride > c is a channel slice [data, data + c) of a wider NHWC buffer -- this is how the decoder's

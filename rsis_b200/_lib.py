@@ -160,9 +160,29 @@ class lane:
         return False
 
 
+_no_splitk = False
+
+
+class no_splitk:
+    """Context manager: launches issued inside get no split-K exchange buffer (the kernels then keep every tile's K
+    loop in one CTA: fewer, longer CTAs -- what a pipelined schedule of concurrent small launches wants)."""
+
+    def __enter__(self):
+        global _no_splitk
+        self.prev, _no_splitk = _no_splitk, True
+        return self
+
+    def __exit__(self, *exc):
+        global _no_splitk
+        _no_splitk = self.prev
+        return False
+
+
 def workspace():
     """(pointer, bytes) of the split-K exchange buffer of the current (device, lane): allocated and zero-filled once;
     the kernels leave its counters at zero.  All launches of a lane are issued in one stream order."""
+    if _no_splitk:
+        return None, 0
     dev = torch.cuda.current_device()
     key = (dev, _lane)
     ws = _workspaces.get(key)

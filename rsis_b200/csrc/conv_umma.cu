@@ -1588,10 +1588,14 @@ cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cuda
   return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CELL, PW, SPLIT>, maps, p);
 }
 
+thread_local int t_cta_cap = 0;  // > 0: at most this many CTAs for the next cell launch (set by convlstm_cell_umma)
+
 template <bool CELL>
 int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   const int work = p.num_tiles * p.ksplit;
-  const int grid = work < g_num_sms ? work : g_num_sms;
+  int grid = work < g_num_sms ? work : g_num_sms;
+  // a split-K launch needs all its slices co-resident; a plain persistent launch walks its tiles with any grid
+  if (CELL && t_cta_cap > 0 && p.ksplit == 1 && grid > t_cta_cap) grid = t_cta_cap;
   cudaError_t e;
   if (p.ksplit > 1)
     e = p.pw == 32 ? launch_one<CELL, 32, true>(maps, p, grid, st) : launch_one<CELL, 16, true>(maps, p, grid, st);
@@ -1669,7 +1673,9 @@ int setup_swap(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_c
 
 int launch_swap(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms);
+  int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  if (t_cta_cap > 0 && grid > t_cta_cap) grid = t_cta_cap;
+  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsUmma);
   cfg.dynamicSmemBytes = kDynSmem;
   cfg.stream = st;
@@ -2045,8 +2051,12 @@ bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st) {
+                       int cta_cap, cudaStream_t st) {
   (void)n_src;
+  struct CapGuard {
+    explicit CapGuard(int c) { t_cta_cap = c; }
+    ~CapGuard() { t_cta_cap = 0; }
+  } cap_guard(cta_cap);
   UmmaMaps maps;
   UmmaParams p{};
   const bool swapped = swap_eligible(srcs[0], w);

@@ -18,7 +18,7 @@ bool convlstm_cell_umma_supported(const rsis_tensor* srcs, int n_src, const rsis
 int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weights* w, const float* c_prev,
                        const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st);
+                       int cta_cap, cudaStream_t st);
 }  // namespace rsis
 
 using namespace rsis;
@@ -47,6 +47,8 @@ int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
                        size_t workspace_bytes, rsis_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const int cta_cap = (impl >> 8) & 0xffff;  // RSIS_IMPL_CTA_CAP(n)
+  impl &= 0xff;
   if (gate_preact && (impl == RSIS_IMPL_SIMT || !(srcs && w && convlstm_cell_umma_supported(srcs, n_src, w))))
     return RSIS_ERR_UNSUPPORTED;  // the hoisted-gates form exists in the tcgen05 kernel only
   if (impl == RSIS_IMPL_SIMT)
@@ -55,11 +57,11 @@ int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   if (impl == RSIS_IMPL_TCGEN05) {
     if (!ok) return RSIS_ERR_UNSUPPORTED;
     return convlstm_cell_umma(srcs, n_src, w, c_prev, gate_preact, h_out, h_split, c_out, side_max, side_stride, side_offset,
-                              workspace, workspace_bytes, st);
+                              workspace, workspace_bytes, cta_cap, st);
   }
   if (impl != RSIS_IMPL_AUTO) return RSIS_ERR_BAD_ARG;
   return ok ? convlstm_cell_umma(srcs, n_src, w, c_prev, gate_preact, h_out, h_split, c_out, side_max, side_stride, side_offset,
-                                 workspace, workspace_bytes, st)
+                                 workspace, workspace_bytes, cta_cap, st)
             : convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  st);
 }

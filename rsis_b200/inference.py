@@ -11,6 +11,7 @@ launch-latency-bound at batch 8).
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -53,6 +54,19 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
         else:
             ws.load_feats(decoder, feats_op, impl)
         ws.reset()
+        # RSIS_B200_PIPELINE: 0 = one step after the other (12 launches in stream order), 1 = wavefront over
+        # (level, step) on per-level streams, 2 (default) = wavefront and no split-K in the cells (measured on B200 at
+        # B=8 256x256 T=10: 3.60 / 3.40 / 3.24 ms per pass)
+        mode = os.environ.get("RSIS_B200_PIPELINE", "2")
+        last = ws.h[-1]
+        if mode != "0" and last.c % 4 == 0 and last.c <= 16:
+            # wavefront schedule over (level, step); "2": additionally no split-K in the cells (fewer, longer CTAs)
+            caps = os.environ.get("RSIS_B200_PIPE_CAPS", "")   # per-level CTA caps, e.g. "0,0,0,40,96" (tuning aid)
+            caps = [int(v) for v in caps.split(",")] if caps else None
+            split = os.environ.get("RSIS_B200_PIPE_SPLIT", "")  # per-level split-K switches, e.g. "1,1,0,0,0" (tuning aid)
+            split = [int(v) for v in split.split(",")] if split else (mode != "2")
+            decoder.run_pipelined(ws, impl, T, out_classes, out_masks, out_stops, split_k=split, cta_caps=caps)
+            return ws
         for t in range(T):
             decoder.step_ws(ws, impl, None, out_classes[:, t], T * C, None, T, mask_prob=out_masks[:, t],
                             mask_prob_stride=T * H * W, stop_prob=out_stops[:, t])

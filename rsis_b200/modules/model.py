@@ -172,6 +172,9 @@ class DecoderWorkspace:
         self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
         self.side_stream = torch.cuda.Stream(device=device)  # forked work: skip heads, class/stop heads
+        self.level_streams = None   # pipelined schedule (run_pipelined): one stream per level + the mask head's
+        self.mask_stream = None
+        self.sides = None           # [T, n, F] side-feature keys, one slab per step (pipelined schedule)
         self.t = 0
 
     def packs(self, decoder: "RSIS", l: int):
@@ -219,7 +222,17 @@ class DecoderWorkspace:
         for l in range(len(self.X)):
             sl = slice(self.up_c[l], self.up_c[l] + self.hidden[l])
             self.X[l][0].t[..., sl].zero_()
+        if self.sides is not None:
+            self.sides.zero_()
         self.t = 0
+
+    def prepare_pipeline(self, T: int):
+        dev = self.side.device
+        if self.level_streams is None:
+            self.level_streams = [torch.cuda.Stream(device=dev) for _ in self.X]
+            self.mask_stream = torch.cuda.Stream(device=dev)
+        if self.sides is None or self.sides.shape[0] < T:
+            self.sides = torch.zeros((T,) + tuple(self.side.shape), dtype=torch.int32, device=dev)
 
 
 class RSIS(nn.Module):
@@ -293,6 +306,73 @@ class RSIS(nn.Module):
                           mask_prob_stride)
         main.wait_stream(ws.side_stream)
         ws.t += 1
+
+    def run_pipelined(self, ws: DecoderWorkspace, impl: int, T: int, class_probs: torch.Tensor,
+                      mask_prob: torch.Tensor, stop_prob: torch.Tensor, split_k: bool = True,
+                      cta_caps: Optional[Sequence[int]] = None):
+        """All T decoder steps as a WAVEFRONT over (level, step): level l of step t only needs level l-1 of step t and
+        level l of step t-1 (model.py:132-153 re-feeds `prev_hidden_list[i]` per level), so level l of step t runs
+        concurrently with level l-1 of step t+1.  One stream per level (its upsample + cell in program order), one for
+        the mask head, one for the class/stop heads; cross-stream edges are events:
+            U(l,t) <- C(l-1,t)                       (reads h[l-1])
+            C(l,t) <- U(l+1,t-1) / mask head (t-1)   (they read the h[l] this cell overwrites)
+            mask head(t) <- C(4,t);  heads(t) <- C(0..4,t)   (side keys live in one slab per step)
+        Outputs: class_probs [B,T,C], mask_prob [B,T,H,W], stop_prob [B,T,1] (the stacked tensors of test.py:46-50).
+        Requires ws.reset() before (t = 0 state) and hidden sizes the fused upsample + mask head takes."""
+        nlev = len(self.clstm_list)
+        hl = ws.h[nlev - 1]
+        assert hl.c % 4 == 0 and hl.c <= 16 and ws.t == 0
+        ws.prepare_pipeline(T)
+        dev = hl.t.device
+        main = torch.cuda.current_stream(dev)
+        B, _, H, W = mask_prob.shape
+        C = class_probs.shape[-1]
+        streams = list(ws.level_streams) + [ws.mask_stream, ws.side_stream]
+        start = torch.cuda.Event()
+        start.record(main)
+        for s_ in streams:
+            s_.wait_event(start)
+        ev_cell, ev_up, ev_mask = {}, {}, {}
+        offs = [sum(ws.hidden[:l]) for l in range(nlev)]
+        for t in range(T):
+            p = t & 1
+            for l in range(nlev):
+                S = ws.level_streams[l]
+                with torch.cuda.stream(S), _lib.lane(2 + l):
+                    x = ws.X[l][p]
+                    if l > 0:
+                        S.wait_event(ev_cell[(l - 1, t)])
+                        ops.upsample_bilinear(ws.h[l - 1], x.h, x.w, out=ws.up_view(l, p))
+                        ev_up[(l, t)] = torch.cuda.Event()
+                        ev_up[(l, t)].record(S)
+                    if t > 0:  # the readers of the h[l] this cell is about to overwrite
+                        S.wait_event(ev_up[(l + 1, t - 1)] if l + 1 < nlev else ev_mask[t - 1])
+                    _, pc = ws.packs(self, l)
+                    cap = int(cta_caps[l]) if cta_caps is not None else 0
+                    if split_k if isinstance(split_k, bool) else bool(split_k[l]):
+                        ops.convlstm_cell_x(x, pc, ws.c[l].t if t > 0 else None, ws.sides[t], offs[l], h_out=ws.h[l],
+                                            c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p), impl=impl, gate_preact=ws.P[l])
+                    else:
+                        with _lib.no_splitk():
+                            ops.convlstm_cell_x(x, pc, ws.c[l].t if t > 0 else None, ws.sides[t], offs[l],
+                                                h_out=ws.h[l], c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p), impl=impl,
+                                                gate_preact=ws.P[l], cta_cap=cap)
+                    ev_cell[(l, t)] = torch.cuda.Event()
+                    ev_cell[(l, t)].record(S)
+            with torch.cuda.stream(ws.mask_stream):
+                ws.mask_stream.wait_event(ev_cell[(nlev - 1, t)])
+                ops.upsample_mask_head(hl, 2 * hl.h, 2 * hl.w, self.conv_out.weight, self.conv_out.bias, None,
+                                       mask_prob[:, t], T * H * W)
+                ev_mask[t] = torch.cuda.Event()
+                ev_mask[t].record(ws.mask_stream)
+            with torch.cuda.stream(ws.side_stream):
+                for l in range(nlev):
+                    ws.side_stream.wait_event(ev_cell[(l, t)])
+                ops.class_stop_heads(ws.sides[t], self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight,
+                                     self.fc_stop.bias, class_probs[:, t], T * C, None, stop_prob[:, t], T)
+        for s_ in streams:
+            main.wait_stream(s_)
+        ws.t = T
 
     def step_act(self, feats: Sequence[Act], prev, impl: int, mask_logits: torch.Tensor,
                  class_probs: torch.Tensor, class_stride: int, stop_logit: Optional[torch.Tensor],

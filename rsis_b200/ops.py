@@ -238,7 +238,8 @@ def uses_tcgen05(impl: int) -> bool:
 
 def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
                     side_offset: int = 0, h_out: Optional[Act] = None, c_out: Optional[Act] = None,
-                    h16_out: Optional[Act] = None, impl: int = IMPL_AUTO, gate_preact: Optional[Act] = None):
+                    h16_out: Optional[Act] = None, impl: int = IMPL_AUTO, gate_preact: Optional[Act] = None,
+                    cta_cap: int = 0):
     """One fused ConvLSTM step on the already-concatenated input buffer `x` = [input_ | prev_hidden] (split-bf16,
     all w.cin channels; the prev_hidden slice is zeros when the state is None).  `h16_out` (optional, may be a
     pitched view) receives the new hidden state in the operand format, e.g. the prev_hidden slice of the next
@@ -255,7 +256,8 @@ def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side
         assert gate_preact.fmt == FMT_F32 and gate_preact.dense and gate_preact.c == pc.cout
         pre = gate_preact.t.data_ptr()
     check(lib.rsis_convlstm_cell(srcs, 1, pc.ref(), _ptr(c_prev), pre, h.ref(), h16_out.ref() if h16_out else None,
-                                 c.ref(), _ptr(side_max), stride, side_offset, impl, *_lib.workspace(),
+                                 c.ref(), _ptr(side_max), stride, side_offset, impl | ((cta_cap & 0xffff) << 8),
+                                 *_lib.workspace(),
                                  _lib.stream_ptr()),
           "convlstm_cell")
     _lib.count_launch(1)

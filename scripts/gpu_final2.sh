@@ -1,0 +1,20 @@
+#!/bin/bash
+# Evidence pass for the inference path after the wavefront schedule became the default.
+TAG=${1:-final2}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -q > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
+tail -3 $OUT/pytest.log; grep -E "^(FAILED|ERROR)" $OUT/pytest.log | head
+timeout 300 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke exit $?" >> $OUT/smoke.log; tail -3 $OUT/smoke.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?" >> $OUT/bench.err
+cat $OUT/bench.json | cut -c1-1500; tail -3 $OUT/bench.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/bench_ref.json 2>> $OUT/bench.err; cut -c1-200 $OUT/bench_ref.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
+python scripts/summarize_launches.py $OUT/launches.csv > $OUT/launches.md 2>&1; head -14 $OUT/launches.md
+for wl in cfg3 cfg5; do
+  timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err
+  python -c "
+import json; d=json.load(open('$OUT/bench_$wl.json')); r=d['roofline']
+print('$wl: %.0f masks/s %.2f ms/pass; cell step %.0f us, HBM frac %.3f, %.0f TFLOP/s' % (d['value'], d['ms_per_step'], r['step_us'], r['frac'], r['tensor']['achieved_TFLOPs']))" 2>&1 | tail -1
+done
