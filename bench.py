@@ -367,6 +367,9 @@ def run_ours(a):
                        "T": T, "num_classes": NUM_CLASSES, "parallelism": f"dp{world} (batch sharded per image, "
                        "no data-path collective)", "l2": "flushed between timed steps (512 MiB fill); per-step CUDA "
                        "events summed", "cuda_graph": True,
+                       "decoder_schedule": {"0": "sequential", "1": "wavefront over (level, step), split-K cells",
+                                            "2": "wavefront over (level, step), cells without split-K"}.get(
+                           os.environ.get("RSIS_B200_PIPELINE", "2"), "custom"),
                        "impl": {ops.IMPL_SIMT: "simt", ops.IMPL_AUTO: "auto", ops.IMPL_TCGEN05: "tcgen05"}[impl],
                        "tcgen05": bool(ops.has_tcgen05())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -43,14 +43,7 @@ def _nchw(v: torch.Tensor) -> torch.Tensor:
     return v.permute(0, 3, 1, 2)
 
 
-def _vec(ptr, n, dtype=torch.float32):
-    return None if not ptr else _buf(ptr, n, dtype)
-
-
 class FakeLib:
-    def __init__(self):
-        self.calls = []
-
     def __getattr__(self, name):
         raise AttributeError(f"fake ABI has no {name}")
 
