@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 12
+#define RSIS_ABI_VERSION 13
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -287,6 +287,18 @@ int rsis_soft_iou_bwd(const float* logits, const void* gt, int gt_is_u8, int row
  * square matrix; when several assignments are optimal (equal costs) any one of them is returned. */
 int rsis_hungarian_match(const float* cost, int64_t stride_b, int64_t stride_r, int64_t stride_c, int b, int rows,
                          int cols, int32_t* perm, int perm_len, float* total_cost, rsis_stream_t stream);
+
+/* ---- evaluation post-processing ------------------------------------------------------ */
+/* eval.py:97-127 per predicted instance, on the device: segmentation = masks > threshold (`(pred_mask > th)`), zeroed
+ * where ignore == 1 (`segmentation[ignore_pixels==1] = 0`; ignore optional, uint8 [n][h][w]), areas[i] =
+ * sum(segmentation) (the `min_size` filter of eval.py:119), and the COLUMN-MAJOR run-length encoding of
+ * coco/common/maskApi.c:32-41 (`rleEncode`, reached through `mask.encode(np.asfortranarray(...))`): counts[i][0] =
+ * number of leading zeros (0 when the mask starts with a one), then alternating run lengths; n_runs[i] runs (when
+ * n_runs[i] > max_runs only the first max_runs counts were written).  masks: float32 [n][h][w] row-major.
+ * workspace: rsis_rle_workspace_bytes(n, h, w) bytes, 16-byte aligned (no initialisation needed). */
+size_t rsis_rle_workspace_bytes(int n, int h, int w);
+int rsis_rle_encode(const float* masks, float threshold, const uint8_t* ignore, int n, int h, int w, void* workspace,
+                    uint32_t* counts, int max_runs, int32_t* n_runs, uint32_t* areas, rsis_stream_t stream);
 
 #ifdef __cplusplus
 }

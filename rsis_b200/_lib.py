@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class Tensor(C.Structure):
@@ -84,6 +84,8 @@ SIGNATURES = {
                                 _P, _P]),
     "rsis_soft_iou_bwd": (_I, [_P, _P, _I, _I, C.c_int64, _P, _P, _P, C.c_float, _P, _P]),
     "rsis_hungarian_match": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, _I, _I, _I, _P, _I, _P, _P]),
+    "rsis_rle_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "rsis_rle_encode": (_I, [_P, C.c_float, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "rsis_class_stop_heads_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
