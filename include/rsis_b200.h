@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 13
+#define RSIS_ABI_VERSION 14
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -108,6 +108,17 @@ int rsis_conv_umma_coutpad(int cout);
 size_t rsis_conv_pack_bytes_umma(int cout, int kh, int kw, int n_src, const int32_t* src_c);
 int rsis_conv_pack_umma(const float* w_oihw, int cout, int cin, int kh, int kw, int n_src, const int32_t* src_c,
                         int gate_interleave, void* w_umma, rsis_stream_t stream);
+
+/* rsis_conv_pack + rsis_conv_pack_umma in ONE launch (a training step re-packs every convolution: launches matter), and
+ * optionally of the DATA-GRADIENT convolution directly from the stored parameter: dgrad != 0 packs the logical
+ * weights w'[co'][ci'][i][j] = w[ci'][ci0 + co'][kh-1-i][kw-1-j] (co' in [0, nci), ci' in [0, w_cout)) that
+ * rsis_conv_dgrad_weights would materialise (then bias / bn_* / gate_interleave must be unset).  w_oihw is the stored
+ * [w_cout][w_cin][kh][kw] tensor.  w_kc and w_umma may each be NULL (that pack is skipped); src_c / n_src describe
+ * the tcgen05 K layout of the logical input channels (see rsis_conv_pack_umma). */
+int rsis_conv_pack_all(const float* w_oihw, int w_cout, int w_cin, int kh, int kw, int dgrad, int ci0, int nci,
+                       const float* bias, const float* bn_weight, const float* bn_bias, const float* bn_mean,
+                       const float* bn_var, float bn_eps, int gate_interleave, int n_src, const int32_t* src_c,
+                       float* w_kc, float* scale, float* shift, void* w_umma, rsis_stream_t stream);
 
 /* ---- layout / format plumbing ---------------------------------------------------------------------------- */
 /* float32 NCHW (the reference's layout, e.g. the image batch of test.py:35) -> NHWC tensor (either format). */

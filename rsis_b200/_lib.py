@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class Tensor(C.Structure):
@@ -53,6 +53,8 @@ SIGNATURES = {
     "rsis_conv_umma_coutpad": (_I, [_I]),
     "rsis_conv_pack_bytes_umma": (C.c_size_t, [_I, _I, _I, _I, C.POINTER(C.c_int32)]),
     "rsis_conv_pack_umma": (_I, [_P, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), _I, _P, _P]),
+    "rsis_conv_pack_all": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, C.c_float, _I, _I,
+                                C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
     "rsis_nchw_to_nhwc": (_I, [_P, _TP, _P]),
     "rsis_convert": (_I, [_TP, _TP, _P]),
     "rsis_conv_workspace_bytes": (C.c_size_t, []),

@@ -79,10 +79,10 @@ class _DgradCache:
         ver = (weight.data_ptr(), weight._version)
         hit = self.packs.get(key)
         if hit is None or hit[0] != ver:
-            wt = ops.dgrad_weights(weight, ci0, nci)
-            k = wt.shape[-1]
-            umma = want_umma and k in (1, 3) and wt.shape[0] % 4 == 0 and wt.shape[1] % 8 == 0
-            hit = (ver, PackedConv(wt, None, None, want_umma=umma))
+            cout, cin, k, _ = weight.shape
+            n_in = cin - ci0 if nci is None else nci    # output channels of the data-gradient convolution
+            umma = want_umma and k in (1, 3) and n_in % 4 == 0 and cout % 8 == 0
+            hit = (ver, PackedConv(weight, None, None, want_umma=umma, dgrad=(ci0, n_in)))
             self.packs[key] = hit
         return hit[1]
 

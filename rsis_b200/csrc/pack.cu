@@ -95,6 +95,87 @@ __global__ void pack_umma_kernel(const float* __restrict__ w, __nv_bfloat16* __r
   }
 }
 
+
+// ---- one-launch pack: CUDA-core pack + folded affine + tcgen05 pack, optionally of the DATA-GRADIENT weights ---------
+// `dgrad` != 0: the logical weight tensor being packed is w'[co'][ci'][tap'] = w[ci'][ci0 + co'][taps - 1 - tap'] (the
+// rotated, in/out swapped kernel of rsis_conv_dgrad_weights) read straight from the OIHW parameter -- no intermediate.
+struct PackSrc {
+  const float* w;
+  int cin_src;   // input channels of the stored OIHW tensor
+  int taps;
+  int dgrad, ci0;
+};
+__device__ __forceinline__ float pack_src(const PackSrc& s, int co, int c, int tap) {
+  return s.dgrad ? s.w[((size_t)c * s.cin_src + s.ci0 + co) * s.taps + (s.taps - 1 - tap)]
+                 : s.w[((size_t)co * s.cin_src + c) * s.taps + tap];
+}
+
+__global__ void pack_all_kernel(PackSrc src, const float* __restrict__ bias, const float* __restrict__ bn_w,
+                                const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                const float* __restrict__ bn_var, float eps, int cout, int cin, int cout_pad,
+                                int gate_interleave, float* __restrict__ w_kc, float* __restrict__ scale,
+                                float* __restrict__ shift, __nv_bfloat16* __restrict__ w_umma, int cout_pad_umma,
+                                int k_pad, int n_src, int c0, int c1, int c2) {
+  const int taps = src.taps;
+  const size_t total_simt = w_kc ? (size_t)taps * cin * cout_pad : 0;
+  const size_t plane = w_umma ? (size_t)cout_pad_umma * k_pad : 0;
+  const size_t total = total_simt > plane ? total_simt : plane;
+  const int cs[3] = {c0, c1, c2};
+  int chunk_base[4];
+  chunk_base[0] = 0;
+  for (int q = 0; q < 3; ++q) chunk_base[q + 1] = chunk_base[q] + (q < n_src ? (cs[q] + 63) / 64 : 0);
+  const int chunks_per_tap = chunk_base[3];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total || i < (size_t)cout_pad;
+       i += (size_t)gridDim.x * blockDim.x) {
+    if (i < (size_t)cout_pad) {  // folded affine (pack_affine_kernel)
+      const int j = (int)i;
+      float sc = 0.f, sh = 0.f;
+      if (j < cout) {
+        const int co = ref_cout(j, cout, gate_interleave);
+        const float b = bias ? bias[co] : 0.f;
+        if (bn_w) {
+          sc = bn_w[co] / sqrtf(bn_var[co] + eps);
+          sh = (b - bn_mean[co]) * sc + bn_b[co];
+        } else {
+          sc = 1.f;
+          sh = b;
+        }
+      }
+      scale[j] = sc;
+      shift[j] = sh;
+    }
+    if (i < total_simt) {  // pack_simt_kernel
+      const int j = (int)(i % cout_pad);
+      const int k = (int)(i / cout_pad);
+      float v = 0.f;
+      if (j < cout) v = pack_src(src, ref_cout(j, cout, gate_interleave), k % cin, k / cin);
+      w_kc[i] = v;
+    }
+    if (i < plane) {  // pack_umma_kernel
+      const int kk = (int)(i % k_pad);
+      const int j = (int)(i / k_pad);
+      float v = 0.f;
+      const int chunk = kk / 64, within = kk % 64;
+      const int tap = chunk / chunks_per_tap;
+      const int cidx = chunk % chunks_per_tap;
+      if (j < cout && tap < taps) {
+        int q = 0;
+        while (q < 2 && cidx >= chunk_base[q + 1]) ++q;
+        const int cl = (cidx - chunk_base[q]) * 64 + within;
+        if (cl < cs[q]) {
+          int c = cl;
+          for (int r = 0; r < q; ++r) c += cs[r];
+          v = pack_src(src, ref_cout(j, cout, gate_interleave), c, tap);
+        }
+      }
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      w_umma[i] = hi;
+      w_umma[i + plane] = lo;
+    }
+  }
+}
+
 }  // namespace rsis
 
 using namespace rsis;
@@ -163,6 +244,45 @@ int rsis_conv_pack_umma(const float* w_oihw, int cout, int cin, int kh, int kw, 
   pack_umma_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       w_oihw, reinterpret_cast<__nv_bfloat16*>(w_umma), cout, cin, kh * kw, cp, kp, n_src, src_c[0],
       n_src > 1 ? src_c[1] : 0, n_src > 2 ? src_c[2] : 0, gate_interleave);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_conv_pack_all(const float* w_oihw, int w_cout, int w_cin, int kh, int kw, int dgrad, int ci0, int nci,
+                       const float* bias, const float* bn_weight, const float* bn_bias, const float* bn_mean,
+                       const float* bn_var, float bn_eps, int gate_interleave, int n_src, const int32_t* src_c,
+                       float* w_kc, float* scale, float* shift, void* w_umma, rsis_stream_t stream) {
+  if (!w_oihw || !scale || !shift || w_cout <= 0 || w_cin <= 0 || kh <= 0 || kw <= 0) return RSIS_ERR_BAD_ARG;
+  if (bn_weight && (!bn_bias || !bn_mean || !bn_var)) return RSIS_ERR_BAD_ARG;
+  if (dgrad && (ci0 < 0 || nci < 1 || ci0 + nci > w_cin || bias || bn_weight || gate_interleave)) return RSIS_ERR_BAD_ARG;
+  // logical convolution being packed
+  const int cout = dgrad ? nci : w_cout;
+  const int cin = dgrad ? w_cout : w_cin;
+  if (gate_interleave && (cout % 4) != 0) return RSIS_ERR_BAD_ARG;
+  int kp = 0, cpu = 0, cs[3] = {0, 0, 0};
+  if (w_umma) {
+    if (!src_c || n_src < 1 || n_src > 3) return RSIS_ERR_BAD_ARG;
+    kp = rsis_conv_umma_kpad(kh, kw, n_src, src_c);
+    if (kp == 0) return RSIS_ERR_BAD_ARG;
+    int csum = 0;
+    for (int q = 0; q < n_src; ++q) {
+      cs[q] = src_c[q];
+      csum += src_c[q];
+    }
+    if (csum != cin) return RSIS_ERR_BAD_ARG;
+    cpu = rsis_conv_umma_coutpad(cout);
+  }
+  const int cp = cout_pad_of(cout);
+  const size_t total_simt = w_kc ? (size_t)kh * kw * cin * cp : 0;
+  const size_t plane = (size_t)cpu * kp;
+  size_t total = total_simt > plane ? total_simt : plane;
+  if (total < (size_t)cp) total = cp;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  const PackSrc src{w_oihw, w_cin, kh * kw, dgrad ? 1 : 0, ci0};
+  pack_all_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, bias, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, cout,
+                                                           cin, cp, gate_interleave, w_kc, scale, shift,
+                                                           reinterpret_cast<__nv_bfloat16*>(w_umma), cpu, kp, n_src,
+                                                           cs[0], cs[1], cs[2]);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

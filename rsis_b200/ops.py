@@ -81,11 +81,20 @@ class PackedConv:
     """
 
     def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, bn=None, gate_interleave=False,
-                 src_channels: Optional[Sequence[int]] = None, want_umma: bool = False):
+                 src_channels: Optional[Sequence[int]] = None, want_umma: bool = False, dgrad=None):
+        """dgrad=(ci0, nci): pack the DATA-GRADIENT convolution of `weight` w.r.t. its input channels [ci0, ci0+nci)
+        (rotated, in/out swapped; see rsis_conv_pack_all) straight from the stored parameter."""
         lib = _lib.load()
         require_cuda(weight, "PackedConv")
         w = weight.detach().contiguous().float()
-        cout, cin, kh, kw = w.shape
+        w_cout, w_cin, kh, kw = w.shape
+        if dgrad is not None:
+            ci0, nci = dgrad
+            cout, cin = nci, w_cout
+            assert bias is None and bn is None and not gate_interleave
+        else:
+            ci0, nci = 0, 0
+            cout, cin = w_cout, w_cin
         dev = w.device
         self.cout, self.cin, self.kh, self.kw = cout, cin, kh, kw
         self.gate_interleave = bool(gate_interleave)
@@ -103,20 +112,31 @@ class PackedConv:
                    bn.running_mean.detach().contiguous().float(), bn.running_var.detach().contiguous().float()]
             eps = float(bn.eps)
         st = _lib.stream_ptr()
-        check(lib.rsis_conv_pack(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), eps, cout,
-                                 cin, kh, kw, int(self.gate_interleave), _ptr(self.w_kc), _ptr(self.scale),
-                                 _ptr(self.shift), st), "conv_pack")
-        _lib.count_launch(2)
+        sc = (C.c_int32 * len(self.src_channels))(*self.src_channels)
         self.w_umma = None
         self.k_pad = 0
         if want_umma:
-            sc = (C.c_int32 * len(self.src_channels))(*self.src_channels)
             nbytes = lib.rsis_conv_pack_bytes_umma(cout, kh, kw, len(self.src_channels), sc)
             self.k_pad = lib.rsis_conv_umma_kpad(kh, kw, len(self.src_channels), sc)
             self.w_umma = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=dev)
-            check(lib.rsis_conv_pack_umma(_ptr(w), cout, cin, kh, kw, len(self.src_channels), sc,
-                                          int(self.gate_interleave), _ptr(self.w_umma), st), "conv_pack_umma")
-        _lib.count_launch(1)
+        if os.environ.get("RSIS_B200_FUSED_PACK", "1") != "0":
+            # ONE launch: CUDA-core pack + folded affine + tcgen05 pack (+ the data-gradient index mapping)
+            check(lib.rsis_conv_pack_all(_ptr(w), w_cout, w_cin, kh, kw, int(dgrad is not None), ci0, nci, _ptr(b),
+                                         _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), eps,
+                                         int(self.gate_interleave), len(self.src_channels), sc, _ptr(self.w_kc),
+                                         _ptr(self.scale), _ptr(self.shift), _ptr(self.w_umma), st), "conv_pack_all")
+            _lib.count_launch(1)
+        else:
+            if dgrad is not None:
+                w = dgrad_weights(weight, ci0, nci)
+            check(lib.rsis_conv_pack(_ptr(w), _ptr(b), _ptr(bnp[0]), _ptr(bnp[1]), _ptr(bnp[2]), _ptr(bnp[3]), eps, cout,
+                                     cin, kh, kw, int(self.gate_interleave), _ptr(self.w_kc), _ptr(self.scale),
+                                     _ptr(self.shift), st), "conv_pack")
+            _lib.count_launch(2)
+            if want_umma:
+                check(lib.rsis_conv_pack_umma(_ptr(w), cout, cin, kh, kw, len(self.src_channels), sc,
+                                              int(self.gate_interleave), _ptr(self.w_umma), st), "conv_pack_umma")
+                _lib.count_launch(1)
         # plane-interleaved copy [cout_pad][2][k_pad] for the swapped-operand cell kernel of the narrow decoder levels
         self.w_umma_il = None
         if (self.w_umma is not None and self.gate_interleave and cout in (32, 64) and len(self.src_channels) == 1

@@ -94,6 +94,18 @@ class FakeLib:
         t_[:cout] = sh
         return 0
 
+    def rsis_conv_pack_all(self, w, w_cout, w_cin, kh, kw, dgrad, ci0, nci, bias, bn_w, bn_b, bn_m, bn_v, eps, gate_il,
+                           n_src, src_c, w_kc, scale, shift, w_umma, st):
+        assert not w_umma, "fake ABI: no tcgen05 pack"
+        if dgrad:
+            wt = _buf(w, w_cout * w_cin * kh * kw).view(w_cout, w_cin, kh, kw)
+            logical = wt[:, ci0:ci0 + nci].flip(2, 3).permute(1, 0, 2, 3).contiguous()
+            self._keep = logical  # stays alive for the duration of the call below
+            return self.rsis_conv_pack(logical.data_ptr(), bias, bn_w, bn_b, bn_m, bn_v, eps, nci, w_cout, kh, kw,
+                                       gate_il, w_kc, scale, shift, st)
+        return self.rsis_conv_pack(w, bias, bn_w, bn_b, bn_m, bn_v, eps, w_cout, w_cin, kh, kw, gate_il, w_kc, scale,
+                                   shift, st)
+
     # ---- layout ----
     def rsis_nchw_to_nhwc(self, src, dst, st):
         d = _view(dst)
