@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 14
+#define RSIS_ABI_VERSION 15
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -310,6 +310,15 @@ int rsis_hungarian_match(const float* cost, int64_t stride_b, int64_t stride_r, 
 size_t rsis_rle_workspace_bytes(int n, int h, int w);
 int rsis_rle_encode(const float* masks, float threshold, const uint8_t* ignore, int n, int h, int w, void* workspace,
                     uint32_t* counts, int max_runs, int32_t* n_runs, uint32_t* areas, rsis_stream_t stream);
+
+/* ---- optimiser step ------------------------------------------------------------------ */
+/* torch.optim.Adam as utils/utils.py:72-83 builds it (train.py:185-187), on n contiguous float32 elements: per element,
+ * `repeats` sequential updates with step counts step0+1 .. step0+repeats (a parameter listed k times in an optimiser --
+ * utils/utils.py:34-52 does that -- is updated k times per step()):
+ *   g' = g + weight_decay*p;  m += (g' - m)*(1 - beta1);  v = v*beta2 + (1 - beta2)*g'^2;
+ *   p -= lr/(1 - beta1^t) * m / (sqrt(v)/sqrt(1 - beta2^t) + eps).   repeats <= 8. */
+int rsis_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int64_t step0, int repeats, rsis_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,7 @@ class _DgradCache:
 
     def get(self, weight: torch.Tensor, want_umma: bool, ci0: int = 0, nci: Optional[int] = None) -> PackedConv:
         key = (id(weight), ci0, nci, want_umma)
-        ver = (weight.data_ptr(), weight._version)
+        ver = (weight.data_ptr(), weight._version, ops.weights_epoch())
         hit = self.packs.get(key)
         if hit is None or hit[0] != ver:
             cout, cin, k, _ = weight.shape
@@ -443,17 +443,34 @@ class GradBucket:
     the views) -> forward -> `loss.backward()` (autograd accumulates into the views in place) ->
     `bucket.all_reduce()` -> optimiser step."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, flatten_params: bool = False):
+        seen = set()
+        self.params = []
+        for p in params:  # first occurrence only (the reference's parameter lists contain duplicates)
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
         if not self.params:
             raise ValueError("GradBucket: no trainable parameters")
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.offsets = {}
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.offsets[id(p)] = off
             off += p.numel()
+        self.flat_params = None
+        if flatten_params:
+            # the parameters themselves become views of ONE buffer, in the same order (what a fused optimiser walks)
+            self.flat_params = torch.empty(total, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for p in self.params:
+                    o = self.offsets[id(p)]
+                    view = self.flat_params[o:o + p.numel()].view_as(p)
+                    view.copy_(p.detach())
+                    p.data = view
 
     def zero(self):
         self.flat.zero_()

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librsis_b200.so")
-SOURCES = ["api.cu", "pack.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "decoder_ops.cu", "bn_train.cu", "backward.cu", "objectives.cu", "postprocess.cu", "dispatch.cu"]
+SOURCES = ["api.cu", "pack.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "decoder_ops.cu", "bn_train.cu", "backward.cu", "objectives.cu", "postprocess.cu", "optim.cu", "dispatch.cu"]
 NVCC_FLAGS = (["-DRSIS_DEBUG_TIMING"] if os.environ.get("RSIS_B200_BUILD_DEBUG_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -118,7 +118,7 @@ class InferenceSession:
         self.graph = g
 
     def _key(self):
-        return sum(t._version for t in self._tensors), len(self._tensors)
+        return sum(t._version for t in self._tensors), len(self._tensors), ops.weights_epoch()
 
     def stale(self) -> bool:
         return self._key() != self.weights_key

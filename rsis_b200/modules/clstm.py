@@ -33,7 +33,7 @@ class ConvLSTMCell(nn.Module):
         """Packed (gate-interleaved) weights for a given split of the input channels into sources."""
         w, b = self.Gates.weight, self.Gates.bias
         key = (tuple(src_channels), want_umma)
-        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version, ops.weights_epoch())
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
             hit = (ver, PackedConv(w, b, None, gate_interleave=True, src_channels=src_channels, want_umma=want_umma))
@@ -46,7 +46,7 @@ class ConvLSTMCell(nn.Module):
         gates for the backward (rsis_lstm_gates_fwd / _bwd)."""
         w, b = self.Gates.weight, self.Gates.bias
         key = ("plain", want_umma)
-        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version, ops.weights_epoch())
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
             hit = (ver, PackedConv(w, b, None, want_umma=want_umma))
@@ -62,7 +62,7 @@ class ConvLSTMCell(nn.Module):
         w, b = self.Gates.weight, self.Gates.bias
         assert up_c + skip_c == self.input_size
         key = ("hoisted", up_c, skip_c)
-        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        ver = (w.data_ptr(), w._version, b.data_ptr(), b._version, ops.weights_epoch())
         hit = self._packed.get(key)
         if hit is None or hit[0] != ver:
             wd = w.detach()

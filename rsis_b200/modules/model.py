@@ -64,7 +64,7 @@ class FeatureExtractor(nn.Module):
         tensors = []
         for sk, bn in self._heads():
             tensors += [sk.weight, sk.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = (tuple((t.data_ptr(), t._version) for t in tensors), want_umma)
+        key = (tuple((t.data_ptr(), t._version) for t in tensors), want_umma, ops.weights_epoch())
         if self._packed is None or self._packed_key != key:
             self._packed = [PackedConv(sk.weight, sk.bias, bn, want_umma=want_umma) for sk, bn in self._heads()]
             self._packed_key = key
@@ -72,7 +72,8 @@ class FeatureExtractor(nn.Module):
 
     def packed_heads_train(self, want_umma: bool):
         """Skip-head packs without BatchNorm (bias only), for the training-mode forward."""
-        key = (tuple((sk.weight.data_ptr(), sk.weight._version, sk.bias._version) for sk, _ in self._heads()), want_umma)
+        key = (tuple((sk.weight.data_ptr(), sk.weight._version, sk.bias._version) for sk, _ in self._heads()), want_umma,
+               ops.weights_epoch())
         if getattr(self, "_packed_tr", None) is None or self._packed_tr_key != key:
             self._packed_tr = [PackedConv(sk.weight, sk.bias, None, want_umma=want_umma) for sk, _ in self._heads()]
             self._packed_tr_key = key

@@ -72,7 +72,8 @@ class ResNet101(nn.Module):
 
     # ---- packed-weight cache (derived from the nn.Parameters; rebuilt when they change) ----------------------
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        return (ops.weights_epoch(),) + tuple((p.data_ptr(), p._version)
+                                             for p in list(self.parameters()) + list(self.buffers()))
 
     def packed(self, want_umma: bool):
         key = (self._weights_key(), want_umma)
@@ -96,7 +97,7 @@ class ResNet101(nn.Module):
         convs = [self.conv1] + [m for li in range(1, 5) for blk in getattr(self, f"layer{li}")
                                 for m in ([blk.conv1, blk.conv2, blk.conv3] +
                                           ([blk.downsample[0]] if blk.downsample is not None else []))]
-        key = (tuple((c.weight.data_ptr(), c.weight._version) for c in convs), want_umma)
+        key = (tuple((c.weight.data_ptr(), c.weight._version) for c in convs), want_umma, ops.weights_epoch())
         if getattr(self, "_packed_tr", None) is None or self._packed_tr_key != key:
             pk = {"stem": PackedConv(self.conv1.weight, None, None)}
             for li in range(1, 5):

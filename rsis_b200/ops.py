@@ -11,6 +11,20 @@ from . import _lib
 from ._lib import FMT_F32, FMT_SPLIT_BF16, IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, Act, check  # noqa: F401
 
 
+_weights_epoch = 0
+
+
+def weights_epoch() -> int:
+    """Part of every derived weight-pack cache key next to the parameters' (data_ptr, _version): bumped by writers that
+    change parameter VALUES without going through torch (the fused optimiser writes through a flat buffer)."""
+    return _weights_epoch
+
+
+def bump_weights_epoch():
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def launch_count() -> int:
     """Number of CUDA kernels this process has enqueued through the C ABI so far."""
     return _lib._launches

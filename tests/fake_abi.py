@@ -395,6 +395,21 @@ class FakeLib:
         return 0
 
 
+def _adam(self, p, g, m, v, n, lr, b1, b2, eps, wd, step0, repeats, st):
+    P, G, M, V = _buf(p, n), _buf(g, n), _buf(m, n), _buf(v, n)
+    for r in range(repeats):
+        t = step0 + r + 1
+        gg = G + wd * P
+        M.copy_(M + (gg - M) * (1 - b1))
+        V.copy_(V * b2 + (1 - b2) * gg * gg)
+        denom = V.sqrt() / (1 - b2 ** t) ** 0.5 + eps
+        P.sub_((lr / (1 - b1 ** t)) * (M / denom))
+    return 0
+
+
+FakeLib.rsis_adam_step = _adam
+
+
 def install(monkeypatch):
     """Routes rsis_b200's ABI calls to FakeLib and lifts the CUDA-only guards (host-logic tests on CPU)."""
     from rsis_b200 import _lib, ops
