@@ -4,6 +4,7 @@ and the ONE data-parallel gradient all-reduce.
 
     step = TrainStep(encoder, decoder, T, loss_fn, cuda_graph=True)
     loss = step(x)            # gradients are in step.bucket.flat / every parameter's .grad; then optimiser.step()
+                              # (or pass optimizer=rsis_b200.optim.FusedAdam(...) and the step includes it)
 
 `loss_fn(masks, classes, stops) -> scalar` receives the lists of per-step outputs (mask logits [B,1,H,W], class
 probabilities [B,C], stop logits [B,1]); the reference's criteria (train.py:159-176) are outside the hot path.
@@ -26,8 +27,14 @@ from .autograd import GradBucket, _DgradCache
 
 class TrainStep:
     def __init__(self, encoder, decoder, T: int, loss_fn: Callable, bucket: Optional[GradBucket] = None,
-                 cuda_graph: bool = True, all_reduce: bool = True):
+                 cuda_graph: bool = True, all_reduce: bool = True, optimizer=None):
+        """optimizer (optional): an `rsis_b200.optim.FusedAdam` over `bucket` (which then must have been built with
+        flatten_params=True); its step runs after the all-reduce, outside the captured graph (a handful of launches
+        whose bias-correction coefficients change every step)."""
         self.enc, self.dec, self.T, self.loss_fn = encoder, decoder, int(T), loss_fn
+        self.optimizer = optimizer
+        if optimizer is not None and bucket is None:
+            bucket = optimizer.bucket
         self.bucket = bucket if bucket is not None else GradBucket(list(encoder.parameters()) + list(decoder.parameters()))
         self.use_graph = bool(cuda_graph)
         self.do_all_reduce = bool(all_reduce)
@@ -101,6 +108,8 @@ class TrainStep:
             loss = self.static_loss
         if self.do_all_reduce:
             self.bucket.all_reduce()
+        if self.optimizer is not None:
+            self.optimizer.step()
         return loss
 
     @property

@@ -81,3 +81,33 @@ def test_train_step_object_eager_matches_manual_loop(fake):
     assert abs(l1 - l2) <= 1e-4 * abs(l1)  # running statistics move, the train-mode outputs do not
     assert float((step.bucket.flat - g1).abs().max()) <= 1e-3 * float(g1.abs().max())
     assert float(g1.abs().sum()) > 0
+
+
+def test_train_step_with_fused_adam_moves_the_parameters(fake):
+    """TrainStep(optimizer=FusedAdam): forward + backward + optimiser step in one call; the next forward uses the
+    updated parameters (pack caches follow ops.weights_epoch) and the loss goes down on a fixed batch."""
+    import rsis_b200
+    from rsis_b200 import optim
+    from rsis_b200.autograd import GradBucket
+    from rsis_b200.training import TrainStep
+    from oracle import synth_weights as sw
+    from train_parity import _args
+    args = _args(5, 2)
+    args.lr, args.lr_cnn, args.weight_decay, args.weight_decay_cnn = 1e-3, 1e-6, 1e-6, 1e-6
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1, num_classes=5))
+    enc.train()
+    dec.train()
+    x = sw.synthetic_images(123, 2, 64, 64)
+
+    def loss_fn(masks, classes, stops):
+        return sum((m ** 2).mean() + (s ** 2).sum() for m, c, s in zip(masks, classes, stops))
+
+    bucket = GradBucket(list(enc.parameters()) + list(dec.parameters()), flatten_params=True)
+    fused = optim.FusedAdam(bucket, optim.reference_param_groups(args, enc, dec))
+    step = TrainStep(enc, dec, 2, loss_fn, cuda_graph=False, all_reduce=False, optimizer=fused)
+    w0 = dec.conv_out.weight.detach().clone()
+    losses = [float(step(x)) for _ in range(4)]
+    assert float((dec.conv_out.weight.detach() - w0).abs().max()) > 0
+    assert losses[-1] < losses[0], losses
