@@ -2,7 +2,9 @@
 masks that are already at the output size: threshold, ignore mask, area, and the COCO
 run-length encoding (`mask.encode(np.asfortranarray(segmentation))`, coco/common/maskApi.c:32-41 + :203-215).
 Only the run lengths (a few hundred integers per instance) are copied to the host instead of the float masks.
-The bilinear resize to the original image size (`scipy.ndimage.zoom(order=1)`, eval.py:111-115) is not built.
+The resize to the original image size (eval.py:111-115: `scipy.ndimage.zoom(pred_mask, [h/H, w/W, 1], order=1)`) is the
+align-corners bilinear interpolation the decoder already uses (`rsis_upsample_bilinear`): zoom with its default
+`grid_mode=False` maps output index i to input coordinate i*(in-1)/(out-1).
 """
 from __future__ import annotations
 
@@ -12,6 +14,24 @@ import torch
 
 from . import _lib, ops
 from ._lib import check
+
+
+def resize_masks(masks: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """eval.py:111-115 on the device: [n, H, W] float masks -> [n, height, width], order-1 (bilinear) interpolation with
+    scipy.ndimage.zoom's default coordinate mapping (= align_corners=True)."""
+    ops.require_cuda(masks, "resize_masks")
+    n, h, w = masks.shape
+    if (h, w) == (int(height), int(width)):
+        return masks
+    # the interpolation kernel works on NHWC activations with a multiple-of-4 channel count: 4 masks per "pixel"
+    pad = (-n) % 4
+    m = masks.detach().float()
+    if pad:
+        m = torch.cat([m, m.new_zeros((pad, h, w))], 0)
+    groups = (n + pad) // 4
+    x = ops.Act(m.view(groups, 4, h, w).permute(0, 2, 3, 1).contiguous(), ops.FMT_F32)
+    y = ops.upsample_bilinear(x, int(height), int(width), ops.FMT_F32)
+    return y.t.permute(0, 3, 1, 2).reshape(groups * 4, int(height), int(width))[:n].contiguous()
 
 
 def rle_encode(masks: torch.Tensor, threshold: float = 0.5, ignore: Optional[torch.Tensor] = None,
@@ -58,9 +78,13 @@ def rle_to_string(cnts) -> bytes:
     return bytes(out)
 
 
-def encode_instances(masks: torch.Tensor, threshold: float = 0.5, ignore: Optional[torch.Tensor] = None) -> List[dict]:
+def encode_instances(masks: torch.Tensor, threshold: float = 0.5, ignore: Optional[torch.Tensor] = None,
+                     size=None) -> List[dict]:
     """COCO-style segmentations of `masks` [n, H, W]: [{'size': [H, W], 'counts': bytes, 'area': int}, ...] (what
-    eval.py:122 obtains from pycocotools), with one small D2H copy for all instances."""
+    eval.py:122 obtains from pycocotools), with one small D2H copy for all instances.  size=(height, width): resize
+    first (`resize_mask` of eval.py:97-127 end to end)."""
+    if size is not None:
+        masks = resize_masks(masks, size[0], size[1])
     n, h, w = masks.shape
     counts, n_runs, areas = rle_encode(masks, threshold, ignore, max_runs=h * w + 1 if h * w < 4096 else None)
     nr = n_runs.cpu().tolist()

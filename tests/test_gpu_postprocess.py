@@ -64,3 +64,29 @@ def test_encode_instances_strings(PP):
         assert o["counts"] == PP.rle_to_string(w)
         if R.ref_available():
             assert o["counts"] == R.rle_to_string_ref(w, masks.shape[1], masks.shape[2])
+
+
+@pytest.mark.parametrize("shape", [(5, 64, 64, 96, 80), (3, 48, 64, 37, 101), (8, 256, 256, 375, 500)])
+def test_resize_matches_scipy_zoom_and_rle_of_it(PP, shape):
+    """eval.py:97-127 end to end: zoom(order=1) -> threshold -> RLE.  The interpolation runs in fp32 on the device and in
+    fp64 in scipy, so pixels whose interpolated value is within 1e-5 of the threshold may differ: the values are
+    compared with a tolerance, the RLE against the oracle applied to the DEVICE's own resized mask."""
+    from scipy.ndimage import zoom
+    from oracle import rle_oracle as R
+    n, h, w, H, W = shape
+    gen = torch.Generator().manual_seed(H)
+    low = torch.rand((n, 1, max(h // 8, 2), max(w // 8, 2)), generator=gen)
+    probs = torch.nn.functional.interpolate(low, size=(h, w), mode="bicubic", align_corners=True)[:, 0].contiguous()
+    want = np.stack([zoom(probs[i].numpy().reshape(h, w, 1), [float(H) / h, float(W) / w, 1], order=1)[:, :, 0]
+                     for i in range(n)])
+    got = PP.resize_masks(probs.cuda(), H, W)
+    assert tuple(got.shape) == (n, H, W) == want.shape
+    assert float(np.abs(got.cpu().numpy() - want).max()) <= 2e-5
+    th = 0.5
+    out = PP.encode_instances(probs.cuda(), th, size=(H, W))
+    seg = (got.cpu().numpy() > th).astype(np.uint8)
+    cnts, areas = R.rle_encode(seg)
+    for o, c, a in zip(out, cnts, areas):
+        assert o["size"] == [H, W] and o["area"] == int(a) and o["counts"] == PP.rle_to_string(c)
+    agree = ((want > th) == (seg == 1)).mean()
+    assert agree >= 0.9999
