@@ -212,6 +212,80 @@ def match(t_mask, t_class, overlaps):
     return t_mask_perm, t_class_perm, idx, torch.from_numpy(total)
 
 
+def masked_nll(target, probs):
+    """utils/hungarian.py:10-33 `MaskedNLL` (balance_weights=None)."""
+    return -torch.gather(torch.log(probs), dim=1, index=target).squeeze()
+
+
+def stable_balanced_bce(target, out):
+    """utils/hungarian.py:35-61 `StableBalancedMaskedBCE` (balance_weight=None: computed from the targets)."""
+    num_positive = target.sum()
+    num_negative = (1 - target).sum()
+    balance_weight = num_positive / (num_positive + num_negative)
+    max_val = (-out).clamp(min=0)
+    loss_values = out - out * target + max_val + ((-max_val).exp() + (-out - max_val).exp()).log()
+    losses = (1 - balance_weight) * loss_values * target + balance_weight * loss_values * (1 - target)
+    return losses.squeeze()
+
+
+def run_iter(encode, step, x, y_mask, y_class, sw_mask, sw_class, args, cost_matrix=None, match_fn=None,
+             iou_loss=None):
+    """The forward + loss portion of `runIter` (train.py:71-176) as a recipe over callables, so that the SAME statement
+    sequence runs over the CPU oracle (defaults) and over the modules / kernels under test:
+        encode(x) -> feats;  step(feats, hidden) -> (out_mask [B,1,H,W], class_probs [B,C], stop [B,1], hidden);
+        cost_matrix(out_mask [B,HW], y_mask [B,gtT,HW], iou_weight) -> [B,gtT]        (train.py:96-110)
+        match_fn(y_mask, y_class, scores [B,gtT,T]) -> (y_mask_perm, y_class_perm)    (train.py:137, hungarian.py:91-125)
+        iou_loss(y_true [R,HW], y_pred [R,HW], sw [R,1]) -> scalar                    (objectives.py:27-34)
+    Returns (loss, [loss_mask_iou, loss_stop, loss_class], y_class_perm)."""
+    cost_matrix = cost_matrix or soft_iou_cost_matrix
+    match_fn = match_fn or (lambda m, c, sc: match(m, c, sc)[:2])
+    iou_loss = iou_loss or soft_iou_loss
+    B, gtT = y_mask.shape[0], y_mask.shape[1]
+    T = args.maxseqlen
+    if args.curriculum_learning:
+        T = min(args.maxseqlen, args.limit_seqlen_to)
+    feats = encode(x)
+    scores = torch.ones(B, args.gt_maxseqlen, args.maxseqlen, device=y_mask.device)
+    hidden = None
+    out_masks, out_classes, out_stops = [], [], []
+    stop_next = False
+    for t in range(T):
+        if stop_next:
+            break
+        if float(sw_mask[:, t].sum()) == 0:      # train.py:91 (a host read in the reference as well)
+            stop_next = True
+        out_mask, out_class, out_stop, hidden = step(feats, hidden)
+        out_mask = out_mask.reshape(out_mask.shape[0], -1)   # train.py:96-98 (the resize is an identity at full size)
+        scores[:, :, t] = cost_matrix(out_mask.detach(), y_mask, args.iou_weight)
+        out_masks.append(out_mask)
+        out_classes.append(out_class.reshape(B, -1))
+        out_stops.append(out_stop.reshape(B, -1))
+    t = len(out_masks)
+    out_masks = torch.cat(out_masks, 1).view(B, t, -1)
+    out_classes = torch.cat(out_classes, 1).view(B, t, -1)
+    out_stops = torch.cat(out_stops, 1).view(B, t, -1)
+    sw_mult = sw_mask.unsqueeze(-1).repeat(1, 1, args.maxseqlen)
+    sw_mult_t = sw_mask[:, 0:args.maxseqlen].unsqueeze(-1).repeat(1, 1, args.gt_maxseqlen).permute(0, 2, 1)
+    sw_mult = sw_mult * sw_mult_t                                        # train.py:121-124 (the byte AND)
+    scores = scores * sw_mult + (1 - sw_mult) * 10                       # train.py:125
+    y_mask_perm, y_class_perm = match_fn(y_mask, y_class, scores)
+    y_mask_perm, y_class_perm = y_mask_perm[:, 0:t], y_class_perm[:, 0:t]
+    sw_m = sw_mask[:, 0:t].contiguous().float()
+    sw_c = sw_class[:, 0:t].contiguous().float()
+    loss_class = masked_nll(y_class_perm.reshape(-1, 1).long(), out_classes.view(-1, out_classes.size()[-1])).view(-1, 1)
+    loss_class = torch.mean(torch.masked_select(loss_class, sw_m.view(-1, 1).bool()))
+    loss_mask_iou = iou_loss(y_mask_perm.reshape(-1, y_mask_perm.size()[-1]), out_masks.view(-1, out_masks.size()[-1]),
+                             sw_m.view(-1, 1))
+    loss_stop = stable_balanced_bce(sw_m, out_stops.squeeze(-1)).view(-1, 1)
+    loss_stop = torch.mean(torch.masked_select(loss_stop, sw_c.view(-1, 1).bool()))
+    loss = args.iou_weight * loss_mask_iou
+    if args.use_class_loss:
+        loss = loss + args.class_weight * loss_class
+    if args.use_stop_loss:
+        loss = loss + args.stop_weight * loss_stop
+    return loss, [loss_mask_iou, loss_stop, loss_class], y_class_perm
+
+
 # ----------------------------------------------------------------------------------------------
 # precision emulators (design aids; not part of any parity claim)
 # ----------------------------------------------------------------------------------------------

@@ -406,3 +406,20 @@ def test_train_step_cuda_graph_matches_eager(R):
                 pg.add_(pe.grad, alpha=-1e-4)
     assert int(enc_g.base.bn1.num_batches_tracked) == int(enc_e.base.bn1.num_batches_tracked) == 3
     assert float((enc_g.base.bn1.running_mean - enc_e.base.bn1.running_mean).abs().max()) <= 1e-5
+
+
+def test_run_iter_whole_training_iteration(R, families):
+    """`runIter` (train.py:56-197) end to end on the GPU -- train-mode encoder, T decoder steps, the fused soft-IoU cost
+    matrix per step, Hungarian matching on the device, softIoULoss (fused forward + backward), class / stop losses,
+    `loss.backward()` -- against the oracle recipe, which tests/test_oracle_golden.py pins to the reference's own
+    runIter.  Losses to 1e-4; matched classes exactly; gradients in the relative-L2 metric of the whole-step test."""
+    from run_iter_parity import modules_run_iter, oracle_run_iter
+    if "ri" not in _ref_cache:
+        _ref_cache["ri"] = oracle_run_iter()
+    want_l, want_perm, want_g = _ref_cache["ri"]
+    got_l, got_perm, got_g = modules_run_iter("cuda")
+    assert max(abs(a - b) for a, b in zip(got_l, want_l)) <= 1e-4, (got_l, want_l)
+    assert (got_perm == want_perm).all()
+    tol = 2e-2 if families == ("simt", "simt") else 1e-1   # 2 x 64x64: layer4 normalises over 8 samples (see above)
+    compare_grads({"loss": got_l[0], "grads": got_g}, {"loss": want_l[0], "grads": want_g}, tol=tol, metric="l2",
+                  verbose=True)

@@ -118,3 +118,24 @@ def test_match_oracle_matches_reference_golden(golden_dir):
     assert (pc.numpy() == g["t_class"]).all()
     assert np.abs(pm.sum(-1).numpy() - g["t_mask_sum"]).max() == 0
     assert (perm[:, overlaps.shape[2]:] == 0).all()   # the zero-initialised tail of permute_indices
+
+
+def test_run_iter_oracle_matches_the_reference_runIter(golden_dir):
+    """oracle.run_iter (forward, soft-IoU costs, matching, the three losses) + torch autograd == the reference's OWN
+    `runIter` (train.py:56-197) executed in the build container by oracle/run_iter_ref.py: losses, matched classes and
+    every parameter gradient (norm + 32 samples per tensor)."""
+    import numpy as np
+    from run_iter_parity import digest, oracle_run_iter
+    from train_parity import ZERO_GRAD
+    g = np.load(os.path.join(golden_dir, "run_iter.npz"))
+    losses, perm, grads = oracle_run_iter()
+    assert np.abs(np.array(losses) - g["losses"]).max() <= 1e-6
+    assert (perm.numpy() == g["perm_class"]).all()
+    names = [str(n) for n in g["names"]]
+    assert sorted(grads) == names
+    for n, d in zip(names, g["digests"]):
+        if n in ZERO_GRAD:
+            continue
+        got = digest(grads[n])
+        assert abs(got[0] - d[0]) <= 1e-4 * d[0] + 1e-12, n                        # gradient norm
+        assert np.abs(got[2:] - d[2:]).max() <= 1e-4 * np.abs(d[2:]).max() + 1e-9, n   # samples

@@ -111,3 +111,15 @@ def test_train_step_with_fused_adam_moves_the_parameters(fake):
     losses = [float(step(x)) for _ in range(4)]
     assert float((dec.conv_out.weight.detach() - w0).abs().max()) > 0
     assert losses[-1] < losses[0], losses
+
+
+def test_run_iter_through_modules_matches_oracle(fake):
+    """The whole training iteration of train.py:56-197 through the modules' autograd nodes (host logic, fake ABI)."""
+    from run_iter_parity import modules_run_iter, oracle_run_iter
+    want_l, want_perm, want_g = oracle_run_iter()
+    got_l, got_perm, got_g = modules_run_iter("cpu")
+    assert max(abs(a - b) for a, b in zip(got_l, want_l)) <= 1e-5
+    assert (got_perm == want_perm).all()
+    res = {"loss": got_l[0], "grads": got_g}
+    ref = {"loss": want_l[0], "grads": want_g}
+    compare_grads(res, ref, tol=1e-2, metric="l2")
