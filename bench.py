@@ -277,7 +277,8 @@ def run_ours(a):
 
     # ---- e2e: public API call with HOST buffers (pinned); H2D + graph + D2H inside the timed region ----
     # Results are read back on a copy stream into two alternating pinned buffers, so the D2H of pass i overlaps the
-    # H2D + compute of pass i+1 (every pass still pays its own H2D and D2H inside the timed region).
+    # compute of pass i+1, and the H2D of pass i+1 is issued under the compute of pass i (every pass still pays its own
+    # H2D and D2H inside the timed region).
     nbuf = 2
     masks_h = [torch.empty((B, T, H, W), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
     classes_h = [torch.empty((B, T, NUM_CLASSES), dtype=torch.float32).pin_memory() for _ in range(nbuf)]
@@ -286,10 +287,28 @@ def run_ours(a):
     main_stream = torch.cuda.current_stream(dev)
     copied = [torch.cuda.Event() for _ in range(nbuf)]
 
+    # Inputs: two device buffers filled from pinned host memory on an H2D stream, one step ahead -- the copy for pass
+    # i+1 runs under the compute of pass i (every timed pass issues exactly one H2D and one D2H of a full batch).
+    h2d_stream = torch.cuda.Stream(device=dev)
+    xbuf = [torch.empty_like(x_dev) for _ in range(nbuf)]
+    h2d_done = [torch.cuda.Event() for _ in range(nbuf)]
+    consumed = [torch.cuda.Event() for _ in range(nbuf)]
+    for ev in consumed:
+        ev.record(main_stream)
+
+    def issue_h2d(i):
+        k = i % nbuf
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(consumed[k])              # the pass that last read this buffer has finished
+            xbuf[k].copy_(x_host, non_blocking=True)
+            h2d_done[k].record(h2d_stream)
+
     def e2e_step(i):
         k = i % nbuf
-        xd = x_host.to(dev, non_blocking=True)
-        m, c, s = rsis_b200.test(args, enc, dec, xd)          # fresh result tensors (clones of the session outputs)
+        issue_h2d(i + 1)                                     # next pass's input, under this pass's compute
+        main_stream.wait_event(h2d_done[k])
+        m, c, s = rsis_b200.test(args, enc, dec, xbuf[k])    # fresh result tensors (clones of the session outputs)
+        consumed[k].record(main_stream)
         done = torch.cuda.Event()
         done.record(main_stream)
         with torch.cuda.stream(copy_stream):
@@ -301,15 +320,18 @@ def run_ours(a):
         for t in (m, c, s):
             t.record_stream(copy_stream)
 
+    issue_h2d(0)
     for i in range(3):
         e2e_step(i)
     torch.cuda.synchronize(dev)
     rdist.barrier()
+    # re-prime: the input of the first timed pass (3 % nbuf) was already issued by the last warm-up pass
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(a.steps):
+    for i in range(3, 3 + a.steps):
         e2e_step(i)
     main_stream.wait_stream(copy_stream)   # the timed region ends when the last result has reached host memory
+    main_stream.wait_stream(h2d_stream)    # ... and the last issued input copy has landed
     e1.record()
     torch.cuda.synchronize(dev)
     rdist.barrier()
