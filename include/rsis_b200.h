@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 15
+#define RSIS_ABI_VERSION 16
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -125,6 +125,11 @@ int rsis_conv_pack_all(const float* w_oihw, int w_cout, int w_cin, int kh, int k
 int rsis_nchw_to_nhwc(const float* src_nchw, const rsis_tensor* dst, rsis_stream_t stream);
 /* NHWC tensor -> NHWC tensor of the other element format (same shape). */
 int rsis_convert(const rsis_tensor* src, const rsis_tensor* dst, rsis_stream_t stream);
+
+/* im2col: y[n,ho,wo,(i*kw + j)*C + c] = x[n, ho*stride - pad + i, wo*stride - pad + j, c] (zero outside the image and in
+ * y's channels beyond kh*kw*C).  x float32 dense, y split-bf16 dense with y->c % 8 == 0.  Turns the 3-channel 7x7/s2 stem
+ * (vision.py:12) into a 1x1 tensor-core convolution over 147 (+5) channels. */
+int rsis_im2col(const rsis_tensor* x, int kh, int kw, int stride, int pad, const rsis_tensor* y, rsis_stream_t stream);
 
 /* ---- workspace ------------------------------------------------------------------------------------------------ */
 /* The tcgen05 convolution splits K across co-resident CTAs when a launch has fewer output tiles than SMs; the

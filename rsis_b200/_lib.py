@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 
 class Tensor(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
                                 C.POINTER(C.c_int32), _P, _P, _P, _P, _P]),
     "rsis_nchw_to_nhwc": (_I, [_P, _TP, _P]),
     "rsis_convert": (_I, [_TP, _TP, _P]),
+    "rsis_im2col": (_I, [_TP, _I, _I, _I, _I, _TP, _P]),
     "rsis_conv_workspace_bytes": (C.c_size_t, []),
     "rsis_conv2d": (_I, [_TP, _I, _WP, _TP, _TP, _TP, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "rsis_maxpool3x3s2": (_I, [_TP, _TP, _P]),

@@ -27,6 +27,42 @@ __global__ void convert_kernel(View src, int scs, void* dst, size_t plane, int f
   }
 }
 
+// im2col for the ResNet stem (vision.py:12: 7x7, stride 2, pad 3 on a 3-channel image): y[n,ho,wo,(kh*KW+kw)*C + c] =
+// x[n, ho*stride - pad + kh, wo*stride - pad + kw, c] (zero outside the image and for the padding channels beyond
+// KH*KW*C), written in the split-bf16 operand format so that the stem becomes a 1x1 tensor-core convolution over
+// K = 147 (+5) channels instead of a CUDA-core kernel.  One thread per (output pixel, group of 8 output channels).
+__global__ void im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t y_plane, int N, int H,
+                              int W, int C, int Ho, int Wo, int KH, int KW, int stride, int pad, int Cy) {
+  pdl_trigger();
+  const int G = Cy >> 3;
+  const size_t total = (size_t)N * Ho * Wo * G;
+  const int K = KH * KW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    size_t r = i / G;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int kh = tap / KW, kw = tap - kh * KW;
+        const int hi_ = ho * stride - pad + kh, wi_ = wo * stride - pad + kw;
+        if (hi_ >= 0 && hi_ < H && wi_ >= 0 && wi_ < W) v = x[(((size_t)n * H + hi_) * W + wi_) * C + c];
+      }
+      split_bf16(v, hi[j], lo[j]);
+    }
+    const size_t o = (r * Wo + wo) * Cy + g * 8;  // r == n*Ho + ho here
+    *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(y + o + y_plane) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 }  // namespace rsis
 
 using namespace rsis;
@@ -55,6 +91,20 @@ int rsis_convert(const rsis_tensor* src, const rsis_tensor* dst, rsis_stream_t s
   const size_t total = numel(*dst);
   convert_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       make_view(*src), pitch(*src), dst->data, plane_elems(*dst), dst->fmt, pitch(*dst), dst->c, total);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_im2col(const rsis_tensor* x, int kh, int kw, int stride, int pad, const rsis_tensor* y, rsis_stream_t stream) {
+  if (!valid_tensor(x) || !valid_tensor(y) || kh < 1 || kw < 1 || stride < 1 || pad < 0) return RSIS_ERR_BAD_ARG;
+  if (x->fmt != RSIS_FMT_F32 || y->fmt != RSIS_FMT_SPLIT_BF16 || !is_dense(*x) || !is_dense(*y)) return RSIS_ERR_UNSUPPORTED;
+  const int Ho = (x->h + 2 * pad - kh) / stride + 1, Wo = (x->w + 2 * pad - kw) / stride + 1;
+  if (y->n != x->n || y->h != Ho || y->w != Wo || y->c < kh * kw * x->c || y->c % 8 != 0) return RSIS_ERR_BAD_ARG;
+  if (!aligned16(y->data)) return RSIS_ERR_ALIGN;
+  const size_t total = (size_t)y->n * Ho * Wo * (y->c / 8);
+  im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(x->data), reinterpret_cast<__nv_bfloat16*>(y->data), plane_elems(*y), x->n, x->h,
+      x->w, x->c, Ho, Wo, kh, kw, stride, pad, y->c);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

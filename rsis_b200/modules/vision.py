@@ -7,6 +7,7 @@ torchvision's, including the never-executed `avgpool`/`fc`); the arithmetic runs
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -79,6 +80,15 @@ class ResNet101(nn.Module):
         key = (self._weights_key(), want_umma)
         if self._packed is None or self._packed_key != key:
             pk = {"stem": PackedConv(self.conv1.weight, None, self.bn1)}
+            if want_umma and os.environ.get("RSIS_B200_TC_STEM", "1") != "0":
+                # the stem as a 1x1 tensor-core convolution over the im2col'd image: K = (kh, kw, c) order of
+                # rsis_im2col, zero padded from 147 to 152 channels
+                w = self.conv1.weight.detach()
+                k = w.shape[1] * w.shape[2] * w.shape[3]
+                cy = (k + 7) // 8 * 8
+                w1 = torch.zeros((w.shape[0], cy, 1, 1), dtype=torch.float32, device=w.device)
+                w1[:, :k, 0, 0] = w.permute(0, 2, 3, 1).reshape(w.shape[0], k)
+                pk["stem_tc"] = PackedConv(w1, None, self.bn1, want_umma=True)
             for li in range(1, 5):
                 for bi, blk in enumerate(getattr(self, f"layer{li}")):
                     p = f"layer{li}.{bi}"
@@ -161,7 +171,12 @@ class ResNet101(nn.Module):
         fmt = ops.activation_format(impl)
         pk = self.packed(want_umma=(fmt == ops.FMT_SPLIT_BF16))
         xa = ops.act_from_nchw(x, ops.FMT_F32)
-        x1 = ops.conv2d([xa], pk["stem"], stride=2, pad=3, relu=True, out_fmt=fmt, impl=ops.IMPL_SIMT)
+        if "stem_tc" in pk:
+            st = pk["stem_tc"]
+            cols = ops.im2col(xa, self.conv1.kernel_size[0], self.conv1.kernel_size[1], 2, 3, st.cin)
+            x1 = ops.conv2d([cols], st, relu=True, out_fmt=fmt, impl=impl)
+        else:
+            x1 = ops.conv2d([xa], pk["stem"], stride=2, pad=3, relu=True, out_fmt=fmt, impl=ops.IMPL_SIMT)
         if on_tap is not None:
             on_tap(4, x1)
         cur = ops.maxpool3x3s2(x1)

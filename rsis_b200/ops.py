@@ -209,6 +209,17 @@ def nchw_to_nhwc(x: torch.Tensor, fmt: int = FMT_F32) -> Act:
     return y
 
 
+def im2col(x: Act, kh: int, kw: int, stride: int, pad: int, cy: int) -> Act:
+    """float32 NHWC -> split-bf16 [N, Ho, Wo, cy] patch matrix (cy >= kh*kw*C, multiple of 8; the tail is zero)."""
+    lib = _lib.load()
+    ho = (x.h + 2 * pad - kh) // stride + 1
+    wo = (x.w + 2 * pad - kw) // stride + 1
+    y = Act.empty(x.n, ho, wo, cy, FMT_SPLIT_BF16, x.t.device)
+    check(lib.rsis_im2col(x.ref(), kh, kw, stride, pad, y.ref(), _lib.stream_ptr()), "im2col")
+    _lib.count_launch(1)
+    return y
+
+
 def convert(x: Act, fmt: int, out: Optional[Act] = None) -> Act:
     """Element-format conversion and/or channel-slice copy (`out` may be a pitched view of a wider buffer)."""
     lib = _lib.load()
