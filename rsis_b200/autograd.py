@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import _lib, ops
+from . import ops
 from .ops import Act, PackedConv
 
 F32 = ops.FMT_F32
