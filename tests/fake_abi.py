@@ -410,6 +410,87 @@ def _adam(self, p, g, m, v, n, lr, b1, b2, eps, wd, step0, repeats, st):
 FakeLib.rsis_adam_step = _adam
 
 
+# ---- section 8f entry points (objectives / post-processing), restated from the header contracts ----
+def _gt_rows(ptr, is_u8, n):
+    return _buf(ptr, n, torch.uint8).float() if is_u8 else _buf(ptr, n)
+
+
+def _soft_iou_ws(self, b, g):
+    return (b * g * 2 + b + 1) * 4
+
+
+def _soft_iou_cost(self, logits, gt, is_u8, b, g, hw, eps, weight, ws, cost, sb, sg, num_out, den_out, st):
+    s = torch.sigmoid(_buf(logits, b * hw).view(b, 1, hw))
+    y = _gt_rows(gt, is_u8, b * g * hw).view(b, g, hw)
+    num = (s * y).sum(-1)
+    den = (s + y - s * y).sum(-1) + eps
+    span = (b - 1) * sb + (g - 1) * sg + 1
+    out = _buf(cost, span).as_strided((b, g), (sb, sg))
+    out.copy_(weight * (1 - num / den))
+    if num_out:
+        _buf(num_out, b * g).copy_(num.reshape(-1))
+    if den_out:
+        _buf(den_out, b * g).copy_(den.reshape(-1))
+    return 0
+
+
+def _soft_iou_bwd(self, logits, gt, is_u8, rows, hw, num, den, dcost, weight, dlogits, st):
+    s = torch.sigmoid(_buf(logits, rows * hw).view(rows, hw))
+    y = _gt_rows(gt, is_u8, rows * hw).view(rows, hw)
+    n, d, dc = (_buf(p_, rows).view(rows, 1) for p_ in (num, den, dcost))
+    _buf(dlogits, rows * hw).view(rows, hw).copy_(-weight * dc * (y * d - n * (1 - y)) / (d * d) * s * (1 - s))
+    return 0
+
+
+def _hungarian(self, cost, sb, sr, sc, b, rows, cols, perm, perm_len, total, st):
+    import numpy as np
+    from scipy.optimize import linear_sum_assignment
+    span = (b - 1) * sb + (rows - 1) * sr + (cols - 1) * sc + 1
+    c = _buf(cost, span).as_strided((b, rows, cols), (sb, sr, sc)).double().numpy()
+    p = _buf(perm, b * perm_len, torch.int32).view(b, perm_len)
+    p.zero_()
+    for i in range(b):
+        r, cc = linear_sum_assignment(c[i])
+        for row, col in zip(r, cc):
+            if col < perm_len:
+                p[i, col] = int(row)
+        if total:
+            _buf(total, b)[i] = float(c[i][r, cc].sum())
+    return 0
+
+
+def _rle_ws(self, n, h, w):
+    return 16
+
+
+def _rle_encode(self, masks, th, ignore, n, h, w, ws, counts, max_runs, n_runs, areas, st):
+    import numpy as np
+    m = _buf(masks, n * h * w).view(n, h, w).numpy()
+    seg = (m > th).astype(np.uint8)
+    if ignore:
+        seg[_buf(ignore, n * h * w, torch.uint8).view(n, h, w).numpy() == 1] = 0
+    cnt = _buf(counts, n * max_runs, torch.int32).view(n, max_runs)
+    nr = _buf(n_runs, n, torch.int32)
+    for i in range(n):
+        t = seg[i].T.reshape(-1)
+        pos = np.flatnonzero(t != np.concatenate([[0], t[:-1]]))
+        runs = np.diff(np.concatenate([[0], pos, [t.size]]))
+        nr[i] = len(runs)
+        k = min(len(runs), max_runs)
+        cnt[i, :k] = torch.from_numpy(runs[:k].astype(np.int32))
+        if areas:
+            _buf(areas, n, torch.int32)[i] = int(t.sum())
+    return 0
+
+
+FakeLib.rsis_soft_iou_workspace_bytes = _soft_iou_ws
+FakeLib.rsis_soft_iou_cost = _soft_iou_cost
+FakeLib.rsis_soft_iou_bwd = _soft_iou_bwd
+FakeLib.rsis_hungarian_match = _hungarian
+FakeLib.rsis_rle_workspace_bytes = _rle_ws
+FakeLib.rsis_rle_encode = _rle_encode
+
+
 def install(monkeypatch):
     """Routes rsis_b200's ABI calls to FakeLib and lifts the CUDA-only guards (host-logic tests on CPU)."""
     from rsis_b200 import _lib, ops
