@@ -319,12 +319,15 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, View y, int ha
   const size_t per_block = (M + gridDim.x - 1) / gridDim.x;
   const size_t p0 = (size_t)blockIdx.x * per_block;
   const size_t p1 = p0 + per_block < M ? p0 + per_block : M;
-  for (int c4 = threadIdx.x % lanes_c; c4 < C4; c4 += lanes_c) {
+  // uniform trip count (the body holds block barriers); threads past C4 in the last round carry no pixels
+  for (int c4base = 0; c4base < C4; c4base += lanes_c) {
+    const int c4 = c4base + threadIdx.x % lanes_c;
+    const bool live = c4 < C4;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    const float4 mu = *reinterpret_cast<const float4*>(mean + 4 * c4);
-    const float4 is = *reinterpret_cast<const float4*>(invstd + 4 * c4);
+    const float4 mu = live ? *reinterpret_cast<const float4*>(mean + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 is = live ? *reinterpret_cast<const float4*>(invstd + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
-    if (threadIdx.x < rows_per_iter * lanes_c) {
+    if (live && threadIdx.x < rows_per_iter * lanes_c) {
 #pragma unroll 4
       for (size_t p = p0 + threadIdx.x / lanes_c; p < p1; p += rows_per_iter) {
         const size_t idx = p * C + 4 * c4;
@@ -352,7 +355,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, View y, int ha
       mine[4 + j] = q[j];
     }
     __syncthreads();
-    if (threadIdx.x < lanes_c) {
+    if (threadIdx.x < lanes_c && live) {
       double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
       for (int r = 0; r < rows_per_iter; ++r) {
         const float* o = red + (r * lanes_c + threadIdx.x) * 8;

@@ -19,10 +19,14 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, size_t M, int C, do
   const size_t per_block = (M + gridDim.x - 1) / gridDim.x;
   const size_t p0 = (size_t)blockIdx.x * per_block;
   const size_t p1 = p0 + per_block < M ? p0 + per_block : M;
-  for (int c4 = threadIdx.x % lanes_c; c4 < C4; c4 += lanes_c) {
+  // uniform trip count (the body holds block barriers): threads whose channel group falls beyond C4 in the last
+  // round run it with an empty pixel range
+  for (int c4base = 0; c4base < C4; c4base += lanes_c) {
+    const int c4 = c4base + threadIdx.x % lanes_c;
+    const bool live = c4 < C4 && threadIdx.x < rows_per_iter * lanes_c;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-    for (size_t p = p0 + threadIdx.x / lanes_c; p < p1; p += rows_per_iter) {
+    for (size_t p = live ? p0 + threadIdx.x / lanes_c : p1; p < p1; p += rows_per_iter) {
       const float4 v = *reinterpret_cast<const float4*>(x + p * C + 4 * c4);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
@@ -34,7 +38,7 @@ __global__ void bn_stats_kernel(const float* __restrict__ x, size_t M, int C, do
       mine[4 + j] = q[j];
     }
     __syncthreads();
-    if (threadIdx.x < lanes_c) {  // one thread per channel group combines the rows of the block in double
+    if (threadIdx.x < lanes_c && c4 < C4) {  // one thread per channel group combines the rows of the block in double
       double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
       for (int r = 0; r < rows_per_iter; ++r) {
         const float* o = red + (r * lanes_c + threadIdx.x) * 8;

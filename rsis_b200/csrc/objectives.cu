@@ -175,7 +175,10 @@ __global__ void hungarian_kernel(const float* __restrict__ cost, long long sb, l
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
     const int r = i / C, c = i - r * C;
-    a[r][c] = (double)cost[b * sb + r * sr + c * sc];
+    // non-finite costs (a diverged step: NaN logits -> NaN soft-IoU) would leave `way[]` unset and the augmenting
+    // loop without a minimum: map them to a large finite cost so the solver always terminates with a valid assignment
+    const float cv = cost[b * sb + r * sr + c * sc];
+    a[r][c] = isfinite(cv) ? (double)cv : (cv < 0.f ? -1e30 : 1e30);
   }
   for (int i = threadIdx.x; i < perm_len; i += blockDim.x) perm[(size_t)b * perm_len + i] = 0;
   __syncthreads();
@@ -190,6 +193,7 @@ __global__ void hungarian_kernel(const float* __restrict__ cost, long long sb, l
   for (int j = 0; j <= m; ++j) {
     v[j] = 0;
     p[j] = 0;
+    way[j] = 0;
   }
   for (int i = 0; i <= n; ++i) u[i] = 0;
   for (int i = 1; i <= n; ++i) {

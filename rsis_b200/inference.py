@@ -12,7 +12,8 @@ launch-latency-bound at batch 8).
 from __future__ import annotations
 
 import os
-from typing import Dict, Optional, Tuple
+from collections import OrderedDict
+from typing import Optional, Tuple
 
 import torch
 
@@ -118,7 +119,9 @@ class InferenceSession:
         self.graph = g
 
     def _key(self):
-        return sum(t._version for t in self._tensors), len(self._tensors), ops.weights_epoch()
+        # per-tensor (storage, version): a parameter re-pointed without a version bump (GradBucket's `p.data = view`,
+        # `.to()` / `.cuda()` re-materialisation) or a reload must invalidate the graph, which reads raw pointers
+        return (tuple((t.data_ptr(), t._version) for t in self._tensors), ops.weights_epoch(), ops.bn_stats_epoch())
 
     def stale(self) -> bool:
         return self._key() != self.weights_key
@@ -133,7 +136,8 @@ class InferenceSession:
         return self.masks, self.classes, self.stops
 
 
-_sessions: Dict[tuple, InferenceSession] = {}
+_sessions: "OrderedDict[tuple, InferenceSession]" = OrderedDict()
+_MAX_SESSIONS = int(os.environ.get("RSIS_B200_MAX_SESSIONS", "8"))  # LRU bound: a graph + workspace per input shape
 
 
 def test(args, encoder, decoder, x):
@@ -152,9 +156,14 @@ def test(args, encoder, decoder, x):
     if getattr(args, "cuda_graph", True):
         key = (id(encoder), id(decoder), tuple(x.shape), T, x.device.index, impl)
         s = _sessions.get(key)
-        if s is None or s.stale():
+        if s is None or s.stale() or s.encoder is not encoder or s.decoder is not decoder:
+            _sessions.pop(key, None)
             s = InferenceSession(args, encoder, decoder, x.shape, x.device, impl)
             _sessions[key] = s
+            while len(_sessions) > _MAX_SESSIONS:
+                _sessions.popitem(last=False)
+        else:
+            _sessions.move_to_end(key)
         masks, classes, stops = s(x)
         return masks.clone(), classes.clone(), stops.clone()
     H, W = x.shape[-2:]

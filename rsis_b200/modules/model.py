@@ -64,7 +64,7 @@ class FeatureExtractor(nn.Module):
         tensors = []
         for sk, bn in self._heads():
             tensors += [sk.weight, sk.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
-        key = (tuple((t.data_ptr(), t._version) for t in tensors), want_umma, ops.weights_epoch())
+        key = (tuple((t.data_ptr(), t._version) for t in tensors), want_umma, ops.weights_epoch(), ops.bn_stats_epoch())
         if self._packed is None or self._packed_key != key:
             self._packed = [PackedConv(sk.weight, sk.bias, bn, want_umma=want_umma) for sk, bn in self._heads()]
             self._packed_key = key

@@ -73,7 +73,7 @@ class ResNet101(nn.Module):
 
     # ---- packed-weight cache (derived from the nn.Parameters; rebuilt when they change) ----------------------
     def _weights_key(self):
-        return (ops.weights_epoch(),) + tuple((p.data_ptr(), p._version)
+        return (ops.weights_epoch(), ops.bn_stats_epoch()) + tuple((p.data_ptr(), p._version)
                                              for p in list(self.parameters()) + list(self.buffers()))
 
     def packed(self, want_umma: bool):

@@ -25,6 +25,21 @@ def bump_weights_epoch():
     _weights_epoch += 1
 
 
+_bn_stats_epoch = 0
+
+
+def bn_stats_epoch() -> int:
+    """Part of every EVAL-side cache key (BatchNorm-folded packs, captured inference graphs): bumped whenever a
+    train-mode BatchNorm kernel advances running_mean / running_var through raw pointers (torch's `_version` does not
+    move then).  Train-mode packs do not fold the statistics and do not key on it."""
+    return _bn_stats_epoch
+
+
+def bump_bn_stats_epoch():
+    global _bn_stats_epoch
+    _bn_stats_epoch += 1
+
+
 def launch_count() -> int:
     """Number of CUDA kernels this process has enqueued through the C ABI so far."""
     return _lib._launches
@@ -233,7 +248,8 @@ _bn_workspaces = {}
 
 
 def _bn_workspace(dev, c: int) -> torch.Tensor:
-    key = dev.index
+    # per (device, stream): two train forwards on different streams must not share the accumulator
+    key = (dev.index, _lib.stream_ptr())
     ws = _bn_workspaces.get(key)
     if ws is None or ws.numel() < 2 * c:
         ws = torch.zeros(max(2 * c, 8192), dtype=torch.float64, device=dev)
@@ -261,6 +277,8 @@ def bn_train_stats(x: Act, bn, want_stats: bool = False):
                                   _ptr(bn.num_batches_tracked) if track else None, ws.data_ptr(), scale.data_ptr(),
                                   shift.data_ptr(), _ptr(mean), _ptr(invstd), _lib.stream_ptr()), "bn_train_stats")
     _lib.count_launch(2)
+    if track:
+        bump_bn_stats_epoch()  # eval-side packs fold these statistics: they are stale now
     return (scale, shift, mean, invstd) if want_stats else (scale, shift)
 
 

@@ -26,24 +26,39 @@ from ._lib import check
 from .autograd import GradBucket
 
 
+def _base_param_multiplicity(encoder):
+    """(parameter, how many times utils.py:34-52 yields it), in first-occurrence order.
+
+    The reference walks `m.modules()` of each backbone child (conv1, bn1, layer1..4) and, for every module visited,
+    all of its `.parameters()` recursively -- so a parameter is yielded once per module on the path from that child
+    down to the parameter's owner.  That is the depth of its qualified name below the child: `layer3.5.conv2.weight`
+    -> (layer3, layer3.5, layer3.5.conv2) = 3, `layer2.0.downsample.0.weight` -> 4, `conv1.weight` -> 1.  The first
+    visit of a child (the child itself) yields its parameters in `named_parameters()` order, which fixes the
+    first-occurrence order.  Pinned by tests/golden/optim_groups.json (made by the unmodified reference)."""
+    base = encoder.base
+    out = []
+    for child in (base.conv1, base.bn1, base.layer1, base.layer2, base.layer3, base.layer4):
+        for name, p in child.named_parameters():
+            if p.requires_grad:
+                out.append((p, name.count(".") + 1))
+    return out
+
+
 def get_base_params(args, model):
-    """utils/utils.py:34-52, statement for statement (ResNet branch): duplicates included."""
-    b = [model.base.conv1, model.base.bn1, model.base.layer1, model.base.layer2, model.base.layer3, model.base.layer4]
-    for i in range(len(b)):
-        for j in b[i].modules():
-            for k in j.parameters():
-                if k.requires_grad:
-                    yield k
+    """Same multiset and first-occurrence order as utils/utils.py:34-52 (ResNet branch), duplicates included."""
+    pairs = _base_param_multiplicity(model)
+    for p, _ in pairs:
+        yield p
+    for p, r in pairs:
+        for _ in range(r - 1):
+            yield p
 
 
 def get_skip_params(model):
-    """utils/utils.py:54-71."""
-    b = [model.sk1.parameters(), model.sk2.parameters(), model.sk3.parameters(), model.sk4.parameters(),
-         model.sk5.parameters(), model.bn1.parameters(), model.bn2.parameters(), model.bn3.parameters(),
-         model.bn4.parameters(), model.bn5.parameters()]
-    for j in range(len(b)):
-        for i in b[j]:
-            yield i
+    """utils/utils.py:54-71: the five skip convolutions, then the five skip BatchNorms, level 1 to 5."""
+    for kind in ("sk", "bn"):
+        for level in range(1, 6):
+            yield from getattr(model, f"{kind}{level}").parameters()
 
 
 def reference_param_groups(args, encoder, decoder, update_encoder: bool = True):
@@ -111,3 +126,72 @@ class FusedAdam:
         # the kernel wrote the parameters through the flat buffer: their `_version`s did not move, so tell the derived
         # weight-pack caches explicitly
         ops.bump_weights_epoch()
+
+    # ---- checkpointing (utils/utils.py:86-111 saves / restores enc_opt.pt and dec_opt.pt; train.py:314-316 switches
+    # the encoder group on mid-run) ---------------------------------------------------------------------------------
+    def state_dict(self):
+        """First / second moments and step counts per optimised parameter, keyed by the parameter's position in the
+        bucket (stable for a given model), plus the hyper-parameters of each run."""
+        b = self.bucket
+        state = {}
+        for idx, p in enumerate(b.params):
+            off = b.offsets[id(p)]
+            run = self._run_of(off)
+            if run is None:
+                continue
+            state[idx] = {"step": int(run[5]), "exp_avg": self.m[off:off + p.numel()].view_as(p).clone(),
+                          "exp_avg_sq": self.v[off:off + p.numel()].view_as(p).clone()}
+        return {"state": state, "betas": self.betas, "eps": self.eps,
+                "runs": [[int(r[0]), int(r[1]), float(r[2]), float(r[3]), int(r[4]), int(r[5])] for r in self.runs]}
+
+    def _run_of(self, off: int):
+        for run in self.runs:
+            if run[0] <= off < run[0] + run[1]:
+                return run
+        return None
+
+    def load_state_dict(self, sd):
+        """Restores moments and step counts for every parameter present in BOTH the checkpoint and this optimiser
+        (so a checkpoint written before the encoder group was enabled loads into an optimiser that has it)."""
+        b = self.bucket
+        steps = {}
+        with torch.no_grad():
+            for idx, st in sd["state"].items():
+                p = b.params[int(idx)]
+                off = b.offsets[id(p)]
+                run = self._run_of(off)
+                if run is None:
+                    continue
+                self.m[off:off + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                self.v[off:off + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.setdefault(id(run), (run, set()))[1].add(int(st["step"]))
+        for run, seen in steps.values():
+            if len(seen) != 1:
+                raise ValueError("FusedAdam.load_state_dict: parameters of one run carry different step counts")
+            run[5] = seen.pop()
+
+    def add_groups(self, groups):
+        """Enables further parameter groups (e.g. the encoder when `update_encoder` flips on, train.py:314-316) without
+        touching the moments / step counts of the parameters already optimised."""
+        b = self.bucket
+        hyper = {}
+        for g in groups:
+            for p, r in zip(g["params"], g["repeats"]):
+                hyper[id(p)] = (float(g["lr"]), float(g["weight_decay"]), int(r))
+        for p in b.params:
+            h = hyper.get(id(p))
+            if h is None:
+                continue
+            off = b.offsets[id(p)]
+            if self._run_of(off) is not None:
+                raise ValueError("FusedAdam.add_groups: parameter is already optimised")
+            self.runs.append([off, p.numel(), h[0], h[1], h[2], 0])
+        self.runs.sort(key=lambda r: r[0])
+        merged: List[list] = []
+        for r in self.runs:
+            last = merged[-1] if merged else None
+            if last is not None and last[0] + last[1] == r[0] and last[2:] == r[2:]:
+                last[1] += r[1]
+            else:
+                merged.append(r)
+        self.runs = merged

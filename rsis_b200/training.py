@@ -105,6 +105,9 @@ class TrainStep:
                 self._capture(x)
             self.static_x.copy_(x, non_blocking=True)
             self.graph.replay()
+            # the replay advanced every BatchNorm's running statistics on the device without any Python-side signal:
+            # eval-side packs / captured inference graphs that folded the old statistics are stale
+            ops.bump_bn_stats_epoch()
             loss = self.static_loss
         if self.do_all_reduce:
             self.bucket.all_reduce()
