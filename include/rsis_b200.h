@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 16
+#define RSIS_ABI_VERSION 17
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -294,6 +294,27 @@ int rsis_soft_iou_cost(const float* logits, const void* gt, int gt_is_u8, int b,
 /* dlogits[r][p] = dcost[r] * d cost[r] / d logits[r][p] for row-wise softIoU (logits, gt: [rows][hw]). */
 int rsis_soft_iou_bwd(const float* logits, const void* gt, int gt_is_u8, int rows, int64_t hw, const float* num,
                       const float* den, const float* dcost, float weight, float* dlogits, rsis_stream_t stream);
+
+/* Masked class / stop losses (utils/objectives.py:6-25 over utils/hungarian.py:10-59; train.py:159-168).  A row is
+ * selected when (uint8)sw != 0, the reference's `sw.byte()` mask.
+ * rsis_masked_nll_fwd (MaskedNLLLoss / MaskedNLL): cost[r] = -balance[target[r]] * log(probs[r][target[r]]) (balance
+ * optional, [num_classes]); probs float32 [rows][num_classes] dense, target int64 [rows], sw float32 [rows].
+ * cost_rows (optional, [rows]): the per-row costs, 0 on unselected rows; sum_count [2] = {sum of the selected costs,
+ * number of selected rows} (overwritten) -- the mean of train.py:161 without masked_select.
+ * rsis_masked_nll_bwd: dprobs [rows][num_classes] (overwritten) for upstream dcost[r * dcost_stride] (stride 0 = one
+ * scalar for every row, e.g. dloss / count).
+ * rsis_masked_bce_fwd (MaskedBCELoss / StableBalancedMaskedBCE): target, logits, sw float32 [n]; balance_weight < 0
+ * means "None" (sum(target) / n, computed in the kernel); sum_count_bw [3] = {sum, count, balance weight used}.
+ * rsis_masked_bce_bwd: balance_weight points at the weight the forward used (sum_count_bw + 2). */
+int rsis_masked_nll_fwd(const float* probs, const int64_t* target, const float* sw, const float* balance, int rows,
+                        int num_classes, float* cost_rows, float* sum_count, rsis_stream_t stream);
+int rsis_masked_nll_bwd(const float* probs, const int64_t* target, const float* sw, const float* balance,
+                        const float* dcost, int64_t dcost_stride, int rows, int num_classes, float* dprobs,
+                        rsis_stream_t stream);
+int rsis_masked_bce_fwd(const float* target, const float* logits, const float* sw, float balance_weight, int64_t n,
+                        float* cost_rows, float* sum_count_bw, rsis_stream_t stream);
+int rsis_masked_bce_bwd(const float* target, const float* logits, const float* sw, const float* balance_weight,
+                        const float* dcost, int64_t dcost_stride, int64_t n, float* dlogits, rsis_stream_t stream);
 
 /* Hungarian matching on the device (replaces `Munkres().compute` per image on the host,
  * utils/hungarian.py:91-125, train.py:137).  cost: float32 [b][rows][cols] with element strides (rows = ground-truth

@@ -212,20 +212,36 @@ def match(t_mask, t_class, overlaps):
     return t_mask_perm, t_class_perm, idx, torch.from_numpy(total)
 
 
-def masked_nll(target, probs):
-    """utils/hungarian.py:10-33 `MaskedNLL` (balance_weights=None)."""
-    return -torch.gather(torch.log(probs), dim=1, index=target).squeeze()
+def masked_nll(target, probs, balance_weights=None):
+    """utils/hungarian.py:10-33 `MaskedNLL`: -log(probs)[target], optionally scaled per class."""
+    log_probs = torch.log(probs)
+    if balance_weights is not None:
+        log_probs = torch.mul(log_probs, balance_weights)
+    return -torch.gather(log_probs, dim=1, index=target).squeeze()
 
 
-def stable_balanced_bce(target, out):
+def stable_balanced_bce(target, out, balance_weight=None):
     """utils/hungarian.py:35-61 `StableBalancedMaskedBCE` (balance_weight=None: computed from the targets)."""
-    num_positive = target.sum()
-    num_negative = (1 - target).sum()
-    balance_weight = num_positive / (num_positive + num_negative)
+    if balance_weight is None:
+        num_positive = target.sum()
+        num_negative = (1 - target).sum()
+        balance_weight = num_positive / (num_positive + num_negative)
     max_val = (-out).clamp(min=0)
     loss_values = out - out * target + max_val + ((-max_val).exp() + (-out - max_val).exp()).log()
     losses = (1 - balance_weight) * loss_values * target + balance_weight * loss_values * (1 - target)
     return losses.squeeze()
+
+
+def masked_nll_loss(y_true, y_pred, sw, balance_weight=None):
+    """utils/objectives.py:6-15 `MaskedNLLLoss.forward`: the selected costs (the caller takes the mean, train.py:161)."""
+    costs = masked_nll(y_true, y_pred, balance_weight).view(-1, 1)
+    return torch.masked_select(costs, sw.to(torch.uint8).bool())
+
+
+def masked_bce_loss(y_true, y_pred, sw, balance_weight=None):
+    """utils/objectives.py:17-25 `MaskedBCELoss.forward`."""
+    costs = stable_balanced_bce(y_true, y_pred, balance_weight).view(-1, 1)
+    return torch.masked_select(costs, sw.to(torch.uint8).bool())
 
 
 def run_iter(encode, step, x, y_mask, y_class, sw_mask, sw_class, args, cost_matrix=None, match_fn=None,

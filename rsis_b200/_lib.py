@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 
 class Tensor(C.Structure):
@@ -87,6 +87,10 @@ SIGNATURES = {
                                 _P, _P]),
     "rsis_soft_iou_bwd": (_I, [_P, _P, _I, _I, C.c_int64, _P, _P, _P, C.c_float, _P, _P]),
     "rsis_hungarian_match": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, _I, _I, _I, _P, _I, _P, _P]),
+    "rsis_masked_nll_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "rsis_masked_nll_bwd": (_I, [_P, _P, _P, _P, _P, C.c_int64, _I, _I, _P, _P]),
+    "rsis_masked_bce_fwd": (_I, [_P, _P, _P, C.c_float, C.c_int64, _P, _P, _P]),
+    "rsis_masked_bce_bwd": (_I, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "rsis_rle_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "rsis_rle_encode": (_I, [_P, C.c_float, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "rsis_adam_step": (_I, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,

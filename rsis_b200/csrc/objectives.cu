@@ -247,6 +247,132 @@ __global__ void hungarian_kernel(const float* __restrict__ cost, long long sb, l
   if (total_out) total_out[b] = (float)total;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Masked class / stop losses (utils/objectives.py:6-25 over utils/hungarian.py:10-59).  Tiny tensors ([B*T, C] and
+// [B, T]): one CTA, one launch each way; the selected-row sum and count are produced on the device so that the mean of
+// train.py:161,168 needs no masked_select (no host synchronisation, capturable).
+// A row is selected when (uint8)sw != 0 -- the reference's `sw.byte()` mask.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sw_selected(float sw) { return (unsigned char)sw != 0; }
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(256) masked_nll_fwd_kernel(const float* __restrict__ probs,
+                                                             const long long* __restrict__ target,
+                                                             const float* __restrict__ sw,
+                                                             const float* __restrict__ balance, int rows, int C,
+                                                             float* __restrict__ cost_rows, float* __restrict__ sum_count) {
+  __shared__ float red[32];
+  float s = 0.f, n = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const long long t = target[r];
+    float cost = 0.f;
+    const bool sel = sw_selected(sw[r]);
+    if (t >= 0 && t < C) {
+      cost = -logf(probs[(size_t)r * C + t]);
+      if (balance) cost *= balance[t];
+    }
+    if (cost_rows) cost_rows[r] = sel ? cost : 0.f;
+    if (sel) {
+      s += cost;
+      n += 1.f;
+    }
+  }
+  s = block_sum_256(s, red);
+  n = block_sum_256(n, red);
+  if (threadIdx.x == 0) {
+    sum_count[0] = s;
+    sum_count[1] = n;
+  }
+}
+
+__global__ void __launch_bounds__(256) masked_nll_bwd_kernel(const float* __restrict__ probs,
+                                                             const long long* __restrict__ target,
+                                                             const float* __restrict__ sw,
+                                                             const float* __restrict__ balance,
+                                                             const float* __restrict__ dcost, long long dstride, int rows,
+                                                             int C, float* __restrict__ dprobs) {
+  const size_t total = (size_t)rows * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i - (size_t)r * C);
+    float g = 0.f;
+    if (sw_selected(sw[r]) && (long long)c == target[r])
+      g = -dcost[(size_t)r * dstride] * (balance ? balance[c] : 1.f) / probs[i];
+    dprobs[i] = g;
+  }
+}
+
+// StableBalancedMaskedBCE (hungarian.py:34-59): lv = out - out*t + max(-out,0) + log(exp(-max) + exp(-out-max));
+// cost = (1-bw)*lv*t + bw*lv*(1-t);  bw = balance_weight, or sum(t) / n when none is given (computed here, pass 1).
+__global__ void __launch_bounds__(256) masked_bce_fwd_kernel(const float* __restrict__ target,
+                                                             const float* __restrict__ logits,
+                                                             const float* __restrict__ sw, float balance_weight,
+                                                             long long n, float* __restrict__ cost_rows,
+                                                             float* __restrict__ out3) {
+  __shared__ float red[32];
+  float bw = balance_weight;
+  if (bw < 0.f) {
+    float pos = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) pos += target[i];
+    pos = block_sum_256(pos, red);
+    bw = pos / (float)n;  // num_positive / (num_positive + num_negative), the latter sum being n exactly
+  }
+  float s = 0.f, cnt = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float o = logits[i], t = target[i];
+    const float mx = fmaxf(-o, 0.f);
+    const float lv = o - o * t + mx + logf(expf(-mx) + expf(-o - mx));
+    const float cost = (1.f - bw) * lv * t + bw * lv * (1.f - t);
+    const bool sel = sw_selected(sw[i]);
+    if (cost_rows) cost_rows[i] = sel ? cost : 0.f;
+    if (sel) {
+      s += cost;
+      cnt += 1.f;
+    }
+  }
+  s = block_sum_256(s, red);
+  cnt = block_sum_256(cnt, red);
+  if (threadIdx.x == 0) {
+    out3[0] = s;
+    out3[1] = cnt;
+    out3[2] = bw;
+  }
+}
+
+__global__ void __launch_bounds__(256) masked_bce_bwd_kernel(const float* __restrict__ target,
+                                                             const float* __restrict__ logits,
+                                                             const float* __restrict__ sw, const float* __restrict__ bw_ptr,
+                                                             const float* __restrict__ dcost, long long dstride,
+                                                             long long n, float* __restrict__ dlogits) {
+  const float bw = *bw_ptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float g = 0.f;
+    if (sw_selected(sw[i])) {
+      const float o = logits[i], t = target[i];
+      const float sig = 1.f / (1.f + expf(-o));
+      // d lv / d out = sigmoid(out) - t
+      g = dcost[i * dstride] * ((1.f - bw) * t + bw * (1.f - t)) * (sig - t);
+    }
+    dlogits[i] = g;
+  }
+}
+
 }  // namespace rsis
 
 using namespace rsis;
@@ -310,6 +436,51 @@ int rsis_hungarian_match(const float* cost, int64_t stride_b, int64_t stride_r, 
   if (rows > kHungMax || cols > kHungMax) return RSIS_ERR_UNSUPPORTED;
   hungarian_kernel<<<b, 32, 0, (cudaStream_t)stream>>>(cost, (long long)stride_b, (long long)stride_r,
                                                       (long long)stride_c, rows, cols, perm, perm_len, total_cost);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_masked_nll_fwd(const float* probs, const int64_t* target, const float* sw, const float* balance, int rows,
+                        int num_classes, float* cost_rows, float* sum_count, rsis_stream_t stream) {
+  if (!probs || !target || !sw || !sum_count || rows < 1 || num_classes < 1) return RSIS_ERR_BAD_ARG;
+  masked_nll_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(probs, reinterpret_cast<const long long*>(target), sw,
+                                                             balance, rows, num_classes, cost_rows, sum_count);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_masked_nll_bwd(const float* probs, const int64_t* target, const float* sw, const float* balance,
+                        const float* dcost, int64_t dcost_stride, int rows, int num_classes, float* dprobs,
+                        rsis_stream_t stream) {
+  if (!probs || !target || !sw || !dcost || !dprobs || rows < 1 || num_classes < 1 || dcost_stride < 0)
+    return RSIS_ERR_BAD_ARG;
+  const size_t total = (size_t)rows * num_classes;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  masked_nll_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      probs, reinterpret_cast<const long long*>(target), sw, balance, dcost, (long long)dcost_stride, rows, num_classes,
+      dprobs);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_masked_bce_fwd(const float* target, const float* logits, const float* sw, float balance_weight, int64_t n,
+                        float* cost_rows, float* sum_count_bw, rsis_stream_t stream) {
+  if (!target || !logits || !sw || !sum_count_bw || n < 1) return RSIS_ERR_BAD_ARG;
+  masked_bce_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(target, logits, sw, balance_weight, (long long)n, cost_rows,
+                                                             sum_count_bw);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_masked_bce_bwd(const float* target, const float* logits, const float* sw, const float* balance_weight,
+                        const float* dcost, int64_t dcost_stride, int64_t n, float* dlogits, rsis_stream_t stream) {
+  if (!target || !logits || !sw || !balance_weight || !dcost || !dlogits || n < 1 || dcost_stride < 0)
+    return RSIS_ERR_BAD_ARG;
+  size_t blocks = ((size_t)n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  masked_bce_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(target, logits, sw, balance_weight, dcost,
+                                                                            (long long)dcost_stride, (long long)n, dlogits);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

@@ -1,7 +1,7 @@
-"""Soft-IoU cost and loss -- counterparts of /root/reference/src/utils/hungarian.py:64-90 (`softIoU`),
-/root/reference/src/utils/objectives.py:27-34 (`softIoULoss`) and the per-step cost matrix of
-/root/reference/src/train.py:96-110 (the component right after the decoder step in the
-training loop).  One fused, HBM-bound CUDA kernel per call (`csrc/objectives.cu`) instead of the reference's
+"""The criteria of the training loop -- counterparts of /root/reference/src/utils/hungarian.py:10-90 (`MaskedNLL`,
+`StableBalancedMaskedBCE`, `softIoU`), /root/reference/src/utils/objectives.py:6-34 (`MaskedNLLLoss`, `MaskedBCELoss`,
+`softIoULoss`) and the per-step cost matrix of /root/reference/src/train.py:96-110 (the
+component right after the decoder step in the training loop).  One fused, HBM-bound CUDA kernel per call (`csrc/objectives.cu`) instead of the reference's
 `repeat` + ~8 elementwise / reduction kernels; ground-truth masks may stay uint8 on the device (4x fewer bytes).
 """
 from __future__ import annotations
@@ -103,6 +103,136 @@ class softIoULoss(nn.Module):
     def forward(self, y_true, y_pred, sw):
         costs = softIoU(y_true, y_pred).view(-1, 1)
         return torch.mean(torch.masked_select(costs, sw.bool()))
+
+
+# ---- masked class / stop losses (objectives.py:6-25) ------------------------------------------------------------------
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().contiguous().float()
+
+
+class _MaskedNLLRows(torch.autograd.Function):
+    """Per-row `-balance[target] * log(probs[row, target])` (0 on rows whose `sw.byte()` is 0) + (sum, count) of the
+    selected rows, one kernel; backward one kernel."""
+
+    @staticmethod
+    def forward(ctx, target, probs, sw, balance):
+        lib = _lib.load()
+        rows, c = probs.shape
+        p = _f32(probs)
+        t = target.detach().reshape(-1).contiguous().long()
+        m = _f32(sw.reshape(-1))
+        assert t.numel() == rows and m.numel() == rows
+        bal = None if balance is None else _f32(balance).to(p.device)
+        cost = torch.empty(rows, dtype=torch.float32, device=p.device)
+        sc = torch.empty(2, dtype=torch.float32, device=p.device)
+        check(lib.rsis_masked_nll_fwd(p.data_ptr(), t.data_ptr(), m.data_ptr(), None if bal is None else bal.data_ptr(),
+                                      rows, c, cost.data_ptr(), sc.data_ptr(), _lib.stream_ptr()), "masked_nll_fwd")
+        _lib.count_launch(1)
+        ctx.saved = (p, t, m, bal)
+        ctx.mark_non_differentiable(sc)
+        return cost, sc
+
+    @staticmethod
+    def backward(ctx, dcost, _dsc):
+        lib = _lib.load()
+        p, t, m, bal = ctx.saved
+        rows, c = p.shape
+        d = torch.empty_like(p)
+        g = dcost.contiguous().float()
+        check(lib.rsis_masked_nll_bwd(p.data_ptr(), t.data_ptr(), m.data_ptr(), None if bal is None else bal.data_ptr(),
+                                      g.data_ptr(), 1, rows, c, d.data_ptr(), _lib.stream_ptr()), "masked_nll_bwd")
+        _lib.count_launch(1)
+        return None, d, None, None
+
+
+class _MaskedBCERows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, target, out, sw, balance_weight):
+        lib = _lib.load()
+        o = _f32(out.reshape(-1))
+        t = _f32(target.reshape(-1))
+        m = _f32(sw.reshape(-1))
+        n = o.numel()
+        assert t.numel() == n and m.numel() == n
+        cost = torch.empty(n, dtype=torch.float32, device=o.device)
+        sc = torch.empty(3, dtype=torch.float32, device=o.device)
+        bw = -1.0 if balance_weight is None else float(balance_weight)
+        check(lib.rsis_masked_bce_fwd(t.data_ptr(), o.data_ptr(), m.data_ptr(), bw, n, cost.data_ptr(), sc.data_ptr(),
+                                      _lib.stream_ptr()), "masked_bce_fwd")
+        _lib.count_launch(1)
+        ctx.saved = (t, o, m, sc, tuple(out.shape))
+        ctx.mark_non_differentiable(sc)
+        return cost, sc
+
+    @staticmethod
+    def backward(ctx, dcost, _dsc):
+        lib = _lib.load()
+        t, o, m, sc, shape = ctx.saved
+        d = torch.empty_like(o)
+        g = dcost.contiguous().float()
+        check(lib.rsis_masked_bce_bwd(t.data_ptr(), o.data_ptr(), m.data_ptr(), sc.data_ptr() + 8, g.data_ptr(), 1,
+                                      o.numel(), d.data_ptr(), _lib.stream_ptr()), "masked_bce_bwd")
+        _lib.count_launch(1)
+        return None, d.view(shape), None, None
+
+
+def masked_mean(cost_rows: torch.Tensor, sum_count: torch.Tensor, group=None) -> torch.Tensor:
+    """`torch.mean(masked_select(costs, sw.byte()))` (train.py:161,168) from the per-row costs (0 on unselected rows) and
+    the device-side selected count: no masked_select, no host synchronisation (capturable).
+
+    Data-parallel rule: the reference's DataParallel criteria return the UN-reduced selected
+    vectors, which are concatenated and averaged globally.  With one process per GPU and gradients AVERAGED over ranks,
+    each rank must therefore contribute `local_sum * world / n_valid_global`: one scalar all-reduce of the count."""
+    import torch.distributed as dist
+    count = sum_count[1]
+    scale = 1.0
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        count = count.clone()
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+        scale = float(dist.get_world_size(group))
+    return cost_rows.sum() * scale / count
+
+
+class MaskedNLLLoss(nn.Module):
+    """utils/objectives.py:6-15: the vector of selected `MaskedNLL` costs (its mean is taken by the caller,
+    train.py:161).  `mean(...)` is the fused, synchronisation-free form of `torch.mean(self(...))`."""
+
+    def __init__(self, balance_weight=None):
+        super().__init__()
+        self.balance_weight = balance_weight
+
+    def rows(self, y_true, y_pred, sw):
+        ops.require_cuda(y_pred, "MaskedNLLLoss")
+        return _MaskedNLLRows.apply(y_true, y_pred, sw, self.balance_weight)
+
+    def forward(self, y_true, y_pred, sw):
+        costs, _ = self.rows(y_true, y_pred, sw)
+        return torch.masked_select(costs.view(-1, 1), sw.reshape(-1, 1).to(torch.uint8).bool())
+
+    def mean(self, y_true, y_pred, sw, group=None):
+        costs, sc = self.rows(y_true, y_pred, sw)
+        return masked_mean(costs, sc, group)
+
+
+class MaskedBCELoss(nn.Module):
+    """utils/objectives.py:17-25 over `StableBalancedMaskedBCE` (hungarian.py:34-59); `balance_weight=None` derives it
+    from the targets like the reference does."""
+
+    def __init__(self, balance_weight=None):
+        super().__init__()
+        self.balance_weight = balance_weight
+
+    def rows(self, y_true, y_pred, sw):
+        ops.require_cuda(y_pred, "MaskedBCELoss")
+        return _MaskedBCERows.apply(y_true, y_pred, sw, self.balance_weight)
+
+    def forward(self, y_true, y_pred, sw):
+        costs, _ = self.rows(y_true, y_pred, sw)
+        return torch.masked_select(costs.view(-1, 1), sw.reshape(-1, 1).to(torch.uint8).bool())
+
+    def mean(self, y_true, y_pred, sw, group=None):
+        costs, sc = self.rows(y_true, y_pred, sw)
+        return masked_mean(costs, sc, group)
 
 
 def hungarian_match(overlaps: torch.Tensor):

@@ -483,6 +483,60 @@ def _rle_encode(self, masks, th, ignore, n, h, w, ws, counts, max_runs, n_runs, 
     return 0
 
 
+def _sel(sw_ptr, n):
+    return _buf(sw_ptr, n).to(torch.uint8) != 0          # the reference's `sw.byte()` mask
+
+
+def _masked_nll_fwd(self, probs, target, sw, balance, rows, c, cost_rows, sum_count, st):
+    p = _buf(probs, rows * c).view(rows, c)
+    t = _buf(target, rows, torch.int64)
+    cost = -torch.log(p.gather(1, t.view(-1, 1))).view(-1)
+    if balance:
+        cost = cost * _buf(balance, c)[t]
+    sel = _sel(sw, rows)
+    if cost_rows:
+        _buf(cost_rows, rows).copy_(torch.where(sel, cost, torch.zeros_like(cost)))
+    _buf(sum_count, 2).copy_(torch.stack([cost[sel].sum(), sel.float().sum()]))
+    return 0
+
+
+def _masked_nll_bwd(self, probs, target, sw, balance, dcost, dstride, rows, c, dprobs, st):
+    p = _buf(probs, rows * c).view(rows, c)
+    t = _buf(target, rows, torch.int64)
+    g = _buf(dcost, (rows - 1) * dstride + 1)[::dstride] if dstride else _buf(dcost, 1).expand(rows)
+    w = _buf(balance, c)[t] if balance else torch.ones(rows)
+    d = torch.zeros(rows, c)
+    d.scatter_(1, t.view(-1, 1), (-g * w / p.gather(1, t.view(-1, 1)).view(-1) * _sel(sw, rows).float()).view(-1, 1))
+    _buf(dprobs, rows * c).view(rows, c).copy_(d)
+    return 0
+
+
+def _masked_bce_fwd(self, target, logits, sw, bw, n, cost_rows, out3, st):
+    t, o = _buf(target, n), _buf(logits, n)
+    if bw < 0:
+        bw = float(t.sum() / n)
+    mx = (-o).clamp(min=0)
+    lv = o - o * t + mx + ((-mx).exp() + (-o - mx).exp()).log()
+    cost = (1 - bw) * lv * t + bw * lv * (1 - t)
+    sel = _sel(sw, n)
+    if cost_rows:
+        _buf(cost_rows, n).copy_(torch.where(sel, cost, torch.zeros_like(cost)))
+    _buf(out3, 3).copy_(torch.stack([cost[sel].sum(), sel.float().sum(), torch.tensor(bw)]))
+    return 0
+
+
+def _masked_bce_bwd(self, target, logits, sw, bw_ptr, dcost, dstride, n, dlogits, st):
+    t, o = _buf(target, n), _buf(logits, n)
+    bw = float(_buf(bw_ptr, 1)[0])
+    g = _buf(dcost, (n - 1) * dstride + 1)[::dstride] if dstride else _buf(dcost, 1).expand(n)
+    _buf(dlogits, n).copy_(g * ((1 - bw) * t + bw * (1 - t)) * (torch.sigmoid(o) - t) * _sel(sw, n).float())
+    return 0
+
+
+FakeLib.rsis_masked_nll_fwd = _masked_nll_fwd
+FakeLib.rsis_masked_nll_bwd = _masked_nll_bwd
+FakeLib.rsis_masked_bce_fwd = _masked_bce_fwd
+FakeLib.rsis_masked_bce_bwd = _masked_bce_bwd
 FakeLib.rsis_soft_iou_workspace_bytes = _soft_iou_ws
 FakeLib.rsis_soft_iou_cost = _soft_iou_cost
 FakeLib.rsis_soft_iou_bwd = _soft_iou_bwd

@@ -36,7 +36,7 @@ def test_ctypes_table_covers_header():
 
 def test_host_only_entry_points():
     lib = _lib.load()
-    assert lib.rsis_abi_version() == 16
+    assert lib.rsis_abi_version() == _lib.ABI_VERSION
     assert lib.rsis_strerror(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -99):
         assert len(lib.rsis_strerror(code)) > 0

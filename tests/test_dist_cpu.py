@@ -45,6 +45,22 @@ WORKER = textwrap.dedent("""
         p_.grad = None                                            # an optimiser's zero_grad(set_to_none=True)
     bucket.zero()                                                  # ... re-attaches the views
     assert params[1].grad is not None and float(bucket.flat.abs().sum()) == 0.0
+    # masked class / stop losses (SURVEY.md section 8e): the reference's DataParallel criteria return the un-reduced
+    # selected vectors, averaged GLOBALLY (train.py:161,168).  With gradients averaged over ranks each rank contributes
+    # local_sum * world / n_valid_global -- rsis_b200.objectives.masked_mean.
+    from rsis_b200.objectives import masked_mean
+    gen = torch.Generator().manual_seed(3)
+    costs_all = torch.rand(10, generator=gen)
+    sel_all = torch.tensor([1, 0, 1, 1, 0, 0, 1, 0, 0, 1], dtype=torch.bool)   # 3 valid rows on rank 0, 2 on rank 1
+    lo, hi = rd.shard_range(10, rank, world)
+    c = torch.where(sel_all[lo:hi], costs_all[lo:hi], torch.zeros(hi - lo))
+    sc = torch.stack([c.sum(), sel_all[lo:hi].float().sum()])
+    mine = masked_mean(c, sc)
+    both = mine.clone()
+    dist.all_reduce(both)
+    want = costs_all[sel_all].mean()
+    assert abs(float(both / world) - float(want)) < 1e-6, (both, want)       # DDP-style average of per-rank losses
+    assert abs(float(mine) - float(c.sum() * 2 / 5)) < 1e-6
     rd.barrier()
     print(f"rank {rank} ok [{b},{e})")
 """)

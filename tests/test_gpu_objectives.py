@@ -125,3 +125,61 @@ def test_hungarian_match_with_ties_is_optimal(OBJ):
     for i in range(b):   # a valid assignment: the first T entries are distinct rows, the tail is zero
         assert len(set(p[i, :t].tolist())) == t and int(p[i, t:].abs().sum()) == 0
         assert abs(float(scores[i, p[i, :t], torch.arange(t)].sum()) - float(want_total[i])) <= 1e-4
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_masked_losses_match_reference_golden(OBJ, golden_dir, fused):
+    """MaskedNLLLoss / MaskedBCELoss kernels (forward + backward) against goldens produced by the UNMODIFIED
+    utils/objectives.py:6-25 called as train.py:159-168 calls them.  Tolerance 1e-5 (logf / expf vs torch CPU)."""
+    from oracle.make_golden import masked_loss_inputs
+    g = np.load(os.path.join(golden_dir, "masked_losses.npz"))
+    probs, target, sw, sw_class, stop_logits, balance = masked_loss_inputs()
+    for tag, bal in (("none", None), ("bal", balance)):
+        p = probs.cuda().requires_grad_(True)
+        crit = OBJ.MaskedNLLLoss(balance_weight=None if bal is None else bal.cuda())
+        if fused:
+            loss = crit.mean(target.cuda(), p, sw.view(-1, 1).cuda())
+        else:
+            sel = crit(target.cuda(), p, sw.view(-1, 1).cuda())
+            assert rel(sel.detach(), g[f"nll_{tag}_sel"]) <= 1e-5
+            loss = torch.mean(sel)
+        assert abs(float(loss.detach()) - float(g[f"nll_{tag}_sel"].mean())) <= 1e-5
+        loss.backward()
+        assert rel(p.grad, g[f"nll_{tag}_grad"]) <= 1e-5
+    for tag, bw in (("half", 0.5), ("none", None)):
+        o = stop_logits.cuda().requires_grad_(True)
+        crit = OBJ.MaskedBCELoss(balance_weight=bw)
+        if fused:
+            loss = crit.mean(sw.cuda(), o.squeeze(), sw_class.view(-1, 1).cuda())
+        else:
+            sel = crit(sw.cuda(), o.squeeze(), sw_class.view(-1, 1).cuda())
+            assert rel(sel.detach(), g[f"bce_{tag}_sel"]) <= 1e-5
+            loss = torch.mean(sel)
+        assert abs(float(loss.detach()) - float(g[f"bce_{tag}_sel"].mean())) <= 1e-5
+        loss.backward()
+        assert rel(o.grad, g[f"bce_{tag}_grad"]) <= 1e-5
+
+
+def test_masked_losses_match_oracle_large(OBJ):
+    """configs[3] scale: B*T = 640 rows, 21 classes; every row masked in a seeded pattern incl. all-unselected tail."""
+    from oracle import rsis_oracle as O
+    gen = torch.Generator().manual_seed(21)
+    rows, c = 640, 21
+    probs = torch.softmax(torch.randn((rows, c), generator=gen) * 3, -1)
+    target = torch.randint(0, c, (rows, 1), generator=gen)
+    sw = (torch.rand((rows, 1), generator=gen) < 0.4).float()
+    sw[500:] = 0
+    p1, p2 = probs.cuda().requires_grad_(True), probs.clone().requires_grad_(True)
+    OBJ.MaskedNLLLoss().mean(target.cuda(), p1, sw.cuda()).backward()
+    torch.mean(O.masked_nll_loss(target, p2, sw)).backward()
+    assert rel(p1.grad, p2.grad) <= 1e-5
+    logits = torch.randn((64, 10), generator=gen) * 4
+    tgt = (torch.rand((64, 10), generator=gen) < 0.3).float()
+    swc = (torch.rand((640, 1), generator=gen) < 0.7).float()
+    o1, o2 = logits.cuda().requires_grad_(True), logits.clone().requires_grad_(True)
+    l1 = OBJ.MaskedBCELoss(None).mean(tgt.cuda(), o1, swc.cuda())
+    l2 = torch.mean(O.masked_bce_loss(tgt, o2, swc, None))
+    l1.backward()
+    l2.backward()
+    assert abs(float(l1.detach()) - float(l2.detach())) <= 1e-5 * abs(float(l2.detach()))
+    assert rel(o1.grad, o2.grad) <= 1e-5

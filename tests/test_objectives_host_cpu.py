@@ -36,6 +36,41 @@ def test_cost_matrix_loss_and_matching_follow_the_oracle(fake):
     assert torch.equal(perm.long(), wperm) and torch.equal(pc, wc) and torch.equal(pm, wm)
 
 
+def test_masked_losses_follow_the_reference_golden(fake, golden_dir):
+    """MaskedNLLLoss / MaskedBCELoss host logic (argument marshalling, autograd wiring, the fused mean) through the fake
+    ABI against the goldens made by the unmodified utils/objectives.py:6-25."""
+    import os
+    from rsis_b200 import objectives as OBJ
+    from oracle.make_golden import masked_loss_inputs
+    g = np.load(os.path.join(golden_dir, "masked_losses.npz"))
+    probs, target, sw, sw_class, stop_logits, balance = masked_loss_inputs()
+    for tag, bal in (("none", None), ("bal", balance)):
+        for fused in (False, True):
+            p = probs.clone().requires_grad_(True)
+            crit = OBJ.MaskedNLLLoss(balance_weight=bal)
+            if fused:
+                loss = crit.mean(target, p, sw.view(-1, 1))
+            else:
+                sel = crit(target, p, sw.view(-1, 1))
+                assert np.abs(sel.detach().numpy() - g[f"nll_{tag}_sel"]).max() <= 1e-6
+                loss = torch.mean(sel)
+            assert abs(float(loss) - float(g[f"nll_{tag}_sel"].mean())) <= 1e-6
+            loss.backward()
+            assert np.abs(p.grad.numpy() - g[f"nll_{tag}_grad"]).max() <= 2e-6 * np.abs(g[f"nll_{tag}_grad"]).max()
+    for tag, bw in (("half", 0.5), ("none", None)):
+        for fused in (False, True):
+            o = stop_logits.clone().requires_grad_(True)
+            crit = OBJ.MaskedBCELoss(balance_weight=bw)
+            if fused:
+                loss = crit.mean(sw, o.squeeze(), sw_class.view(-1, 1))
+            else:
+                sel = crit(sw, o.squeeze(), sw_class.view(-1, 1))          # train.py:167
+                assert np.abs(sel.detach().numpy() - g[f"bce_{tag}_sel"]).max() <= 1e-6
+                loss = torch.mean(sel)
+            loss.backward()
+            assert np.abs(o.grad.numpy() - g[f"bce_{tag}_grad"]).max() <= 2e-6 * np.abs(g[f"bce_{tag}_grad"]).max()
+
+
 def test_resize_and_encode_instances(fake):
     from scipy.ndimage import zoom
     from rsis_b200 import postprocess as PP

@@ -105,6 +105,30 @@ def test_soft_iou_oracle_matches_reference_golden(golden_dir):
     assert np.abs(pred.grad.numpy()[:, ::16] - g["grad"]).max() <= 1e-9 + 1e-5 * np.abs(g["grad"]).max()
 
 
+def test_masked_losses_oracle_matches_reference_golden(golden_dir):
+    """oracle.masked_nll_loss / masked_bce_loss == the unmodified utils/objectives.py:6-25 (over hungarian.py:10-59) called
+    as train.py:159-168 calls them; selected costs and the gradients of their means."""
+    import numpy as np
+    import torch
+    from oracle import rsis_oracle as O
+    from oracle.make_golden import masked_loss_inputs
+    g = np.load(os.path.join(golden_dir, "masked_losses.npz"))
+    probs, target, sw, sw_class, stop_logits, balance = masked_loss_inputs()
+    for tag, bal in (("none", None), ("bal", balance)):
+        p = probs.clone().requires_grad_(True)
+        sel = O.masked_nll_loss(target, p, sw.view(-1, 1), bal)
+        torch.mean(sel).backward()
+        assert np.abs(sel.detach().numpy() - g[f"nll_{tag}_sel"]).max() <= 1e-6
+        assert np.abs(p.grad.numpy() - g[f"nll_{tag}_grad"]).max() <= 1e-6 * np.abs(g[f"nll_{tag}_grad"]).max()
+    assert np.abs(g["nll_bal_sel"] - g["nll_none_sel"]).max() > 1e-3      # the class weights really were applied
+    for tag, bw in (("half", 0.5), ("none", None)):
+        o = stop_logits.clone().requires_grad_(True)
+        sel = O.masked_bce_loss(sw, o, sw_class.view(-1, 1), bw)
+        torch.mean(sel).backward()
+        assert np.abs(sel.detach().numpy() - g[f"bce_{tag}_sel"]).max() <= 1e-6
+        assert np.abs(o.grad.numpy() - g[f"bce_{tag}_grad"]).max() <= 1e-6 * np.abs(g[f"bce_{tag}_grad"]).max()
+
+
 def test_match_oracle_matches_reference_golden(golden_dir):
     """oracle.match == the unmodified utils/hungarian.py:91-125 `match` (its Munkres stubbed by scipy: see
     oracle/make_golden.py::golden_match) -- pins the permutation / gather conventions."""
