@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 17
+#define RSIS_ABI_VERSION 18
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -191,8 +191,30 @@ int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, int impl, void* workspace,
                        size_t workspace_bytes, rsis_stream_t stream);
+/* One WAVEFRONT of the decoder in one launch.  The 5-level ConvLSTM stack of model.py:129-165 only has the dependencies
+ * cell(level l, step t) <- cell(l-1, t) (through the x2 upsampling) and cell(l, t-1) (its own state), so the cells
+ * {(l, t) : l + t = w} of one anti-diagonal are independent: rsis_convlstm_cell_group runs up to
+ * rsis_convlstm_cell_group_max() of them (each described like one rsis_convlstm_cell call on its concatenated input
+ * buffer `x` = [up(h_below) | h_prev], tcgen05 kernel family) side by side, every cell on a share of the SMs in
+ * proportion to its tensor-core work.  Results are identical to the one-by-one calls. */
+typedef struct rsis_cell_args {
+  const rsis_tensor* x;          /* split-bf16, all w->cin channels */
+  const rsis_conv_weights* w;    /* packed with gate_interleave=1 */
+  const float* c_prev;           /* or NULL */
+  const float* gate_preact;      /* or NULL */
+  const rsis_tensor* h_out;
+  const rsis_tensor* h_split;    /* or NULL */
+  const rsis_tensor* c_out;
+  uint32_t* side_max;            /* or NULL */
+  int32_t side_stride, side_offset;
+} rsis_cell_args;
+int rsis_convlstm_cell_group_max(void);
+int rsis_convlstm_cell_group(const rsis_cell_args* cells, int n_cells, rsis_stream_t stream);
 /* nn.UpsamplingBilinear2d(size=(y.h, y.w)) == bilinear, align_corners=True (model.py:149-150,163-164). */
 int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream);
+/* n (<= 4) independent rsis_upsample_bilinear calls xs[i] -> ys[i] in one launch (the upsamplings between two
+ * wavefronts of the decoder). */
+int rsis_upsample_bilinear_group(const rsis_tensor* xs, const rsis_tensor* ys, int n, rsis_stream_t stream);
 /* conv_out (model.py:167): ksize x ksize (1 or 3), Cin -> 1, on an NHWC float32 input; writes logits [N,H,W] float32 (when
  * logits != NULL) and, when prob_out != NULL, sigmoid(logit) at prob_out[n*prob_stride_n + pixel] (the stacking + sigmoid of test.py:46,50). */
 int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias, int ksize, float* logits,

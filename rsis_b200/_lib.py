@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 
 class Tensor(C.Structure):
@@ -32,6 +32,14 @@ class ConvWeights(C.Structure):
     _fields_ = [("w_kc", C.c_void_p), ("w_umma", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("gate_interleaved", C.c_int32), ("w_umma_il", C.c_void_p)]
+
+
+class CellArgs(C.Structure):
+    """`rsis_cell_args`: one cell of a grouped (wavefront) launch."""
+    _fields_ = [("x", C.POINTER(Tensor)), ("w", C.POINTER(ConvWeights)), ("c_prev", C.c_void_p),
+                ("gate_preact", C.c_void_p), ("h_out", C.POINTER(Tensor)), ("h_split", C.POINTER(Tensor)),
+                ("c_out", C.POINTER(Tensor)), ("side_max", C.c_void_p), ("side_stride", C.c_int32),
+                ("side_offset", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -87,6 +95,9 @@ SIGNATURES = {
                                 _P, _P]),
     "rsis_soft_iou_bwd": (_I, [_P, _P, _I, _I, C.c_int64, _P, _P, _P, C.c_float, _P, _P]),
     "rsis_hungarian_match": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, _I, _I, _I, _P, _I, _P, _P]),
+    "rsis_convlstm_cell_group_max": (_I, []),
+    "rsis_convlstm_cell_group": (_I, [C.POINTER(CellArgs), _I, _P]),
+    "rsis_upsample_bilinear_group": (_I, [_TP, _TP, _I, _P]),
     "rsis_masked_nll_fwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "rsis_masked_nll_bwd": (_I, [_P, _P, _P, _P, _P, C.c_int64, _I, _I, _P, _P]),
     "rsis_masked_bce_fwd": (_I, [_P, _P, _P, C.c_float, C.c_int64, _P, _P, _P]),

@@ -108,6 +108,7 @@ struct UmmaParams {
   int hs_cs;
   uint32_t* side_max;
   int side_stride, side_offset;
+  int cell_rows;           // 1: row-wise cell epilogue (thread = pixel, no shared-memory transpose); 0: staged transpose
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -463,7 +464,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // warp write 32 consecutive floats), waits for the other K slices of its tile, then reduces and finishes its share.
 template <bool CELL, int PW, bool SPLIT>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
-                                              uint32_t tempty0, float* stage, int warp, int lane) {
+                                              uint32_t tempty0, float* stage, int warp, int lane, const int bid,
+                                              const int nblk) {
   const int quarter = warp & 3;       // TMEM lane quarter this warp may read
   const int half = warp >> 2;         // which pieces (even / odd) of the quarter this warp handles
   const int rows_per_img = p.BW * p.BH;
@@ -474,7 +476,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   int acc = 0;
   uint32_t acc_phase = 0;
   CellPiece<PW> cpz_cur;
-  for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+  for (int work = bid; work < num_work; work += nblk) {
     const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
     const int nt = tile % p.tiles_n;
     int mt = tile / p.tiles_n;
@@ -487,12 +489,12 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
     if constexpr (CELL && !SPLIT) {
       // the very first piece of this warp; afterwards every piece's c_prev / hoisted-gate loads are issued one piece
       // ahead (rolling, across tiles), so their DRAM latency hides behind the previous piece instead of stalling it
-      if (work == (int)blockIdx.x && half < npc) cell_prefetch<PW>(p, cpz_cur, lane, mypix, nt * p.BN + PW * half);
+      if (work == bid && half < npc) cell_prefetch<PW>(p, cpz_cur, lane, mypix, nt * p.BN + PW * half);
     }
     mbar_wait(tfull0 + 8 * acc, acc_phase);
     tc_fence_after();
     if (threadIdx.x == 0) STAMP(7);
-    if (threadIdx.x == 0) STAMP_T(3, (work - (int)blockIdx.x) / (int)gridDim.x);
+    if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
     if constexpr (!SPLIT) {
       for (int j = half; j < npc; j += 2) {
@@ -503,8 +505,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           const int coln = col0 + 2 * PW;
           if (j + 2 < npc && coln < p.Cout) {
             cell_prefetch<PW>(p, cpz_next, lane, mypix, coln);
-          } else if (work + (int)gridDim.x < num_work) {
-            const int tile2 = (work + (int)gridDim.x) / p.ksplit;
+          } else if (work + nblk < num_work) {
+            const int tile2 = (work + nblk) / p.ksplit;
             const int nt2 = tile2 % p.tiles_n;
             int mt2 = tile2 / p.tiles_n;
             const int tw2 = mt2 % p.tiles_w;
@@ -536,7 +538,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
       }
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * acc);
-      if (threadIdx.x == 0) STAMP_T(4, (work - (int)blockIdx.x) / (int)gridDim.x);
+      if (threadIdx.x == 0) STAMP_T(4, (work - bid) / nblk);
     } else {
       // ---- split-K (1): park this CTA's partial accumulator in the scratch as [row][column] (staged transpose,
       // so each row's 32 columns are one 128-byte store)
@@ -567,7 +569,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + 2 * tile) : "memory");
           if (clock64() - t0 > 4000000000LL) {
-            printf("rsis_b200 conv_umma: split-K wait timed out (block %d tile %d seen %u of %d)\n", blockIdx.x, tile,
+            printf("rsis_b200 conv_umma: split-K wait timed out (block %d tile %d seen %u of %d)\n", bid, tile,
                    seen, p.ksplit);
             __trap();
           }
@@ -712,11 +714,161 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   }
 }
 
-// One instantiation per (epilogue kind, piece width, split-K or not): each carries a single epilogue variant, which
-// keeps the 11 differently-specialised warps of a CTA inside the instruction cache.
+// ---- ConvLSTM epilogue, row-wise (clstm.py:50-58) ------------------------------------------------------------------
+// The accumulator leaves TMEM with thread = pixel (TMEM lane) and registers = gate columns in (hidden channel, gate)
+// order, so ONE thread holds i, f, o, g of a hidden channel of its pixel: the gate math needs no data exchange at all.
+// A unit = 16 gate columns = 4 hidden channels of 32 pixels.  Per thread and unit: one 16-byte load of c_prev, four of
+// the hoisted gate share (64 contiguous bytes), the stores of c, h (16 bytes each) and of h as split bf16 (2 x 8 bytes),
+// all independent across the 4 channels -- instruction-level parallelism instead of the staged transpose's dependent
+// STS -> sync -> LDS chain (with 2-3 warps per scheduler that chain, not the instruction count, set the epilogue time:
+// in-kernel stamps, profiles/r2f_group_stamps.txt).  The two warps of a TMEM lane quarter split a tile's units; the loads
+// of the next unit (possibly of the next tile) are issued before the current one is finished, and the accumulator stage
+// is handed back to the MMA warp as soon as its last unit is in registers.
+struct CellUnitIn {
+  float4 pre[4];
+  float4 cp;
+};
+
+__device__ __forceinline__ void cell_unit_load(const UmmaParams& p, CellUnitIn& in, uint32_t pix, int chg0) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int Ch = p.Cout >> 2;
+  const bool ok = pix != 0xffffffffu && chg0 < Ch;
+  const size_t base = (size_t)pix * Ch + chg0;
+  in.cp = (ok && p.c_prev) ? __ldg(reinterpret_cast<const float4*>(p.c_prev + base)) : z;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    in.pre[j] = (ok && p.preact) ? __ldg(reinterpret_cast<const float4*>(p.preact + (base + j) * 4)) : z;
+}
+
+__device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
+                                                   uint32_t tempty0, int warp, int lane, const int bid, const int nblk) {
+  const int quarter = warp & 3, half = warp >> 2;
+  const int Ch = p.Cout >> 2;
+  const int nu = p.BN >> 4;  // units per output-channel tile
+  const bool warp_one_image = p.BW * p.BH >= 32;  // the 32 rows of a warp lie in one image
+  const int num_work = p.num_tiles;               // no split-K on this path
+  auto tile_pix = [&](int tile, int& nt, int& img) -> uint32_t {
+    nt = tile % p.tiles_n;
+    int mt = tile / p.tiles_n;
+    const int tw = mt % p.tiles_w;
+    mt /= p.tiles_w;
+    const RowGeom g = row_geom(p, quarter * 32 + lane, tw, mt % p.tiles_h, mt / p.tiles_h);
+    img = g.img;
+    return g.ok ? (uint32_t)g.pix : 0xffffffffu;
+  };
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  CellUnitIn cur;
+  bool have_cur = false;
+  int nt = 0, img = 0;
+  uint32_t mypix = 0xffffffffu;
+  if (bid < num_work) mypix = tile_pix(bid, nt, img);
+  for (int work = bid; work < num_work; work += nblk) {
+    // geometry of the next tile (for the cross-tile prefetch)
+    int nt2 = 0, img2 = 0;
+    uint32_t pix2 = 0xffffffffu;
+    const bool more = work + nblk < num_work;
+    if (more) pix2 = tile_pix(work + nblk, nt2, img2);
+    if (!have_cur && half < nu) cell_unit_load(p, cur, mypix, ((nt * p.BN) >> 2) + 4 * half);
+    have_cur = false;
+    mbar_wait(tfull0 + 8 * acc, acc_phase);
+    tc_fence_after();
+    if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
+    bool released = false;
+    for (int u = half; u < nu; u += 2) {
+      const int col0 = nt * p.BN + 16 * u;
+      if (col0 >= p.Cout) break;
+      const int chg0 = col0 >> 2;
+      const bool last_unit = u + 2 >= nu || col0 + 32 >= p.Cout;
+      // loads of the unit after this one
+      CellUnitIn nxt;
+      bool have_nxt = false;
+      if (!last_unit) {
+        cell_unit_load(p, nxt, mypix, chg0 + 8);
+        have_nxt = true;
+      } else if (more && half < nu) {
+        cell_unit_load(p, nxt, pix2, ((nt2 * p.BN) >> 2) + 4 * half);
+        have_nxt = true;
+      }
+      uint32_t r[16];
+      tmem_ld16(taddr + 16 * u, r);
+      if (p.stacked) {
+        uint32_t r2[16];
+        tmem_ld16(taddr + p.BN + 16 * u, r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+      } else {
+        tmem_ld_wait();
+      }
+      if (last_unit) {  // the accumulator stage is free for the MMAs of the tile after next
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc);
+        released = true;
+        if (threadIdx.x == 0) STAMP_T(4, (work - bid) / nblk);
+      }
+      const bool ok = mypix != 0xffffffffu;
+      float cv[4], hv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
+        const float gi = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x) + cur.pre[j].x);
+        const float gf = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y) + cur.pre[j].y);
+        const float go = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z) + cur.pre[j].z);
+        const float gg = fast_tanh(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w) + cur.pre[j].w);
+        const float cpj = j == 0 ? cur.cp.x : (j == 1 ? cur.cp.y : (j == 2 ? cur.cp.z : cur.cp.w));
+        cv[j] = fmaf(gf, cpj, gi * gg);
+        hv[j] = go * fast_tanh(cv[j]);
+      }
+      if (ok) {
+        const size_t idx = (size_t)mypix * Ch + chg0;
+        *reinterpret_cast<float4*>(p.c_out + idx) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        *reinterpret_cast<float4*>(p.h_out + idx) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        if (p.h_split) store4(p.h_split, p.hs_plane, RSIS_FMT_SPLIT_BF16, (size_t)mypix * p.hs_cs + chg0, hv);
+      }
+      if (p.side_max) {  // the global nn.MaxPool2d of model.py:143 as order-preserving keys
+        if (warp_one_image) {
+          const int img0 = __shfl_sync(0xffffffffu, img, 0);
+          uint32_t mine = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t m = __reduce_max_sync(0xffffffffu, ok ? float_to_key(hv[j]) : 0u);
+            if (lane == j) mine = m;
+          }
+          if (lane < 4 && mine != 0u)
+            atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg0 + lane, mine);
+        } else if (ok) {  // maps smaller than a warp's 32 rows: rows of several images share the warp
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg0 + j, float_to_key(hv[j]));
+        }
+      }
+      if (have_nxt) {
+        cur = nxt;
+        have_cur = last_unit;  // loaded for the next tile
+      }
+    }
+    if (!released) {
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+    }
+    mypix = pix2;
+    nt = nt2;
+    img = img2;
+    if (++acc == kAccStages) {
+      acc = 0;
+      acc_phase ^= 1u;
+    }
+  }
+}
+
+// The whole CTA program.  `bid` / `nblk`: this CTA's index among the `nblk` CTAs that share the problem `p` (the whole
+// grid for a plain launch; a contiguous CTA range of a grouped launch, cell_group_kernel).  PW = 0: the epilogue piece
+// width is taken from p.pw at run time (grouped launches mix levels that want 16 and 32).
 template <bool CELL, int PW, bool SPLIT>
-__global__ void __launch_bounds__(kThreadsUmma, 1)
-conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+__device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams& p, const int bid, const int nblk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages];
   __shared__ uint32_t tmem_slot;
@@ -784,7 +936,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     // =============================== TMA producer: activations (A ring) ===============================
     int as = 0;
     uint32_t aph = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = bid; work < num_work; work += nblk) {
       const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
       const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
       int mt = tile / p.tiles_n;
@@ -817,7 +969,7 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
         }
         __syncwarp();
         if (lane == 0 && ai == item0) STAMP(2);
-        if (lane == 0 && ai == item0) STAMP_T(0, (work - (int)blockIdx.x) / (int)gridDim.x);
+        if (lane == 0 && ai == item0) STAMP_T(0, (work - bid) / nblk);
         if (++as == p.a_stages) {
           as = 0;
           aph ^= 1u;
@@ -830,8 +982,8 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     // Its own warp, so that activation tiles run a_stages items ahead no matter how far the weight ring is.
     int bs = 0;
     uint32_t bph = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      if (p.b_resident && work != (int)blockIdx.x) break;  // resident weights: loaded for the first tile only
+    for (int work = bid; work < num_work; work += nblk) {
+      if (p.b_resident && work != bid) break;  // resident weights: loaded for the first tile only
       const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
       const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
       const int nt = tile % p.tiles_n;
@@ -860,92 +1012,112 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     // STACKED (BN <= 128): the weight stage holds [W_hi (BN rows) | W_lo (BN rows)] contiguously, so ONE MMA with
     // N = 2*BN multiplies an activation plane by both weight planes (columns [0,BN) and [BN,2BN) of the
     // accumulator, added in the epilogue): 2 MMAs per K step (x_hi, x_lo) give all four partial products.
-    // An SS-mode MMA costs ~128 cycles of A-operand reads whatever N is, so wide N is what makes it efficient.
-    // descriptors are linear in the smem address (a 14-bit field of 16-byte units): build one per ring, then add offsets
-    const uint64_t adesc0 = make_smem_desc(smem_a, p.a_sbo);
-    const uint64_t bdesc0 = make_smem_desc(smem_b, 1024);
-    const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
-    int as = 0, bs = 0;
-    uint32_t aph = 0, bph = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
-      mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d = tmem_base + acc * kStageCols;
-      uint32_t accumulate = 0;
-      for (int ai = item0; ai < item1; ++ai) {
-        const int cc = p.halo ? ai : ai % p.chunks;
-        const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
-        mbar_wait(afull0 + 8 * as, aph);
+    // ONE elected thread runs the whole issue loop (waits included).  This warp shares its scheduler with two epilogue
+    // warps, so every instruction it spends between two UTCHMMAs delays the tensor pipe: the shared-memory descriptors
+    // are a constant high word plus a 32-bit low word (14-bit address field in 16-byte units -- shared memory is
+    // < 256 KB, the field cannot overflow), advanced with plain 32-bit adds.
+    if (elect_one()) {
+      const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
+      const uint64_t a_hiword = (uint64_t)(make_smem_desc(0, p.a_sbo) >> 32) << 32;
+      const uint64_t b_hiword = (uint64_t)(make_smem_desc(0, 1024) >> 32) << 32;
+      const uint32_t a_low0 = (uint32_t)make_smem_desc(smem_a, p.a_sbo);
+      const uint32_t b_low0 = (uint32_t)make_smem_desc(smem_b, 1024);
+      const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)(p.BN * 128) >> 4;
+      const bool stacked = p.stacked != 0, halo = p.halo != 0, resident = p.b_resident != 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int work = bid; work < num_work; work += nblk) {
+        const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
+        const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
+        const bool first_work = work == bid;
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0 && ai == item0) STAMP(4);
-        if (lane == 0 && ai == item0) STAMP_T(1, (work - (int)blockIdx.x) / (int)gridDim.x);
-        for (int bi = 0; bi < b_per_a; ++bi) {
-          if (p.b_resident) {
-            bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
-            bph = 0;
-          }
-          if (!(p.b_resident && work != (int)blockIdx.x)) {
-            mbar_wait(bfull0 + 8 * bs, bph);
-            tc_fence_after();
-          }
-          if (lane == 0 && ai == item0 && bi == 0) STAMP(5);
-          uint32_t aoff = (uint32_t)(as * p.a_stage_bytes);
-          if (p.halo) {
-            const int kh = bi / 3, kw = bi - kh * 3;
-            aoff += (uint32_t)(kh * (kHaloBW + 2) + kw) * 128u;
-          }
-          const uint64_t a_hi = adesc0 + (uint64_t)(aoff >> 4);
-          const uint64_t a_lo = a_hi + (uint64_t)(p.a_plane_bytes >> 4);
-          const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)(bs * p.b_stage_bytes) >> 4);
-          const uint64_t b_lo = b_hi + (uint64_t)((uint32_t)(p.BN * 128) >> 4);
-          if (elect_one()) {
-            if (p.stacked) {
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 bytes along K inside the swizzle row
-                umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
-                umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
-                accumulate = 1u;
+        const uint32_t d = tmem_base + acc * kStageCols;
+        uint32_t accumulate = 0;
+        for (int ai = item0; ai < item1; ++ai) {
+          const int cc = halo ? ai : ai % p.chunks;
+          const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+          mbar_wait(afull0 + 8 * as, aph);
+          tc_fence_after();
+          if (ai == item0) STAMP(4);
+          if (ai == item0) STAMP_T(1, (work - bid) / nblk);
+          const uint32_t a_stage = a_low0 + (uint32_t)as * a_stage16;
+          for (int bi = 0; bi < b_per_a; ++bi) {
+            if (resident) {
+              bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
+              bph = 0;
+            }
+            if (!(resident && !first_work)) {
+              mbar_wait(bfull0 + 8 * bs, bph);
+              tc_fence_after();
+            }
+            if (ai == item0 && bi == 0) STAMP(5);
+            // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 units of 16 bytes per row)
+            const uint32_t a0 = a_stage + (halo ? (uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u : 0u);
+            const uint32_t b0 = b_low0 + (uint32_t)bs * b_stage16;
+            if (stacked) {
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                if (k < ksteps) {
+                  const uint64_t bd = b_hiword | (uint64_t)(b0 + 2u * k);  // 16 bf16 = 32 bytes along K per step
+                  umma_bf16(d, a_hiword | (uint64_t)(a0 + 2u * k), bd, idesc, accumulate);
+                  umma_bf16(d, a_hiword | (uint64_t)(a0 + a_plane16 + 2u * k), bd, idesc, 1u);
+                  accumulate = 1u;
+                }
               }
             } else {
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
-                umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
-                umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
-                accumulate = 1u;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                if (k < ksteps) {
+                  const uint64_t ad = a_hiword | (uint64_t)(a0 + 2u * k);
+                  umma_bf16(d, ad, b_hiword | (uint64_t)(b0 + 2u * k), idesc, accumulate);
+                  umma_bf16(d, ad, b_hiword | (uint64_t)(b0 + b_plane16 + 2u * k), idesc, 1u);
+                  umma_bf16(d, a_hiword | (uint64_t)(a0 + a_plane16 + 2u * k), b_hiword | (uint64_t)(b0 + 2u * k), idesc, 1u);
+                  accumulate = 1u;
+                }
               }
             }
-            if (!p.b_resident) umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
-            if (bi == b_per_a - 1) umma_commit(aempty0 + 8 * as);  // activation slot free
-            if (bi == b_per_a - 1 && ai == item1 - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+            if (!resident) {
+              umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+              if (++bs == p.b_stages) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
           }
-          __syncwarp();
-          accumulate = 1u;
-          if (!p.b_resident && ++bs == p.b_stages) {
-            bs = 0;
-            bph ^= 1u;
+          umma_commit(aempty0 + 8 * as);  // activation slot free
+          if (++as == p.a_stages) {
+            as = 0;
+            aph ^= 1u;
           }
         }
-        if (++as == p.a_stages) {
-          as = 0;
-          aph ^= 1u;
+        umma_commit(tfull0 + 8 * acc);  // accumulator complete
+        STAMP(6);
+        STAMP_T(2, (work - bid) / nblk);
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
         }
-      }
-      if (lane == 0) STAMP(6);
-      if (lane == 0) STAMP_T(2, (work - (int)blockIdx.x) / (int)gridDim.x);
-      if (++acc == kAccStages) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
+    __syncwarp();
   } else if (warp < kEpiWarps) {
     // =============================== epilogue (warps 0-7) ===============================
-    epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage_base + warp * kStageFloats, warp, lane);
+    float* stage = stage_base + warp * kStageFloats;
+    if (CELL && !SPLIT && p.cell_rows) {
+      cell_rows_epilogue(p, tmem_base, tfull0, tempty0, warp, lane, bid, nblk);
+    } else if constexpr (PW != 0) {
+      epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
+    } else {
+      if (p.pw == 32)
+        epilogue_role<CELL, 32, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
+      else
+        epilogue_role<CELL, 16, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
+    }
   }
 
   tc_fence_before();
@@ -955,6 +1127,35 @@ conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
+}
+
+// One instantiation per (epilogue kind, piece width, split-K or not): each carries a single epilogue variant, which
+// keeps the 11 differently-specialised warps of a CTA inside the instruction cache.
+template <bool CELL, int PW, bool SPLIT>
+__global__ void __launch_bounds__(kThreadsUmma, 1)
+conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+  umma_cta<CELL, PW, SPLIT>(maps, p, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Grouped launch: up to kMaxGroup independent ConvLSTM cells (different decoder levels, different time-steps: the
+// anti-diagonal of the (level, step) wavefront, model.py:129-165) in ONE launch.  Problem i owns the CTA range
+// [first[i], first[i+1]); every CTA runs the ordinary persistent program on its own problem.  No inter-CTA dependency
+// exists inside the launch, so the fixed costs of a launch (tensor-map fetch, first cold TMA, epilogue drain) are paid
+// once per wavefront instead of once per level, and the small levels run beside the large ones.
+constexpr int kMaxGroup = 5;
+struct alignas(64) CellGroup {
+  UmmaMaps maps[kMaxGroup];
+  UmmaParams p[kMaxGroup];
+  int first[kMaxGroup + 1];
+  int n;
+};
+
+__global__ void __launch_bounds__(kThreadsUmma, 1) cell_group_kernel(const __grid_constant__ CellGroup g) {
+  int i = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxGroup; ++k)
+    if (k < g.n && (int)blockIdx.x >= g.first[k]) i = k;
+  umma_cta<true, 0, false>(g.maps[i], g.p[i], (int)blockIdx.x - g.first[i], g.first[i + 1] - g.first[i]);
 }
 
 // ===================================================================================================================
@@ -1288,6 +1489,8 @@ unsigned* g_debug_counters = nullptr;  // set by the last non-swapped setup when
 int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
+int g_cell_rows = 1;       // RSIS_B200_CELL_ROWS=0: the staged-transpose cell epilogue instead of the row-wise one (A/B timing)
+int g_mma_model = 1;       // RSIS_B200_MMA_MODEL=0: planner assumes 70 ns per MMA whatever its N (round-1 model)
 int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
 std::once_flag g_once;
 
@@ -1305,6 +1508,8 @@ void init_once() {
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PDL")) g_pdl = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_MMA_MODEL")) g_mma_model = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_CELL_ROWS")) g_cell_rows = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PRINT_PLAN")) g_print_plan = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SWAP")) g_swap = atoi(e) != 0;
 
@@ -1325,6 +1530,8 @@ void init_once() {
       (e = set_smem_attr<true, 32, false>()) != cudaSuccess || (e = set_smem_attr<true, 32, true>()) != cudaSuccess ||
       (e = set_smem_attr<true, 16, false>()) != cudaSuccess || (e = set_smem_attr<true, 16, true>()) != cudaSuccess ||
       (e = cudaFuncSetAttribute(cell_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
+          cudaSuccess ||
+      (e = cudaFuncSetAttribute(cell_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
           cudaSuccess) {
     set_cuda_error(e);
     g_init_status = RSIS_ERR_CUDA;
@@ -1391,15 +1598,26 @@ struct Plan {
   long long cost;
 };
 
+// Cost of one tcgen05.mma (M = 128, K = 16, kind::f16, SS mode) in ns, from scripts/mma_probe.cu on B200
+// (profiles/r2b_mma_probe.txt): max(N/2, 32 + N/4) cycles -- the tensor pipe needs N/2 cycles, the shared-memory
+// operand reads (A: 4 KB, B: N x 32 B at 128 B/clk) 32 + N/4.  The extra 8 cycles and the 1.9 GHz stand for the
+// operand-port contention with TMA fills seen in the in-kernel stamps (N = 256: 70 ns measured, 67 modelled).
+inline double mma_ns(int n_mma) {
+  if (!g_mma_model) return 70.0;  // RSIS_B200_MMA_MODEL=0: the round-1 constant (A/B timing)
+  const double a = n_mma / 2.0, b = 40.0 + n_mma / 4.0;
+  return (a > b ? a : b) / 1.9;
+}
+
 Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
-               bool can_split, bool cell) {
+               bool can_split, bool cell, int ctas) {
   // Cost model in nanoseconds, calibrated on B200 with in-kernel %globaltimer stamps and graph-replay timings
   // (scripts/stamp_probe.py, scripts/gap_probe.py):
   //   launch -> first MMA and exit: ~3000;  one tcgen05.mma instruction: ~70 whatever its N;
   //   TMA ingest of one SM: ~80 bytes/ns, of the whole chip (L2 -> SMs): ~12000 bytes/ns;
   //   finishing one 32 x 32 accumulator piece on one epilogue warp: ~900 (conv) / ~1300 (cell), 8 warps per CTA;
   //   split-K hand-over (park the partial, wait for the slowest slice, reduce): ~4500 + 110 per (unit, slice).
-  const double kFixed = 3000, kMma = 70, kPiece = cell ? 1300 : 900, kSmBw = 80, kChipBw = 12000;
+  const double kFixed = 3000, kPiece = cell ? 1300 : 900, kSmBw = 80, kChipBw = 12000;
+  if (ctas <= 0 || ctas > g_num_sms) ctas = g_num_sms;  // CTAs this problem may use (its share of a grouped launch)
   const double ksteps_tile = (double)taps * ((chunks - 1) * (kBK / 16) + last_ksteps);
   const int items = taps * chunks;
   Plan best{0, 0, 1, 0, -1};
@@ -1411,6 +1629,7 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     if (g_force_bn && BN != g_force_bn) continue;
     const int stacked = BN <= 128 ? 1 : 0;
     const double mpk = stacked ? 2 : 3;
+    const double kMma = mma_ns(stacked ? 2 * BN : BN);
     const int tiles_n = ceil_div(cout, BN);
     const double b_item = 2.0 * BN * 128;
     const double pieces_per_warp = BN >= 64 ? ceil_div(4 * (BN / 32), kEpiWarps) : 0.6;
@@ -1418,7 +1637,7 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     // (a) no split: persistent CTAs, HALO staging when eligible; MMAs of tile i+1 overlap the epilogue of tile i
     if (!(halo_ok && BN == 256)) {  // a HALO stage + 64 KB weight stages do not leave room for a pipeline
       const double tiles = (double)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
-      const double per_cta = ceil(tiles / g_num_sms);
+      const double per_cta = ceil(tiles / ctas);
       const double bytes_tile = (halo_ok ? chunks * 2.0 * kHaloRows * 128 : items * 32768.0) + items * b_item;
       const double mma_tile = ksteps_tile * mpk * kMma;
       double tile_t = mma_tile > epi_tile ? mma_tile : epi_tile;
@@ -1465,7 +1684,7 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
 
 // Fills geometry, tensor maps and the K loop.
 int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w, int stride, int pad,
-          void* workspace, size_t workspace_bytes) {
+          void* workspace, size_t workspace_bytes, int cta_share = 0) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK) return g_init_status;
   p.N = x.n;
@@ -1488,7 +1707,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   if (mt_tap > 0x3fffffLL || mt_halo > 0x3fffffLL) return RSIS_ERR_UNSUPPORTED;
   const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
   const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
-                              w->gate_interleaved != 0);
+                              w->gate_interleaved != 0, cta_share);
   if (g_print_plan)
     fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d halo=%d est %lld ns\n",
             x.n, x.h, x.w, x.c, w->cout, w->kh, stride, w->gate_interleaved ? " cell/gates" : "", plan.BN, plan.stacked,
@@ -1544,7 +1763,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     // Weight residency: a persistent CTA that walks several pixel tiles of ONE output-channel tile re-reads the same
     // taps x chunks weight boxes for every tile; when they all fit next to two activation stages, load them once.
     const int items_b = p.taps * p.chunks;
-    const bool many_tiles = p.num_tiles >= 2 * g_num_sms;
+    const bool many_tiles = p.num_tiles >= 2 * (cta_share > 0 ? cta_share : g_num_sms);
     if (g_b_resident && p.ksplit == 1 && p.tiles_n == 1 && many_tiles && items_b <= kMaxStages &&
         2 * p.a_stage_bytes + items_b * p.b_stage_bytes <= budget) {
       p.b_resident = 1;
@@ -1556,6 +1775,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
   p.scale = w->scale;
   p.shift = w->shift;
+  p.cell_rows = g_cell_rows;
   const int cout_pad = round_up(w->cout, 16);
   const int k_pad = p.taps * p.chunks * kBK;
   if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN)) return e;
@@ -2089,6 +2309,115 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   p.side_offset = side_offset;
   if (swapped) return launch_swap(maps, p, st);
   return launch<true>(maps, p, st);
+}
+
+
+// ---- grouped cells: the cells of one wavefront of the decoder in one launch ----------------------------------------
+int convlstm_cell_group_max() { return kMaxGroup; }
+
+bool convlstm_cell_group_supported(const rsis_cell_args* cells, int n) {
+  if (!cells || n < 1 || n > kMaxGroup) return false;
+  for (int i = 0; i < n; ++i) {
+    const rsis_cell_args& c = cells[i];
+    if (!c.x || !c.w || !c.h_out || !c.c_out || !convlstm_cell_umma_supported(c.x, 1, c.w)) return false;
+  }
+  return true;
+}
+
+int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st) {
+  std::call_once(g_once, init_once);
+  if (g_init_status != RSIS_OK) return g_init_status;
+  static_assert(sizeof(CellGroup) < 32000, "kernel parameter space");
+  CellGroup g{};
+  g.n = n;
+  // (1) CTA shares in proportion to the tensor-core work of each cell (pixel tiles x K steps x gate columns); every
+  // cell at least one CTA, none more CTAs than it has pixel tiles
+  double work[kMaxGroup], total = 0;
+  int tiles[kMaxGroup], share[kMaxGroup];
+  for (int i = 0; i < n; ++i) {
+    const rsis_tensor& x = *cells[i].x;
+    const rsis_conv_weights* w = cells[i].w;
+    tiles[i] = ceil_div(x.n * x.h * x.w, kBM);
+    const double cols = w->cout < 16 ? 16 : w->cout;
+    // narrow gate blocks are bound by the shared-memory operand reads, not by the tensor pipe: 32 + N/4 vs N/2 cycles
+    const double per_col = cols >= 128 ? 1.0 : (40.0 + cols / 2.0) / cols;
+    work[i] = (double)tiles[i] * w->kh * w->kw * ceil_div(x.c, 16) * cols * per_col;
+    total += work[i];
+  }
+  int used = 0;
+  for (int i = 0; i < n; ++i) {
+    tiles[i] *= ceil_div(cells[i].w->cout, 32);  // most (pixel tile, gate-column tile) units a plan can have
+    share[i] = (int)(g_num_sms * work[i] / total);
+    if (share[i] < 1) share[i] = 1;
+    if (share[i] > tiles[i]) share[i] = tiles[i];
+    used += share[i];
+  }
+  // hand out what rounding left over (or take back an overshoot) one CTA at a time, to / from the cell with the most
+  // work per CTA / the least
+  for (int guard = 0; used != g_num_sms && guard < 4 * g_num_sms; ++guard) {
+    int best = -1;
+    for (int i = 0; i < n; ++i) {
+      if (used < g_num_sms) {
+        if (share[i] >= tiles[i]) continue;
+        if (best < 0 || work[i] / share[i] > work[best] / share[best]) best = i;
+      } else {
+        if (share[i] <= 1) continue;
+        if (best < 0 || work[i] / share[i] < work[best] / share[best]) best = i;
+      }
+    }
+    if (best < 0) break;
+    share[best] += used < g_num_sms ? 1 : -1;
+    used += used < g_num_sms ? 1 : -1;
+  }
+  // (2) plan every cell for its share; no split-K (the wavefront supplies the parallelism)
+  int first = 0;
+  for (int i = 0; i < n; ++i) {
+    const rsis_cell_args& c = cells[i];
+    UmmaParams& p = g.p[i];
+    if (int e = setup(g.maps[i], p, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i])) return e;
+    const int Ch = p.Cout / 4;
+    auto ok = [&](const rsis_tensor* t, int fmt) {
+      return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&
+             aligned16(t->data);
+    };
+    if (!ok(c.h_out, RSIS_FMT_F32) || !ok(c.c_out, RSIS_FMT_F32) || pitch(*c.h_out) != Ch || pitch(*c.c_out) != Ch)
+      return RSIS_ERR_BAD_ARG;
+    if (c.h_split && (!ok(c.h_split, RSIS_FMT_SPLIT_BF16) || pitch(*c.h_split) % 8 != 0)) return RSIS_ERR_BAD_ARG;
+    if (c.side_max && (c.side_stride < c.side_offset + Ch || c.side_offset < 0)) return RSIS_ERR_BAD_ARG;
+    if ((c.c_prev && !aligned16(c.c_prev)) || (c.gate_preact && !aligned16(c.gate_preact))) return RSIS_ERR_ALIGN;
+    p.c_prev = c.c_prev;
+    p.preact = c.gate_preact;
+    p.h_out = reinterpret_cast<float*>(c.h_out->data);
+    p.c_out = reinterpret_cast<float*>(c.c_out->data);
+    if (c.h_split) {
+      p.h_split = reinterpret_cast<__nv_bfloat16*>(c.h_split->data);
+      p.hs_cs = pitch(*c.h_split);
+      p.hs_plane = plane_elems(*c.h_split);
+    }
+    p.side_max = c.side_max;
+    p.side_stride = c.side_stride;
+    p.side_offset = c.side_offset;
+    if (getenv("RSIS_B200_DEBUG_TIMING")) p.counters = g_debug_counters;  // in-kernel stamps of block 0 (debug builds)
+    int ctas = share[i] < p.num_tiles ? share[i] : p.num_tiles;
+    if (ctas < 1) ctas = 1;
+    g.first[i] = first;
+    first += ctas;
+    if (g_print_plan) fprintf(stderr, "rsis group: cell %d -> %d CTAs for %d tiles\n", i, ctas, p.num_tiles);
+  }
+  for (int i = n; i <= kMaxGroup; ++i) g.first[i] = first;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(first);
+  cfg.blockDim = dim3(kThreadsUmma);
+  cfg.dynamicSmemBytes = kDynSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  RSIS_CUDA_TRY(cudaLaunchKernelEx(&cfg, cell_group_kernel, g));
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
 }
 
 }  // namespace rsis

@@ -70,34 +70,64 @@ __global__ void maxpool3x3s2_kernel(View x, void* y, size_t y_plane, int y_fmt, 
 // nn.UpsamplingBilinear2d(size) == bilinear with align_corners=True -- /root/reference/src/modules/model.py:149-150,
 // 163-164.  Index arithmetic follows ATen's area_pixel_compute_source_index(align_corners=true): src = scale * dst with
 // scale = (in - 1) / (out - 1) evaluated in float.
-__global__ void upsample_bilinear_kernel(View x, void* y, size_t y_plane, int y_fmt, int y_cs, int N, int H, int W,
-                                         int C, int Ho, int Wo, float sh, float sw) {
-  pdl_trigger();
-  const int C4 = C >> 2;
-  const size_t total = (size_t)N * Ho * Wo * C4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+struct UpsampleArgs {
+  View x;
+  void* y;
+  size_t y_plane;
+  int y_fmt, y_cs, N, H, W, C, Ho, Wo;
+  float sh, sw;
+};
+
+__device__ __forceinline__ void upsample_bilinear_body(const UpsampleArgs& a, size_t first, size_t stride) {
+  const int C4 = a.C >> 2;
+  const size_t total = (size_t)a.N * a.Ho * a.Wo * C4;
+  for (size_t i = first; i < total; i += stride) {
     const int c = (int)(i % C4) * 4;
     size_t r = i / C4;
-    const int wo = (int)(r % Wo);
-    r /= Wo;
-    const int ho = (int)(r % Ho);
-    const int n = (int)(r / Ho);
-    const float fh = sh * ho, fw = sw * wo;
-    const int h1 = min((int)fh, H - 1), w1 = min((int)fw, W - 1);  // ATen guard_index_and_lambda
-    const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
+    const int wo = (int)(r % a.Wo);
+    r /= a.Wo;
+    const int ho = (int)(r % a.Ho);
+    const int n = (int)(r / a.Ho);
+    const float fh = a.sh * ho, fw = a.sw * wo;
+    const int h1 = min((int)fh, a.H - 1), w1 = min((int)fw, a.W - 1);  // ATen guard_index_and_lambda
+    const int h1p = h1 < a.H - 1 ? 1 : 0, w1p = w1 < a.W - 1 ? 1 : 0;
     const float h1l = fminf(fmaxf(fh - h1, 0.f), 1.f), h0l = 1.f - h1l;
     const float w1l = fminf(fmaxf(fw - w1, 0.f), 1.f), w0l = 1.f - w1l;
     float v00[4], v01[4], v10[4], v11[4], o[4];
-    const size_t base = (((size_t)n * H + h1) * W + w1) * C + c;
-    load4(x, base, v00);
-    load4(x, base + (size_t)w1p * C, v01);
-    load4(x, base + (size_t)h1p * W * C, v10);
-    load4(x, base + (size_t)h1p * W * C + (size_t)w1p * C, v11);
+    const size_t base = (((size_t)n * a.H + h1) * a.W + w1) * a.C + c;
+    load4(a.x, base, v00);
+    load4(a.x, base + (size_t)w1p * a.C, v01);
+    load4(a.x, base + (size_t)h1p * a.W * a.C, v10);
+    load4(a.x, base + (size_t)h1p * a.W * a.C + (size_t)w1p * a.C, v11);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       o[j] = h0l * (w0l * v00[j] + w1l * v01[j]) + h1l * (w0l * v10[j] + w1l * v11[j]);
-    store4v(y, y_plane, y_fmt, (((size_t)n * Ho + ho) * Wo + wo) * y_cs + c, o);
+    store4v(a.y, a.y_plane, a.y_fmt, (((size_t)n * a.Ho + ho) * a.Wo + wo) * a.y_cs + c, o);
   }
+}
+
+__global__ void upsample_bilinear_kernel(const UpsampleArgs a) {
+  pdl_trigger();
+  upsample_bilinear_body(a, blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// Several independent upsamplings in one launch (the decoder's wavefront schedule: the x2 upsamplings feeding levels
+// 1..4 at four different time-steps); problem i owns the block range [first[i], first[i+1]).
+constexpr int kMaxUpsampleGroup = 4;
+struct UpsampleGroup {
+  UpsampleArgs a[kMaxUpsampleGroup];
+  int first[kMaxUpsampleGroup + 1];
+  int n;
+};
+
+__global__ void upsample_bilinear_group_kernel(const __grid_constant__ UpsampleGroup g) {
+  pdl_trigger();
+  int i = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxUpsampleGroup; ++k)
+    if (k < g.n && (int)blockIdx.x >= g.first[k]) i = k;
+  const int nb = g.first[i + 1] - g.first[i];
+  upsample_bilinear_body(g.a[i], (size_t)(blockIdx.x - g.first[i]) * blockDim.x + threadIdx.x, (size_t)nb * blockDim.x);
 }
 
 // conv_out (model.py:167): k x k conv (k = 1 or 3), Cin -> 1, + bias; optional sigmoid copy (test.py:50).
@@ -383,15 +413,50 @@ int rsis_maxpool3x3s2(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t 
   return RSIS_OK;
 }
 
-int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
+static int fill_upsample(UpsampleArgs& a, const rsis_tensor* x, const rsis_tensor* y) {
   if (!valid_tensor(x) || !valid_tensor(y) || y->n != x->n || y->c != x->c) return RSIS_ERR_BAD_ARG;
   if (x->c % 4 != 0 || !is_dense(*x) || pitch(*y) % 4 != 0) return RSIS_ERR_UNSUPPORTED;
   if (!aligned16(x->data) || !aligned16(y->data)) return RSIS_ERR_ALIGN;
-  const float sh = y->h > 1 ? (float)(x->h - 1) / (float)(y->h - 1) : 0.f;
-  const float sw = y->w > 1 ? (float)(x->w - 1) / (float)(y->w - 1) : 0.f;
+  a.x = make_view(*x);
+  a.y = y->data;
+  a.y_plane = plane_elems(*y);
+  a.y_fmt = y->fmt;
+  a.y_cs = pitch(*y);
+  a.N = x->n;
+  a.H = x->h;
+  a.W = x->w;
+  a.C = x->c;
+  a.Ho = y->h;
+  a.Wo = y->w;
+  a.sh = y->h > 1 ? (float)(x->h - 1) / (float)(y->h - 1) : 0.f;
+  a.sw = y->w > 1 ? (float)(x->w - 1) / (float)(y->w - 1) : 0.f;
+  return RSIS_OK;
+}
+
+int rsis_upsample_bilinear(const rsis_tensor* x, const rsis_tensor* y, rsis_stream_t stream) {
+  UpsampleArgs a;
+  if (int e = fill_upsample(a, x, y)) return e;
   const size_t total = numel(*y) / 4;
-  upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      make_view(*x), y->data, plane_elems(*y), y->fmt, pitch(*y), x->n, x->h, x->w, x->c, y->h, y->w, sh, sw);
+  upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_upsample_bilinear_group(const rsis_tensor* xs, const rsis_tensor* ys, int n, rsis_stream_t stream) {
+  if (!xs || !ys || n < 1 || n > kMaxUpsampleGroup) return RSIS_ERR_BAD_ARG;
+  UpsampleGroup g{};
+  g.n = n;
+  int first = 0;
+  for (int i = 0; i < n; ++i) {
+    if (int e = fill_upsample(g.a[i], xs + i, ys + i)) return e;
+    g.first[i] = first;
+    // blocks in proportion to the output sizes (every problem at least one block, at most four per SM)
+    size_t blocks = (numel(ys[i]) / 4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    first += (int)(blocks < 1 ? 1 : blocks);
+  }
+  for (int i = n; i <= kMaxUpsampleGroup; ++i) g.first[i] = first;
+  upsample_bilinear_group_kernel<<<first, 256, 0, (cudaStream_t)stream>>>(g);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }

@@ -19,6 +19,9 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
                        int cta_cap, cudaStream_t st);
+int convlstm_cell_group_max();
+bool convlstm_cell_group_supported(const rsis_cell_args* cells, int n);
+int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st);
 }  // namespace rsis
 
 using namespace rsis;
@@ -64,6 +67,14 @@ int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                                  workspace, workspace_bytes, cta_cap, st)
             : convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  st);
+}
+
+int rsis_convlstm_cell_group_max(void) { return convlstm_cell_group_max(); }
+
+int rsis_convlstm_cell_group(const rsis_cell_args* cells, int n_cells, rsis_stream_t stream) {
+  if (!cells || n_cells < 1) return RSIS_ERR_BAD_ARG;
+  if (!convlstm_cell_group_supported(cells, n_cells)) return RSIS_ERR_UNSUPPORTED;
+  return convlstm_cell_group_umma(cells, n_cells, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -56,10 +56,14 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
             ws.load_feats(decoder, feats_op, impl)
         ws.reset()
         # RSIS_B200_PIPELINE: 0 = one step after the other (12 launches in stream order), 1 = wavefront over
-        # (level, step) on per-level streams, 2 (default) = wavefront and no split-K in the cells (measured on B200 at
-        # B=8 256x256 T=10: 3.60 / 3.40 / 3.24 ms per pass)
-        mode = os.environ.get("RSIS_B200_PIPELINE", "2")
+        # (level, step) on per-level streams, 2 = wavefront and no split-K in the cells (measured on B200 at
+        # B=8 256x256 T=10: 3.60 / 3.40 / 3.24 ms per pass), 3 (default) = grouped wavefront launches
+        mode = os.environ.get("RSIS_B200_PIPELINE", "3")
         last = ws.h[-1]
+        if mode == "3" and last.c % 4 == 0 and last.c <= 16 and len(ws.h) <= ops.cell_group_max():
+            # grouped wavefront: the independent cells of an anti-diagonal of (level, step) in ONE launch each
+            decoder.run_wavefront(ws, impl, T, out_classes, out_masks, out_stops)
+            return ws
         if mode != "0" and last.c % 4 == 0 and last.c <= 16:
             # wavefront schedule over (level, step); "2": additionally no split-K in the cells (fewer, longer CTAs)
             caps = os.environ.get("RSIS_B200_PIPE_CAPS", "")   # per-level CTA caps, e.g. "0,0,0,40,96" (tuning aid)

@@ -171,6 +171,7 @@ class DecoderWorkspace:
         self.h = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
+        self.h_last = None   # [2] float32 hidden state of the last level, double-buffered (run_wavefront)
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
         self.side_stream = torch.cuda.Stream(device=device)  # forked work: skip heads, class/stop heads
         self.level_streams = None   # pipelined schedule (run_pipelined): one stream per level + the mask head's
@@ -373,6 +374,69 @@ class RSIS(nn.Module):
                                      self.fc_stop.bias, class_probs[:, t], T * C, None, stop_prob[:, t], T)
         for s_ in streams:
             main.wait_stream(s_)
+        ws.t = T
+
+    def run_wavefront(self, ws: DecoderWorkspace, impl: int, T: int, class_probs: torch.Tensor,
+                      mask_prob: torch.Tensor, stop_prob: torch.Tensor):
+        """All T decoder steps as T + 4 GROUPED launches: wavefront w runs the independent cells {(l, t) : l + t = w}
+        (model.py:132-153: cell (l, t) needs (l-1, t) through the upsampling and (l, t-1) through its own state) in ONE
+        kernel launch (`ops.convlstm_cell_group`), followed by ONE launch with the x2 upsamplings that feed the next
+        wavefront.  The mask head of step t (fused upsample + conv_out + sigmoid) and the class/stop heads run on side
+        streams beside the following wavefronts.  Per pass at T = 10: 14 + 13 + 10 + 10 launches instead of 120, and the
+        small levels no longer pay a launch each -- they share the chip with the large ones.
+        The last level's float32 hidden state is double-buffered (`ws.h_last`) so that the mask head of step t may still
+        be reading it while cell (4, t+1) runs.  Requires ws.reset() before."""
+        nlev = len(self.clstm_list)
+        hl = ws.h[nlev - 1]
+        assert hl.c % 4 == 0 and hl.c <= 16 and ws.t == 0
+        ws.prepare_pipeline(T)
+        if ws.h_last is None:
+            ws.h_last = [hl, ops.Act.empty(hl.n, hl.h, hl.w, hl.c, ops.FMT_F32, hl.t.device)]
+        dev = hl.t.device
+        main = torch.cuda.current_stream(dev)
+        B, _, H, W = mask_prob.shape
+        C = class_probs.shape[-1]
+        offs = [sum(ws.hidden[:l]) for l in range(nlev)]
+        ev_mask = {}
+        for w in range(T + nlev - 1):
+            cells, ups = [], []
+            for l in range(nlev):
+                t = w - l
+                if t < 0 or t >= T:
+                    continue
+                p = t & 1
+                _, pc = ws.packs(self, l)
+                h_out = ws.h_last[p] if l == nlev - 1 else ws.h[l]
+                cells.append(dict(x=ws.X[l][p], pc=pc, c_prev=ws.c[l].t if t > 0 else None, side_max=ws.sides[t],
+                                  side_offset=offs[l], h_out=h_out, c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p),
+                                  gate_preact=ws.P[l]))
+                if l + 1 < nlev:
+                    x_next = ws.X[l + 1][p]
+                    ups.append((ws.h[l], ws.up_view(l + 1, p)))
+                    assert x_next.h == ws.up_view(l + 1, p).h
+            t_last = w - (nlev - 1)          # the step whose last level runs in this wavefront
+            if t_last >= 2 and t_last < T:
+                main.wait_event(ev_mask[t_last - 2])   # its mask head read the buffer cell (4, t_last) overwrites
+            ops.convlstm_cell_group(cells)
+            if 0 <= t_last < T:
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(ws.mask_stream):
+                    ws.mask_stream.wait_event(done)
+                    src = ws.h_last[t_last & 1]
+                    ops.upsample_mask_head(src, 2 * src.h, 2 * src.w, self.conv_out.weight, self.conv_out.bias, None,
+                                           mask_prob[:, t_last], T * H * W)
+                    ev_mask[t_last] = torch.cuda.Event()
+                    ev_mask[t_last].record(ws.mask_stream)
+                with torch.cuda.stream(ws.side_stream):
+                    ws.side_stream.wait_event(done)
+                    ops.class_stop_heads(ws.sides[t_last], self.fc_class.weight, self.fc_class.bias,
+                                         self.fc_stop.weight, self.fc_stop.bias, class_probs[:, t_last], T * C, None,
+                                         stop_prob[:, t_last], T)
+            if ups and w + 1 < T + nlev - 1:
+                ops.upsample_bilinear_group(ups)
+        main.wait_stream(ws.mask_stream)
+        main.wait_stream(ws.side_stream)
         ws.t = T
 
     def step_act(self, feats: Sequence[Act], prev, impl: int, mask_logits: torch.Tensor,

@@ -327,6 +327,52 @@ def convlstm_cell_x(x: Act, pc: PackedConv, c_prev: Optional[torch.Tensor], side
     return h, c
 
 
+def cell_group_max() -> int:
+    return int(_lib.load().rsis_convlstm_cell_group_max())
+
+
+def convlstm_cell_group(cells: Sequence[dict]):
+    """One wavefront of the decoder in ONE launch (rsis_convlstm_cell_group): `cells` = dicts with the keyword arguments
+    of convlstm_cell_x (x, pc, c_prev, side_max, side_offset, h_out, c_out, h16_out, gate_preact), all buffers given."""
+    lib = _lib.load()
+    arr = (_lib.CellArgs * len(cells))()
+    keep = []
+    for i, c in enumerate(cells):
+        x, pc = c["x"], c["pc"]
+        pre = c.get("gate_preact")
+        if pre is not None:
+            assert pre.fmt == FMT_F32 and pre.dense and pre.c == pc.cout
+        side = c.get("side_max")
+        h16 = c.get("h16_out")
+        a = arr[i]
+        a.x = C.pointer(x.desc)
+        a.w = C.pointer(pc.desc)
+        a.c_prev = _ptr(c.get("c_prev"))
+        a.gate_preact = None if pre is None else pre.t.data_ptr()
+        a.h_out = C.pointer(c["h_out"].desc)
+        a.h_split = C.pointer(h16.desc) if h16 is not None else None
+        a.c_out = C.pointer(c["c_out"].desc)
+        a.side_max = _ptr(side)
+        a.side_stride = side.shape[-1] if side is not None else 0
+        a.side_offset = int(c.get("side_offset", 0))
+        keep.append((x, pc, pre, h16))
+    check(lib.rsis_convlstm_cell_group(arr, len(cells), _lib.stream_ptr()), "convlstm_cell_group")
+    _lib.count_launch(1)
+
+
+def upsample_bilinear_group(pairs: Sequence[tuple]):
+    """[(x Act f32 dense, out Act -- may be a pitched slice)] -> one launch (rsis_upsample_bilinear_group)."""
+    lib = _lib.load()
+    n = len(pairs)
+    xs = (_lib.Tensor * n)()
+    ys = (_lib.Tensor * n)()
+    for i, (x, y) in enumerate(pairs):
+        xs[i] = x.desc
+        ys[i] = y.desc
+    check(lib.rsis_upsample_bilinear_group(xs, ys, n, _lib.stream_ptr()), "upsample_bilinear_group")
+    _lib.count_launch(1)
+
+
 def convlstm_cell(srcs: Sequence[Act], pc: PackedConv, c_prev: Optional[torch.Tensor], side_max: Optional[torch.Tensor],
                   side_offset: int = 0, want_split: bool = False, impl: int = IMPL_AUTO):
     """One fused ConvLSTM step. `srcs` = [input_ parts..., prev_hidden] (prev_hidden omitted when the state is None).

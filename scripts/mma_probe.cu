@@ -37,22 +37,38 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
       : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 struct Cfg {
   int ts, M, N, nacc, reps, bvar;  // bvar: number of distinct B descriptors cycled through (1..8)
+  int amode;   // 0: A tile of 8-row groups 1024 B apart, 1024-aligned; 1: HALO staging of the convolution kernels --
+               //    groups 1280 B apart (10-pixel rows), start shifted by (kh*10+kw) rows per tap
+  int commit;  // > 0: a tcgen05.commit to a scratch mbarrier after every `commit` MMAs
 };
 
+template <int TS, int COMMIT>
 __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long* out_cyc, long long* out_ns) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  // A: 128 rows x 128 B (16 KB) at base; B: 8 variants x 256 rows x 128 B at base + 16 KB (first 64 KB used twice)
-  for (int i = threadIdx.x; i < (16384 + 2 * 32768) / 2; i += blockDim.x)
+  // A: 48 KB region at base (aligned tile: 16 KB; halo tile: 180 rows x 128 B); B: 2 x 32 KB at base + 48 KB
+  for (int i = threadIdx.x; i < (49152 + 2 * 32768) / 2; i += blockDim.x)
     reinterpret_cast<__nv_bfloat16*>(gen)[i] = __float2bfloat16(((i * 37) % 17 - 8) * 0.01f);
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -77,23 +93,37 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long* out_cyc, long 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)c.N >> 3) << 17) | (((uint32_t)c.M >> 4) << 24);
-    const uint64_t adesc = make_desc(base, 1024);
-    const uint64_t bdesc = make_desc(base + 16384, 1024);
+    const uint64_t adesc = make_desc(base, c.amode ? 1280 : 1024);
+    const uint64_t bdesc = make_desc(base + 49152, 1024);
     const int stage_cols = c.N;  // accumulators side by side (nacc * N <= 480)
     long long t0 = clock64();
     unsigned long long g0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
-    for (int r = 0; r < c.reps; ++r) {
-      const uint32_t d = tmem + (uint32_t)((r % c.nacc) * stage_cols);
-      const int v = r % c.bvar;
-      // variants: K advance inside the swizzle row (v & 3) * 32 B, and a second 32 KB tile (v >> 2)
-      const uint64_t b = bdesc + (uint64_t)(((v & 3) * 32 + (v >> 2) * 32768) >> 4);
-      if (c.ts)
-        mma_ts(d, tmem + 480 + (uint32_t)((v & 1) * 8), b, idesc, r >= c.nacc);
-      else
-        mma_ss(d, adesc + (uint64_t)(((v & 3) * 32) >> 4), b, idesc, r >= c.nacc);
+    // tight issue loop: 8 MMAs per iteration, every descriptor precomputed (no integer division on the issue path)
+    uint64_t bv[8];
+    uint64_t av[8];
+    uint32_t atm[8], dv[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const int vv = c.bvar == 1 ? 0 : v;
+      bv[v] = bdesc + (uint64_t)(((vv & 3) * 32 + (vv >> 2) * 32768) >> 4);
+      av[v] = adesc + (uint64_t)(((vv & 3) * 32 + (c.amode ? ((v % 3) * 10 + (v / 3)) * 128 : 0)) >> 4);
+      atm[v] = tmem + 480 + (uint32_t)((vv & 1) * 8);
+      dv[v] = tmem + (uint32_t)((v & (c.nacc - 1)) * stage_cols);
+    }
+    for (int r = 0; r < c.reps; r += 8) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        if (TS)
+          mma_ts(dv[v], atm[v], bv[v], idesc, 1u);
+        else
+          mma_ss(dv[v], av[v], bv[v], idesc, 1u);
+        if (COMMIT > 0 && (v + 1) % COMMIT == 0)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2))
+                       : "memory");
+      }
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar))
                  : "memory");
@@ -124,40 +154,48 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long* out_cyc, long 
 int main() {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int smem = 16384 + 2 * 32768 + 1024 + 34816;  // + slack: an M=128/N=256 descriptor may read past the tile
-  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  const int smem = 49152 + 2 * 32768 + 1024 + 34816;  // + slack: an M=128/N=256 descriptor may read past the tile
+  cudaFuncSetAttribute(probe<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(probe<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   long long *d_cyc, *d_ns;
   cudaMalloc(&d_cyc, sizeof(long long) * 2 * 256);
   cudaMalloc(&d_ns, sizeof(long long) * 256);
   std::vector<long long> cyc(512), ns(256);
   printf("sms %d\n", sms);
-  printf("%-4s %4s %4s %5s %5s %6s %5s | %10s %10s %10s %10s\n", "mode", "M", "N", "nacc", "bvar", "reps", "grid",
-         "cyc/mma b0", "cyc/mma mx", "issue cyc", "ns/mma b0");
-  const int Ms[2] = {128, 64};
-  const int Ns[5] = {256, 128, 64, 32, 16};
-  for (int grid : {1, sms}) {
+  printf("%-4s %4s %4s %5s %5s %6s %6s %5s | %10s %10s %10s\n", "mode", "M", "N", "nacc", "amode", "commit", "reps", "grid",
+         "cyc/mma b0", "issue cyc", "ns/mma b0");
+  for (int grid : {1, sms})
     for (int ts = 0; ts < 2; ++ts)
-      for (int M : Ms)
-        for (int N : Ns)
-          for (int nacc : {1, 2})
-            for (int bvar : {1, 8}) {
-              if (nacc * N > 480) continue;
-              if (grid == sms && (bvar == 1 || (nacc == 2 && N < 128))) continue;
-              Cfg c{ts, M, N, nacc, 2048, bvar};
-              for (int it = 0; it < 2; ++it) probe<<<grid, 128, smem>>>(c, d_cyc, d_ns);
-              cudaError_t e = cudaDeviceSynchronize();
-              if (e != cudaSuccess) {
-                printf("%s M=%d N=%d: %s\n", ts ? "TS" : "SS", M, N, cudaGetErrorString(e));
-                return 1;
+      for (int N : {256, 128, 64, 32})
+        for (int amode = 0; amode < 2; ++amode)
+          for (int commit : {0, 4, 1}) {
+            if (ts && amode) continue;
+            if (grid == sms && commit == 1) continue;
+            Cfg c{ts, 128, N, 1, 4096, 8, amode, commit};
+            for (int it = 0; it < 2; ++it) {
+              if (ts) {
+                if (commit == 0) probe<1, 0><<<grid, 128, smem>>>(c, d_cyc, d_ns);
+                else if (commit == 4) probe<1, 4><<<grid, 128, smem>>>(c, d_cyc, d_ns);
+                else probe<1, 1><<<grid, 128, smem>>>(c, d_cyc, d_ns);
+              } else {
+                if (commit == 0) probe<0, 0><<<grid, 128, smem>>>(c, d_cyc, d_ns);
+                else if (commit == 4) probe<0, 4><<<grid, 128, smem>>>(c, d_cyc, d_ns);
+                else probe<0, 1><<<grid, 128, smem>>>(c, d_cyc, d_ns);
               }
-              cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
-              cudaMemcpy(ns.data(), d_ns, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
-              long long mx = 0;
-              for (int b = 0; b < grid; ++b) mx = cyc[2 * b] > mx ? cyc[2 * b] : mx;
-              printf("%-4s %4d %4d %5d %5d %6d %5d | %10.1f %10.1f %10.1f %10.1f\n", ts ? "TS" : "SS", M, N, nacc, bvar,
-                     c.reps, grid, (double)cyc[0] / c.reps, (double)mx / c.reps, (double)cyc[1] / c.reps,
-                     (double)ns[0] / c.reps);
             }
-  }
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+              printf("%s N=%d amode=%d: %s\n", ts ? "TS" : "SS", N, amode, cudaGetErrorString(e));
+              return 1;
+            }
+            cudaMemcpy(cyc.data(), d_cyc, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ns.data(), d_ns, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+            printf("%-4s %4d %4d %5d %5d %6d %6d %5d | %10.1f %10.1f %10.1f\n", ts ? "TS" : "SS", 128, N, 1, amode, commit,
+                   c.reps, grid, (double)cyc[0] / c.reps, (double)cyc[1] / c.reps, (double)ns[0] / c.reps);
+          }
   return 0;
 }
