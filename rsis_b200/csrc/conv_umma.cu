@@ -60,12 +60,32 @@ constexpr int kHaloRows = (kHaloBW + 2) * (kHaloBH + 2);  // 180 pixels
 struct alignas(64) UmmaMaps {
   CUtensorMap a[4];  // stride 1: a[0]; stride 2: one per (row parity, column parity)
   CUtensorMap b;
+  CUtensorMap pre;   // cells with pre_tma: the hoisted gate share [N][H][W][4*Ch] fp32, boxes of 32 columns
 };
+
+// Division by a launch constant without the ~30-instruction integer-division sequence: q = umulhi(n, ceil(2^32 / d)),
+// exact for n * d < 2^32 (tile counts are < 2^22 and the divisors used here < 2^10; larger divisors keep magic = 0 and
+// divide for real).  The per-tile paths of every warp role decode (tile -> n tile, w, h, image) with these: with
+// runtime divisions the decode alone cost a few microseconds per tile on the latency-bound single-warp roles.
+struct FastDiv {
+  uint32_t d, magic;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (uint32_t)d;
+  f.magic = (d > 1 && d < 1024) ? (uint32_t)((0x100000000ULL + (uint32_t)d - 1) / (uint32_t)d) : 0u;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  return f.magic ? __umulhi(n, f.magic) : n / f.d;
+}
 
 struct UmmaParams {
   // tile geometry
   int BW, BH, BI;          // output-pixel box: width x height x images, product 128
   int tiles_w, tiles_h, tiles_i, tiles_n, num_tiles;
+  FastDiv dn, dw, dh, dks; // dividers by tiles_n, tiles_w, tiles_h, ksplit
   int BN;                  // output channels per tile (32 / 64 / 128 / 256)
   int stacked;             // 1: one MMA multiplies by [W_hi | W_lo] (N = 2*BN), 2 MMAs per K step; 0: 3 MMAs, N = BN
   int pw;                  // epilogue piece width in accumulator columns (32, or 16 so that BN = 32 keeps all 8 warps busy)
@@ -109,6 +129,8 @@ struct UmmaParams {
   uint32_t* side_max;
   int side_stride, side_offset;
   int cell_rows;           // 1: row-wise cell epilogue (thread = pixel, no shared-memory transpose); 0: staged transpose
+  int pre_tma;             // 1: the hoisted gate share of a tile is staged in shared memory by TMA (two stages)
+  int p_stage_bytes;       // BN/32 boxes of 128 rows x 128 bytes
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -152,6 +174,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -440,6 +469,46 @@ __device__ __forceinline__ RowGeom row_geom(const UmmaParams& p, int row, int tw
   return g;
 }
 
+// (tile, K slice) of a work unit and (n tile, w, h, image tile) of a tile, with the launch's fast dividers.
+struct TileCoord {
+  int nt, tw, th, ti;
+};
+__device__ __forceinline__ void decode_work(const UmmaParams& p, int work, int& tile, int& ks) {
+  tile = (int)fdiv((uint32_t)work, p.dks);
+  ks = work - tile * p.ksplit;
+}
+__device__ __forceinline__ TileCoord decode_tile(const UmmaParams& p, int tile) {
+  TileCoord t;
+  uint32_t mt = fdiv((uint32_t)tile, p.dn);
+  t.nt = tile - (int)mt * p.tiles_n;
+  uint32_t q = fdiv(mt, p.dw);
+  t.tw = (int)mt - (int)q * p.tiles_w;
+  mt = q;
+  q = fdiv(mt, p.dh);
+  t.th = (int)mt - (int)q * p.tiles_h;
+  t.ti = (int)q;
+  return t;
+}
+// A thread's position inside the pixel box never changes: computed once per thread (three real divisions).
+struct RowPos {
+  int wl, hl, il;
+};
+__device__ __forceinline__ RowPos row_pos(const UmmaParams& p, int row) {
+  RowPos r;
+  r.wl = row % p.BW;
+  r.hl = (row / p.BW) % p.BH;
+  r.il = row / (p.BW * p.BH);
+  return r;
+}
+__device__ __forceinline__ RowGeom row_geom(const UmmaParams& p, const RowPos& r, const TileCoord& t) {
+  const int wo = t.tw * p.BW + r.wl, ho = t.th * p.BH + r.hl, img = t.ti * p.BI + r.il;
+  RowGeom g;
+  g.ok = wo < p.Wo && ho < p.Ho && img < p.N;
+  g.pix = ((size_t)img * p.Ho + ho) * p.Wo + wo;
+  g.img = img;
+  return g;
+}
+
 #ifdef RSIS_DEBUG_TIMING
 __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   if (blockIdx.x == 0 && p.counters) {
@@ -473,18 +542,16 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   const int npc = p.BN / PW;          // output pieces per row quarter
   const int ncols = p.stacked ? 2 * p.BN : p.BN;
   const int num_work = p.num_tiles * p.ksplit;
+  const RowPos rpos = row_pos(p, quarter * 32 + lane);
   int acc = 0;
   uint32_t acc_phase = 0;
   CellPiece<PW> cpz_cur;
   for (int work = bid; work < num_work; work += nblk) {
-    const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-    const int nt = tile % p.tiles_n;
-    int mt = tile / p.tiles_n;
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    const int ti = mt / p.tiles_h;
-    const RowGeom g = row_geom(p, quarter * 32 + lane, tw, th, ti);
+    int tile, ks;
+    decode_work(p, work, tile, ks);
+    const TileCoord tc = decode_tile(p, tile);
+    const int nt = tc.nt, tw = tc.tw, th = tc.th, ti = tc.ti;
+    const RowGeom g = row_geom(p, rpos, tc);
     const uint32_t mypix = g.ok ? (uint32_t)g.pix : 0xffffffffu;
     if constexpr (CELL && !SPLIT) {
       // the very first piece of this warp; afterwards every piece's c_prev / hoisted-gate loads are issued one piece
@@ -506,12 +573,11 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           if (j + 2 < npc && coln < p.Cout) {
             cell_prefetch<PW>(p, cpz_next, lane, mypix, coln);
           } else if (work + nblk < num_work) {
-            const int tile2 = (work + nblk) / p.ksplit;
-            const int nt2 = tile2 % p.tiles_n;
-            int mt2 = tile2 / p.tiles_n;
-            const int tw2 = mt2 % p.tiles_w;
-            mt2 /= p.tiles_w;
-            const RowGeom g2 = row_geom(p, quarter * 32 + lane, tw2, mt2 % p.tiles_h, mt2 / p.tiles_h);
+            int tile2, ks2;
+            decode_work(p, work + nblk, tile2, ks2);
+            const TileCoord tc2 = decode_tile(p, tile2);
+            const int nt2 = tc2.nt;
+            const RowGeom g2 = row_geom(p, rpos, tc2);
             cell_prefetch<PW>(p, cpz_next, lane, g2.ok ? (uint32_t)g2.pix : 0xffffffffu, nt2 * p.BN + PW * half);
           }
         }
@@ -714,6 +780,48 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   }
 }
 
+// Bounded wait without the diagnostic printf (used inside fully unrolled issue sequences, where code size matters).
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// All MMAs of one HALO activation item whose nine weight taps sit in slots 0..8 of the B ring (resident weights): a
+// straight line of up to 9 x KS x {2, 3} UTCHMMAs whose descriptors are `uniform base + compile-time offset`, so they
+// issue back to back from uniform registers (the generic loop spends ~50 dependent instructions per tap in one thread,
+// which at 4 MMAs of 48 cycles per tap is slower than the tensor pipe: profiles/r2i_group_stamps.txt).
+// tap (kh, kw) = the activation tile shifted by kh*10 + kw rows of 128 bytes = (kh*10 + kw) * 8 descriptor units.
+template <int KS, bool STACKED>
+__device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
+                                                    uint32_t b_stage16, uint32_t b_plane16, uint32_t idesc,
+                                                    uint32_t accumulate, bool wait_b, uint32_t bfull0) {
+#pragma unroll
+  for (int bi = 0; bi < 9; ++bi) {
+    if (wait_b) {
+      mbar_wait_lean(bfull0 + 8 * bi, 0);
+      tc_fence_after();
+    }
+    const uint64_t toff = (uint64_t)(((bi / 3) * (kHaloBW + 2) + (bi % 3)) * 8);
+    const uint64_t b = bdesc0 + (uint64_t)((uint32_t)bi * b_stage16);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K
+      const uint32_t first = (bi == 0 && k == 0) ? accumulate : 1u;
+      if (STACKED) {
+        umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
+        umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+      } else {
+        umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
+        umma_bf16(d, a_hi + toff + adv, b + b_plane16 + adv, idesc, 1u);
+        umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+      }
+    }
+  }
+}
+
 // ---- ConvLSTM epilogue, row-wise (clstm.py:50-58) ------------------------------------------------------------------
 // The accumulator leaves TMEM with thread = pixel (TMEM lane) and registers = gate columns in (hidden channel, gate)
 // order, so ONE thread holds i, f, o, g of a hidden channel of its pixel: the gate math needs no data exchange at all.
@@ -735,29 +843,39 @@ __device__ __forceinline__ void cell_unit_load(const UmmaParams& p, CellUnitIn& 
   const bool ok = pix != 0xffffffffu && chg0 < Ch;
   const size_t base = (size_t)pix * Ch + chg0;
   in.cp = (ok && p.c_prev) ? __ldg(reinterpret_cast<const float4*>(p.c_prev + base)) : z;
+  if (p.pre_tma) return;  // the gate share comes through shared memory (cell_rows_epilogue)
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     in.pre[j] = (ok && p.preact) ? __ldg(reinterpret_cast<const float4*>(p.preact + (base + j) * 4)) : z;
 }
 
+// pre_tma: a thread = pixel load of the hoisted gate share touches one 128-byte line per lane (32 L1 wavefronts per
+// instruction), and L1 shares its data path with the shared-memory operand reads of the tensor core -- measured: the
+// MMAs of a 32-gate-column level ran at 74 ns instead of 26 (profiles/r2k_group_stamps.txt).  With pre_tma the A
+// producer warp brings the tile's [128 pixels][32 columns] fp32 boxes in by TMA (SWIZZLE_128B, two stages), and a thread
+// reads its own 128-byte row with conflict-free 16-byte shared-memory loads (chunk ^ (row & 7)).
 __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
-                                                   uint32_t tempty0, int warp, int lane, const int bid, const int nblk) {
+                                                   uint32_t tempty0, uint32_t smem_p, uint32_t pfull0, uint32_t pempty0,
+                                                   int warp, int lane, const int bid, const int nblk) {
   const int quarter = warp & 3, half = warp >> 2;
   const int Ch = p.Cout >> 2;
   const int nu = p.BN >> 4;  // units per output-channel tile
   const bool warp_one_image = p.BW * p.BH >= 32;  // the 32 rows of a warp lie in one image
   const int num_work = p.num_tiles;               // no split-K on this path
+  const RowPos rpos = row_pos(p, quarter * 32 + lane);
   auto tile_pix = [&](int tile, int& nt, int& img) -> uint32_t {
-    nt = tile % p.tiles_n;
-    int mt = tile / p.tiles_n;
-    const int tw = mt % p.tiles_w;
-    mt /= p.tiles_w;
-    const RowGeom g = row_geom(p, quarter * 32 + lane, tw, mt % p.tiles_h, mt / p.tiles_h);
+    const TileCoord tc = decode_tile(p, tile);
+    nt = tc.nt;
+    const RowGeom g = row_geom(p, rpos, tc);
     img = g.img;
     return g.ok ? (uint32_t)g.pix : 0xffffffffu;
   };
   int acc = 0;
   uint32_t acc_phase = 0;
+  int ps = 0;
+  uint32_t pph = 0;
+  const uint32_t prow = smem_p + (uint32_t)(quarter * 32 + lane) * 128u;  // this thread's row inside a box
+  const uint32_t pxor = (uint32_t)(lane & 7);                               // (row & 7): quarter * 32 is a multiple of 8
   CellUnitIn cur;
   bool have_cur = false;
   int nt = 0, img = 0;
@@ -771,11 +889,14 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
     if (more) pix2 = tile_pix(work + nblk, nt2, img2);
     if (!have_cur && half < nu) cell_unit_load(p, cur, mypix, ((nt * p.BN) >> 2) + 4 * half);
     have_cur = false;
+    if (threadIdx.x == 0) STAMP_T(7, (work - bid) / nblk);
     mbar_wait(tfull0 + 8 * acc, acc_phase);
     tc_fence_after();
     if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
     bool released = false;
+    if (p.pre_tma) mbar_wait(pfull0 + 8 * ps, pph);
+    if (threadIdx.x == 0) STAMP_T(5, (work - bid) / nblk);
     for (int u = half; u < nu; u += 2) {
       const int col0 = nt * p.BN + 16 * u;
       if (col0 >= p.Cout) break;
@@ -809,6 +930,17 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
         if (threadIdx.x == 0) STAMP_T(4, (work - bid) / nblk);
       }
       const bool ok = mypix != 0xffffffffu;
+      if (p.pre_tma) {
+        // unit u = columns [16u, 16u + 16) of the tile: box u / 2, 16-byte chunks 4 * (u & 1) .. + 3 of the row
+        const uint32_t rowaddr = prow + (uint32_t)ps * (uint32_t)p.p_stage_bytes + (uint32_t)(u >> 1) * 16384u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t chunk = (uint32_t)(4 * (u & 1) + j) ^ pxor;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(cur.pre[j].x), "=f"(cur.pre[j].y), "=f"(cur.pre[j].z), "=f"(cur.pre[j].w)
+                       : "r"(rowaddr + (chunk << 4)));
+        }
+      }
       float cv[4], hv[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -854,6 +986,14 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * acc);
     }
+    if (threadIdx.x == 0) STAMP_T(6, (work - bid) / nblk);
+    if (p.pre_tma) {  // this thread has consumed its part of the staged gate share
+      mbar_arrive(pempty0 + 8 * ps);
+      if (++ps == 2) {
+        ps = 0;
+        pph ^= 1u;
+      }
+    }
     mypix = pix2;
     nt = nt2;
     img = img2;
@@ -870,13 +1010,16 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
 template <bool CELL, int PW, bool SPLIT>
 __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams& p, const int bid, const int nblk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages];
+  __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages + 4];
   __shared__ uint32_t tmem_slot;
 
   if (threadIdx.x == 0) STAMP(0);
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_b = smem_a + p.a_stages * p.a_stage_bytes;
+  const uint32_t smem_p = smem_b + p.b_stages * p.b_stage_bytes;  // pre_tma: two stages of the hoisted gate share
+  const uint32_t pfull0 = smem_u32(&bars[4 * kMaxStages + 2 * kAccStages]);
+  const uint32_t pempty0 = smem_u32(&bars[4 * kMaxStages + 2 * kAccStages + 2]);
   float* stage_base = reinterpret_cast<float*>(smem_raw + (smem_a - smem_u32(smem_raw)) + p.a_stages * p.a_stage_bytes +
                                                p.b_stages * p.b_stage_bytes);
   const int warp = threadIdx.x >> 5;
@@ -896,6 +1039,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       prefetch_tmap(&maps.a[3]);
     }
     prefetch_tmap(&maps.b);
+    if (CELL && p.pre_tma) prefetch_tmap(&maps.pre);
   }
   if (warp == kEpiWarps + 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
@@ -903,6 +1047,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       mbar_init(aempty0 + 8 * s, 1);
       mbar_init(bfull0 + 8 * s, 1);
       mbar_init(bempty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(pfull0 + 8 * s, 1);
+      mbar_init(pempty0 + 8 * s, kEpiThreads);
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -936,18 +1084,40 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     // =============================== TMA producer: activations (A ring) ===============================
     int as = 0;
     uint32_t aph = 0;
+    int ps = 0;
+    uint32_t pph = 0;
     for (int work = bid; work < num_work; work += nblk) {
-      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
-      int mt = tile / p.tiles_n;
-      const int tw = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int ti = mt / p.tiles_h;
+      int tile, ks;
+      decode_work(p, work, tile, ks);
+      const int item0 = (int)fdiv((uint32_t)(ks * a_items), p.dks), item1 = (int)fdiv((uint32_t)((ks + 1) * a_items), p.dks);
+      const TileCoord tc = decode_tile(p, tile);
+      const int tw = tc.tw, th = tc.th, ti = tc.ti;
       const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
+      if (CELL && p.pre_tma) {
+        // the tile's share of the hoisted gates: BN/32 boxes {32 columns, BW, BH, BI} -> [128 rows][128 bytes] each
+        mbar_wait(pempty0 + 8 * ps, pph ^ 1u);
+        if (elect_one()) {
+          const int nt = tc.nt;
+          mbar_arrive_expect_tx(pfull0 + 8 * ps, (uint32_t)p.p_stage_bytes);
+          for (int j = 0; j < (p.BN >> 5); ++j)
+            tma_load_4d(smem_p + ps * p.p_stage_bytes + j * 16384, &maps.pre, pfull0 + 8 * ps, nt * p.BN + 32 * j, w0, h0,
+                        i0);
+        }
+        __syncwarp();
+        if (++ps == 2) {
+          ps = 0;
+          pph ^= 1u;
+        }
+      }
+      // (tap, chunk) of the items walked incrementally: one division per K slice instead of three per item
+      int cc = item0, kh = 0, kw = 0;
+      if (!p.halo) {
+        const int tap0 = item0 / p.chunks;
+        cc = item0 - tap0 * p.chunks;
+        kh = tap0 / p.ksize;
+        kw = tap0 - kh * p.ksize;
+      }
       for (int ai = item0; ai < item1; ++ai) {
-        const int cc = p.halo ? ai : ai % p.chunks;
-        const int tap0 = p.halo ? 0 : ai / p.chunks;
         mbar_wait(aempty0 + 8 * as, aph ^ 1u);
         if (elect_one()) {
           const uint32_t sa = smem_a + as * p.a_stage_bytes;
@@ -956,7 +1126,6 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
           if (p.halo) {
             tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
           } else {
-            const int kh = tap0 / p.ksize, kw = tap0 - kh * p.ksize;
             if (p.stride == 1) {
               tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
             } else {
@@ -970,6 +1139,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
         __syncwarp();
         if (lane == 0 && ai == item0) STAMP(2);
         if (lane == 0 && ai == item0) STAMP_T(0, (work - bid) / nblk);
+        if (++cc == p.chunks && !p.halo) {
+          cc = 0;
+          if (++kw == p.ksize) {
+            kw = 0;
+            ++kh;
+          }
+        }
         if (++as == p.a_stages) {
           as = 0;
           aph ^= 1u;
@@ -984,12 +1160,16 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     uint32_t bph = 0;
     for (int work = bid; work < num_work; work += nblk) {
       if (p.b_resident && work != bid) break;  // resident weights: loaded for the first tile only
-      const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-      const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
-      const int nt = tile % p.tiles_n;
+      int tile, ks;
+      decode_work(p, work, tile, ks);
+      const int item0 = (int)fdiv((uint32_t)(ks * a_items), p.dks), item1 = (int)fdiv((uint32_t)((ks + 1) * a_items), p.dks);
+      const int nt = tile - (int)fdiv((uint32_t)tile, p.dn) * p.tiles_n;
+      int cc = item0, tap0 = 0;
+      if (!p.halo) {
+        tap0 = item0 / p.chunks;
+        cc = item0 - tap0 * p.chunks;
+      }
       for (int ai = item0; ai < item1; ++ai) {
-        const int cc = p.halo ? ai : ai % p.chunks;
-        const int tap0 = p.halo ? 0 : ai / p.chunks;
         for (int bi = 0; bi < b_per_a; ++bi) {
           const int tap = tap0 + bi;
           mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
@@ -1004,6 +1184,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
             bph ^= 1u;
           }
         }
+        if (++cc == p.chunks && !p.halo) {
+          cc = 0;
+          ++tap0;
+        }
       }
     }
   } else if (warp == kEpiWarps + 1) {
@@ -1012,80 +1196,104 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     // STACKED (BN <= 128): the weight stage holds [W_hi (BN rows) | W_lo (BN rows)] contiguously, so ONE MMA with
     // N = 2*BN multiplies an activation plane by both weight planes (columns [0,BN) and [BN,2BN) of the
     // accumulator, added in the epilogue): 2 MMAs per K step (x_hi, x_lo) give all four partial products.
-    // ONE elected thread runs the whole issue loop (waits included).  This warp shares its scheduler with two epilogue
-    // warps, so every instruction it spends between two UTCHMMAs delays the tensor pipe: the shared-memory descriptors
-    // are a constant high word plus a 32-bit low word (14-bit address field in 16-byte units -- shared memory is
-    // < 256 KB, the field cannot overflow), advanced with plain 32-bit adds.
+    // ONE elected thread runs the whole issue loop, waits included (measured faster than a warp-wide loop with an
+    // elected region per tap: no per-tap reconvergence).  This warp shares its scheduler with two epilogue warps, so
+    // every dependent instruction between two UTCHMMAs delays the tensor pipe: resident HALO weights (the narrow,
+    // many-tile decoder levels) take the unrolled straight-line form of issue_halo_resident.
     if (elect_one()) {
+      const uint64_t adesc0 = make_smem_desc(smem_a, p.a_sbo);
+      const uint64_t bdesc0 = make_smem_desc(smem_b, 1024);
       const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
-      const uint64_t a_hiword = (uint64_t)(make_smem_desc(0, p.a_sbo) >> 32) << 32;
-      const uint64_t b_hiword = (uint64_t)(make_smem_desc(0, 1024) >> 32) << 32;
-      const uint32_t a_low0 = (uint32_t)make_smem_desc(smem_a, p.a_sbo);
-      const uint32_t b_low0 = (uint32_t)make_smem_desc(smem_b, 1024);
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)(p.BN * 128) >> 4;
       const bool stacked = p.stacked != 0, halo = p.halo != 0, resident = p.b_resident != 0;
+      const bool fast = halo && resident && p.chunks == 1 && p.taps == 9;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int work = bid; work < num_work; work += nblk) {
-        const int tile = work / p.ksplit, ks = work - tile * p.ksplit;
-        const int item0 = ks * a_items / p.ksplit, item1 = (ks + 1) * a_items / p.ksplit;
+        int tile, ks;
+        decode_work(p, work, tile, ks);
+        const int item0 = (int)fdiv((uint32_t)(ks * a_items), p.dks), item1 = (int)fdiv((uint32_t)((ks + 1) * a_items), p.dks);
         const bool first_work = work == bid;
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * kStageCols;
         uint32_t accumulate = 0;
+        int cc = halo ? item0 : item0 % p.chunks;
         for (int ai = item0; ai < item1; ++ai) {
-          const int cc = halo ? ai : ai % p.chunks;
           const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+          if (++cc == p.chunks) cc = 0;  // (only read above: the chunk of the NEXT item)
           mbar_wait(afull0 + 8 * as, aph);
           tc_fence_after();
           if (ai == item0) STAMP(4);
           if (ai == item0) STAMP_T(1, (work - bid) / nblk);
-          const uint32_t a_stage = a_low0 + (uint32_t)as * a_stage16;
-          for (int bi = 0; bi < b_per_a; ++bi) {
-            if (resident) {
-              bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
-              bph = 0;
-            }
-            if (!(resident && !first_work)) {
-              mbar_wait(bfull0 + 8 * bs, bph);
-              tc_fence_after();
-            }
-            if (ai == item0 && bi == 0) STAMP(5);
-            // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 units of 16 bytes per row)
-            const uint32_t a0 = a_stage + (halo ? (uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u : 0u);
-            const uint32_t b0 = b_low0 + (uint32_t)bs * b_stage16;
+          const uint64_t a_hi0 = adesc0 + (uint64_t)((uint32_t)as * a_stage16);
+          const uint64_t a_lo0 = a_hi0 + (uint64_t)a_plane16;
+          if (fast) {
+            const bool wb = first_work;  // the nine taps are loaded once, for this CTA's first tile
             if (stacked) {
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                if (k < ksteps) {
-                  const uint64_t bd = b_hiword | (uint64_t)(b0 + 2u * k);  // 16 bf16 = 32 bytes along K per step
-                  umma_bf16(d, a_hiword | (uint64_t)(a0 + 2u * k), bd, idesc, accumulate);
-                  umma_bf16(d, a_hiword | (uint64_t)(a0 + a_plane16 + 2u * k), bd, idesc, 1u);
-                  accumulate = 1u;
-                }
+              switch (ksteps) {
+                case 1: issue_halo_resident<1, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                case 2: issue_halo_resident<2, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                case 3: issue_halo_resident<3, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                default: issue_halo_resident<4, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
               }
             } else {
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                if (k < ksteps) {
-                  const uint64_t ad = a_hiword | (uint64_t)(a0 + 2u * k);
-                  umma_bf16(d, ad, b_hiword | (uint64_t)(b0 + 2u * k), idesc, accumulate);
-                  umma_bf16(d, ad, b_hiword | (uint64_t)(b0 + b_plane16 + 2u * k), idesc, 1u);
-                  umma_bf16(d, a_hiword | (uint64_t)(a0 + a_plane16 + 2u * k), b_hiword | (uint64_t)(b0 + 2u * k), idesc, 1u);
-                  accumulate = 1u;
-                }
+              switch (ksteps) {
+                case 1: issue_halo_resident<1, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                case 2: issue_halo_resident<2, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                case 3: issue_halo_resident<3, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
+                default: issue_halo_resident<4, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
               }
             }
-            if (!resident) {
-              umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
-              if (++bs == p.b_stages) {
-                bs = 0;
-                bph ^= 1u;
+            accumulate = 1u;
+          } else {
+            for (int bi = 0; bi < b_per_a; ++bi) {
+              if (resident) {
+                bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
+                bph = 0;
+              }
+              if (!(resident && !first_work)) {
+                mbar_wait(bfull0 + 8 * bs, bph);
+                tc_fence_after();
+              }
+              if (ai == item0 && bi == 0) STAMP(5);
+              // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 descriptor units per row)
+              const uint64_t toff = halo ? (uint64_t)((uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u) : 0ull;
+              const uint64_t a_hi = a_hi0 + toff, a_lo = a_lo0 + toff;
+              const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16);
+              const uint64_t b_lo = b_hi + (uint64_t)b_plane16;
+              if (stacked) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K inside the swizzle row
+                    umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
+                    umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+                    accumulate = 1u;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  if (k < ksteps) {
+                    const uint64_t adv = (uint64_t)(2 * k);
+                    umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
+                    umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+                    accumulate = 1u;
+                  }
+                }
+              }
+              if (!resident) {
+                umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+                if (++bs == p.b_stages) {
+                  bs = 0;
+                  bph ^= 1u;
+                }
               }
             }
           }
@@ -1109,7 +1317,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     // =============================== epilogue (warps 0-7) ===============================
     float* stage = stage_base + warp * kStageFloats;
     if (CELL && !SPLIT && p.cell_rows) {
-      cell_rows_epilogue(p, tmem_base, tfull0, tempty0, warp, lane, bid, nblk);
+      cell_rows_epilogue(p, tmem_base, tfull0, tempty0, smem_p, pfull0, pempty0, warp, lane, bid, nblk);
     } else if constexpr (PW != 0) {
       epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
     } else {
@@ -1489,6 +1697,8 @@ unsigned* g_debug_counters = nullptr;  // set by the last non-swapped setup when
 int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
+int g_pre_tma = 0;         // RSIS_B200_PRE_TMA=1: the hoisted gate share of a tile is staged in shared memory by TMA (no measured
+                           // gain at B=8, and its two stages cost the third activation stage: off by default)
 int g_cell_rows = 1;       // RSIS_B200_CELL_ROWS=0: the staged-transpose cell epilogue instead of the row-wise one (A/B timing)
 int g_mma_model = 1;       // RSIS_B200_MMA_MODEL=0: planner assumes 70 ns per MMA whatever its N (round-1 model)
 int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
@@ -1510,6 +1720,7 @@ void init_once() {
   if (const char* e = getenv("RSIS_B200_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_MMA_MODEL")) g_mma_model = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_CELL_ROWS")) g_cell_rows = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_PRE_TMA")) g_pre_tma = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PRINT_PLAN")) g_print_plan = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SWAP")) g_swap = atoi(e) != 0;
 
@@ -1684,7 +1895,8 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
 
 // Fills geometry, tensor maps and the K loop.
 int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_weights* w, int stride, int pad,
-          void* workspace, size_t workspace_bytes, int cta_share = 0) {
+          void* workspace, size_t workspace_bytes, int cta_share = 0, const float* preact = nullptr,
+          bool is_cell = false) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK) return g_init_status;
   p.N = x.n;
@@ -1732,6 +1944,10 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const long long nt = (long long)p.tiles_w * p.tiles_h * p.tiles_i * p.tiles_n;
   if (nt * p.ksplit > 0x7fffffffLL) return RSIS_ERR_UNSUPPORTED;
   p.num_tiles = (int)nt;
+  p.dn = make_fastdiv(p.tiles_n);
+  p.dw = make_fastdiv(p.tiles_w);
+  p.dh = make_fastdiv(p.tiles_h);
+  p.dks = make_fastdiv(p.ksplit);
   if (can_split && getenv("RSIS_B200_DEBUG_TIMING")) g_debug_counters = reinterpret_cast<unsigned*>(workspace);
   if (p.ksplit > 1 || (can_split && getenv("RSIS_B200_DEBUG_TIMING"))) {
     p.counters = reinterpret_cast<unsigned*>(workspace);
@@ -1745,9 +1961,18 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.b_stage_bytes = 2 * p.BN * 128;
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   p.pw = p.BN >= 64 ? 32 : 16;
-  const int budget = kDynSmem - 1023 - kStageBytes;
+  // pre_tma (cells with hoisted gates on the row-wise epilogue): two stages of BN/32 boxes of 16 KB take the place of
+  // the transpose staging area, which that epilogue does not use
+  p.pre_tma = (g_pre_tma && preact && is_cell && g_cell_rows && p.ksplit == 1 && p.BN <= 64) ? 1 : 0;
+  p.p_stage_bytes = (p.BN >> 5) * 16384;
+  // the row-wise cell epilogue needs no transpose staging area: its 33 KB go to the operand rings (a third activation
+  // stage on the narrow levels, whose 46 KB halo boxes take ~2.5 us from issue to landing: profiles/r2l_group_stamps.txt)
+  const bool rows_epi = is_cell && g_cell_rows && p.ksplit == 1;  // (a hoisted-gate CONVOLUTION also has gate-interleaved weights)
+  const int budget = kDynSmem - 1023 - (p.pre_tma ? 2 * p.p_stage_bytes : (rows_epi ? 0 : kStageBytes));
   if (p.halo) {
-    p.a_stages = 2;
+    // a third activation stage when at least four weight stages still fit next to it: a halo box needs ~2.5 us from
+    // issue to landing, longer than the MMAs of one tile on the narrow levels
+    p.a_stages = (budget - 3 * p.a_stage_bytes) / p.b_stage_bytes >= 4 ? 3 : 2;
     p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
     if (p.b_stages > kMaxStages) {
       p.b_stages = kMaxStages;
@@ -1773,6 +1998,17 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     }
   }
   if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
+  if (p.pre_tma) {
+    // [N][Ho][Wo][Cout] float32 as {Cout, Wo, Ho, N}; box {32, BW, BH, BI} = the pixel tile, rows in TMEM lane order
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.Wo * p.Cout * 4, (cuuint64_t)p.Ho * p.Wo * p.Cout * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, (cuuint32_t)p.BI};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&maps.pre, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(preact), dims, strides, box,
+                          estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return RSIS_ERR_CUDA;
+  }
   p.scale = w->scale;
   p.shift = w->shift;
   p.cell_rows = g_cell_rows;
@@ -2283,7 +2519,8 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   if (swapped) {
     if (int e = setup_swap(maps, p, srcs[0], w)) return e;
   } else {
-    if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2, workspace, workspace_bytes)) return e;
+    if (gate_preact && !aligned16(gate_preact)) return RSIS_ERR_ALIGN;
+    if (int e = setup(maps, p, srcs[0], w, 1, w->kh / 2, workspace, workspace_bytes, 0, gate_preact, true)) return e;
   }
   const int Ch = p.Cout / 4;
   auto ok = [&](const rsis_tensor* t, int fmt) {
@@ -2374,7 +2611,8 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
   for (int i = 0; i < n; ++i) {
     const rsis_cell_args& c = cells[i];
     UmmaParams& p = g.p[i];
-    if (int e = setup(g.maps[i], p, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i])) return e;
+    if (c.gate_preact && !aligned16(c.gate_preact)) return RSIS_ERR_ALIGN;
+    if (int e = setup(g.maps[i], p, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i], c.gate_preact, true)) return e;
     const int Ch = p.Cout / 4;
     auto ok = [&](const rsis_tensor* t, int fmt) {
       return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&

@@ -452,7 +452,9 @@ int rsis_upsample_bilinear_group(const rsis_tensor* xs, const rsis_tensor* ys, i
     g.first[i] = first;
     // blocks in proportion to the output sizes (every problem at least one block, at most four per SM)
     size_t blocks = (numel(ys[i]) / 4 + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;  // one 16-byte output vector per thread up to 16 blocks per SM: the kernel
+                                               // is latency-bound (4 dependent-free loads per thread), so more threads
+                                               // in flight, not longer grid-stride loops
     first += (int)(blocks < 1 ? 1 : blocks);
   }
   for (int i = n; i <= kMaxUpsampleGroup; ++i) g.first[i] = first;

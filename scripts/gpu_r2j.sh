@@ -1,0 +1,7 @@
+#!/bin/bash
+OUT=gpurun_out/r2j
+mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > $OUT/pytest_parity.log 2>&1; echo "parity exit $?"; tail -3 $OUT/pytest_parity.log
+timeout 300 python scripts/decoder_probe.py 8 256 256 10 3 > $OUT/decoder_probe.txt 2>&1; cat $OUT/decoder_probe.txt
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err
+python -c "import json,sys; d=json.loads(open('$OUT/bench.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['step_us'])"
