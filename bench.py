@@ -163,8 +163,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": B, "height": H, "width": W, "T": T, "num_classes": NUM_CLASSES,
-                   "device": "host CPU", "note": "reference CPU path: the same torch.nn CPU primitives the reference's "
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B, "height": H, "width": W, "T": T,
+                   "num_classes": NUM_CLASSES, "device": "host CPU", "note": "reference CPU path: the same torch.nn CPU primitives the reference's "
                    "modules call (src/test.py:16-50), driven by oracle/rsis_oracle.py because /root/reference does "
                    "not exist on the GPU box; one step = one full test() pass over one batch of 8"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -174,6 +174,94 @@ def run_reference(a):
     }
     print(json.dumps(line))
     return 0
+
+
+def torch_gpu_time(dev, passes=5, warmup=2):
+    """Secondary baseline: the SAME oracle restatement of test() (stock torch ops: cuDNN / cuBLAS fp32, TF32 off) on the
+    same GPU, eager, CUDA-event timed.  Not a product path: it answers "what does stock PyTorch do here"."""
+    from oracle import rsis_oracle as O, synth_weights as sw
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        esd = {k: v.to(dev) for k, v in sw.encoder_state_dict(1).items()}
+        dsd = {k: v.to(dev) for k, v in sw.decoder_state_dict(1, num_classes=NUM_CLASSES).items()}
+        x = sw.synthetic_images(123, B, H, W).to(dev)
+        with torch.no_grad():
+            for _ in range(warmup):
+                O.test_loop(esd, dsd, x, T)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(passes):
+                O.test_loop(esd, dsd, x, T)
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / passes
+        return {"value": B * T / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": "stock torch eager on the same "
+                "GPU (cuDNN/cuBLAS fp32, TF32 off), the oracle's op sequence", "passes": passes}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+def train_record(rsis_b200, rdist, dev, rank, world, steps=5, warmup=3):
+    """BASELINE.json configs[3] per-rank shard (8 images 256x256, T=10): train-mode encoder + T decoder steps +
+    loss.backward() as ONE CUDA graph, then the ONE data-parallel collective of the design -- an NCCL all-reduce of the
+    flat gradient buffer (replaces nn.DataParallel, /root/reference/src/train.py:269-274).  Timed per step with CUDA
+    events (max over ranks); the all-reduce additionally on its own."""
+    import bench_train
+    from rsis_b200.autograd import GradBucket
+    from rsis_b200.training import TrainStep
+    from oracle import synth_weights as sw   # deterministic synthetic weights / images only
+    from oracle import ref_shims as rs
+    args = rs.make_args(num_classes=NUM_CLASSES, maxseqlen=T)
+    args.hidden_size = int(args.hidden_size)
+    args.use_gpu = True
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1, num_classes=NUM_CLASSES))
+    enc.to(dev).train()
+    dec.to(dev).train()
+    x = sw.synthetic_images(500 + rank, B, H, W).to(dev)
+    bucket = GradBucket(list(enc.parameters()) + list(dec.parameters()))
+    step = TrainStep(enc, dec, T, bench_train.loss_fn, bucket=bucket, cuda_graph=True)
+    for _ in range(max(warmup, 3)):
+        step(x)
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    evs = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(x)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    rdist.barrier()
+    step_s = rdist.max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3) / steps
+    ar = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rdist.barrier()
+        e0.record()
+        bucket.all_reduce()
+        e1.record()
+        ar.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    ar_s = rdist.max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in ar) * 1e-3) / steps
+    nbytes = bucket.flat.numel() * 4
+    rec = {"workload": "BASELINE.json configs[3] per-rank shard: training step, 8 images 256x256 per GPU, T=10 "
+                       "(global batch = 8 x n_gpus; 64 at 8 GPUs)",
+           "ms_per_step": step_s * 1e3, "images_per_s": world * B / step_s, "n_gpus": world,
+           "collective": "one NCCL all-reduce (sum, / world) of the flat float32 gradient buffer per step"
+                         if world > 1 else "none at 1 GPU (the all-reduce is skipped)",
+           "allreduce_ms": ar_s * 1e3 if world > 1 else 0.0, "allreduce_bytes": nbytes,
+           "allreduce_busbw_GBps": (2 * (world - 1) / world * nbytes / ar_s / 1e9) if world > 1 and ar_s > 0 else None,
+           "precision": os.environ.get("RSIS_B200_PRECISION", "split-bf16 (fp32-grade)"),
+           "steps": steps, "cuda_graph": True}
+    del step, bucket, enc, dec
+    torch.cuda.empty_cache()
+    return rec
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -420,12 +508,21 @@ def run_ours(a):
                 "impl": {ops.IMPL_SIMT: "simt-fp32", ops.IMPL_AUTO: "auto", ops.IMPL_TCGEN05: "tcgen05"}[impl],
                 "per_level": per_level}
         # ---- CPU baseline: the reference's CPU path (oracle port) on the host cores, bounded sample ----
-        if not a.no_cpu_baseline:
+        # rank 0 at N = 1 only: at N > 1 the other ranks would spin in the next barrier while rank 0 runs the CPU leg
+        # (and their spinning would steal the host cores it is timed on)
+        if not a.no_cpu_baseline and world == 1:
             times, threads = cpu_reference_time(a.cpu_passes, 1)
             cv = B * T * len(times) / sum(times)
             cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{len(times)} full test() passes of the same workload (B={B}, {H}x{W}, T={T}) after 1 "
                              f"warm-up; torch CPU fp32, {threads} threads"}
+    torch_gpu = None
+    if rank == 0 and not a.no_torch_gpu:
+        torch_gpu = torch_gpu_time(dev)
+    rdist.barrier()
+    train = None
+    if not a.no_train and a.workload == "cfg2":
+        train = train_record(rsis_b200, rdist, dev, rank, world, steps=a.train_steps)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -444,7 +541,9 @@ def run_ours(a):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / a.steps},
             "gpu_launches": launches, "launches_per_step": sess.launches,
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "train": train,
+            "weights": "synthetic, conditioned (oracle/synth_weights.py: damped residual branches, calibrated BatchNorm "
+                       "statistics; SURVEY.md H3) -- the parity claims are stated on these weights",
         }
         print(json.dumps(line))
     rdist.barrier()
@@ -460,6 +559,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-passes", type=int, default=5, help="timed CPU test() passes for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the stock-torch-on-the-same-GPU secondary baseline")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step record (the collective)")
+    ap.add_argument("--train-steps", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     a = ap.parse_args()
     set_workload(a.workload)

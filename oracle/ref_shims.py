@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE -- import the UNMODIFIED reference modules in the build container.
 
-Only `oracle/make_golden.py` and the `not gpu` pinning tests use this; it needs
-`/root/reference`, which does not exist on the GPU box.  Nothing in the product
-package, `bench.py` or `smoke()` imports it.
+`load_reference()` is used by `oracle/make_golden.py` and the `not gpu` pinning
+tests only; it needs `/root/reference`, which does not exist on the GPU box.
+`make_args()` (a plain Namespace with the reference's default flags, no reference
+file involved) is also used by `bench.py`, `smoke()` and the GPU tests to
+construct the modules.  Nothing in the product package imports this module.
 
 Shims, none of which touches a reference file:
   1. Py2 integer division: `model.py:45-47,52-54,91-93` compute `hidden_size/2`;

@@ -72,9 +72,13 @@ class FakeLib:
         return ((cout + 63) // 64 * 64) * 4
 
     def rsis_conv_pack(self, w, bias, bn_w, bn_b, bn_m, bn_v, eps, cout, cin, kh, kw, gate_il, w_kc, scale, shift, st):
-        assert not gate_il, "fake ABI: no gate interleave"
         cp = (cout + 63) // 64 * 64
         wt = _buf(w, cout * cin * kh * kw).view(cout, cin, kh, kw)
+        perm = None
+        if gate_il:  # packed channel j <- reference channel (j & 3) * Ch + (j >> 2)   (pack.cu::ref_cout)
+            ch = cout // 4
+            perm = torch.tensor([(j & 3) * ch + (j >> 2) for j in range(cout)])
+            wt = wt[perm]
         if w_kc:
             dst = _buf(w_kc, kh * kw * cin * cp).view(kh * kw * cin, cp)
             dst.zero_()
@@ -86,6 +90,8 @@ class FakeLib:
             inv = g / torch.sqrt(v + eps)
             sh = (sh - m) * inv + b
             sc = inv
+        if perm is not None:
+            sc, sh = sc[perm], sh[perm]
         s_ = _buf(scale, cp)
         s_.zero_()
         s_[:cout] = sc
@@ -205,8 +211,38 @@ class FakeLib:
         wt = _buf(w, c * ks * ks).view(1, c, ks, ks)
         b = _buf(bias, 1) if bias else None
         out = F.conv2d(_nchw(v), wt, b, padding=ks // 2)
-        assert logits and not prob
-        _buf(logits, n * h * w_).copy_(out.reshape(-1))
+        if logits:
+            _buf(logits, n * h * w_).copy_(out.reshape(-1))
+        if prob:
+            span = (n - 1) * prob_stride + h * w_
+            _buf(prob, span).as_strided((n, h * w_), (prob_stride, 1)).copy_(torch.sigmoid(out.reshape(n, -1)))
+        return 0
+
+    def rsis_convlstm_cell(self, srcs, n_src, wref, c_prev, gate_preact, h_out, h_split, c_out, side_max, side_stride,
+                           side_offset, impl, ws, ws_bytes, st):
+        """Header contract of rsis_convlstm_cell, float32 sources only: gates in (hidden channel, gate) order."""
+        assert not gate_preact and h_split is None
+        xs = [_view(C.byref(srcs[i])) for i in range(n_src)]
+        x = torch.cat(xs, 3)
+        wt, sc, sh, w = self._weights(wref, x.shape[3])
+        assert w.gate_interleaved
+        if x.shape[3] < w.cin:   # state None: the prev_hidden block of the input is zeros
+            x = torch.cat([x, torch.zeros(x.shape[:3] + (w.cin - x.shape[3],))], 3)
+        g = F.conv2d(_nchw(x), wt, padding=w.kh // 2) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+        g = g.permute(0, 2, 3, 1)
+        n, h, w_, _ = g.shape
+        ch = w.cout // 4
+        g = g.reshape(n, h, w_, ch, 4)
+        i, f, o = torch.sigmoid(g[..., 0]), torch.sigmoid(g[..., 1]), torch.sigmoid(g[..., 2])
+        gg = torch.tanh(g[..., 3])
+        cp = _buf(c_prev, n * h * w_ * ch).view(n, h, w_, ch) if c_prev else torch.zeros(n, h, w_, ch)
+        c = f * cp + i * gg
+        hh = o * torch.tanh(c)
+        _view(c_out).copy_(c)
+        _view(h_out).copy_(hh)
+        if side_max:
+            keys = _buf(side_max, n * side_stride, torch.int32).view(n, side_stride)
+            keys[:, side_offset:side_offset + ch] = self._float_to_key(hh.amax(dim=(1, 2)).contiguous())
         return 0
 
     @staticmethod
@@ -229,10 +265,12 @@ class FakeLib:
             _buf(feat_out, n * f).view(n, f).copy_(feat)
         logits = F.linear(feat, _buf(wc, nc * f).view(nc, f), _buf(bc, nc))
         p = torch.softmax(logits, 1)
-        assert pstride == nc and sstride == 1 and not stop_prob
-        _buf(probs, n * nc).view(n, nc).copy_(p)
+        _buf(probs, (n - 1) * pstride + nc).as_strided((n, nc), (pstride, 1)).copy_(p)
+        sl = F.linear(feat, _buf(ws_, f).view(1, f), _buf(bs, 1)).view(-1)
         if stop:
-            _buf(stop, n).copy_(F.linear(feat, _buf(ws_, f).view(1, f), _buf(bs, 1)).view(-1))
+            _buf(stop, (n - 1) * sstride + 1).as_strided((n,), (sstride,)).copy_(sl)
+        if stop_prob:
+            _buf(stop_prob, (n - 1) * sstride + 1).as_strided((n,), (sstride,)).copy_(torch.sigmoid(sl))
         return 0
 
     @staticmethod
