@@ -204,7 +204,7 @@ def torch_gpu_time(dev, passes=5, warmup=2):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
 
 
-def train_record(rsis_b200, rdist, dev, rank, world, steps=5, warmup=3):
+def train_record(rsis_b200, rdist, dev, rank, world, steps=5, warmup=3, precision=None):
     """BASELINE.json configs[3] per-rank shard (8 images 256x256, T=10): train-mode encoder + T decoder steps +
     loss.backward() as ONE CUDA graph, then the ONE data-parallel collective of the design -- an NCCL all-reduce of the
     flat gradient buffer (replaces nn.DataParallel, /root/reference/src/train.py:269-274).  Timed per step with CUDA
@@ -224,7 +224,7 @@ def train_record(rsis_b200, rdist, dev, rank, world, steps=5, warmup=3):
     dec.to(dev).train()
     x = sw.synthetic_images(500 + rank, B, H, W).to(dev)
     bucket = GradBucket(list(enc.parameters()) + list(dec.parameters()))
-    step = TrainStep(enc, dec, T, bench_train.loss_fn, bucket=bucket, cuda_graph=True)
+    step = TrainStep(enc, dec, T, bench_train.loss_fn, bucket=bucket, cuda_graph=True, precision=precision)
     for _ in range(max(warmup, 3)):
         step(x)
     torch.cuda.synchronize(dev)
@@ -257,7 +257,9 @@ def train_record(rsis_b200, rdist, dev, rank, world, steps=5, warmup=3):
                          if world > 1 else "none at 1 GPU (the all-reduce is skipped)",
            "allreduce_ms": ar_s * 1e3 if world > 1 else 0.0, "allreduce_bytes": nbytes,
            "allreduce_busbw_GBps": (2 * (world - 1) / world * nbytes / ar_s / 1e9) if world > 1 and ar_s > 0 else None,
-           "precision": os.environ.get("RSIS_B200_PRECISION", "split-bf16 (fp32-grade)"),
+           "precision": ("bf16: single-pass bf16 tensor-core products, fp32 accumulation / master weights / gradients "
+                         "(BASELINE.json configs[3])" if precision == "bf16" else
+                         "split bf16: fp32-grade products (three / four bf16 passes)"),
            "steps": steps, "cuda_graph": True}
     del step, bucket, enc, dec
     torch.cuda.empty_cache()
@@ -520,9 +522,10 @@ def run_ours(a):
     if rank == 0 and not a.no_torch_gpu:
         torch_gpu = torch_gpu_time(dev)
     rdist.barrier()
-    train = None
+    train = train_bf16 = None
     if not a.no_train and a.workload == "cfg2":
         train = train_record(rsis_b200, rdist, dev, rank, world, steps=a.train_steps)
+        train_bf16 = train_record(rsis_b200, rdist, dev, rank, world, steps=a.train_steps, precision="bf16")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -542,6 +545,7 @@ def run_ours(a):
                     "ms_per_step": 1e3 * e2e_s / a.steps},
             "gpu_launches": launches, "launches_per_step": sess.launches,
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "train": train,
+            "train_bf16": train_bf16,
             "weights": "synthetic, conditioned (oracle/synth_weights.py: damped residual branches, calibrated BatchNorm "
                        "statistics; SURVEY.md H3) -- the parity claims are stated on these weights",
         }

@@ -75,6 +75,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true", help="time the eager step only")
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16"],
+                    help="bf16: single-pass bf16 tensor-core products (BASELINE.json configs[3])")
     a = ap.parse_args()
 
     import rsis_b200
@@ -91,6 +93,8 @@ def main():
     args = rs.make_args(num_classes=NUM_CLASSES, maxseqlen=T)
     args.hidden_size = int(args.hidden_size)
     args.use_gpu = True
+    if a.precision:
+        args.precision = a.precision
     enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
     enc.load_state_dict(sw.encoder_state_dict(1))
     dec.load_state_dict(sw.decoder_state_dict(1, num_classes=NUM_CLASSES))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 18
+#define RSIS_ABI_VERSION 19
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -80,6 +80,17 @@ typedef struct rsis_conv_weights {
                              * swapped-operand kernel (weights as the M operand, 256 pixels as N) on maps whose width is
                              * a multiple of 8 and height a multiple of 32.  May be NULL. */
 } rsis_conv_weights;
+
+/* Precision of the tcgen05 convolution family (process-wide; read when a launch is set up, so a captured CUDA graph
+ * keeps the mode it was captured in).
+ *   RSIS_PRECISION_SPLIT_BF16 (default): a*b = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (+ a_lo*b_lo) on bf16 tensor cores with
+ *     fp32 accumulation -- fp32-grade products, the mode every 1e-3 parity claim is made in.
+ *   RSIS_PRECISION_BF16: single-pass bf16 operands (the hi planes only), fp32 accumulation, fp32 master weights and
+ *     gradients -- the "training step bf16" of BASELINE.json configs[3]; loss-level tolerance.
+ * rsis_set_precision returns the previous mode (>= 0) or RSIS_ERR_BAD_ARG. */
+enum { RSIS_PRECISION_SPLIT_BF16 = 0, RSIS_PRECISION_BF16 = 1 };
+int rsis_set_precision(int mode);
+int rsis_get_precision(void);
 
 /* ---- library -------------------------------------------------------------------------------------------- */
 int rsis_abi_version(void);

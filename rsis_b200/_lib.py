@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 
 class Tensor(C.Structure):
@@ -95,6 +95,8 @@ SIGNATURES = {
                                 _P, _P]),
     "rsis_soft_iou_bwd": (_I, [_P, _P, _I, _I, C.c_int64, _P, _P, _P, C.c_float, _P, _P]),
     "rsis_hungarian_match": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, _I, _I, _I, _P, _I, _P, _P]),
+    "rsis_set_precision": (_I, [_I]),
+    "rsis_get_precision": (_I, []),
     "rsis_convlstm_cell_group_max": (_I, []),
     "rsis_convlstm_cell_group": (_I, [C.POINTER(CellArgs), _I, _P]),
     "rsis_upsample_bilinear_group": (_I, [_TP, _TP, _I, _P]),

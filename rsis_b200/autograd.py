@@ -201,7 +201,9 @@ class EncoderFunction(torch.autograd.Function):
     def forward(ctx, enc, x, *params):
         impl = ops.default_impl()
         tape: dict = {}
-        feats, feats_op = enc.forward_act(x, impl, tape=tape)
+        ctx.prec = getattr(enc, "precision", None)   # "bf16": BASELINE.json configs[3] single-pass mode (ops.precision)
+        with ops.precision(ctx.prec):
+            feats, feats_op = enc.forward_act(x, impl, tape=tape)
         ctx.enc, ctx.tape, ctx.impl, ctx.params = enc, tape, impl, params
         ctx.set_materialize_grads(False)
         enc._last_feats_op = feats_op
@@ -209,7 +211,7 @@ class EncoderFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *dfeats):
-        with torch.no_grad():
+        with torch.no_grad(), ops.precision(ctx.prec):
             G = encoder_backward(ctx.enc, ctx.tape, dfeats, ctx.impl)
         ctx.tape = None
         return (None, None) + tuple(G.get(id(p)) if p.requires_grad else None for p in ctx.params)
@@ -389,7 +391,9 @@ class DecoderStepFunction(torch.autograd.Function):
         if has_state:
             prev = [(ops.act_from_nchw(state_t[2 * l], fmt), ops.act_from_nchw(state_t[2 * l + 1], F32))
                     for l in range(nlev)]
-        out_mask, class_probs, stop, state, saved = decoder_step_train(dec, feats, prev, impl)
+        ctx.prec = getattr(dec, "precision", None)
+        with ops.precision(ctx.prec):
+            out_mask, class_probs, stop, state, saved = decoder_step_train(dec, feats, prev, impl)
         ctx.dec, ctx.saved, ctx.impl, ctx.has_state, ctx.params, ctx.nlev = dec, saved, impl, has_state, params, nlev
         ctx.needs_feats = [t.requires_grad for t in feats_t]
         ctx.set_materialize_grads(False)
@@ -403,7 +407,7 @@ class DecoderStepFunction(torch.autograd.Function):
         nlev = ctx.nlev
         dh_out = [dstate[2 * l] for l in range(nlev)]
         dc_out = [dstate[2 * l + 1] for l in range(nlev)]
-        with torch.no_grad():
+        with torch.no_grad(), ops.precision(ctx.prec):
             dfeats, dh_prev, dc_prev, G = decoder_step_backward(ctx.dec, ctx.saved, dmask, dclass, dstop, dh_out,
                                                                 dc_out, ctx.has_state, ctx.impl)
         ctx.saved = None

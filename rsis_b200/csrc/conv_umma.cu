@@ -129,6 +129,8 @@ struct UmmaParams {
   uint32_t* side_max;
   int side_stride, side_offset;
   int cell_rows;           // 1: row-wise cell epilogue (thread = pixel, no shared-memory transpose); 0: staged transpose
+  int single;              // 1: single-pass bf16 (training mode of BASELINE.json configs[3]): only the hi planes are loaded
+                           //    and multiplied -- one MMA of N = BN per K step instead of 2 (stacked) or 3
   int pre_tma;             // 1: the hoisted gate share of a tile is staged in shared memory by TMA (two stages)
   int p_stage_bytes;       // BN/32 boxes of 128 rows x 128 bytes
 };
@@ -794,7 +796,7 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
 // issue back to back from uniform registers (the generic loop spends ~50 dependent instructions per tap in one thread,
 // which at 4 MMAs of 48 cycles per tap is slower than the tensor pipe: profiles/r2i_group_stamps.txt).
 // tap (kh, kw) = the activation tile shifted by kh*10 + kw rows of 128 bytes = (kh*10 + kw) * 8 descriptor units.
-template <int KS, bool STACKED>
+template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
 __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
                                                     uint32_t b_stage16, uint32_t b_plane16, uint32_t idesc,
                                                     uint32_t accumulate, bool wait_b, uint32_t bfull0) {
@@ -810,7 +812,9 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
     for (int k = 0; k < KS; ++k) {
       const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K
       const uint32_t first = (bi == 0 && k == 0) ? accumulate : 1u;
-      if (STACKED) {
+      if (PASSES == 1) {
+        umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
+      } else if (PASSES == 2) {
         umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
         umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
       } else {
@@ -1207,7 +1211,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)(p.BN * 128) >> 4;
-      const bool stacked = p.stacked != 0, halo = p.halo != 0, resident = p.b_resident != 0;
+      const bool stacked = p.stacked != 0, halo = p.halo != 0, resident = p.b_resident != 0, single = p.single != 0;
       const bool fast = halo && resident && p.chunks == 1 && p.taps == 9;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -1234,21 +1238,21 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
           const uint64_t a_lo0 = a_hi0 + (uint64_t)a_plane16;
           if (fast) {
             const bool wb = first_work;  // the nine taps are loaded once, for this CTA's first tile
-            if (stacked) {
-              switch (ksteps) {
-                case 1: issue_halo_resident<1, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                case 2: issue_halo_resident<2, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                case 3: issue_halo_resident<3, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                default: issue_halo_resident<4, true>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-              }
+#define RSIS_ISSUE_HALO(PASSES)                                                                                          \
+  switch (ksteps) {                                                                                                      \
+    case 1: issue_halo_resident<1, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
+    case 2: issue_halo_resident<2, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
+    case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
+    default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
+  }
+            if (single) {
+              RSIS_ISSUE_HALO(1)
+            } else if (stacked) {
+              RSIS_ISSUE_HALO(2)
             } else {
-              switch (ksteps) {
-                case 1: issue_halo_resident<1, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                case 2: issue_halo_resident<2, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                case 3: issue_halo_resident<3, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-                default: issue_halo_resident<4, false>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break;
-              }
+              RSIS_ISSUE_HALO(3)
             }
+#undef RSIS_ISSUE_HALO
             accumulate = 1u;
           } else {
             for (int bi = 0; bi < b_per_a; ++bi) {
@@ -1266,7 +1270,15 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
               const uint64_t a_hi = a_hi0 + toff, a_lo = a_lo0 + toff;
               const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16);
               const uint64_t b_lo = b_hi + (uint64_t)b_plane16;
-              if (stacked) {
+              if (single) {
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                  if (k < ksteps) {
+                    umma_bf16(d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, accumulate);
+                    accumulate = 1u;
+                  }
+                }
+              } else if (stacked) {
 #pragma unroll
                 for (int k = 0; k < kBK / 16; ++k) {
                   if (k < ksteps) {
@@ -1697,6 +1709,7 @@ unsigned* g_debug_counters = nullptr;  // set by the last non-swapped setup when
 int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
+int g_precision = 0;       // rsis_set_precision: 0 = split bf16 (fp32-grade products), 1 = single-pass bf16 operands
 int g_pre_tma = 0;         // RSIS_B200_PRE_TMA=1: the hoisted gate share of a tile is staged in shared memory by TMA (no measured
                            // gain at B=8, and its two stages cost the third activation stage: off by default)
 int g_cell_rows = 1;       // RSIS_B200_CELL_ROWS=0: the staged-transpose cell epilogue instead of the row-wise one (A/B timing)
@@ -1757,12 +1770,13 @@ int next_pow2(int v) {
 
 // 5-D view {C, W', H', N, plane} of a split-bf16 NHWC activation with pixel pitch `cs` elements
 // (sub = 2: one parity sub-grid of a stride-2 conv).
-int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw, int BW, int BH, int BI) {
+int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw, int BW, int BH, int BI,
+                   int planes = 2) {
   const size_t C = t.c, W = t.w, H = t.h, N = t.n, P = pitch(t);
   char* base = reinterpret_cast<char*>(t.data) + ((size_t)ph * W + pw) * P * 2;
   cuuint64_t dims[5] = {C, W / sub, H / sub, N, 2};
   cuuint64_t strides[4] = {P * 2 * sub, W * P * 2 * sub, H * W * P * 2, N * H * W * P * 2};
-  cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, 2};
+  cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, (cuuint32_t)planes};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1770,10 +1784,10 @@ int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
 }
 
-int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int k_pad, int BN) {
+int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int k_pad, int BN, int planes = 2) {
   cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)cout_pad, 2};
   cuuint64_t strides[2] = {(cuuint64_t)k_pad * 2, (cuuint64_t)cout_pad * k_pad * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 2};
+  cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, (cuuint32_t)planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1820,7 +1834,7 @@ inline double mma_ns(int n_mma) {
 }
 
 Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
-               bool can_split, bool cell, int ctas) {
+               bool can_split, bool cell, int ctas, bool single = false) {
   // Cost model in nanoseconds, calibrated on B200 with in-kernel %globaltimer stamps and graph-replay timings
   // (scripts/stamp_probe.py, scripts/gap_probe.py):
   //   launch -> first MMA and exit: ~3000;  one tcgen05.mma instruction: ~70 whatever its N;
@@ -1838,11 +1852,11 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     if (BN >= 2 * cout && BN > 32) continue;              // wider than the layer: nothing but padding
     if (cout <= 128 && BN > 128) continue;
     if (g_force_bn && BN != g_force_bn) continue;
-    const int stacked = BN <= 128 ? 1 : 0;
-    const double mpk = stacked ? 2 : 3;
+    const int stacked = (BN <= 128 && !single) ? 1 : 0;
+    const double mpk = single ? 1 : (stacked ? 2 : 3);
     const double kMma = mma_ns(stacked ? 2 * BN : BN);
     const int tiles_n = ceil_div(cout, BN);
-    const double b_item = 2.0 * BN * 128;
+    const double b_item = (single ? 1.0 : 2.0) * BN * 128;
     const double pieces_per_warp = BN >= 64 ? ceil_div(4 * (BN / 32), kEpiWarps) : 0.6;
     const double epi_tile = pieces_per_warp * kPiece;
     // (a) no split: persistent CTAs, HALO staging when eligible; MMAs of tile i+1 overlap the epilogue of tile i
@@ -1918,8 +1932,9 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const long long mt_halo = (long long)(p.Wo / kHaloBW) * (p.Ho / kHaloBH) * p.N;
   if (mt_tap > 0x3fffffLL || mt_halo > 0x3fffffLL) return RSIS_ERR_UNSUPPORTED;
   const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
+  p.single = g_precision == 1 ? 1 : 0;
   const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
-                              w->gate_interleaved != 0, cta_share);
+                              w->gate_interleaved != 0, cta_share, p.single != 0);
   if (g_print_plan)
     fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d halo=%d est %lld ns\n",
             x.n, x.h, x.w, x.c, w->cout, w->kh, stride, w->gate_interleaved ? " cell/gates" : "", plan.BN, plan.stacked,
@@ -1955,10 +1970,11 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   }
   const int a_rows = p.halo ? kHaloRows : kBM;
   p.a_plane_bytes = a_rows * 128;
-  p.a_tx_bytes = (uint32_t)(2 * p.a_plane_bytes);
-  p.a_stage_bytes = round_up(2 * p.a_plane_bytes, 1024);
+  const int planes = p.single ? 1 : 2;
+  p.a_tx_bytes = (uint32_t)(planes * p.a_plane_bytes);
+  p.a_stage_bytes = round_up(planes * p.a_plane_bytes, 1024);
   p.a_sbo = p.halo ? (uint32_t)(kHaloBW + 2) * 128u : 1024u;
-  p.b_stage_bytes = 2 * p.BN * 128;
+  p.b_stage_bytes = planes * p.BN * 128;
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   p.pw = p.BN >= 64 ? 32 : 16;
   // pre_tma (cells with hoisted gates on the row-wise epilogue): two stages of BN/32 boxes of 16 KB take the place of
@@ -2014,17 +2030,17 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.cell_rows = g_cell_rows;
   const int cout_pad = round_up(w->cout, 16);
   const int k_pad = p.taps * p.chunks * kBK;
-  if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN)) return e;
+  if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN, planes)) return e;
   if (stride == 1) {
     if (p.halo) {
-      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1)) return e;
+      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes)) return e;
     } else {
-      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, p.BW, p.BH, p.BI)) return e;
+      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, p.BW, p.BH, p.BI, planes)) return e;
     }
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
-        if (int e = encode_act_map(&maps.a[ph * 2 + pw], x, 2, ph, pw, p.BW, p.BH, p.BI)) return e;
+        if (int e = encode_act_map(&maps.a[ph * 2 + pw], x, 2, ph, pw, p.BW, p.BH, p.BI, planes)) return e;
   }
   return RSIS_OK;
 }
@@ -2077,7 +2093,7 @@ int encode_weight_map_swapped(CUtensorMap* m, const void* w, int cout_pad, int k
 
 bool swap_eligible(const rsis_tensor& x, const rsis_conv_weights* w) {
   std::call_once(g_once, init_once);
-  return g_swap && g_init_status == RSIS_OK && w->w_umma_il && aligned16(w->w_umma_il) && w->kh == 3 &&
+  return g_swap && g_precision == 0 && g_init_status == RSIS_OK && w->w_umma_il && aligned16(w->w_umma_il) && w->kh == 3 &&
          (w->cout == 32 || w->cout == 64) && x.c <= kBK &&
          x.w % kHaloBW == 0 && x.h % kSwTileH == 0;
 }
@@ -2187,6 +2203,7 @@ struct WgParams {
   int units_n, co_blocks;
   int pairs, chunks, ksize, pad, stride;
   int Cout, ci_pad;
+  int single;  // single-pass bf16: dY_hi * X_hi only
   float* scratch;
 };
 
@@ -2309,8 +2326,10 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             const uint64_t a_hi = a_hi0 + adv, a_lo = a_hi + (kWgPlaneBytes >> 4);
             const uint64_t b_hi = b_hi0 + adv, b_lo = b_hi + (kWgPlaneBytes >> 4);
             umma_bf16(tmem_base, a_hi, b_hi, idesc, (it | ks) ? 1u : 0u);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
+            if (!p.single) {
+              umma_bf16(tmem_base, a_hi, b_lo, idesc, 1u);
+              umma_bf16(tmem_base, a_lo, b_hi, idesc, 1u);
+            }
           }
           umma_commit(empty0 + 8 * st);  // the stage is free once these MMAs have read it
         }
@@ -2424,6 +2443,7 @@ int conv_wgrad_umma(const rsis_tensor* x, const rsis_tensor* dy, int ksize, int 
   p.Cout = dy->c;
   p.ci_pad = p.chunks * 64;
   p.scratch = reinterpret_cast<float*>(workspace);
+  p.single = g_precision == 1 ? 1 : 0;
   // 1x1 convolutions whose Cin is a multiple of 64: the scratch layout [co][ci] IS the OIHW tensor -- reduce straight
   // into the gradient (no finishing pass)
   const bool direct = ksize == 1 && x->c % 64 == 0 && aligned16(dw_oihw);
@@ -2548,6 +2568,14 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
   return launch<true>(maps, p, st);
 }
 
+
+// ---- precision mode -----------------------------------------------------------------------------------------------
+int set_precision(int mode) {
+  const int prev = g_precision;
+  if (mode == 0 || mode == 1) g_precision = mode;
+  return prev;
+}
+int get_precision() { return g_precision; }
 
 // ---- grouped cells: the cells of one wavefront of the decoder in one launch ----------------------------------------
 int convlstm_cell_group_max() { return kMaxGroup; }

@@ -19,6 +19,8 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        const float* gate_preact, const rsis_tensor* h_out, const rsis_tensor* h_split, const rsis_tensor* c_out,
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
                        int cta_cap, cudaStream_t st);
+int set_precision(int mode);
+int get_precision();
 int convlstm_cell_group_max();
 bool convlstm_cell_group_supported(const rsis_cell_args* cells, int n);
 int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st);
@@ -68,6 +70,12 @@ int rsis_convlstm_cell(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
             : convlstm_cell_simt(srcs, n_src, w, c_prev, h_out, h_split, c_out, side_max, side_stride, side_offset,
                                  st);
 }
+
+int rsis_set_precision(int mode) {
+  if (mode != RSIS_PRECISION_SPLIT_BF16 && mode != RSIS_PRECISION_BF16) return RSIS_ERR_BAD_ARG;
+  return set_precision(mode);
+}
+int rsis_get_precision(void) { return get_precision(); }
 
 int rsis_convlstm_cell_group_max(void) { return convlstm_cell_group_max(); }
 

@@ -43,10 +43,33 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
     share of every level's gates is computed once, and every step is 13 launches with no allocation.
     Returns the workspace (tcgen05) or the final state list (CUDA-core family)."""
     B, _, H, W = x.shape
-    if _mask_size(H, W) != (H, W):
-        raise NotImplementedError("rsis_b200.test: input height and width must be even (mask is produced at "
-                                  "2*ceil(H/2) x 2*ceil(W/2); the resize of test.py:39-40 is not implemented)")
     C = out_classes.shape[-1]
+    Hm, Wm = _mask_size(H, W)
+    if (Hm, Wm) != (H, W):
+        # odd input sizes: the decoder's mask lives at 2*ceil(H/2) x 2*ceil(W/2); test.py:39-40 resizes the LOGITS to the
+        # input size (nn.UpsamplingBilinear2d = bilinear, align_corners) before the sigmoid of test.py:50
+        from . import postprocess
+        logits = torch.empty((T, B, Hm, Wm), dtype=torch.float32, device=x.device)   # one contiguous [B,Hm,Wm] per step
+        if ops.uses_tcgen05(impl):
+            if ws is None:
+                ws = decoder.workspace(B, feature_sizes(H, W), x.device)
+            if feats_op is None:
+                keep = ws.encode_into(encoder, decoder, x, impl)  # noqa: F841
+            else:
+                ws.load_feats(decoder, feats_op, impl)
+            ws.reset()
+            for t in range(T):
+                decoder.step_ws(ws, impl, logits[t], out_classes[:, t], T * C, None, T, stop_prob=out_stops[:, t])
+        else:
+            if feats_op is None:
+                _, feats_op = encoder.forward_act(x, impl)
+            state = None
+            for t in range(T):
+                state = decoder.step_act(feats_op, state, impl, logits[t], out_classes[:, t], T * C, None, T,
+                                         stop_prob=out_stops[:, t])
+        resized = postprocess.resize_masks(logits.view(T * B, Hm, Wm), H, W)
+        torch.sigmoid(resized.view(T, B, H, W).permute(1, 0, 2, 3), out=out_masks)
+        return ws
     if ops.uses_tcgen05(impl):
         if ws is None:
             ws = decoder.workspace(B, feature_sizes(H, W), x.device)

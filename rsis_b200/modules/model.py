@@ -39,6 +39,9 @@ class FeatureExtractor(nn.Module):
         # access, so the base starts from torchvision's random initialisation and real weights arrive through
         # load_state_dict (the reference's own checkpoint path, utils/utils.py:97-111).
         self.base = ResNet101()
+        # "bf16": the TRAINING-mode forward / backward of this module run single-pass bf16 tensor-core products
+        # (BASELINE.json configs[3]; loss-level tolerance).  Inference and the default stay fp32-grade (split bf16).
+        self.precision = getattr(args, "precision", None)
         self.hidden_size = int(args.hidden_size)
         self.kernel_size = int(args.kernel_size)
         self.padding = 0 if self.kernel_size == 1 else 1
@@ -243,6 +246,7 @@ class RSIS(nn.Module):
     def __init__(self, args):
         super().__init__()
         get_skip_dims(args.base_model)
+        self.precision = getattr(args, "precision", None)   # see FeatureExtractor
         self.hidden_size = int(args.hidden_size)
         self.num_classes = int(args.num_classes)
         self.kernel_size = int(args.kernel_size)

@@ -40,6 +40,36 @@ def bump_bn_stats_epoch():
     _bn_stats_epoch += 1
 
 
+PRECISIONS = {"fp32": 0, "split": 0, "split-bf16": 0, "bf16": 1}
+
+
+def get_precision() -> str:
+    return "bf16" if _lib.load().rsis_get_precision() == 1 else "fp32"
+
+
+class precision:
+    """`with ops.precision("bf16"):` -- the tcgen05 convolutions set up inside run single-pass bf16 (BASELINE.json
+    configs[3] "training step bf16": hi planes only, fp32 accumulation, fp32 master weights and gradients) instead of the
+    default split-bf16 fp32-grade products.  Process-wide (the autograd worker thread must see it too); a CUDA graph keeps
+    the mode it was captured in.  None / "fp32" = leave the default."""
+
+    def __init__(self, mode: Optional[str]):
+        mode = "fp32" if mode is None else str(mode).lower()
+        if mode not in PRECISIONS:
+            raise ValueError(f"rsis_b200: precision must be one of {sorted(PRECISIONS)}, got {mode!r}")
+        self.mode = PRECISIONS[mode]
+        self.prev = None
+
+    def __enter__(self):
+        self.prev = _lib.load().rsis_set_precision(self.mode)
+        check(min(self.prev, 0), "set_precision")
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().rsis_set_precision(self.prev)
+        return False
+
+
 def launch_count() -> int:
     """Number of CUDA kernels this process has enqueued through the C ABI so far."""
     return _lib._launches

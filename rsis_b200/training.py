@@ -27,11 +27,14 @@ from .autograd import GradBucket, _DgradCache
 
 class TrainStep:
     def __init__(self, encoder, decoder, T: int, loss_fn: Callable, bucket: Optional[GradBucket] = None,
-                 cuda_graph: bool = True, all_reduce: bool = True, optimizer=None):
+                 cuda_graph: bool = True, all_reduce: bool = True, optimizer=None, precision: Optional[str] = None):
         """optimizer (optional): an `rsis_b200.optim.FusedAdam` over `bucket` (which then must have been built with
         flatten_params=True); its step runs after the all-reduce, outside the captured graph (a handful of launches
         whose bias-correction coefficients change every step)."""
         self.enc, self.dec, self.T, self.loss_fn = encoder, decoder, int(T), loss_fn
+        if precision is not None:  # "bf16": BASELINE.json configs[3] (single-pass bf16 products); None: the modules' own
+            ops.precision(precision)  # validates the name
+            encoder.precision = decoder.precision = precision
         self.optimizer = optimizer
         if optimizer is not None and bucket is None:
             bucket = optimizer.bucket

@@ -61,6 +61,14 @@ class FakeLib:
     def rsis_device_check(self):
         return 0
 
+    def rsis_set_precision(self, mode):
+        prev = getattr(self, "_precision", 0)
+        self._precision = mode
+        return prev
+
+    def rsis_get_precision(self):
+        return getattr(self, "_precision", 0)
+
     def rsis_has_tcgen05(self):
         return 0
 

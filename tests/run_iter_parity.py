@@ -25,7 +25,7 @@ def oracle_run_iter(num_classes=5):
     return [float(loss)] + [float(p) for p in parts], perm, grads
 
 
-def modules_run_iter(device, num_classes=5):
+def modules_run_iter(device, num_classes=5, precision=None):
     """The same recipe over the rsis_b200 modules, the fused soft-IoU cost / loss kernels and the device matching."""
     import rsis_b200
     from rsis_b200 import objectives as OBJ
@@ -34,6 +34,8 @@ def modules_run_iter(device, num_classes=5):
     from train_parity import _args
     args = iter_args()
     margs = _args(num_classes, args.maxseqlen)
+    if precision is not None:
+        margs.precision = precision       # "bf16": BASELINE.json configs[3] single-pass training mode
     enc, dec = rsis_b200.FeatureExtractor(margs), rsis_b200.RSIS(margs)
     enc.load_state_dict(sw.encoder_state_dict(1))
     dec.load_state_dict(sw.decoder_state_dict(1, num_classes=num_classes))

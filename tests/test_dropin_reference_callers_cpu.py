@@ -103,3 +103,23 @@ def test_reference_run_iter_runs_on_repo_modules(fake, golden_dir):
         scale = max(abs(dig[0]), 1e-12)                          # the tensor's norm
         worst = max(worst, abs(mine[0] - dig[0]) / scale, float(np.abs(mine[2:] - dig[2:]).max()) / scale)
     assert worst <= 5e-3, worst
+
+
+def test_odd_input_size_resize_matches_the_reference_caller(fake):
+    """test.py:39-40 on an odd-sized input: the reference's own loop (its nn.UpsamplingBilinear2d on the module's
+    mask logits) and `rsis_b200.test()` (resize of the logits, then the sigmoid) agree."""
+    import rsis_b200
+    from oracle import synth_weights as sw
+    ref = rs.load_reference()
+    B, H, W, T = 2, 63, 49, 2
+    args = rs.make_args(num_classes=21, maxseqlen=T)
+    enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
+    enc.load_state_dict(sw.encoder_state_dict(1))
+    dec.load_state_dict(sw.decoder_state_dict(1))
+    x = sw.synthetic_images(3, B, H, W)
+    want = ref.test(args, enc, dec, x)
+    args.cuda_graph = False
+    got = rsis_b200.test(args, enc, dec, x)
+    assert tuple(got[0].shape) == (B, T, H, W)
+    for a, b in zip(got, want):
+        assert rel(a, b) < 2e-5

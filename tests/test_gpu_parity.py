@@ -585,3 +585,20 @@ def test_errors_are_reported_not_swallowed(R):
         cell(torch.zeros((1, 12, 8, 8), device="cuda"), None)
     from rsis_b200 import _lib
     assert _lib.load().rsis_device_check() == 0
+
+
+@pytest.mark.parametrize("size", [(63, 97), (64, 95)])
+def test_odd_input_sizes_follow_the_reference_resize(R, O, sw, impl, size):
+    """test.py:39-40: the mask logits (produced at 2*ceil(H/2) x 2*ceil(W/2)) are resized to the INPUT size with
+    nn.UpsamplingBilinear2d before the sigmoid.  Odd H / W against the oracle's test loop."""
+    H, W = size
+    T, B = 2, 2
+    args, enc, dec = _models(R, sw, 21, T, 1)
+    x = sw.synthetic_images(11, B, H, W)
+    want_m, want_c, want_s = O.test_loop(sw.encoder_state_dict(1), sw.decoder_state_dict(1), x, T)
+    for graph in (False, True):
+        args.cuda_graph = graph
+        masks, classes, stops = R.test(args, enc, dec, x.cuda())
+        assert tuple(masks.shape) == (B, T, H, W)
+        tol = _tol(impl)
+        assert rel(masks, want_m) < tol and rel(classes, want_c) < tol and rel(stops, want_s) < tol
