@@ -514,8 +514,9 @@ __device__ __forceinline__ RowGeom row_geom(const UmmaParams& p, const RowPos& r
 #ifdef RSIS_DEBUG_TIMING
 __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   if (blockIdx.x == 0 && p.counters) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    // SM cycle counter (all stamps of the table come from block 0, i.e. one SM): ~20 cycles, where %globaltimer costs
+    // hundreds of nanoseconds and visibly stretched the roles it was stamping; readers divide by the SM clock
+    const unsigned long long t = (unsigned long long)clock64();
     reinterpret_cast<unsigned long long*>(p.counters)[256 + slot] = t;
   }
 }
@@ -863,148 +864,154 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
                                                    int warp, int lane, const int bid, const int nblk) {
   const int quarter = warp & 3, half = warp >> 2;
   const int Ch = p.Cout >> 2;
-  const int nu = p.BN >> 4;  // units per output-channel tile
+  const int nu = p.BN >> 4;  // units per output-channel tile; this warp takes units half, half + 2, ...
   const bool warp_one_image = p.BW * p.BH >= 32;  // the 32 rows of a warp lie in one image
   const int num_work = p.num_tiles;               // no split-K on this path
   const RowPos rpos = row_pos(p, quarter * 32 + lane);
-  auto tile_pix = [&](int tile, int& nt, int& img) -> uint32_t {
-    const TileCoord tc = decode_tile(p, tile);
-    nt = tc.nt;
-    const RowGeom g = row_geom(p, rpos, tc);
-    img = g.img;
-    return g.ok ? (uint32_t)g.pix : 0xffffffffu;
-  };
-  int acc = 0;
-  uint32_t acc_phase = 0;
-  int ps = 0;
-  uint32_t pph = 0;
-  const uint32_t prow = smem_p + (uint32_t)(quarter * 32 + lane) * 128u;  // this thread's row inside a box
+  const uint32_t prow = smem_p + (uint32_t)(quarter * 32 + lane) * 128u;  // this thread's row inside a staged box
   const uint32_t pxor = (uint32_t)(lane & 7);                               // (row & 7): quarter * 32 is a multiple of 8
-  CellUnitIn cur;
-  bool have_cur = false;
-  int nt = 0, img = 0;
-  uint32_t mypix = 0xffffffffu;
-  if (bid < num_work) mypix = tile_pix(bid, nt, img);
-  for (int work = bid; work < num_work; work += nblk) {
-    // geometry of the next tile (for the cross-tile prefetch)
-    int nt2 = 0, img2 = 0;
-    uint32_t pix2 = 0xffffffffu;
-    const bool more = work + nblk < num_work;
-    if (more) pix2 = tile_pix(work + nblk, nt2, img2);
-    if (!have_cur && half < nu) cell_unit_load(p, cur, mypix, ((nt * p.BN) >> 2) + 4 * half);
-    have_cur = false;
-    if (threadIdx.x == 0) STAMP_T(7, (work - bid) / nblk);
-    mbar_wait(tfull0 + 8 * acc, acc_phase);
-    tc_fence_after();
-    if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
-    bool released = false;
-    if (p.pre_tma) mbar_wait(pfull0 + 8 * ps, pph);
-    if (threadIdx.x == 0) STAMP_T(5, (work - bid) / nblk);
-    for (int u = half; u < nu; u += 2) {
-      const int col0 = nt * p.BN + 16 * u;
-      if (col0 >= p.Cout) break;
-      const int chg0 = col0 >> 2;
-      const bool last_unit = u + 2 >= nu || col0 + 32 >= p.Cout;
-      // loads of the unit after this one
-      CellUnitIn nxt;
-      bool have_nxt = false;
-      if (!last_unit) {
-        cell_unit_load(p, nxt, mypix, chg0 + 8);
-        have_nxt = true;
-      } else if (more && half < nu) {
-        cell_unit_load(p, nxt, pix2, ((nt2 * p.BN) >> 2) + 4 * half);
-        have_nxt = true;
-      }
-      uint32_t r[16];
-      tmem_ld16(taddr + 16 * u, r);
-      if (p.stacked) {
-        uint32_t r2[16];
-        tmem_ld16(taddr + p.BN + 16 * u, r2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
-      } else {
-        tmem_ld_wait();
-      }
-      if (last_unit) {  // the accumulator stage is free for the MMAs of the tile after next
-        tc_fence_before();
-        mbar_arrive(tempty0 + 8 * acc);
-        released = true;
-        if (threadIdx.x == 0) STAMP_T(4, (work - bid) / nblk);
-      }
-      const bool ok = mypix != 0xffffffffu;
-      if (p.pre_tma) {
-        // unit u = columns [16u, 16u + 16) of the tile: box u / 2, 16-byte chunks 4 * (u & 1) .. + 3 of the row
-        const uint32_t rowaddr = prow + (uint32_t)ps * (uint32_t)p.p_stage_bytes + (uint32_t)(u >> 1) * 16384u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t chunk = (uint32_t)(4 * (u & 1) + j) ^ pxor;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(cur.pre[j].x), "=f"(cur.pre[j].y), "=f"(cur.pre[j].z), "=f"(cur.pre[j].w)
-                       : "r"(rowaddr + (chunk << 4)));
-        }
-      }
-      float cv[4], hv[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
-        const float gi = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x) + cur.pre[j].x);
-        const float gf = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y) + cur.pre[j].y);
-        const float go = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z) + cur.pre[j].z);
-        const float gg = fast_tanh(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w) + cur.pre[j].w);
-        const float cpj = j == 0 ? cur.cp.x : (j == 1 ? cur.cp.y : (j == 2 ? cur.cp.z : cur.cp.w));
-        cv[j] = fmaf(gf, cpj, gi * gg);
-        hv[j] = go * fast_tanh(cv[j]);
-      }
-      if (ok) {
-        const size_t idx = (size_t)mypix * Ch + chg0;
-        *reinterpret_cast<float4*>(p.c_out + idx) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-        *reinterpret_cast<float4*>(p.h_out + idx) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        if (p.h_split) store4(p.h_split, p.hs_plane, RSIS_FMT_SPLIT_BF16, (size_t)mypix * p.hs_cs + chg0, hv);
-      }
-      if (p.side_max) {  // the global nn.MaxPool2d of model.py:143 as order-preserving keys
-        if (warp_one_image) {
-          const int img0 = __shfl_sync(0xffffffffu, img, 0);
-          uint32_t mine = 0u;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t m = __reduce_max_sync(0xffffffffu, ok ? float_to_key(hv[j]) : 0u);
-            if (lane == j) mine = m;
-          }
-          if (lane < 4 && mine != 0u)
-            atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg0 + lane, mine);
-        } else if (ok) {  // maps smaller than a warp's 32 rows: rows of several images share the warp
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            atomicMax(p.side_max + (size_t)img * p.side_stride + p.side_offset + chg0 + j, float_to_key(hv[j]));
-        }
-      }
-      if (have_nxt) {
-        cur = nxt;
-        have_cur = last_unit;  // loaded for the next tile
-      }
+
+  // The warp's work is a flat stream of units (tile, u); a cursor names one.
+  struct Cursor {
+    int work, u, nt, img;
+    uint32_t pix;
+    bool valid;
+  };
+  auto locate = [&](Cursor& c) {  // geometry of c.work's tile for this thread
+    c.valid = c.work < num_work;
+    c.pix = 0xffffffffu;
+    c.nt = c.img = 0;
+    if (c.valid) {
+      const TileCoord tc = decode_tile(p, c.work);
+      const RowGeom g = row_geom(p, rpos, tc);
+      c.nt = tc.nt;
+      c.img = g.img;
+      if (g.ok) c.pix = (uint32_t)g.pix;
     }
-    if (!released) {
+  };
+  auto next_of = [&](const Cursor& c) {
+    Cursor n = c;
+    n.u += 2;
+    if (n.u >= nu) {
+      n.u = half;
+      n.work += nblk;
+      locate(n);
+    }
+    return n;
+  };
+  int acc = 0, ps = 0;
+  uint32_t acc_phase = 0, pph = 0;
+
+  // One unit: `in` was loaded earlier (by the previous step, or before the loop); the loads of the NEXT unit go into
+  // `in_next`.  The two register sets alternate between calls, so no load result is ever copied: a register move of a
+  // prefetched value would stall the warp until that load has landed (it did: ~1 us per tile, profiles/r2q_*).
+  auto step = [&](const Cursor& c, CellUnitIn& in, CellUnitIn& in_next) -> Cursor {
+    const Cursor n = next_of(c);
+    const int col0 = c.nt * p.BN + 16 * c.u;
+    const int chg0 = col0 >> 2;
+    if (n.valid) cell_unit_load(p, in_next, n.pix, ((n.nt * p.BN) >> 2) + 4 * n.u);
+    const bool first_unit = c.u == half, last_unit = c.u + 2 >= nu;
+    if (first_unit) {
+      if (threadIdx.x == 0) STAMP_T(7, (c.work - bid) / nblk);
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      if (threadIdx.x == 0) STAMP_T(3, (c.work - bid) / nblk);
+      if (p.pre_tma) mbar_wait(pfull0 + 8 * ps, pph);
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
+    uint32_t r[16];
+    tmem_ld16(taddr + 16 * c.u, r);
+    if (p.stacked) {
+      uint32_t r2[16];
+      tmem_ld16(taddr + p.BN + 16 * c.u, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+    } else {
+      tmem_ld_wait();
+    }
+    if (last_unit) {  // the accumulator stage is free for the MMAs of the tile after next
       tc_fence_before();
       mbar_arrive(tempty0 + 8 * acc);
+      if (threadIdx.x == 0) STAMP_T(4, (c.work - bid) / nblk);
     }
-    if (threadIdx.x == 0) STAMP_T(6, (work - bid) / nblk);
-    if (p.pre_tma) {  // this thread has consumed its part of the staged gate share
-      mbar_arrive(pempty0 + 8 * ps);
-      if (++ps == 2) {
-        ps = 0;
-        pph ^= 1u;
+    const bool ok = c.pix != 0xffffffffu && chg0 < Ch;
+    if (p.pre_tma) {
+      // unit u = columns [16u, 16u + 16) of the tile: box u / 2, 16-byte chunks 4 * (u & 1) .. + 3 of the row
+      const uint32_t rowaddr = prow + (uint32_t)ps * (uint32_t)p.p_stage_bytes + (uint32_t)(c.u >> 1) * 16384u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t chunk = (uint32_t)(4 * (c.u & 1) + j) ^ pxor;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(in.pre[j].x), "=f"(in.pre[j].y), "=f"(in.pre[j].z), "=f"(in.pre[j].w)
+                     : "r"(rowaddr + (chunk << 4)));
       }
     }
-    mypix = pix2;
-    nt = nt2;
-    img = img2;
-    if (++acc == kAccStages) {
-      acc = 0;
-      acc_phase ^= 1u;
+    float cv[4], hv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
+      const float gi = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x) + in.pre[j].x);
+      const float gf = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y) + in.pre[j].y);
+      const float go = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z) + in.pre[j].z);
+      const float gg = fast_tanh(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w) + in.pre[j].w);
+      const float cpj = j == 0 ? in.cp.x : (j == 1 ? in.cp.y : (j == 2 ? in.cp.z : in.cp.w));
+      cv[j] = fmaf(gf, cpj, gi * gg);
+      hv[j] = go * fast_tanh(cv[j]);
     }
+    if (ok) {
+      const size_t idx = (size_t)c.pix * Ch + chg0;
+      *reinterpret_cast<float4*>(p.c_out + idx) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+      *reinterpret_cast<float4*>(p.h_out + idx) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      if (p.h_split) store4(p.h_split, p.hs_plane, RSIS_FMT_SPLIT_BF16, (size_t)c.pix * p.hs_cs + chg0, hv);
+    }
+    if (p.side_max && chg0 < Ch) {  // the global nn.MaxPool2d of model.py:143 as order-preserving keys
+      if (warp_one_image) {
+        const int img0 = __shfl_sync(0xffffffffu, c.img, 0);
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = __reduce_max_sync(0xffffffffu, ok ? float_to_key(hv[j]) : 0u);
+          if (lane == j) mine = m;
+        }
+        if (lane < 4 && mine != 0u)
+          atomicMax(p.side_max + (size_t)img0 * p.side_stride + p.side_offset + chg0 + lane, mine);
+      } else if (ok) {  // maps smaller than a warp's 32 rows: rows of several images share the warp
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          atomicMax(p.side_max + (size_t)c.img * p.side_stride + p.side_offset + chg0 + j, float_to_key(hv[j]));
+      }
+    }
+    if (last_unit) {
+      if (threadIdx.x == 0) STAMP_T(6, (c.work - bid) / nblk);
+      if (p.pre_tma) {  // this thread has consumed its part of the staged gate share
+        mbar_arrive(pempty0 + 8 * ps);
+        if (++ps == 2) {
+          ps = 0;
+          pph ^= 1u;
+        }
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+    return n;
+  };
+
+  Cursor c;
+  c.work = bid;
+  c.u = half;
+  locate(c);
+  if (!c.valid) return;
+  CellUnitIn set_a, set_b;
+  cell_unit_load(p, set_a, c.pix, ((c.nt * p.BN) >> 2) + 4 * c.u);
+  for (;;) {
+    c = step(c, set_a, set_b);
+    if (!c.valid) break;
+    c = step(c, set_b, set_a);
+    if (!c.valid) break;
   }
 }
 
@@ -1376,6 +1383,14 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) cell_group_kernel(const __gri
   for (int k = 1; k < kMaxGroup; ++k)
     if (k < g.n && (int)blockIdx.x >= g.first[k]) i = k;
   umma_cta<true, 0, false>(g.maps[i], g.p[i], (int)blockIdx.x - g.first[i], g.first[i + 1] - g.first[i]);
+#ifdef RSIS_DEBUG_TIMING
+  // per-cell end time (max over its CTAs) and launch start (min over all CTAs): slots 200 + i and 199 of the stamp table
+  if (threadIdx.x == 0 && g.p[0].counters) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(reinterpret_cast<unsigned long long*>(g.p[0].counters) + 256 + 200 + i, t);
+  }
+#endif
 }
 
 // ===================================================================================================================

@@ -47,15 +47,19 @@ for spec in sys.argv[1:] or ["4", "3", "2", "1", "0", "0,1,2,3,4"]:
         ops.convlstm_cell_group(grp)
     torch.cuda.synchronize()
     wsb[2048:2048 + 8 * 144].zero_()
+    wsb[2048 + 8 * 199:2048 + 8 * 206].zero_()
     flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ops.convlstm_cell_group(grp); e1.record()
     torch.cuda.synchronize()
     st = wsb[2048:2048 + 8 * 12].view(torch.int64).cpu().tolist()
     t0 = st[0]
-    print(f"levels {sub}: event {e0.elapsed_time(e1)*1e3:.1f} us; exit {(st[11]-t0)/1e3:.2f}")
+    ends = wsb[2048 + 8 * 200:2048 + 8 * 205].view(torch.int64).cpu().tolist()
+    CLK = 1965.0   # stamps are SM cycles (clock64) of block 0's SM; cells' end times are %globaltimer (not comparable)
+    print(f"levels {sub}: event {e0.elapsed_time(e1)*1e3:.1f} us; exit {(st[11]-t0)/CLK:.2f}; cell spans (globaltimer, us from "
+          f"the first cell end): " + " ".join(f"{(t - min(ends[:len(sub)]))/1e3:.1f}" for t in ends[:len(sub)]))
     tl = wsb[2048 + 8 * 16:2048 + 8 * 144].view(torch.int64).cpu().view(8, 16)
     for role, rn in enumerate(["A issued", "MMA sees A", "MMAs issued", "epi sees acc", "epi released",
                                "epi sees P", "epi tile done", "epi tile top"]):
-        vals = [f"{(int(t) - t0)/1e3:.1f}" for t in tl[role].tolist() if int(t) >= t0]
+        vals = [f"{(int(t) - t0)/CLK:.1f}" for t in tl[role].tolist() if int(t) >= t0]
         print(f"      {rn:13s}: " + " ".join(vals))

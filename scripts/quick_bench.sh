@@ -1,4 +1,6 @@
-#!/bin/bash
-# usage: bash scripts/quick_bench.sh <outfile-tag>; prints ms/step, e2e ms/step, cell step us and per-level us
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/$1.json 2> gpurun_out/$1.err; tail -2 gpurun_out/$1.err
-python -c "import json,sys; d=json.loads(open('gpurun_out/$1.json').read()); print('$1', round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), round(d['roofline']['step_us'],1), [round(l['us'],1) for l in d['roofline']['per_level']])"
+OUT=gpurun_out/r2r
+mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > $OUT/pytest_parity.log 2>&1; echo "parity exit $?"; tail -3 $OUT/pytest_parity.log
+timeout 300 python scripts/decoder_probe.py 8 256 256 10 3 > $OUT/decoder_probe.txt 2>&1; cat $OUT/decoder_probe.txt
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-train --no-torch-gpu > $OUT/bench.json 2> $OUT/bench.err
+python -c "import json,sys; d=json.loads(open('$OUT/bench.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['step_us'])"
