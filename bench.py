@@ -489,14 +489,18 @@ def run_ours(a):
         # runs the five cells of a decoder step; under the older schedules the step is five launches, timed one by one
         step_s = group_s if group_s is not None else sum(lv_s)
         ach = tot_b / step_s / 1e9
-        traffic = None  # ncu dram__bytes_read.sum + dram__bytes_write.sum of the five cell launches (one --set full capture)
+        # ncu dram__bytes_read.sum + dram__bytes_write.sum of one grouped launch (one `--set full` capture of this kernel,
+        # profiles/cell_traffic.json; reads and writes also separately -- a profiler cannot run inside a timed run)
+        traffic = traffic_rw = None
         tpath = os.path.join(ROOT, "profiles", "cell_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and group_s is not None:
             tj = json.load(open(tpath))
             if tj.get("workload") == a.workload:
                 traffic = tj.get("dram_bytes_per_step")
+                traffic_rw = {"read": tj.get("dram_read_bytes_per_launch"), "write": tj.get("dram_write_bytes_per_launch"),
+                              "note": tj.get("note"), "source": tj.get("source")}
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                "traffic": traffic, "peak_source": pk["source"] + " (burst copy figure; kernel timed alone, L2 flushed)",
+                "traffic": traffic, "traffic_read_write": traffic_rw, "peak_source": pk["source"] + " (burst copy figure; kernel timed alone, L2 flushed)",
                 "kernel": ("cell_group_kernel: the fused ConvLSTM cells of one decoder step (levels 0-4) in ONE grouped "
                            "launch, as the default wavefront schedule issues them; CUDA-event timed live"
                            if group_s is not None else

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""profiles/cell_traffic.json + a markdown summary from one `ncu --set full` capture of the five cell launches of a
-decoder step (scripts/gpu_check.sh).  usage: cell_traffic.py <prof.ncu-rep> <tag> [workload]"""
+"""Round-1 helper: profiles/cell_traffic.json + a markdown summary from one `ncu --set full` capture of the five
+SINGLE cell launches of a decoder step.  Since round 2 the dominant kernel is the grouped launch (`cell_group_kernel`);
+its capture is `scripts/gpu_run.sh <tag> ncu_cell`, summarised by scripts/ncu_summary.py, and profiles/cell_traffic.json
+holds its per-launch DRAM reads and writes.  usage: cell_traffic.py <prof.ncu-rep> <tag> [workload]"""
 import csv, io, json, os, subprocess, sys
 rep, tag = sys.argv[1], sys.argv[2]
 workload = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
