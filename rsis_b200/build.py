@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "librsis_b200.so")
+# RSIS_B200_LIB: load / build another file instead (development: the -DRSIS_DEBUG_TIMING build of the stamp probes)
+LIB_PATH = os.environ.get("RSIS_B200_LIB") or os.path.join(LIB_DIR, "librsis_b200.so")
 SOURCES = ["api.cu", "pack.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "decoder_ops.cu", "bn_train.cu", "backward.cu", "objectives.cu", "postprocess.cu", "optim.cu", "dispatch.cu"]
 NVCC_FLAGS = (["-DRSIS_DEBUG_TIMING"] if os.environ.get("RSIS_B200_BUILD_DEBUG_TIMING") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -32,11 +33,11 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(os.path.dirname(LIB_PATH), src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:

@@ -95,9 +95,18 @@ struct UmmaParams {
   int halo;                // 1: HALO staging, 0: TAP staging
   int a_stages, b_stages;
   int b_resident;          // 1: the tile's whole weight set stays in the B ring for the CTA's lifetime (loaded once)
-  int a_plane_bytes;       // bytes of one bf16 plane of an A stage (rows * 128)
-  int a_stage_bytes;       // both planes, rounded up to 1024
-  int b_stage_bytes;       // 2 * BN * 128
+  int a_plane_bytes;       // bytes of one bf16 plane of one 64-channel chunk of an A stage (rows * 128)
+  int a_chunk_bytes;       // both planes of one chunk, rounded up to 1024
+  int a_stage_bytes;       // ag * a_chunk_bytes = one TMA box
+  int b_chunk_bytes;       // planes * BN * 128: the weights of one (tap, chunk) K block
+  int b_stage_bytes;       // bg * b_chunk_bytes = one TMA box
+  // One elected thread issues a TMA box every ~230-400 ns whatever the box holds (scripts/tma_probe.cu, in-kernel
+  // stamps: profiles/r2v_*), so 8 KB weight boxes starve 25 ns MMAs.  Boxes therefore carry several K blocks:
+  int ag;                  // 64-channel chunks per activation box (flat-pixel 1x1 convolutions: up to 2); otherwise 1
+  int bg;                  // K blocks per weight box: HALO -> taps of one chunk (1 / 3 / 9), TAP -> chunks of one tap
+  int a_flat;              // 1: maps.a[0] is the 4-D flat-pixel view {64, pixels, plane, chunk} of a 1x1 stride-1 input
+  int b_map3d;             // 1: maps.b is the 3-D view {k, cout, plane} (one K block per box)
+  int agroups;             // activation boxes per tap: HALO 1 (the walk is chunk-major), TAP ceil(chunks / ag)
   uint32_t a_tx_bytes, b_tx_bytes;
   uint32_t a_sbo;          // bytes between 8-row core matrices of A
   // K loop
@@ -317,12 +326,54 @@ __device__ __forceinline__ void load4(const View& v, size_t idx, float (&out)[4]
   }
 }
 
+// Four adjacent channels of an activation as they sit in memory (no arithmetic, so a prefetch only issues loads):
+// float32 -> the four floats; split bf16 -> {hi01, hi23, lo01, lo23}.
+__device__ __forceinline__ uint4 load4_raw(const View& v, size_t idx) {
+  if (v.fmt == RSIS_FMT_F32) return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(v.p) + idx));
+  const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(v.p);
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(q + idx));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(q + idx + v.plane));
+  return make_uint4(h.x, h.y, l.x, l.y);
+}
+__device__ __forceinline__ void decode4_raw(int fmt, const uint4& r, float (&out)[4]) {
+  if (fmt == RSIS_FMT_F32) {
+    out[0] = __uint_as_float(r.x); out[1] = __uint_as_float(r.y);
+    out[2] = __uint_as_float(r.z); out[3] = __uint_as_float(r.w);
+  } else {
+    out[0] = __uint_as_float(r.x << 16) + __uint_as_float(r.z << 16);
+    out[1] = __uint_as_float(r.x & 0xffff0000u) + __uint_as_float(r.z & 0xffff0000u);
+    out[2] = __uint_as_float(r.y << 16) + __uint_as_float(r.w << 16);
+    out[3] = __uint_as_float(r.y & 0xffff0000u) + __uint_as_float(r.w & 0xffff0000u);
+  }
+}
+
+// The residual (`out += identity`, torchvision Bottleneck.forward) of one piece, fetched BEFORE the accumulator is
+// waited for: loaded inside the finishing loop, every one of its iterations paid a full DRAM latency (the stores of
+// the previous iteration may alias, so the compiler cannot hoist the loads) -- 54 us for layer1.conv3 at batch 8
+// where the bytes need 12 (profiles/r2a_encoder_ncu_full.md rows 4-5).
+template <int PW>
+struct ResPiece {
+  static constexpr int NIT = 32 / (32 / (PW / 4));
+  uint4 v[NIT];
+};
+template <int PW>
+__device__ __forceinline__ void res_prefetch(const UmmaParams& p, ResPiece<PW>& rp, int lane, uint32_t mypix, int col0) {
+  constexpr int LPR = PW / 4, RPI = 32 / LPR;
+  const int col = col0 + 4 * (lane % LPR);
+  const bool col_ok = col < p.Cout;
+#pragma unroll
+  for (int it = 0; it < 32 / RPI; ++it) {
+    const uint32_t pix = __shfl_sync(0xffffffffu, mypix, it * RPI + lane / LPR);
+    rp.v[it] = (pix != 0xffffffffu && col_ok) ? load4_raw(p.res, (size_t)pix * p.res_cs + col) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // Finishes one staged piece of a plain convolution: folded BN/bias (+residual) (+ReLU) -> y (and y2).
 // stage[row * 33 + c] holds accumulator (row, c); mypix is this lane's row's pixel index (0xffffffff = outside).
 // Lane = (row within the iteration, group of 4 adjacent channels): a pixel's PW channels are one contiguous run.
 template <int PW>
 __device__ __forceinline__ void conv_finish_piece(const UmmaParams& p, const float* stage, int lane, uint32_t mypix,
-                                                  int col0) {
+                                                  int col0, const ResPiece<PW>& rp) {
   constexpr int LPR = PW / 4;    // lanes per row, four adjacent columns each
   constexpr int RPI = 32 / LPR;  // rows per iteration
   const int c = 4 * (lane % LPR);
@@ -347,7 +398,7 @@ __device__ __forceinline__ void conv_finish_piece(const UmmaParams& p, const flo
     if (pix != 0xffffffffu && col_ok) {
       if (p.has_res) {
         float t[4];
-        load4(p.res, (size_t)pix * p.res_cs + col, t);
+        decode4_raw(p.res.fmt, rp.v[it], t);
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += t[j];
       }
@@ -549,6 +600,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
   int acc = 0;
   uint32_t acc_phase = 0;
   CellPiece<PW> cpz_cur;
+  ResPiece<PW> res_cur;
   for (int work = bid; work < num_work; work += nblk) {
     int tile, ks;
     decode_work(p, work, tile, ks);
@@ -560,6 +612,9 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
       // the very first piece of this warp; afterwards every piece's c_prev / hoisted-gate loads are issued one piece
       // ahead (rolling, across tiles), so their DRAM latency hides behind the previous piece instead of stalling it
       if (work == bid && half < npc) cell_prefetch<PW>(p, cpz_cur, lane, mypix, nt * p.BN + PW * half);
+    }
+    if constexpr (!CELL && !SPLIT) {
+      if (p.has_res && work == bid && half < npc) res_prefetch<PW>(p, res_cur, lane, mypix, nt * p.BN + PW * half);
     }
     mbar_wait(tfull0 + 8 * acc, acc_phase);
     tc_fence_after();
@@ -584,6 +639,21 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             cell_prefetch<PW>(p, cpz_next, lane, g2.ok ? (uint32_t)g2.pix : 0xffffffffu, nt2 * p.BN + PW * half);
           }
         }
+        ResPiece<PW> res_next;
+        if constexpr (!CELL) {
+          if (p.has_res) {  // the next piece's residual (of this tile, or the first piece of this CTA's next tile)
+            const int coln = col0 + 2 * PW;
+            if (j + 2 < npc && coln < p.Cout) {
+              res_prefetch<PW>(p, res_next, lane, mypix, coln);
+            } else if (work + nblk < num_work) {
+              int tile2, ks2;
+              decode_work(p, work + nblk, tile2, ks2);
+              const TileCoord tc2 = decode_tile(p, tile2);
+              const RowGeom g2 = row_geom(p, rpos, tc2);
+              res_prefetch<PW>(p, res_next, lane, g2.ok ? (uint32_t)g2.pix : 0xffffffffu, tc2.nt * p.BN + PW * half);
+            }
+          }
+        }
         uint32_t r[PW];
         tmem_ld_piece<PW>(taddr + PW * j, r);
         tmem_ld_wait();
@@ -601,7 +671,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           cell_finish_piece<PW>(p, stage, lane, cpz_cur, g.img, col0, seg);
           cpz_cur = cpz_next;
         } else {
-          conv_finish_piece<PW>(p, stage, lane, mypix, col0);
+          conv_finish_piece<PW>(p, stage, lane, mypix, col0, res_cur);
+          if (p.has_res) res_cur = res_next;
         }
         __syncwarp();
       }
@@ -659,6 +730,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           float cprev;
           float4 pre;
           float4 v;
+          uint4 res;
         };
         // loads of one unit: issued for two units before either is finished, so their L2 / DRAM latencies overlap
         auto unit_load = [&](int u) {
@@ -674,6 +746,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             if (t.ok && p.c_prev) t.cprev = __ldg(p.c_prev + t.g.pix * Ch + (t.col >> 2));
             t.pre = (t.ok && p.preact) ? __ldg(reinterpret_cast<const float4*>(p.preact + t.g.pix * p.Cout + t.col))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          t.res = make_uint4(0u, 0u, 0u, 0u);
+          if constexpr (!CELL) {
+            if (t.ok && p.has_res) t.res = load4_raw(p.res, t.g.pix * p.res_cs + t.col);
           }
           t.v = make_float4(0.f, 0.f, 0.f, 0.f);
           const float* src = p.scratch + ((size_t)(tile * p.ksplit) * kBM + row) * ncols + 32 * cg + 4 * c4;
@@ -741,7 +817,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             if (t.ok) {
               if (p.has_res) {
                 float r4[4];
-                load4(p.res, t.g.pix * p.res_cs + col, r4);
+                decode4_raw(p.res.fmt, t.res, r4);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] += r4[e];
               }
@@ -800,11 +876,12 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
 template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
 __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
                                                     uint32_t b_stage16, uint32_t b_plane16, uint32_t idesc,
-                                                    uint32_t accumulate, bool wait_b, uint32_t bfull0) {
+                                                    uint32_t accumulate, bool wait_b, uint32_t bfull0, int bg) {
+  // b_stage16: one tap's weights (a K block); the taps arrive in boxes of `bg`, one barrier per box
 #pragma unroll
   for (int bi = 0; bi < 9; ++bi) {
-    if (wait_b) {
-      mbar_wait_lean(bfull0 + 8 * bi, 0);
+    if (wait_b && (bg == 1 || bi % bg == 0)) {
+      mbar_wait_lean(bfull0 + 8 * (bg == 1 ? bi : bi / bg), 0);
       tc_fence_after();
     }
     const uint64_t toff = (uint64_t)(((bi / 3) * (kHaloBW + 2) + (bi % 3)) * 8);
@@ -823,6 +900,68 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
         umma_bf16(d, a_hi + toff + adv, b + b_plane16 + adv, idesc, 1u);
         umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
       }
+    }
+  }
+}
+
+// The MMAs of one (tap, chunk) K block: KS steps of 16 channels, compile-time descriptor offsets.
+template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
+__device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t b_plane16,
+                                             uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K inside the swizzle row
+    const uint32_t first = k == 0 ? accumulate : 1u;
+    if (PASSES == 1) {
+      umma_bf16(d, a_hi + adv, b + adv, idesc, first);
+    } else if (PASSES == 2) {
+      umma_bf16(d, a_hi + adv, b + adv, idesc, first);
+      umma_bf16(d, a_lo + adv, b + adv, idesc, 1u);
+    } else {
+      umma_bf16(d, a_hi + adv, b + adv, idesc, first);
+      umma_bf16(d, a_hi + adv, b + b_plane16 + adv, idesc, 1u);
+      umma_bf16(d, a_lo + adv, b + adv, idesc, 1u);
+    }
+  }
+}
+
+// All MMAs of one HALO activation item (a 64-channel chunk, four K steps per tap) whose weights STREAM through the B ring
+// in boxes of three taps: per box one barrier wait, 3 x 4 x PASSES straight-line UTCHMMAs and one commit.  The issuing
+// thread spends ~550 cycles of barrier / descriptor / constant-load overhead per wait-issue-commit round (ncu source
+// view + in-kernel stamps, profiles/r2z_*): with one round per tap (8 MMAs of 48 cycles) the tensor pipe idled 60 % of
+// the main loop of layer3.conv2; a round per 24 MMAs keeps it fed.
+template <int PASSES>  // 2 = stacked weight planes, 3 = three products
+__device__ __forceinline__ void issue_halo_stream3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
+                                                   uint32_t b_stage16, uint32_t b_chunk16, uint32_t b_plane16,
+                                                   uint32_t idesc, uint32_t accumulate, uint32_t bfull0, uint32_t bempty0,
+                                                   int& bs, uint32_t& bph, int b_stages) {
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    mbar_wait_lean(bfull0 + 8 * bs, bph);
+    tc_fence_after();
+    const uint64_t b0 = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const uint64_t toff = (uint64_t)((g * (kHaloBW + 2) + j) * 8);
+      const uint64_t b = b0 + (uint64_t)((uint32_t)j * b_chunk16);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {
+        const uint64_t adv = (uint64_t)(2 * k);
+        const uint32_t first = (g == 0 && j == 0 && k == 0) ? accumulate : 1u;
+        if (PASSES == 2) {
+          umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
+          umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+        } else {
+          umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
+          umma_bf16(d, a_hi + toff + adv, b + b_plane16 + adv, idesc, 1u);
+          umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+        }
+      }
+    }
+    umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+    if (++bs == b_stages) {
+      bs = 0;
+      bph ^= 1u;
     }
   }
 }
@@ -1085,10 +1224,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   pdl_wait();
   if (threadIdx.x == 0) STAMP(1);
 
-  // A "items" per tile: HALO -> one per chunk (nine B items each); TAP -> one per (tap, chunk) (one B item each).
-  // A work unit is (tile, K slice): slice ks of `ksplit` covers items [ks * a_items / ksplit, (ks + 1) * ...).
-  const int b_per_a = p.halo ? p.taps : 1;
-  const int a_items = p.halo ? p.chunks : p.taps * p.chunks;
+  // The K loop walks (tap, chunk) K blocks: HALO chunk-major (an activation box = one chunk's halo tile, nine taps),
+  // TAP tap-major (an activation box = `ag` chunks of one tap).  A "items" per tile: HALO -> one per chunk; TAP -> one per
+  // (tap, chunk group).  A work unit is (tile, K slice): slice ks of `ksplit` covers items [ks * a_items / ksplit,
+  // (ks + 1) * ...) (ag = bg = 1 whenever ksplit > 1).  Weight boxes carry `bg` consecutive K blocks of the walk and
+  // never straddle a tap (TAP) / a chunk (HALO).
+  const int agroups = p.agroups;
+  const int a_items = p.halo ? p.chunks : p.taps * agroups;
   const int num_work = p.num_tiles * p.ksplit;
 
   if (warp == kEpiWarps) {
@@ -1097,13 +1239,17 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     uint32_t aph = 0;
     int ps = 0;
     uint32_t pph = 0;
+    if (lane == 0) STAMP(12);
     for (int work = bid; work < num_work; work += nblk) {
       int tile, ks;
       decode_work(p, work, tile, ks);
+      if (lane == 0 && work == bid) STAMP_T(5, 0);
       const int item0 = (int)fdiv((uint32_t)(ks * a_items), p.dks), item1 = (int)fdiv((uint32_t)((ks + 1) * a_items), p.dks);
+      if (lane == 0 && work == bid) STAMP_T(5, 1);
       const TileCoord tc = decode_tile(p, tile);
       const int tw = tc.tw, th = tc.th, ti = tc.ti;
       const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
+      if (lane == 0 && work == bid) STAMP_T(5, 2);
       if (CELL && p.pre_tma) {
         // the tile's share of the hoisted gates: BN/32 boxes {32 columns, BW, BH, BI} -> [128 rows][128 bytes] each
         mbar_wait(pempty0 + 8 * ps, pph ^ 1u);
@@ -1120,22 +1266,28 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
           pph ^= 1u;
         }
       }
-      // (tap, chunk) of the items walked incrementally: one division per K slice instead of three per item
+      // (tap, chunk group) of the items walked incrementally: one division per K slice instead of three per item
       int cc = item0, kh = 0, kw = 0;
-      if (!p.halo) {
-        const int tap0 = item0 / p.chunks;
-        cc = item0 - tap0 * p.chunks;
+      if (!p.halo && item0 != 0) {  // (only split-K slices start inside the walk)
+        const int tap0 = item0 / agroups;
+        cc = item0 - tap0 * agroups;
         kh = tap0 / p.ksize;
         kw = tap0 - kh * p.ksize;
       }
       for (int ai = item0; ai < item1; ++ai) {
+        if (lane == 0 && ai == item0 && work == bid) STAMP(13);
         mbar_wait(aempty0 + 8 * as, aph ^ 1u);
+        if (lane == 0 && ai == item0 && work == bid) STAMP(14);
         if (elect_one()) {
           const uint32_t sa = smem_a + as * p.a_stage_bytes;
           const uint32_t bar = afull0 + 8 * as;
           mbar_arrive_expect_tx(bar, p.a_tx_bytes);
+          if (ai == item0 && work == bid) STAMP(15);
           if (p.halo) {
             tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
+          } else if (p.a_flat) {
+            // 1x1, stride 1, the tile is 128 consecutive pixels: `ag` chunks x both planes in one box
+            tma_load_4d(sa, &maps.a[0], bar, 0, (i0 * p.Ho + h0) * p.Wo + w0, 0, cc * p.ag);
           } else {
             if (p.stride == 1) {
               tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 + kw - p.pad, h0 + kh - p.pad, i0, 0);
@@ -1150,7 +1302,8 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
         __syncwarp();
         if (lane == 0 && ai == item0) STAMP(2);
         if (lane == 0 && ai == item0) STAMP_T(0, (work - bid) / nblk);
-        if (++cc == p.chunks && !p.halo) {
+        if (lane == 0 && work == bid) STAMP_T(11, ai - item0);
+        if (++cc == agroups && !p.halo) {
           cc = 0;
           if (++kw == p.ksize) {
             kw = 0;
@@ -1175,29 +1328,46 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       decode_work(p, work, tile, ks);
       const int item0 = (int)fdiv((uint32_t)(ks * a_items), p.dks), item1 = (int)fdiv((uint32_t)((ks + 1) * a_items), p.dks);
       const int nt = tile - (int)fdiv((uint32_t)tile, p.dn) * p.tiles_n;
-      int cc = item0, tap0 = 0;
-      if (!p.halo) {
-        tap0 = item0 / p.chunks;
-        cc = item0 - tap0 * p.chunks;
+      // weight boxes of this work unit, in the order the MMA warp consumes them.  maps.b is {64, cout, plane, tap, chunk}.
+      // HALO: per chunk, taps in boxes of bg.  TAP: per tap, chunks in boxes of bg (the last box of a tap may reach past
+      // the last chunk: TMA zero-fills it and still counts the whole box).
+      int o0, o1, i_first, i_last;  // outer range [o0, o1], first inner of o0, last inner (exclusive) of o1
+#ifdef RSIS_DEBUG_TIMING
+      int nbox = 0;
+#endif
+      const int inner = p.halo ? p.taps : p.chunks;
+      if (p.halo) {
+        o0 = item0; o1 = item1 - 1; i_first = 0; i_last = inner;
+      } else {
+        if (p.ksplit == 1) {  // the whole walk
+          o0 = 0; i_first = 0; o1 = p.taps - 1; i_last = inner;
+        } else {
+          o0 = item0 / agroups; i_first = (item0 - o0 * agroups) * p.ag;
+          const int last = item1 - 1;
+          o1 = last / agroups;
+          i_last = (last - o1 * agroups + 1) * p.ag;
+          if (i_last > inner) i_last = inner;
+        }
       }
-      for (int ai = item0; ai < item1; ++ai) {
-        for (int bi = 0; bi < b_per_a; ++bi) {
-          const int tap = tap0 + bi;
+      for (int o = o0; o <= o1; ++o) {
+        const int ib = o == o0 ? i_first : 0, ie = o == o1 ? i_last : inner;
+        for (int i = ib; i < ie; i += p.bg) {
           mbar_wait(bempty0 + 8 * bs, bph ^ 1u);
           if (elect_one()) {
             const uint32_t bar = bfull0 + 8 * bs;
             mbar_arrive_expect_tx(bar, p.b_tx_bytes);
-            tma_load_3d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, (tap * p.chunks + cc) * kBK, nt * p.BN, 0);
+            if (p.b_map3d)  // bg == 1: the plain {k, cout, plane} view
+              tma_load_3d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, ((p.halo ? i : o) * p.chunks + (p.halo ? o : i)) * kBK,
+                          nt * p.BN, 0);
+            else
+              tma_load_5d(smem_b + bs * p.b_stage_bytes, &maps.b, bar, 0, nt * p.BN, 0, p.halo ? i : o, p.halo ? o : i);
           }
           __syncwarp();
+          if (lane == 0 && work == bid) STAMP_T(10, nbox++);
           if (++bs == p.b_stages) {
             bs = 0;
             bph ^= 1u;
           }
-        }
-        if (++cc == p.chunks && !p.halo) {
-          cc = 0;
-          ++tap0;
         }
       }
     }
@@ -1217,9 +1387,14 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
+      const uint32_t a_chunk16 = (uint32_t)p.a_chunk_bytes >> 4, b_chunk16 = (uint32_t)p.b_chunk_bytes >> 4;
+      const int bg = p.bg, ag = p.ag;
       const uint32_t a_plane16 = (uint32_t)p.a_plane_bytes >> 4, b_plane16 = (uint32_t)(p.BN * 128) >> 4;
       const bool stacked = p.stacked != 0, halo = p.halo != 0, resident = p.b_resident != 0, single = p.single != 0;
-      const bool fast = halo && resident && p.chunks == 1 && p.taps == 9;
+      // (cells only: the unrolled form is ~5000 instructions, and the convolution kernels are already larger than the
+      // instruction cache likes -- every role of the CTA runs different code)
+      // Stacked weight planes only: the narrow levels this path exists for have BN <= 64.
+      const bool fast = CELL && halo && resident && p.chunks == 1 && p.taps == 9 && stacked && !single;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int acc = 0;
@@ -1233,85 +1408,90 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
         tc_fence_after();
         const uint32_t d = tmem_base + acc * kStageCols;
         uint32_t accumulate = 0;
-        int cc = halo ? item0 : item0 % p.chunks;
+        int cc = (halo || item0 == 0) ? item0 : item0 % agroups;  // HALO: the item's chunk; TAP: its chunk group within the tap
+        int bgi = 0, b_sub = 0;                   // weight box of this work unit (= its slot when resident), K block inside it
         for (int ai = item0; ai < item1; ++ai) {
-          const int ksteps = (cc == p.chunks - 1) ? p.last_ksteps : kBK / 16;
-          if (++cc == p.chunks) cc = 0;  // (only read above: the chunk of the NEXT item)
+          const int chunk0 = halo ? cc : cc * ag;
+          const int n_in = halo ? p.taps : (p.chunks - chunk0 < ag ? p.chunks - chunk0 : ag);  // K blocks of this item
+          int ksteps = (chunk0 == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+          if (++cc == agroups) cc = 0;  // (only read above: the NEXT item)
           mbar_wait(afull0 + 8 * as, aph);
           tc_fence_after();
           if (ai == item0) STAMP(4);
           if (ai == item0) STAMP_T(1, (work - bid) / nblk);
+          if (first_work) STAMP_T(8, ai - item0);
           const uint64_t a_hi0 = adesc0 + (uint64_t)((uint32_t)as * a_stage16);
           const uint64_t a_lo0 = a_hi0 + (uint64_t)a_plane16;
-          if (fast) {
+          if (CELL && fast) {
             const bool wb = first_work;  // the nine taps are loaded once, for this CTA's first tile
 #define RSIS_ISSUE_HALO(PASSES)                                                                                          \
   switch (ksteps) {                                                                                                      \
-    case 1: issue_halo_resident<1, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
-    case 2: issue_halo_resident<2, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
-    case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
-    default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_plane16, idesc, accumulate, wb, bfull0); break; \
+    case 1: issue_halo_resident<1, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
+    case 2: issue_halo_resident<2, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
+    case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
+    default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
   }
-            if (single) {
-              RSIS_ISSUE_HALO(1)
-            } else if (stacked) {
-              RSIS_ISSUE_HALO(2)
-            } else {
-              RSIS_ISSUE_HALO(3)
-            }
+            RSIS_ISSUE_HALO(2)
 #undef RSIS_ISSUE_HALO
             accumulate = 1u;
+          } else if (!SPLIT && halo && bg == 3 && !resident && !single && ksteps == kBK / 16) {
+            if (stacked)
+              issue_halo_stream3<2>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, accumulate, bfull0,
+                                    bempty0, bs, bph, p.b_stages);
+            else
+              issue_halo_stream3<3>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, accumulate, bfull0,
+                                    bempty0, bs, bph, p.b_stages);
+            bgi += 3;
+            accumulate = 1u;
           } else {
-            for (int bi = 0; bi < b_per_a; ++bi) {
-              if (resident) {
-                bs = (ai - item0) * b_per_a + bi;  // slot = item index; its barrier completed phase 0 once and for all
-                bph = 0;
-              }
-              if (!(resident && !first_work)) {
-                mbar_wait(bfull0 + 8 * bs, bph);
-                tc_fence_after();
+            for (int bi = 0; bi < n_in; ++bi) {
+              if (!halo && bi > 0) ksteps = (chunk0 + bi == p.chunks - 1) ? p.last_ksteps : kBK / 16;
+              if (b_sub == 0) {  // first K block of a weight box
+                if (resident) {
+                  bs = bgi;  // slot = box index; its barrier completed phase 0 once and for all
+                  bph = 0;
+                }
+                if (!(resident && !first_work)) {
+                  mbar_wait(bfull0 + 8 * bs, bph);
+                  tc_fence_after();
+                }
+                if (first_work) STAMP_T(9, bgi);
               }
               if (ai == item0 && bi == 0) STAMP(5);
-              // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 descriptor units per row)
-              const uint64_t toff = halo ? (uint64_t)((uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u) : 0ull;
+              // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 descriptor units per row);
+              // TAP: chunk bi of the activation box
+              const uint64_t toff = halo ? (uint64_t)((uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u)
+                                         : (uint64_t)((uint32_t)bi * a_chunk16);
               const uint64_t a_hi = a_hi0 + toff, a_lo = a_lo0 + toff;
-              const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16);
-              const uint64_t b_lo = b_hi + (uint64_t)b_plane16;
-              if (single) {
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                  if (k < ksteps) {
-                    umma_bf16(d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, accumulate);
-                    accumulate = 1u;
-                  }
-                }
-              } else if (stacked) {
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                  if (k < ksteps) {
-                    const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K inside the swizzle row
-                    umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
-                    umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
-                    accumulate = 1u;
-                  }
-                }
+              const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16 + (uint32_t)b_sub * b_chunk16);
+              // the common full block (four K steps, split operands) straight-line with compile-time descriptor offsets;
+              // partial last chunks and the single-pass bf16 mode take a compact loop (code size: see above)
+              if (ksteps == kBK / 16 && !single) {
+                if (stacked)
+                  issue_kblock<kBK / 16, 2>(d, a_hi, a_lo, b_hi, b_plane16, idesc, accumulate);
+                else
+                  issue_kblock<kBK / 16, 3>(d, a_hi, a_lo, b_hi, b_plane16, idesc, accumulate);
               } else {
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                  if (k < ksteps) {
-                    const uint64_t adv = (uint64_t)(2 * k);
-                    umma_bf16(d, a_hi + adv, b_hi + adv, idesc, accumulate);
-                    umma_bf16(d, a_hi + adv, b_lo + adv, idesc, 1u);
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint64_t adv = (uint64_t)(2 * k);
+                  umma_bf16(d, a_hi + adv, b_hi + adv, idesc, k == 0 ? accumulate : 1u);
+                  if (!single) {
+                    if (!stacked) umma_bf16(d, a_hi + adv, b_hi + b_plane16 + adv, idesc, 1u);
                     umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
-                    accumulate = 1u;
                   }
                 }
               }
-              if (!resident) {
-                umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
-                if (++bs == p.b_stages) {
-                  bs = 0;
-                  bph ^= 1u;
+              accumulate = 1u;
+              // last K block of the weight box: boxes end with the tap (TAP) / the chunk (HALO)
+              if (++b_sub == bg || (halo ? bi == n_in - 1 : chunk0 + bi == p.chunks - 1)) {
+                b_sub = 0;
+                ++bgi;
+                if (!resident) {
+                  umma_commit(bempty0 + 8 * bs);  // weight slot free once these MMAs have read it
+                  if (++bs == p.b_stages) {
+                    bs = 0;
+                    bph ^= 1u;
+                  }
                 }
               }
             }
@@ -1339,12 +1519,9 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       cell_rows_epilogue(p, tmem_base, tfull0, tempty0, smem_p, pfull0, pempty0, warp, lane, bid, nblk);
     } else if constexpr (PW != 0) {
       epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
-    } else {
-      if (p.pw == 32)
-        epilogue_role<CELL, 32, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
-      else
-        epilogue_role<CELL, 16, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
     }
+    // PW == 0 (grouped launch): row-wise epilogue only -- convlstm_cell_group_umma refuses to run without it, and
+    // leaving the two staged-transpose variants out keeps ~4000 instructions out of the kernel
   }
 
   tc_fence_before();
@@ -1730,6 +1907,8 @@ int g_pre_tma = 0;         // RSIS_B200_PRE_TMA=1: the hoisted gate share of a t
 int g_cell_rows = 1;       // RSIS_B200_CELL_ROWS=0: the staged-transpose cell epilogue instead of the row-wise one (A/B timing)
 int g_mma_model = 1;       // RSIS_B200_MMA_MODEL=0: planner assumes 70 ns per MMA whatever its N (round-1 model)
 int g_b_resident = 1;      // RSIS_B200_BRES=0 disables weight residency (debug / A-B timing)
+int g_bmap3d = 1;          // RSIS_B200_BMAP3D=0: the 5-D weight view even for single-block boxes (A/B timing)
+int g_box_group = 1;       // RSIS_B200_BOXGROUP=0: one (tap, chunk) K block per TMA box, as in round 1 (A/B timing)
 std::once_flag g_once;
 
 constexpr int kSmemLimit = 227 * 1024;
@@ -1745,6 +1924,8 @@ void init_once() {
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_BOXGROUP")) g_box_group = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_BMAP3D")) g_bmap3d = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PDL")) g_pdl = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_MMA_MODEL")) g_mma_model = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_CELL_ROWS")) g_cell_rows = atoi(e) != 0;
@@ -1799,12 +1980,43 @@ int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
 }
 
-int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int k_pad, int BN, int planes = 2) {
+int encode_weight_map3(CUtensorMap* m, const void* w, int cout_pad, int k_pad, int BN, int planes) {
   cuuint64_t dims[3] = {(cuuint64_t)k_pad, (cuuint64_t)cout_pad, 2};
   cuuint64_t strides[2] = {(cuuint64_t)k_pad * 2, (cuuint64_t)cout_pad * k_pad * 2};
   cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, (cuuint32_t)planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
+}
+
+// Packed weights [2 planes][cout_pad][tap][chunk][64] as the 5-D view {64, cout, plane, tap, chunk}: a box
+// {64, BN, planes, box_taps, box_chunks} lands as [chunk][tap][plane][BN rows][128 bytes], i.e. as consecutive
+// (tap, chunk) K blocks of the [W_hi | W_lo] stage layout -- several K blocks per TMA instruction.
+// 4-D flat-pixel view {64, pixels, plane, chunk} of a split-bf16 NHWC activation whose channel count is a multiple of
+// 64: the 128-pixel tile of a 1x1 stride-1 convolution with `box_chunks` channel chunks in one box, landing as
+// [chunk][plane][128 rows][128 bytes].
+int encode_act_map_flat(CUtensorMap* m, const rsis_tensor& t, int box_chunks, int planes) {
+  const size_t P = pitch(t), npix = (size_t)t.n * t.h * t.w;
+  cuuint64_t dims[4] = {(cuuint64_t)kBK, npix, 2, (cuuint64_t)(t.c / kBK)};
+  cuuint64_t strides[3] = {P * 2, npix * P * 2, (cuuint64_t)kBK * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)kBM, (cuuint32_t)planes, (cuuint32_t)box_chunks};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.data, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
+}
+
+int encode_weight_map(CUtensorMap* m, const void* w, int cout_pad, int taps, int chunks, int BN, int planes, int box_taps,
+                      int box_chunks) {
+  const cuuint64_t k_pad = (cuuint64_t)taps * chunks * kBK;
+  cuuint64_t dims[5] = {(cuuint64_t)kBK, (cuuint64_t)cout_pad, 2, (cuuint64_t)taps, (cuuint64_t)chunks};
+  cuuint64_t strides[4] = {k_pad * 2, (cuuint64_t)cout_pad * k_pad * 2, (cuuint64_t)chunks * kBK * 2, (cuuint64_t)kBK * 2};
+  cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)BN, (cuuint32_t)planes, (cuuint32_t)box_taps, (cuuint32_t)box_chunks};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(w), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
@@ -1986,11 +2198,29 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   const int a_rows = p.halo ? kHaloRows : kBM;
   p.a_plane_bytes = a_rows * 128;
   const int planes = p.single ? 1 : 2;
-  p.a_tx_bytes = (uint32_t)(planes * p.a_plane_bytes);
-  p.a_stage_bytes = round_up(planes * p.a_plane_bytes, 1024);
+  p.a_chunk_bytes = round_up(planes * p.a_plane_bytes, 1024);
   p.a_sbo = p.halo ? (uint32_t)(kHaloBW + 2) * 128u : 1024u;
-  p.b_stage_bytes = planes * p.BN * 128;
-  p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
+  p.b_chunk_bytes = planes * p.BN * 128;
+  // K blocks per TMA box (see UmmaParams::ag).  Split-K slices cut the walk anywhere, so they keep one block per box.
+  p.ag = p.bg = 1;
+  p.a_flat = 0;
+  if (g_box_group && p.ksplit == 1) {
+    if (p.halo) {
+      p.bg = 3 * p.b_chunk_bytes <= 49152 ? 3 : 1;
+    } else {
+      // flat-pixel view: the pixel box is 128 consecutive pixels (full-width rows, whole images when it spans several)
+      const bool flat = w->kh == 1 && stride == 1 && pad == 0 && x.c % kBK == 0 && tBW == p.Wo &&
+                        (tBI == 1 || tBH == p.Ho) && (p.Ho % tBH == 0 || tBI > 1) && planes == 2;
+      if (flat) {
+        p.a_flat = 1;
+        p.ag = p.chunks >= 2 ? 2 : 1;
+      }
+      p.bg = 32768 / p.b_chunk_bytes;
+      if (p.bg < 1) p.bg = 1;
+      if (p.bg > p.chunks) p.bg = p.chunks;
+      if (p.bg > 4) p.bg = 4;
+    }
+  }
   p.pw = p.BN >= 64 ? 32 : 16;
   // pre_tma (cells with hoisted gates on the row-wise epilogue): two stages of BN/32 boxes of 16 KB take the place of
   // the transpose staging area, which that epilogue does not use
@@ -2000,35 +2230,62 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   // stage on the narrow levels, whose 46 KB halo boxes take ~2.5 us from issue to landing: profiles/r2l_group_stamps.txt)
   const bool rows_epi = is_cell && g_cell_rows && p.ksplit == 1;  // (a hoisted-gate CONVOLUTION also has gate-interleaved weights)
   const int budget = kDynSmem - 1023 - (p.pre_tma ? 2 * p.p_stage_bytes : (rows_epi ? 0 : kStageBytes));
-  if (p.halo) {
-    // a third activation stage when at least four weight stages still fit next to it: a halo box needs ~2.5 us from
-    // issue to landing, longer than the MMAs of one tile on the narrow levels
-    p.a_stages = (budget - 3 * p.a_stage_bytes) / p.b_stage_bytes >= 4 ? 3 : 2;
-    p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
-    if (p.b_stages > kMaxStages) {
-      p.b_stages = kMaxStages;
-      p.a_stages = (budget - p.b_stages * p.b_stage_bytes) / p.a_stage_bytes;
-      if (p.a_stages > 3) p.a_stages = 3;
-    }
-  } else {
-    p.a_stages = budget / (p.a_stage_bytes + p.b_stage_bytes);
-    if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
-    p.b_stages = p.a_stages;
-  }
   {
     // Weight residency: a persistent CTA that walks several pixel tiles of ONE output-channel tile re-reads the same
-    // taps x chunks weight boxes for every tile; when they all fit next to two activation stages, load them once.
+    // taps x chunks weight blocks for every tile; when they all fit next to two activation stages, load them once.
     const int items_b = p.taps * p.chunks;
     const bool many_tiles = p.num_tiles >= 2 * (cta_share > 0 ? cta_share : g_num_sms);
     if (g_b_resident && p.ksplit == 1 && p.tiles_n == 1 && many_tiles && items_b <= kMaxStages &&
-        2 * p.a_stage_bytes + items_b * p.b_stage_bytes <= budget) {
+        2 * p.ag * p.a_chunk_bytes + items_b * p.b_chunk_bytes <= budget) {
       p.b_resident = 1;
-      p.b_stages = items_b;
-      p.a_stages = (budget - items_b * p.b_stage_bytes) / p.a_stage_bytes;
-      if (p.a_stages > 4) p.a_stages = 4;
+      // the whole set in as few boxes as the walk allows: HALO all nine taps of a chunk, TAP all chunks of a tap
+      if (g_box_group) p.bg = p.halo ? p.taps : p.chunks;
     }
   }
+  for (;;) {
+    p.a_stage_bytes = p.ag * p.a_chunk_bytes;
+    p.b_stage_bytes = p.bg * p.b_chunk_bytes;
+    const int inner = p.halo ? p.taps : p.chunks, outer = p.halo ? p.chunks : p.taps;
+    if (p.b_resident) {
+      p.b_stages = outer * ceil_div(inner, p.bg);
+      p.a_stages = (budget - p.b_stages * p.b_stage_bytes) / p.a_stage_bytes;
+      if (p.a_stages > 4) p.a_stages = 4;
+    } else if (p.halo) {
+      // a third activation stage when enough weight stages still fit next to it: a halo box needs ~2.5 us from issue to
+      // landing, longer than the MMAs of one tile on the narrow levels
+      const int min_b = p.bg > 1 ? 2 : 4;
+      p.a_stages = (budget - 3 * p.a_stage_bytes) / p.b_stage_bytes >= min_b ? 3 : 2;
+      p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+      if (p.b_stages > kMaxStages) {
+        p.b_stages = kMaxStages;
+        p.a_stages = (budget - p.b_stages * p.b_stage_bytes) / p.a_stage_bytes;
+        if (p.a_stages > 3) p.a_stages = 3;
+      }
+    } else if (p.ag > 1 || p.bg > 1) {
+      // grouped TAP boxes: two (64 KB) or three activation stages, the rest of the budget for weight stages
+      p.a_stages = p.ag > 1 ? 2 : 3;
+      p.b_stages = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+      if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
+    } else {
+      p.a_stages = budget / (p.a_stage_bytes + p.b_stage_bytes);
+      if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
+      p.b_stages = p.a_stages;
+    }
+    if (p.a_stages >= 2 && p.b_stages >= 2) break;
+    if (p.b_resident && p.a_stages >= 2) break;
+    // does not fit: smaller boxes
+    if (p.bg > 1 && !p.b_resident) p.bg = p.halo ? (p.bg == 9 ? 3 : 1) : p.bg / 2;
+    else if (p.ag > 1) p.ag = 1;
+    else if (p.b_resident) { p.b_resident = 0; p.bg = 1; }
+    else break;
+  }
+  p.agroups = p.halo ? 1 : ceil_div(p.chunks, p.ag);
+  p.a_tx_bytes = (uint32_t)(p.ag * planes * p.a_plane_bytes);
+  p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
+  if (g_print_plan)
+    fprintf(stderr, "rsis stages: ag=%d bg=%d flat=%d a_stages=%d x %d B, b_stages=%d x %d B, resident=%d\n", p.ag, p.bg,
+            p.a_flat, p.a_stages, p.a_stage_bytes, p.b_stages, p.b_stage_bytes, p.b_resident);
   if (p.pre_tma) {
     // [N][Ho][Wo][Cout] float32 as {Cout, Wo, Ho, N}; box {32, BW, BH, BI} = the pixel tile, rows in TMEM lane order
     cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
@@ -2045,8 +2302,16 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.cell_rows = g_cell_rows;
   const int cout_pad = round_up(w->cout, 16);
   const int k_pad = p.taps * p.chunks * kBK;
-  if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, k_pad, p.BN, planes)) return e;
-  if (stride == 1) {
+  p.b_map3d = (p.bg == 1 && g_bmap3d) ? 1 : 0;
+  if (p.b_map3d) {
+    if (int e = encode_weight_map3(&maps.b, w->w_umma, cout_pad, k_pad, p.BN, planes)) return e;
+  } else if (int e = encode_weight_map(&maps.b, w->w_umma, cout_pad, p.taps, p.chunks, p.BN, planes, p.halo ? p.bg : 1,
+                                       p.halo ? 1 : p.bg)) {
+    return e;
+  }
+  if (p.a_flat) {
+    if (int e = encode_act_map_flat(&maps.a[0], x, p.ag, planes)) return e;
+  } else if (stride == 1) {
     if (p.halo) {
       if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes)) return e;
     } else {
@@ -2607,6 +2872,7 @@ bool convlstm_cell_group_supported(const rsis_cell_args* cells, int n) {
 int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st) {
   std::call_once(g_once, init_once);
   if (g_init_status != RSIS_OK) return g_init_status;
+  if (!g_cell_rows) return RSIS_ERR_UNSUPPORTED;  // the grouped kernel carries the row-wise epilogue only
   static_assert(sizeof(CellGroup) < 32000, "kernel parameter space");
   CellGroup g{};
   g.n = n;

@@ -28,7 +28,15 @@ for name, Cin, H, W, Cout, k, has_res in CASES:
     res = ops.act_from_nchw(torch.rand((B, Cout, H, W), device="cuda"), ops.FMT_SPLIT_BF16) if has_res else None
     ts = []
     for it in range(a.iters):
-        flush.fill_(it)
+        mode = os.environ.get("CACHE", "cold")  # cold | insitu (activations in L2, weights from HBM) | warm | wwarm (weights only)
+        if mode != "warm":
+            flush.fill_(it)
+        if mode == "insitu":
+            _ = x.t.view(torch.int16).sum()
+            if res is not None:
+                _ = res.t.view(torch.int16).sum()
+        if mode == "wwarm":
+            _ = pc.w_umma.view(torch.int16).sum() if hasattr(pc, "w_umma") and pc.w_umma is not None else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.conv2d([x], pc, pad=k // 2, relu=True, residual=res, impl=ops.IMPL_TCGEN05, out=y)
