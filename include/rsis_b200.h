@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 19
+#define RSIS_ABI_VERSION 20
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -91,6 +91,15 @@ typedef struct rsis_conv_weights {
 enum { RSIS_PRECISION_SPLIT_BF16 = 0, RSIS_PRECISION_BF16 = 1 };
 int rsis_set_precision(int mode);
 int rsis_get_precision(void);
+
+/* Static-weights mode of the tcgen05 convolution family (process-wide; read when a launch is set up, so a captured CUDA
+ * graph keeps the mode it was captured in).  on != 0 promises that no kernel enqueued on the launch's stream right
+ * before a convolution / cell writes that launch's PACKED WEIGHTS (true for inference: the packs of the reference's
+ * nn.Conv2d / BatchNorm2d parameters, model.py:43-54, clstm.py:17, are built once per load_state_dict).  The kernels then
+ * start streaming weights into shared memory while the previous kernel of the stream is still running (programmatic
+ * dependent launch: only activation reads wait for it).  Off (default) for training steps, which re-pack in-stream.
+ * Returns the previous setting. */
+int rsis_set_static_weights(int on);
 
 /* ---- library -------------------------------------------------------------------------------------------- */
 int rsis_abi_version(void);

@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 
 class Tensor(C.Structure):
@@ -97,6 +97,7 @@ SIGNATURES = {
     "rsis_hungarian_match": (_I, [_P, C.c_int64, C.c_int64, C.c_int64, _I, _I, _I, _P, _I, _P, _P]),
     "rsis_set_precision": (_I, [_I]),
     "rsis_get_precision": (_I, []),
+    "rsis_set_static_weights": (_I, [_I]),
     "rsis_convlstm_cell_group_max": (_I, []),
     "rsis_convlstm_cell_group": (_I, [C.POINTER(CellArgs), _I, _P]),
     "rsis_upsample_bilinear_group": (_I, [_TP, _TP, _I, _P]),

@@ -105,6 +105,10 @@ struct UmmaParams {
   int ag;                  // 64-channel chunks per activation box (flat-pixel 1x1 convolutions: up to 2); otherwise 1
   int bg;                  // K blocks per weight box: HALO -> taps of one chunk (1 / 3 / 9), TAP -> chunks of one tap
   int a_flat;              // 1: maps.a[0] is the 4-D flat-pixel view {64, pixels, plane, chunk} of a 1x1 stride-1 input
+  int early_b;             // 1: the weight producer does not wait for the previous kernel of the stream (static weights)
+  int a_sw64;              // 1: HALO boxes of 32 channels in SWIZZLE_64B rows of 64 bytes (sources of <= 32 channels: the TMA
+                           //    unit spends ~1.6 ns per box ROW and twice that on rows that are mostly zero fill --
+                           //    scripts/halo_probe.cu, profiles/r2ba_halo_probe.txt: 1217 -> 564 ns per 24-channel halo box)
   int b_map3d;             // 1: maps.b is the 3-D view {k, cout, plane} (one K block per box)
   int agroups;             // activation boxes per tap: HALO 1 (the walk is chunk-major), TAP ceil(chunks / ag)
   uint32_t a_tx_bytes, b_tx_bytes;
@@ -142,6 +146,9 @@ struct UmmaParams {
                            //    and multiplied -- one MMA of N = BN per K step instead of 2 (stacked) or 3
   int pre_tma;             // 1: the hoisted gate share of a tile is staged in shared memory by TMA (two stages)
   int p_stage_bytes;       // BN/32 boxes of 128 rows x 128 bytes
+#ifdef RSIS_DEBUG_TIMING
+  unsigned long long* trace;  // per-launch trace row (24 x u64) of rsis_debug_trace, or nullptr
+#endif
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -268,13 +275,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row core matrices `sbo` bytes apart.
 // The swizzle XOR acts on absolute smem address bits, so a start address shifted by whole rows (HALO taps) or by
 // 32 bytes (K step inside the row) addresses the same TMA-written tile.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo, uint32_t layout = 2u) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units
   d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major; canonical 1)
   d |= (uint64_t)(sbo >> 4) << 32;             // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  d |= (uint64_t)layout << 61;                 // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (rows of 64 bytes, 512-byte atoms)
   return d;
 }
 
@@ -569,6 +576,31 @@ __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
     // hundreds of nanoseconds and visibly stretched the roles it was stamping; readers divide by the SM clock
     const unsigned long long t = (unsigned long long)clock64();
     reinterpret_cast<unsigned long long*>(p.counters)[256 + slot] = t;
+  }
+  // per-launch trace (rsis_debug_trace): block 0's first sixteen stamps go to the launch's own row, so that launches
+  // overlapping under programmatic dependent launch do not overwrite each other
+  if (blockIdx.x == 0 && p.trace && slot < 16) p.trace[2 + slot] = (unsigned long long)clock64();
+}
+__device__ __forceinline__ void trace_begin(const UmmaParams& p) {
+  if (threadIdx.x == 0 && p.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.trace + 0, ~t);  // earliest CTA start, inverted
+    if (blockIdx.x == 0) {
+      p.trace[18] = t;
+      p.trace[19] = (unsigned long long)clock64();
+    }
+  }
+}
+__device__ __forceinline__ void trace_end(const UmmaParams& p) {
+  if (threadIdx.x == 0 && p.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.trace + 1, t);  // latest CTA end
+    if (blockIdx.x == 0) {
+      p.trace[20] = t;
+      p.trace[21] = (unsigned long long)clock64();
+    }
   }
 }
 #define STAMP(slot) stamp(p, slot)
@@ -873,7 +905,8 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
 // issue back to back from uniform registers (the generic loop spends ~50 dependent instructions per tap in one thread,
 // which at 4 MMAs of 48 cycles per tap is slower than the tensor pipe: profiles/r2i_group_stamps.txt).
 // tap (kh, kw) = the activation tile shifted by kh*10 + kw rows of 128 bytes = (kh*10 + kw) * 8 descriptor units.
-template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
+template <int KS, int PASSES, int ROW16 = 8>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products;
+                                              // ROW16: bytes / 16 of an activation row (8: SWIZZLE_128B, 4: SWIZZLE_64B)
 __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
                                                     uint32_t b_stage16, uint32_t b_plane16, uint32_t idesc,
                                                     uint32_t accumulate, bool wait_b, uint32_t bfull0, int bg) {
@@ -884,7 +917,7 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
       mbar_wait_lean(bfull0 + 8 * (bg == 1 ? bi : bi / bg), 0);
       tc_fence_after();
     }
-    const uint64_t toff = (uint64_t)(((bi / 3) * (kHaloBW + 2) + (bi % 3)) * 8);
+    const uint64_t toff = (uint64_t)(((bi / 3) * (kHaloBW + 2) + (bi % 3)) * ROW16);
     const uint64_t b = bdesc0 + (uint64_t)((uint32_t)bi * b_stage16);
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
@@ -1218,11 +1251,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; from here on
-  // we read what it produced.  Our own dependents may start their prologue right away.
+  // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail, and our own
+  // dependents may start their prologue right away.  Each role waits for the previous kernel (griddepcontrol.wait) right
+  // before ITS first access to anything that kernel may have produced -- not here: the launch's CTAs are typically
+  // resident ~10 us before the previous grid ends (in-situ trace, profiles/r2be_pass_trace.txt), and the first tile's
+  // decode (cold parameter / instruction fetches, ~2 us), and with static weights the first weight boxes, fit in there.
+  // The MMA issuer reads shared / tensor memory only and never waits.
   pdl_trigger();
-  pdl_wait();
-  if (threadIdx.x == 0) STAMP(1);
 
   // The K loop walks (tap, chunk) K blocks: HALO chunk-major (an activation box = one chunk's halo tile, nine taps),
   // TAP tap-major (an activation box = `ag` chunks of one tap).  A "items" per tile: HALO -> one per chunk; TAP -> one per
@@ -1250,6 +1285,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       const int tw = tc.tw, th = tc.th, ti = tc.ti;
       const int w0 = tw * p.BW, h0 = th * p.BH, i0 = ti * p.BI;
       if (lane == 0 && work == bid) STAMP_T(5, 2);
+      if (work == bid) pdl_wait();  // first activation read of this CTA
       if (CELL && p.pre_tma) {
         // the tile's share of the hoisted gates: BN/32 boxes {32 columns, BW, BH, BI} -> [128 rows][128 bytes] each
         mbar_wait(pempty0 + 8 * ps, pph ^ 1u);
@@ -1322,6 +1358,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     // Its own warp, so that activation tiles run a_stages items ahead no matter how far the weight ring is.
     int bs = 0;
     uint32_t bph = 0;
+    if (!p.early_b) pdl_wait();  // (static weights: nothing the previous kernel wrote is read here)
     for (int work = bid; work < num_work; work += nblk) {
       if (p.b_resident && work != bid) break;  // resident weights: loaded for the first tile only
       int tile, ks;
@@ -1382,8 +1419,9 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     // every dependent instruction between two UTCHMMAs delays the tensor pipe: resident HALO weights (the narrow,
     // many-tile decoder levels) take the unrolled straight-line form of issue_halo_resident.
     if (elect_one()) {
-      const uint64_t adesc0 = make_smem_desc(smem_a, p.a_sbo);
+      const uint64_t adesc0 = make_smem_desc(smem_a, p.a_sbo, p.a_sw64 ? 4u : 2u);
       const uint64_t bdesc0 = make_smem_desc(smem_b, 1024);
+      const uint32_t a_row16 = p.a_sw64 ? 4u : 8u;  // descriptor units per activation row (HALO tap shifts)
       const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
@@ -1431,7 +1469,14 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
     default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
   }
-            RSIS_ISSUE_HALO(2)
+            if (p.a_sw64) {  // <= 32 channels: one or two K steps
+              if (ksteps == 1)
+                issue_halo_resident<1, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
+              else
+                issue_halo_resident<2, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
+            } else {
+              RSIS_ISSUE_HALO(2)
+            }
 #undef RSIS_ISSUE_HALO
             accumulate = 1u;
           } else if (!SPLIT && halo && bg == 3 && !resident && !single && ksteps == kBK / 16) {
@@ -1460,7 +1505,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
               if (ai == item0 && bi == 0) STAMP(5);
               // HALO: tap (kh, kw) = the tile shifted by kh*10 + kw rows of 128 bytes (8 descriptor units per row);
               // TAP: chunk bi of the activation box
-              const uint64_t toff = halo ? (uint64_t)((uint32_t)(bi + 7 * ((bi * 11) >> 5)) * 8u)
+              const uint64_t toff = halo ? (uint64_t)((uint32_t)(bi + 7 * ((bi * 11) >> 5)) * a_row16)
                                          : (uint64_t)((uint32_t)bi * a_chunk16);
               const uint64_t a_hi = a_hi0 + toff, a_lo = a_lo0 + toff;
               const uint64_t b_hi = bdesc0 + (uint64_t)((uint32_t)bs * b_stage16 + (uint32_t)b_sub * b_chunk16);
@@ -1515,6 +1560,8 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   } else if (warp < kEpiWarps) {
     // =============================== epilogue (warps 0-7) ===============================
     float* stage = stage_base + warp * kStageFloats;
+    pdl_wait();  // the epilogues prefetch residual / state operands right away
+    if (threadIdx.x == 0) STAMP(1);
     if (CELL && !SPLIT && p.cell_rows) {
       cell_rows_epilogue(p, tmem_base, tfull0, tempty0, smem_p, pfull0, pempty0, warp, lane, bid, nblk);
     } else if constexpr (PW != 0) {
@@ -1538,7 +1585,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
 template <bool CELL, int PW, bool SPLIT>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
 conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
+#ifdef RSIS_DEBUG_TIMING
+  trace_begin(p);
+#endif
   umma_cta<CELL, PW, SPLIT>(maps, p, (int)blockIdx.x, (int)gridDim.x);
+#ifdef RSIS_DEBUG_TIMING
+  trace_end(p);
+#endif
 }
 
 // Grouped launch: up to kMaxGroup independent ConvLSTM cells (different decoder levels, different time-steps: the
@@ -1559,8 +1612,12 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) cell_group_kernel(const __gri
 #pragma unroll
   for (int k = 1; k < kMaxGroup; ++k)
     if (k < g.n && (int)blockIdx.x >= g.first[k]) i = k;
+#ifdef RSIS_DEBUG_TIMING
+  trace_begin(g.p[0]);
+#endif
   umma_cta<true, 0, false>(g.maps[i], g.p[i], (int)blockIdx.x - g.first[i], g.first[i + 1] - g.first[i]);
 #ifdef RSIS_DEBUG_TIMING
+  trace_end(g.p[0]);
   // per-cell end time (max over its CTAs) and launch start (min over all CTAs): slots 200 + i and 199 of the stamp table
   if (threadIdx.x == 0 && g.p[0].counters) {
     unsigned long long t;
@@ -1895,12 +1952,19 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
+int g_early_b = 1;         // RSIS_B200_EARLY_B=0: weight boxes wait for the previous kernel even with static weights (A-B timing)
+int g_sw64 = 1;            // RSIS_B200_SW64=0: 64-channel SWIZZLE_128B halo boxes for narrow sources too (A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
+#ifdef RSIS_DEBUG_TIMING
+unsigned long long* g_trace = nullptr;  // rsis_debug_trace: rows of 24 x u64, one per tcgen05 launch set up
+int g_trace_rows = 0, g_trace_next = 0;
+#endif
 unsigned* g_debug_counters = nullptr;  // set by the last non-swapped setup when RSIS_B200_DEBUG_TIMING is on
 int g_swap = 1;            // RSIS_B200_SWAP=0 disables the swapped-operand cell kernel for the narrow levels
 int g_print_plan = 0;      // RSIS_B200_PRINT_PLAN=1 logs the tile plan of every launch to stderr
 int g_pdl = 1;             // RSIS_B200_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
+int g_static_weights = 0;  // rsis_set_static_weights: weight boxes may be issued before griddepcontrol.wait
 int g_precision = 0;       // rsis_set_precision: 0 = split bf16 (fp32-grade products), 1 = single-pass bf16 operands
 int g_pre_tma = 0;         // RSIS_B200_PRE_TMA=1: the hoisted gate share of a tile is staged in shared memory by TMA (no measured
                            // gain at B=8, and its two stages cost the third activation stage: off by default)
@@ -1921,6 +1985,8 @@ cudaError_t set_smem_attr() {
 
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_SW64")) g_sw64 = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_EARLY_B")) g_early_b = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("RSIS_B200_BRES")) g_b_resident = atoi(e) != 0;
@@ -1967,16 +2033,17 @@ int next_pow2(int v) {
 // 5-D view {C, W', H', N, plane} of a split-bf16 NHWC activation with pixel pitch `cs` elements
 // (sub = 2: one parity sub-grid of a stride-2 conv).
 int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw, int BW, int BH, int BI,
-                   int planes = 2) {
+                   int planes = 2, int box_c = kBK) {
   const size_t C = t.c, W = t.w, H = t.h, N = t.n, P = pitch(t);
   char* base = reinterpret_cast<char*>(t.data) + ((size_t)ph * W + pw) * P * 2;
   cuuint64_t dims[5] = {C, W / sub, H / sub, N, 2};
   cuuint64_t strides[4] = {P * 2 * sub, W * P * 2 * sub, H * W * P * 2, N * H * W * P * 2};
-  cuuint32_t box[5] = {(cuuint32_t)kBK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, (cuuint32_t)planes};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, (cuuint32_t)planes};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // box_c = 32: rows of 64 bytes, SWIZZLE_64B (UmmaParams::a_sw64)
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == kBK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
 }
 
@@ -2160,6 +2227,15 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   if (mt_tap > 0x3fffffLL || mt_halo > 0x3fffffLL) return RSIS_ERR_UNSUPPORTED;
   const bool can_split = workspace != nullptr && workspace_bytes >= kWorkspaceBytes && aligned16(workspace);
   p.single = g_precision == 1 ? 1 : 0;
+  p.early_b = (g_static_weights && g_early_b) ? 1 : 0;
+#ifdef RSIS_DEBUG_TIMING
+  p.trace = nullptr;
+  if (g_trace && g_trace_next < g_trace_rows) {
+    fprintf(stderr, "rsis trace %d: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s\n", g_trace_next, x.n, x.h, x.w, x.c, w->cout, w->kh,
+            stride, is_cell ? " cell" : "");
+    p.trace = g_trace + (size_t)24 * g_trace_next++;
+  }
+#endif
   const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
                               w->gate_interleaved != 0, cta_share, p.single != 0);
   if (g_print_plan)
@@ -2196,10 +2272,12 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     p.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
   }
   const int a_rows = p.halo ? kHaloRows : kBM;
-  p.a_plane_bytes = a_rows * 128;
+  p.a_sw64 = (g_sw64 && p.halo && x.c <= 32 && p.ksplit == 1) ? 1 : 0;
+  const int a_row_bytes = p.a_sw64 ? 64 : 128;
+  p.a_plane_bytes = a_rows * a_row_bytes;
   const int planes = p.single ? 1 : 2;
   p.a_chunk_bytes = round_up(planes * p.a_plane_bytes, 1024);
-  p.a_sbo = p.halo ? (uint32_t)(kHaloBW + 2) * 128u : 1024u;
+  p.a_sbo = p.halo ? (uint32_t)((kHaloBW + 2) * a_row_bytes) : 1024u;
   p.b_chunk_bytes = planes * p.BN * 128;
   // K blocks per TMA box (see UmmaParams::ag).  Split-K slices cut the walk anywhere, so they keep one block per box.
   p.ag = p.bg = 1;
@@ -2313,7 +2391,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     if (int e = encode_act_map_flat(&maps.a[0], x, p.ag, planes)) return e;
   } else if (stride == 1) {
     if (p.halo) {
-      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes)) return e;
+      if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes, p.a_sw64 ? 32 : kBK)) return e;
     } else {
       if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, p.BW, p.BH, p.BI, planes)) return e;
     }
@@ -2856,6 +2934,11 @@ int set_precision(int mode) {
   return prev;
 }
 int get_precision() { return g_precision; }
+int set_static_weights(int on) {
+  const int prev = g_static_weights;
+  g_static_weights = on != 0;
+  return prev;
+}
 
 // ---- grouped cells: the cells of one wavefront of the decoder in one launch ----------------------------------------
 int convlstm_cell_group_max() { return kMaxGroup; }
@@ -2968,3 +3051,14 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
 }
 
 }  // namespace rsis
+
+#ifdef RSIS_DEBUG_TIMING
+// Debug builds only (not part of the ABI): every tcgen05 launch set up from now on gets a trace row in `buf`
+// (rows x 24 x u64, zeroed by the caller): [0] ~(earliest CTA start), [1] latest CTA end (%globaltimer, ns),
+// [2..17] block 0's stamps 0..15 (SM cycles), [18] / [19] block 0's start as %globaltimer / cycles, [20] / [21] its end.
+extern "C" void rsis_debug_trace(void* buf, int rows) {
+  rsis::g_trace = reinterpret_cast<unsigned long long*>(buf);
+  rsis::g_trace_rows = rows;
+  rsis::g_trace_next = 0;
+}
+#endif

@@ -20,6 +20,7 @@ int convlstm_cell_umma(const rsis_tensor* srcs, int n_src, const rsis_conv_weigh
                        uint32_t* side_max, int side_stride, int side_offset, void* workspace, size_t workspace_bytes,
                        int cta_cap, cudaStream_t st);
 int set_precision(int mode);
+int set_static_weights(int on);
 int get_precision();
 int convlstm_cell_group_max();
 bool convlstm_cell_group_supported(const rsis_cell_args* cells, int n);
@@ -76,6 +77,7 @@ int rsis_set_precision(int mode) {
   return set_precision(mode);
 }
 int rsis_get_precision(void) { return get_precision(); }
+int rsis_set_static_weights(int on) { return set_static_weights(on); }
 
 int rsis_convlstm_cell_group_max(void) { return convlstm_cell_group_max(); }
 

@@ -140,7 +140,9 @@ class InferenceSession:
         torch.cuda.synchronize(device)
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        with torch.cuda.graph(g), torch.no_grad():
+        # the warm-up above built every weight pack, so inside the capture nothing re-packs: the convolutions may stream
+        # their weights while the previous kernel is still running (ops.static_weights)
+        with torch.cuda.graph(g), torch.no_grad(), ops.static_weights():
             run_eager(encoder, decoder, self.x, self.T, self.impl, self.masks, self.classes, self.stops, ws=self.ws)
         self.launches = ops.launch_count() - n0
         self.graph = g

@@ -10,6 +10,7 @@ layout the kernels use (NHWC) -- returning them is zero-copy.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -175,6 +176,8 @@ class DecoderWorkspace:
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
         self.h_last = None   # [2] float32 hidden state of the last level, double-buffered (run_wavefront)
+        self.h2 = None       # [level][2] float32 hidden states of the other levels, double-buffered (skewed wavefront)
+        self.up_stream = None
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
         self.side_stream = torch.cuda.Stream(device=device)  # forked work: skip heads, class/stop heads
         self.level_streams = None   # pipelined schedule (run_pipelined): one stream per level + the mask head's
@@ -402,25 +405,43 @@ class RSIS(nn.Module):
         C = class_probs.shape[-1]
         offs = [sum(ws.hidden[:l]) for l in range(nlev)]
         ev_mask = {}
-        for w in range(T + nlev - 1):
+        # RSIS_B200_WAVE_SKEW=2: cell (l, t) runs in wavefront 2*l + t instead of l + t.  The x2 upsampling of its hidden
+        # state then has a whole wavefront to itself: it runs on a side stream BESIDE the next grouped launch and is
+        # consumed by the one after, instead of sitting between two grouped launches on the critical path (13 gaps of
+        # 15-22 us per pass: profiles/r2be_pass_trace.txt).  T + 2*(nlev-1) grouped launches instead of T + nlev - 1;
+        # the float32 hidden states of levels 0..nlev-2 are double-buffered (cell (l, t+1) runs beside the upsampling
+        # of (l, t)).
+        skew = int(os.environ.get("RSIS_B200_WAVE_SKEW", "2"))
+        if skew == 2:
+            if ws.h2 is None:
+                ws.h2 = [[h, ops.Act.empty(h.n, h.h, h.w, h.c, ops.FMT_F32, dev)] for h in ws.h[:nlev - 1]]
+                ws.up_stream = torch.cuda.Stream(device=dev)
+            ev_up = {}
+        n_waves = T + skew * (nlev - 1)
+        for w in range(n_waves):
             cells, ups = [], []
             for l in range(nlev):
-                t = w - l
+                t = w - skew * l
                 if t < 0 or t >= T:
                     continue
                 p = t & 1
                 _, pc = ws.packs(self, l)
-                h_out = ws.h_last[p] if l == nlev - 1 else ws.h[l]
+                if l == nlev - 1:
+                    h_out = ws.h_last[p]
+                else:
+                    h_out = ws.h2[l][p] if skew == 2 else ws.h[l]
                 cells.append(dict(x=ws.X[l][p], pc=pc, c_prev=ws.c[l].t if t > 0 else None, side_max=ws.sides[t],
                                   side_offset=offs[l], h_out=h_out, c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p),
                                   gate_preact=ws.P[l]))
                 if l + 1 < nlev:
                     x_next = ws.X[l + 1][p]
-                    ups.append((ws.h[l], ws.up_view(l + 1, p)))
+                    ups.append((h_out, ws.up_view(l + 1, p)))
                     assert x_next.h == ws.up_view(l + 1, p).h
-            t_last = w - (nlev - 1)          # the step whose last level runs in this wavefront
+            t_last = w - skew * (nlev - 1)   # the step whose last level runs in this wavefront
             if t_last >= 2 and t_last < T:
                 main.wait_event(ev_mask[t_last - 2])   # its mask head read the buffer cell (4, t_last) overwrites
+            if skew == 2 and (w - 2) in ev_up:
+                main.wait_event(ev_up[w - 2])          # the upsamplings this wavefront's cells read
             ops.convlstm_cell_group(cells)
             if 0 <= t_last < T:
                 done = torch.cuda.Event()
@@ -437,8 +458,18 @@ class RSIS(nn.Module):
                     ops.class_stop_heads(ws.sides[t_last], self.fc_class.weight, self.fc_class.bias,
                                          self.fc_stop.weight, self.fc_stop.bias, class_probs[:, t_last], T * C, None,
                                          stop_prob[:, t_last], T)
-            if ups and w + 1 < T + nlev - 1:
+            if ups and skew == 2:
+                done_up = torch.cuda.Event()
+                done_up.record(main)
+                with torch.cuda.stream(ws.up_stream):
+                    ws.up_stream.wait_event(done_up)
+                    ops.upsample_bilinear_group(ups)
+                    ev_up[w] = torch.cuda.Event()
+                    ev_up[w].record(ws.up_stream)
+            elif ups and w + 1 < n_waves:
                 ops.upsample_bilinear_group(ups)
+        if skew == 2:
+            main.wait_stream(ws.up_stream)
         main.wait_stream(ws.mask_stream)
         main.wait_stream(ws.side_stream)
         ws.t = T

@@ -70,6 +70,24 @@ class precision:
         return False
 
 
+class static_weights:
+    """`with ops.static_weights():` -- launches set up inside may stream their packed weights before the previous
+    kernel of the stream has finished (rsis_set_static_weights): the caller promises that nothing enqueued in between
+    re-packs them.  Used by the inference pass; training steps re-pack in-stream and stay outside."""
+
+    def __init__(self, on: bool = True):
+        self.on = 1 if on else 0
+        self.prev = 0
+
+    def __enter__(self):
+        self.prev = _lib.load().rsis_set_static_weights(self.on)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().rsis_set_static_weights(self.prev)
+        return False
+
+
 def launch_count() -> int:
     """Number of CUDA kernels this process has enqueued through the C ABI so far."""
     return _lib._launches

@@ -69,6 +69,11 @@ class FakeLib:
     def rsis_get_precision(self):
         return getattr(self, "_precision", 0)
 
+    def rsis_set_static_weights(self, on):
+        prev = getattr(self, "_static_weights", 0)
+        self._static_weights = int(on)
+        return prev
+
     def rsis_has_tcgen05(self):
         return 0
 
