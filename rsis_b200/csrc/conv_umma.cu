@@ -570,6 +570,9 @@ __device__ __forceinline__ RowGeom row_geom(const UmmaParams& p, const RowPos& r
 }
 
 #ifdef RSIS_DEBUG_TIMING
+#ifndef RSIS_TRACE_BLOCK
+#define RSIS_TRACE_BLOCK 0  // the block whose stamps go to the per-launch trace (-DRSIS_TRACE_BLOCK=100: a block that
+#endif                      // cannot be resident before the previous kernel's CTAs leave)
 __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   if (blockIdx.x == 0 && p.counters) {
     // SM cycle counter (all stamps of the table come from block 0, i.e. one SM): ~20 cycles, where %globaltimer costs
@@ -579,14 +582,14 @@ __device__ __forceinline__ void stamp(const UmmaParams& p, int slot) {
   }
   // per-launch trace (rsis_debug_trace): block 0's first sixteen stamps go to the launch's own row, so that launches
   // overlapping under programmatic dependent launch do not overwrite each other
-  if (blockIdx.x == 0 && p.trace && slot < 16) p.trace[2 + slot] = (unsigned long long)clock64();
+  if (blockIdx.x == RSIS_TRACE_BLOCK && p.trace && slot < 16) p.trace[2 + slot] = (unsigned long long)clock64();
 }
 __device__ __forceinline__ void trace_begin(const UmmaParams& p) {
   if (threadIdx.x == 0 && p.trace) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     atomicMax(p.trace + 0, ~t);  // earliest CTA start, inverted
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == RSIS_TRACE_BLOCK) {
       p.trace[18] = t;
       p.trace[19] = (unsigned long long)clock64();
     }
@@ -597,7 +600,9 @@ __device__ __forceinline__ void trace_end(const UmmaParams& p) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     atomicMax(p.trace + 1, t);  // latest CTA end
-    if (blockIdx.x == 0) {
+    atomicMax(p.trace + 22, ~t);  // earliest CTA end, inverted
+    atomicAdd(p.trace + 23, 1ull);  // CTAs
+    if (blockIdx.x == RSIS_TRACE_BLOCK) {
       p.trace[20] = t;
       p.trace[21] = (unsigned long long)clock64();
     }
@@ -2127,6 +2132,8 @@ inline double mma_ns(int n_mma) {
   return (a > b ? a : b) / 1.9;
 }
 
+thread_local int t_force_bn = 0;  // > 0: output-channel tile width for the next plan (grouped-launch tuning override)
+
 Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int taps, int chunks, int last_ksteps,
                bool can_split, bool cell, int ctas, bool single = false) {
   // Cost model in nanoseconds, calibrated on B200 with in-kernel %globaltimer stamps and graph-replay timings
@@ -2146,6 +2153,7 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     if (BN >= 2 * cout && BN > 32) continue;              // wider than the layer: nothing but padding
     if (cout <= 128 && BN > 128) continue;
     if (g_force_bn && BN != g_force_bn) continue;
+    if (t_force_bn && BN != t_force_bn) continue;
     const int stacked = (BN <= 128 && !single) ? 1 : 0;
     const double mpk = single ? 1 : (stacked ? 2 : 3);
     const double kMma = mma_ns(stacked ? 2 * BN : BN);
@@ -2230,14 +2238,16 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.early_b = (g_static_weights && g_early_b) ? 1 : 0;
 #ifdef RSIS_DEBUG_TIMING
   p.trace = nullptr;
-  if (g_trace && g_trace_next < g_trace_rows) {
-    fprintf(stderr, "rsis trace %d: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s\n", g_trace_next, x.n, x.h, x.w, x.c, w->cout, w->kh,
-            stride, is_cell ? " cell" : "");
-    p.trace = g_trace + (size_t)24 * g_trace_next++;
-  }
+  if (g_trace && g_trace_next < g_trace_rows) p.trace = g_trace + (size_t)24 * g_trace_next++;
 #endif
   const Plan plan = make_plan((int)mt_halo, (int)mt_tap, halo_ok, w->cout, p.taps, p.chunks, p.last_ksteps, can_split,
                               w->gate_interleaved != 0, cta_share, p.single != 0);
+#ifdef RSIS_DEBUG_TIMING
+  if (p.trace)
+    fprintf(stderr, "rsis trace %d: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s BN=%d ks=%d halo=%d tiles=%d\n", g_trace_next - 1, x.n,
+            x.h, x.w, x.c, w->cout, w->kh, stride, is_cell ? " cell" : "", plan.BN, plan.ksplit, plan.halo,
+            (int)((plan.halo ? mt_halo : mt_tap) * ceil_div(w->cout, plan.BN)) * plan.ksplit);
+#endif
   if (g_print_plan)
     fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d halo=%d est %lld ns\n",
             x.n, x.h, x.w, x.c, w->cout, w->kh, stride, w->gate_interleaved ? " cell/gates" : "", plan.BN, plan.stacked,
@@ -2959,9 +2969,12 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
   static_assert(sizeof(CellGroup) < 32000, "kernel parameter space");
   CellGroup g{};
   g.n = n;
-  // (1) CTA shares in proportion to the tensor-core work of each cell (pixel tiles x K steps x gate columns); every
-  // cell at least one CTA, none more CTAs than it has pixel tiles
-  double work[kMaxGroup], total = 0;
+  // (1) CTA shares.  Model of a cell's time on n CTAs, calibrated with the cold single-launch sweep of
+  // scripts/group_tune.py (profiles/r2bl_group_tune.txt): F + W / n, W proportional to its tensor-core work (pixel tiles x
+  // K steps x gate columns, with the shared-memory-bound cost of narrow N), F an extra fixed cost of the levels whose
+  // weights stream through the B ring for every tile (too large to stay resident, too few gate columns to split).
+  // Greedy min-max: every cell one CTA, each further CTA to the cell that currently finishes last.
+  double work[kMaxGroup], fixed[kMaxGroup];
   int tiles[kMaxGroup], share[kMaxGroup];
   for (int i = 0; i < n; ++i) {
     const rsis_tensor& x = *cells[i].x;
@@ -2970,33 +2983,80 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
     const double cols = w->cout < 16 ? 16 : w->cout;
     // narrow gate blocks are bound by the shared-memory operand reads, not by the tensor pipe: 32 + N/4 vs N/2 cycles
     const double per_col = cols >= 128 ? 1.0 : (40.0 + cols / 2.0) / cols;
-    work[i] = (double)tiles[i] * w->kh * w->kw * ceil_div(x.c, 16) * cols * per_col;
-    total += work[i];
+    work[i] = (double)tiles[i] * w->kh * w->kw * ceil_div(x.c, 16) * cols * per_col * 2.06e-3;  // ~us on one CTA
+    const double w_bytes = 2.0 * w->kh * w->kw * ceil_div(x.c, kBK) * 128.0 * cols;              // [W_hi | W_lo] of a tile
+    fixed[i] = (cols < 128 && w_bytes > 100e3 && tiles[i] >= 2 * g_num_sms / n) ? 5.5 : 0.0;
+    tiles[i] *= ceil_div(w->cout, 32);  // most (pixel tile, gate-column tile) units a plan can have
+    share[i] = 1;
   }
-  int used = 0;
-  for (int i = 0; i < n; ++i) {
-    tiles[i] *= ceil_div(cells[i].w->cout, 32);  // most (pixel tile, gate-column tile) units a plan can have
-    share[i] = (int)(g_num_sms * work[i] / total);
-    if (share[i] < 1) share[i] = 1;
-    if (share[i] > tiles[i]) share[i] = tiles[i];
-    used += share[i];
-  }
-  // hand out what rounding left over (or take back an overshoot) one CTA at a time, to / from the cell with the most
-  // work per CTA / the least
-  for (int guard = 0; used != g_num_sms && guard < 4 * g_num_sms; ++guard) {
+  for (int used = n; used < g_num_sms; ++used) {
     int best = -1;
+    double worst = -1;
     for (int i = 0; i < n; ++i) {
-      if (used < g_num_sms) {
-        if (share[i] >= tiles[i]) continue;
-        if (best < 0 || work[i] / share[i] > work[best] / share[best]) best = i;
-      } else {
-        if (share[i] <= 1) continue;
-        if (best < 0 || work[i] / share[i] < work[best] / share[best]) best = i;
-      }
+      if (share[i] >= tiles[i]) continue;
+      const double t = fixed[i] + work[i] / share[i];
+      if (t > worst) { worst = t; best = i; }
     }
     if (best < 0) break;
-    share[best] += used < g_num_sms ? 1 : -1;
-    used += used < g_num_sms ? 1 : -1;
+    ++share[best];
+  }
+  // (1b) quantisation: a cell with few work units (pixel tile x gate-column tile of the plan its share gets) runs
+  // ceil(units / share) rounds whatever the remainder, so it keeps only the CTAs that round count needs and the
+  // many-tile cells of the group (if there are any) take the rest.  One planning pass to learn the unit counts.
+  {
+    int need[kMaxGroup], freed = 0, n_big = 0;
+    bool big[kMaxGroup];
+    for (int i = 0; i < n; ++i) {
+      UmmaMaps maps_tmp;
+      UmmaParams p_tmp{};
+      const rsis_cell_args& c = cells[i];
+      big[i] = true;
+      need[i] = share[i];
+      if (setup(maps_tmp, p_tmp, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i], c.gate_preact, true) == RSIS_OK) {
+        const int units = p_tmp.num_tiles;
+        big[i] = units >= 4 * share[i];
+        if (!big[i]) need[i] = ceil_div(units, ceil_div(units, share[i]));
+      }
+      if (big[i]) ++n_big;
+    }
+    if (n_big > 0) {
+      for (int i = 0; i < n; ++i) {
+        freed += share[i] - need[i];
+        share[i] = need[i];
+      }
+      for (; freed > 0; --freed) {
+        int best = -1;
+        double worst = -1;
+        for (int i = 0; i < n; ++i) {
+          if (!big[i] || share[i] >= tiles[i]) continue;
+          const double t = fixed[i] + work[i] / share[i];
+          if (t > worst) { worst = t; best = i; }
+        }
+        if (best < 0) break;
+        ++share[best];
+      }
+    }
+  }
+  // tuning overrides (development): RSIS_B200_GROUP_SHARES / RSIS_B200_GROUP_BN = comma lists indexed by the cell's
+  // position in the group
+  int force_bn[kMaxGroup] = {0, 0, 0, 0, 0};
+  if (const char* e = getenv("RSIS_B200_GROUP_SHARES")) {
+    int v[kMaxGroup], k = 0;
+    for (const char* q = e; *q && k < kMaxGroup; ++k) {
+      v[k] = atoi(q);
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (k == n) for (int i = 0; i < n; ++i) share[i] = v[i] < 1 ? 1 : v[i];
+  }
+  if (const char* e = getenv("RSIS_B200_GROUP_BN")) {
+    int k = 0;
+    for (const char* q = e; *q && k < kMaxGroup; ++k) {
+      force_bn[k] = atoi(q);
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (k != n) for (int i = 0; i < kMaxGroup; ++i) force_bn[i] = 0;
   }
   // (2) plan every cell for its share; no split-K (the wavefront supplies the parallelism)
   int first = 0;
@@ -3004,7 +3064,10 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
     const rsis_cell_args& c = cells[i];
     UmmaParams& p = g.p[i];
     if (c.gate_preact && !aligned16(c.gate_preact)) return RSIS_ERR_ALIGN;
-    if (int e = setup(g.maps[i], p, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i], c.gate_preact, true)) return e;
+    t_force_bn = force_bn[i];
+    const int se = setup(g.maps[i], p, *c.x, c.w, 1, c.w->kh / 2, nullptr, 0, share[i], c.gate_preact, true);
+    t_force_bn = 0;
+    if (se) return se;
     const int Ch = p.Cout / 4;
     auto ok = [&](const rsis_tensor* t, int fmt) {
       return valid_tensor(t) && t->fmt == fmt && t->n == p.N && t->h == p.Ho && t->w == p.Wo && t->c == Ch &&

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ CUtensor
   const int issuer = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0 && issuer < c.issuers) {
     const int group = c.csz > 1 ? (int)blockIdx.x / c.csz : (int)blockIdx.x;
-    const int row0 = c.shared_src ? 0 : group * c.region_rows;
+    // shared_src: 0 = every CTA (cluster) its own region, 1 = all the same region, g > 1 = groups of g CTAs share one
+    const int row0 = c.shared_src == 1 ? 0 : (c.shared_src > 1 ? group / c.shared_src : group) * c.region_rows;
     const int slice_rows = c.box_rows / c.csz;
     const uint16_t mask = (uint16_t)((1u << c.csz) - 1u);
     unsigned long long g0, g1;
@@ -102,7 +104,7 @@ int main() {
   cudaDriverEntryPointQueryResult q;
   cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
   EncodeTiledFn encode = (EncodeTiledFn)fn;
-  const size_t rows_total = 1u << 18;  // x 128 B = 32 MB
+  const size_t rows_total = 1u << 20;  // x 128 B = 128 MB
   void* buf;
   cudaMalloc(&buf, rows_total * 128);
   cudaMemset(buf, 1, rows_total * 128);
@@ -115,31 +117,37 @@ int main() {
   printf("%5s %4s %6s %6s %6s %6s %6s | %12s %12s %12s %10s\n", "grid", "csz", "boxKB", "stages", "issuer", "stride", "iters",
          "B/ns per CTA", "min B/ns CTA", "chip GB/s", "ns per box");
   std::vector<long long> out(512);
-  struct Case { int grid, csz, box_rows, stages, shared, planes, issuers, row_stride; };
+  struct Case { int grid, csz, box_rows, stages, shared, planes, issuers, row_stride, region_rows; };
   std::vector<Case> cases;
-  // row stride: 128 = rows contiguous (the probe's default); 512 / 2048 / 4608 = a 64-channel slice of an NHWC activation
-  // with 256 / 1024 channels, a (tap, chunk) block of the packed weights of a 3x3 convolution over 256 channels
-  for (int grid : {1, 128})
-    for (int row_stride : {128, 256, 512, 2048, 4608})
-      for (int box_rows : {64, 256})
-        for (int stages : {1, 3}) cases.push_back({grid, 1, box_rows, stages, 0, 1, 1, row_stride});
-  for (int grid : {128})
-    for (int row_stride : {128, 4608}) cases.push_back({grid, 1, 64, 3, 1, 2, 2, row_stride});
-  const size_t n_stride_cases = cases.size();
-  (void)n_stride_cases;
+  // The A operand of layer3.conv1 (2048 pixels x 1024 channels, 8 MB, L2-resident): a 128-pixel tile = 16 chunks of
+  // 128 rows x 128 B (pitch 2048 B) x 2 planes = 512 KB, walked in 64 KB boxes (2 chunks) by the 8 CTAs that share it
+  // (BN = 32), or 4 (BN = 64), or 1.  region_rows counts 128-byte rows per plane of one region.
+  for (int gsz : {0, 4, 8, 16})
+    for (int stages : {2, 3})
+      for (int issuers : {1, 2}) {
+        cases.push_back({128, 1, 256, stages, gsz, 2, issuers, 128, 2048});   // 64 KB boxes
+        cases.push_back({128, 1, 128, stages, gsz, 2, issuers, 128, 2048});   // 32 KB boxes
+      }
+  for (int gsz : {0, 8}) cases.push_back({128, 1, 64, 4, gsz, 2, 2, 128, 2048});
+  // the same sharing through cluster multicast: each CTA of a cluster issues 1/csz of the box, all receive all of it
+  // (the probe has no empty barriers: a CTA that runs a phase ahead of a peer corrupts the peer's transaction count, so
+  // only deep rings are safe here)
+  if (getenv("PROBE_MULTICAST"))
+    for (int csz : {2, 4, 8}) cases.push_back({128, csz, 64, 6, 0, 2, 1, 128, 2048});
   for (const Case& k : cases) {
+    if ((size_t)k.stages * k.issuers * k.box_rows * 128 * k.planes + 2048 > (size_t)smem) continue;
     Cfg c{};
-    c.iters = 512;
+    c.iters = 256;
     c.stages = k.stages;
     c.box_rows = k.box_rows;
     c.shared_src = k.shared;
     c.csz = k.csz;
-    c.region_rows = 512;  // x 2 planes = 128 KB per CTA (cluster): stays in L2
+    c.region_rows = k.region_rows;
     c.planes = k.planes;
     c.issuers = k.issuers;
     CUtensorMap map;
     // rows of 128 bytes, `row_stride` bytes apart: the buffer holds rows_total * 128 / row_stride of them per plane pair
-    const cuuint64_t rows_avail = rows_total * 128 / (cuuint64_t)k.row_stride / 2;
+    const cuuint64_t rows_avail = rows_total * 128 / (cuuint64_t)k.row_stride / 2;  // per plane
     cuuint64_t dims[3] = {64, rows_avail, 2};
     cuuint64_t strides[2] = {(cuuint64_t)k.row_stride, rows_avail * (cuuint64_t)k.row_stride};
     cuuint32_t box[3] = {64, (cuuint32_t)(k.box_rows / k.csz), (cuuint32_t)k.planes};
@@ -179,9 +187,10 @@ int main() {
       t0 = std::min(t0, out[2 * b]);
       t1 = std::max(t1, out[2 * b + 1]);
     }
-    printf("%5d %4d %6d %6d %6d %6d %6d | %12.1f %12.1f %12.1f %10.1f\n", k.grid, k.csz, k.box_rows * k.planes / 8, k.stages,
+    printf("%5d %4d %6d %6d %6d %6d %6d | %12.1f %12.1f %12.1f %10.1f  shared by %d\n", k.grid, k.csz, k.box_rows * k.planes / 8, k.stages,
            k.issuers, k.row_stride, c.iters, sum / k.grid, mn, bytes_cta * k.grid / (double)(t1 - t0),
-           (double)k.box_rows * 128 * k.planes * k.issuers / (sum / k.grid));
+           (double)k.box_rows * 128 * k.planes * k.issuers / (sum / k.grid), k.shared);
+    fflush(stdout);
   }
   return 0;
 }
