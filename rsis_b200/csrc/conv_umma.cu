@@ -148,6 +148,7 @@ struct UmmaParams {
   int p_stage_bytes;       // BN/32 boxes of 128 rows x 128 bytes
 #ifdef RSIS_DEBUG_TIMING
   unsigned long long* trace;  // per-launch trace row (24 x u64) of rsis_debug_trace, or nullptr
+  int dbg_skip;               // RSIS_B200_DBG_SKIP: 1 = the cell epilogue loads no state / gate share, 2 = stores nothing
 #endif
 };
 
@@ -1086,7 +1087,11 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
     const Cursor n = next_of(c);
     const int col0 = c.nt * p.BN + 16 * c.u;
     const int chg0 = col0 >> 2;
+#ifdef RSIS_DEBUG_TIMING
+    if (n.valid) cell_unit_load(p, in_next, (p.dbg_skip & 1) ? 0xffffffffu : n.pix, ((n.nt * p.BN) >> 2) + 4 * n.u);
+#else
     if (n.valid) cell_unit_load(p, in_next, n.pix, ((n.nt * p.BN) >> 2) + 4 * n.u);
+#endif
     const bool first_unit = c.u == half, last_unit = c.u + 2 >= nu;
     if (first_unit) {
       if (threadIdx.x == 0) STAMP_T(7, (c.work - bid) / nblk);
@@ -1112,7 +1117,11 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
       mbar_arrive(tempty0 + 8 * acc);
       if (threadIdx.x == 0) STAMP_T(4, (c.work - bid) / nblk);
     }
+#ifdef RSIS_DEBUG_TIMING
+    const bool ok = c.pix != 0xffffffffu && chg0 < Ch && !(p.dbg_skip & 2);
+#else
     const bool ok = c.pix != 0xffffffffu && chg0 < Ch;
+#endif
     if (p.pre_tma) {
       // unit u = columns [16u, 16u + 16) of the tile: box u / 2, 16-byte chunks 4 * (u & 1) .. + 3 of the row
       const uint32_t rowaddr = prow + (uint32_t)ps * (uint32_t)p.p_stage_bytes + (uint32_t)(c.u >> 1) * 16384u;
@@ -1958,6 +1967,7 @@ int g_num_sms = 0;
 int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
 int g_early_b = 1;         // RSIS_B200_EARLY_B=0: weight boxes wait for the previous kernel even with static weights (A-B timing)
+int g_max_a_stages = 4;    // RSIS_B200_ASTAGES: most activation stages beside resident weights (cold halo boxes land ~2.5 us after issue)
 int g_sw64 = 1;            // RSIS_B200_SW64=0: 64-channel SWIZZLE_128B halo boxes for narrow sources too (A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
@@ -1991,6 +2001,7 @@ cudaError_t set_smem_attr() {
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SW64")) g_sw64 = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_ASTAGES")) g_max_a_stages = atoi(e) < 2 ? 2 : (atoi(e) > kMaxStages ? kMaxStages : atoi(e));
   if (const char* e = getenv("RSIS_B200_EARLY_B")) g_early_b = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_BN")) g_force_bn = atoi(e);
@@ -2237,6 +2248,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.single = g_precision == 1 ? 1 : 0;
   p.early_b = (g_static_weights && g_early_b) ? 1 : 0;
 #ifdef RSIS_DEBUG_TIMING
+  p.dbg_skip = getenv("RSIS_B200_DBG_SKIP") ? atoi(getenv("RSIS_B200_DBG_SKIP")) : 0;
   p.trace = nullptr;
   if (g_trace && g_trace_next < g_trace_rows) p.trace = g_trace + (size_t)24 * g_trace_next++;
 #endif
@@ -2337,7 +2349,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     if (p.b_resident) {
       p.b_stages = outer * ceil_div(inner, p.bg);
       p.a_stages = (budget - p.b_stages * p.b_stage_bytes) / p.a_stage_bytes;
-      if (p.a_stages > 4) p.a_stages = 4;
+      if (p.a_stages > g_max_a_stages) p.a_stages = g_max_a_stages;
     } else if (p.halo) {
       // a third activation stage when enough weight stages still fit next to it: a halo box needs ~2.5 us from issue to
       // landing, longer than the MMAs of one tile on the narrow levels

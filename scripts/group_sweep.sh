@@ -1,1 +1,4 @@
-RSIS_B200_PRINT_PLAN=1 python scripts/group_tune.py "-;-" "-;-@0,1,2,3" "-;-@1,2,3,4" "-;-@2,3,4" "-;-@3,4" "-;-@0,1,2" "-;-@0,1" 2>&1 | grep "levels\|rsis group" | uniq
+for sk in 0 1 2 3; do
+echo "DBG_SKIP=$sk (1 = no epilogue loads, 2 = no epilogue stores)"
+RSIS_B200_DBG_SKIP=$sk python scripts/group_tune.py "-;-@4" "61;-@4" "-;-@3" "35;-@3" "-;-" 2>&1 | grep "levels"
+done

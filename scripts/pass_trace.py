@@ -54,7 +54,7 @@ inv = lambda v: (~v) & 0xFFFFFFFFFFFFFFFF if v >= 0 else (~(v + (1 << 64))) & 0x
 t_first = None
 prev_end = None
 print(f"{len(rows)} traced launches in one replay; times in us; start/end = grid (all CTAs), rest = block 0, relative to ITS start")
-print(f"{'id':>5s} {'start':>8s} {'dur':>6s} {'gap':>6s} | {'b0 start':>8s} {'pdl ok':>6s} {'A0 iss':>6s} {'MMA A':>7s} {'MMAs':>6s} {'exit':>6s} {'1st end':>7s} {'ctas':>4s} | shape")
+print(f"{'id':>5s} {'start':>8s} {'dur':>6s} {'gap':>6s} | {'b0 start':>8s} {'pdl ok':>6s} {'A0 iss':>6s} {'MMA A':>7s} {'MMAs':>6s} {'exit':>6s} {'1st end':>7s} {'ctas':>4s} {'prod in':>7s} {'dec ok':>6s} {'aempty':>6s} {'exp_tx':>6s} {'epi acc':>7s} | shape")
 tot = 0.0
 for i, rw in rows:
     u = [v & 0xFFFFFFFFFFFFFFFF for v in rw]
@@ -66,8 +66,8 @@ for i, rw in rows:
     c0 = u[19]
     rel = lambda slot: (st[slot] - c0) / GHZ / 1e3 if st[slot] else float("nan")
     gap = (start - prev_end) / 1e3 if prev_end is not None else 0.0
-    print(f"{i:5d} {(start - t_first)/1e3:8.1f} {(end - start)/1e3:6.1f} {gap:6.1f} | {(u[18] - start)/1e3:8.1f} {rel(1):6.1f} {rel(15):6.1f} "
-          f"{rel(4):7.1f} {rel(6):6.1f} {(u[21] - c0)/GHZ/1e3:6.1f} {(((~u[22]) & 0xFFFFFFFFFFFFFFFF) - start)/1e3:7.1f} {u[23]:4d} | {shapes.get(i, '?')}")
+    print(f"{i:5d} {(start - t_first)/1e3:8.1f} {(end - start)/1e3:6.1f} {gap:6.1f} | {(u[18] - start)/1e3:8.1f} {rel(1):6.1f} {rel(2):6.1f} "
+          f"{rel(4):7.1f} {rel(6):6.1f} {(u[21] - c0)/GHZ/1e3:6.1f} {(((~u[22]) & 0xFFFFFFFFFFFFFFFF) - start)/1e3:7.1f} {u[23]:4d} {rel(12):7.1f} {rel(13):6.1f} {rel(14):6.1f} {rel(15):6.1f} {rel(7):7.1f} | {shapes.get(i, '?')}")
     prev_end = end
     tot += (end - start) / 1e3
 print(f"sum of grid durations {tot:.1f} us; span {(prev_end - t_first)/1e3:.1f} us")
