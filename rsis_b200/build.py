@@ -12,7 +12,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 # RSIS_B200_LIB: load / build another file instead (development: the -DRSIS_DEBUG_TIMING build of the stamp probes)
 LIB_PATH = os.environ.get("RSIS_B200_LIB") or os.path.join(LIB_DIR, "librsis_b200.so")
 SOURCES = ["api.cu", "pack.cu", "layout.cu", "conv_simt.cu", "conv_umma.cu", "decoder_ops.cu", "bn_train.cu", "backward.cu", "objectives.cu", "postprocess.cu", "optim.cu", "dispatch.cu"]
-NVCC_FLAGS = (["-DRSIS_DEBUG_TIMING"] if os.environ.get("RSIS_B200_BUILD_DEBUG_TIMING") else []) + ([f"-DRSIS_TRACE_BLOCK={int(os.environ['RSIS_B200_TRACE_BLOCK'])}"] if os.environ.get("RSIS_B200_TRACE_BLOCK") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ([f"-DRSIS_GROUP_EPI_WARPS={int(os.environ['RSIS_B200_GROUP_EPI_WARPS'])}"] if os.environ.get("RSIS_B200_GROUP_EPI_WARPS") else []) + (["-DRSIS_DEBUG_TIMING"] if os.environ.get("RSIS_B200_BUILD_DEBUG_TIMING") else []) + ([f"-DRSIS_TRACE_BLOCK={int(os.environ['RSIS_B200_TRACE_BLOCK'])}"] if os.environ.get("RSIS_B200_TRACE_BLOCK") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:

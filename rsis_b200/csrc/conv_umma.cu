@@ -296,7 +296,16 @@ constexpr int kStagePitch = 33;
 constexpr int kStageFloats = 32 * kStagePitch;             // per epilogue warp
 constexpr int kStageBytes = kEpiWarps * kStageFloats * 4;  // 33792
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) as one MUFU.EX2 and one MUFU.RCP.  __expf wraps the same ex2.approx in a range
+// test and two predicated multiplies so that results below 2^-126 come out denormal; after `1 + ...` that makes no
+// difference in float32, and those three instructions x 20 transcendentals were ~13 % of the row-wise cell epilogue,
+// which runs at latency, not throughput (two epilogue warps per scheduler).
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
@@ -1038,20 +1047,23 @@ __device__ __forceinline__ void cell_unit_load(const UmmaParams& p, CellUnitIn& 
 // producer warp brings the tile's [128 pixels][32 columns] fp32 boxes in by TMA (SWIZZLE_128B, two stages), and a thread
 // reads its own 128-byte row with conflict-free 16-byte shared-memory loads (chunk ^ (row & 7)).
 __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
-                                                   uint32_t tempty0, uint32_t smem_p, uint32_t pfull0, uint32_t pempty0,
-                                                   int warp, int lane, const int bid, const int nblk) {
-  const int quarter = warp & 3, half = warp >> 2;
+                                                   uint32_t tempty0, int warp, int lane, const int bid, const int nblk,
+                                                   const int wpq) {
+  // `wpq` epilogue warps per TMEM lane quarter (2 in the 8-warp kernels, 3 in the grouped launch).  The flat stream of
+  // units f = tile_seq * nu + u of a quarter is dealt round-robin to them: a unit runs at LATENCY here (about 450
+  // dependent-ish instructions: address arithmetic, two tensor-memory loads, 20 transcendentals, stores, the max-pool
+  // reduction -- ~2 us with two such warps per scheduler, ncu source view: profiles/r2bu_*), so a third warp per quarter
+  // is worth more than any trimming of the unit.
+  const int quarter = warp & 3, slot = warp >> 2;
   const int Ch = p.Cout >> 2;
-  const int nu = p.BN >> 4;  // units per output-channel tile; this warp takes units half, half + 2, ...
+  const int nu = p.BN >> 4;                  // units per output-channel tile (a power of two: BN = 32 .. 256)
+  const int nu_shift = 31 - __clz(nu);
   const bool warp_one_image = p.BW * p.BH >= 32;  // the 32 rows of a warp lie in one image
   const int num_work = p.num_tiles;               // no split-K on this path
   const RowPos rpos = row_pos(p, quarter * 32 + lane);
-  const uint32_t prow = smem_p + (uint32_t)(quarter * 32 + lane) * 128u;  // this thread's row inside a staged box
-  const uint32_t pxor = (uint32_t)(lane & 7);                               // (row & 7): quarter * 32 is a multiple of 8
 
-  // The warp's work is a flat stream of units (tile, u); a cursor names one.
   struct Cursor {
-    int work, u, nt, img;
+    int f, seq, u, work, nt, img;
     uint32_t pix;
     bool valid;
   };
@@ -1069,16 +1081,23 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
   };
   auto next_of = [&](const Cursor& c) {
     Cursor n = c;
-    n.u += 2;
-    if (n.u >= nu) {
-      n.u = half;
-      n.work += nblk;
+    n.f += wpq;
+    n.u = n.f & (nu - 1);
+    const int seq = n.f >> nu_shift;
+    if (seq != n.seq) {
+      n.seq = seq;
+      n.work = bid + seq * nblk;
       locate(n);
     }
     return n;
   };
-  int acc = 0, ps = 0;
-  uint32_t acc_phase = 0, pph = 0;
+  // Tile `seq` of this CTA lives in accumulator stage seq & 1, phase (seq >> 1) & 1.  A warp waits ONLY for tiles it has a
+  // unit in.  A parity wait cannot tell a phase from the one two completions away, so the stage's completion count must
+  // be pinned to {seq / 2, seq / 2 + 1} when the warp looks: not more, because tile seq + 2 cannot complete before this
+  // warp has read its unit of tile seq (waiting on a tile WITHOUT a unit in it has no such bound -- it deadlocked once
+  // the MMA warp was two tiles ahead); not less, because the warp's previous unit was in tile seq - 1 or seq - 2 (a
+  // step of wpq <= 3 units with nu >= 2 units per tile), whose completion implies that of tile seq - 2.
+  int waited = -1;
 
   // One unit: `in` was loaded earlier (by the previous step, or before the loop); the loads of the NEXT unit go into
   // `in_next`.  The two register sets alternate between calls, so no load result is ever copied: a register move of a
@@ -1092,14 +1111,23 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
 #else
     if (n.valid) cell_unit_load(p, in_next, n.pix, ((n.nt * p.BN) >> 2) + 4 * n.u);
 #endif
-    const bool first_unit = c.u == half, last_unit = c.u + 2 >= nu;
-    if (first_unit) {
-      if (threadIdx.x == 0) STAMP_T(7, (c.work - bid) / nblk);
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
-      tc_fence_after();
-      if (threadIdx.x == 0) STAMP_T(3, (c.work - bid) / nblk);
-      if (p.pre_tma) mbar_wait(pfull0 + 8 * ps, pph);
+    // the unit's folded affine: issued before the accumulator wait, so its (global, L1 / L2) latency hides behind that
+    // wait and the tensor-memory loads instead of sitting between them and the gate math (ncu source view of the level-4
+    // launch: as many stall samples on the first FFMA below as on the accumulator wait itself)
+    float4 sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
+      sh[j] = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
     }
+    if (waited != c.seq) {
+      if (threadIdx.x == 0) STAMP_T(7, c.seq);
+      waited = c.seq;
+      mbar_wait(tfull0 + 8 * (waited & 1), (uint32_t)(waited >> 1) & 1u);
+      tc_fence_after();
+      if (threadIdx.x == 0) STAMP_T(3, c.seq);
+    }
+    const int acc = c.seq & 1;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
     uint32_t r[16];
     tmem_ld16(taddr + 16 * c.u, r);
@@ -1112,36 +1140,23 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
     } else {
       tmem_ld_wait();
     }
-    if (last_unit) {  // the accumulator stage is free for the MMAs of the tile after next
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
-      if (threadIdx.x == 0) STAMP_T(4, (c.work - bid) / nblk);
-    }
+    // this unit's columns are in registers: one arrival per thread and unit (the stage is free for the MMAs of the tile
+    // after next once all nu * 128 of them are in)
+    tc_fence_before();
+    mbar_arrive(tempty0 + 8 * acc);
+    if (threadIdx.x == 0) STAMP_T(4, c.seq);
 #ifdef RSIS_DEBUG_TIMING
     const bool ok = c.pix != 0xffffffffu && chg0 < Ch && !(p.dbg_skip & 2);
 #else
     const bool ok = c.pix != 0xffffffffu && chg0 < Ch;
 #endif
-    if (p.pre_tma) {
-      // unit u = columns [16u, 16u + 16) of the tile: box u / 2, 16-byte chunks 4 * (u & 1) .. + 3 of the row
-      const uint32_t rowaddr = prow + (uint32_t)ps * (uint32_t)p.p_stage_bytes + (uint32_t)(c.u >> 1) * 16384u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t chunk = (uint32_t)(4 * (c.u & 1) + j) ^ pxor;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(in.pre[j].x), "=f"(in.pre[j].y), "=f"(in.pre[j].z), "=f"(in.pre[j].w)
-                     : "r"(rowaddr + (chunk << 4)));
-      }
-    }
     float cv[4], hv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + 4 * j));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + col0 + 4 * j));
-      const float gi = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 0]), sc.x, sh.x) + in.pre[j].x);
-      const float gf = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y) + in.pre[j].y);
-      const float go = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z) + in.pre[j].z);
-      const float gg = fast_tanh(fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w) + in.pre[j].w);
+      const float gi = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 0]), sc[j].x, sh[j].x) + in.pre[j].x);
+      const float gf = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 1]), sc[j].y, sh[j].y) + in.pre[j].y);
+      const float go = fast_sigmoid(fmaf(__uint_as_float(r[4 * j + 2]), sc[j].z, sh[j].z) + in.pre[j].z);
+      const float gg = fast_tanh(fmaf(__uint_as_float(r[4 * j + 3]), sc[j].w, sh[j].w) + in.pre[j].w);
       const float cpj = j == 0 ? in.cp.x : (j == 1 ? in.cp.y : (j == 2 ? in.cp.z : in.cp.w));
       cv[j] = fmaf(gf, cpj, gi * gg);
       hv[j] = go * fast_tanh(cv[j]);
@@ -1169,26 +1184,15 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
           atomicMax(p.side_max + (size_t)c.img * p.side_stride + p.side_offset + chg0 + j, float_to_key(hv[j]));
       }
     }
-    if (last_unit) {
-      if (threadIdx.x == 0) STAMP_T(6, (c.work - bid) / nblk);
-      if (p.pre_tma) {  // this thread has consumed its part of the staged gate share
-        mbar_arrive(pempty0 + 8 * ps);
-        if (++ps == 2) {
-          ps = 0;
-          pph ^= 1u;
-        }
-      }
-      if (++acc == kAccStages) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
-    }
+    if (threadIdx.x == 0 && c.u + wpq >= nu) STAMP_T(6, c.seq);
     return n;
   };
 
   Cursor c;
-  c.work = bid;
-  c.u = half;
+  c.f = slot;
+  c.u = c.f & (nu - 1);
+  c.seq = c.f >> nu_shift;
+  c.work = bid + c.seq * nblk;
   locate(c);
   if (!c.valid) return;
   CellUnitIn set_a, set_b;
@@ -1204,7 +1208,7 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
 // The whole CTA program.  `bid` / `nblk`: this CTA's index among the `nblk` CTAs that share the problem `p` (the whole
 // grid for a plain launch; a contiguous CTA range of a grouped launch, cell_group_kernel).  PW = 0: the epilogue piece
 // width is taken from p.pw at run time (grouped launches mix levels that want 16 and 32).
-template <bool CELL, int PW, bool SPLIT>
+template <bool CELL, int PW, bool SPLIT, int EW = kEpiWarps>  // EW epilogue warps (then A producer, MMA issuer, B producer)
 __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams& p, const int bid, const int nblk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages + 4];
@@ -1228,7 +1232,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   const uint32_t tfull0 = smem_u32(&bars[4 * kMaxStages]);
   const uint32_t tempty0 = smem_u32(&bars[4 * kMaxStages + kAccStages]);
 
-  if (warp == kEpiWarps && lane == 0) {
+  if (warp == EW && lane == 0) {
     prefetch_tmap(&maps.a[0]);
     if (p.stride == 2) {
       prefetch_tmap(&maps.a[1]);
@@ -1238,7 +1242,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     prefetch_tmap(&maps.b);
     if (CELL && p.pre_tma) prefetch_tmap(&maps.pre);
   }
-  if (warp == kEpiWarps + 1 && lane == 0) {
+  if (warp == EW + 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(afull0 + 8 * s, 1);
       mbar_init(aempty0 + 8 * s, 1);
@@ -1251,7 +1255,9 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, kEpiThreads);
+      // row-wise cell epilogue: one arrival per thread and 16-column unit (BN / 16 units x 128 rows); staged epilogues:
+      // one per epilogue thread and tile
+      mbar_init(tempty0 + 8 * a, (CELL && !SPLIT && p.cell_rows) ? (uint32_t)p.BN * 8u : (uint32_t)kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1282,7 +1288,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   const int a_items = p.halo ? p.chunks : p.taps * agroups;
   const int num_work = p.num_tiles * p.ksplit;
 
-  if (warp == kEpiWarps) {
+  if (warp == EW) {
     // =============================== TMA producer: activations (A ring) ===============================
     int as = 0;
     uint32_t aph = 0;
@@ -1367,7 +1373,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       }
       if (lane == 0) STAMP(3);
     }
-  } else if (warp == kEpiWarps + 2) {
+  } else if (warp == EW + 2) {
     // =============================== TMA producer: weights (B ring) ===============================
     // Its own warp, so that activation tiles run a_stages items ahead no matter how far the weight ring is.
     int bs = 0;
@@ -1422,7 +1428,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
         }
       }
     }
-  } else if (warp == kEpiWarps + 1) {
+  } else if (warp == EW + 1) {
     // =============================== MMA issuer ===============================
     // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128.
     // STACKED (BN <= 128): the weight stage holds [W_hi (BN rows) | W_lo (BN rows)] contiguously, so ONE MMA with
@@ -1483,6 +1489,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
     default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
   }
+#ifdef RSIS_DEBUG_TIMING
+            if (p.dbg_skip & 4) {  // (diagnostic: no MMAs at all -- what the operand pipeline alone sustains)
+            } else
+#endif
             if (p.a_sw64) {  // <= 32 channels: one or two K steps
               if (ksteps == 1)
                 issue_halo_resident<1, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
@@ -1571,13 +1581,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       }
     }
     __syncwarp();
-  } else if (warp < kEpiWarps) {
+  } else if (warp < EW) {
     // =============================== epilogue (warps 0-7) ===============================
     float* stage = stage_base + warp * kStageFloats;
     pdl_wait();  // the epilogues prefetch residual / state operands right away
     if (threadIdx.x == 0) STAMP(1);
     if (CELL && !SPLIT && p.cell_rows) {
-      cell_rows_epilogue(p, tmem_base, tfull0, tempty0, smem_p, pfull0, pempty0, warp, lane, bid, nblk);
+      cell_rows_epilogue(p, tmem_base, tfull0, tempty0, warp, lane, bid, nblk, EW / 4);
     } else if constexpr (PW != 0) {
       epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
     }
@@ -1621,7 +1631,12 @@ struct alignas(64) CellGroup {
   int n;
 };
 
-__global__ void __launch_bounds__(kThreadsUmma, 1) cell_group_kernel(const __grid_constant__ CellGroup g) {
+#ifndef RSIS_GROUP_EPI_WARPS
+#define RSIS_GROUP_EPI_WARPS 12
+#endif
+constexpr int kGroupEpiWarps = RSIS_GROUP_EPI_WARPS;          // three epilogue warps per TMEM lane quarter
+constexpr int kThreadsGroup = kGroupEpiWarps * 32 + 128;       // + A producer, MMA issuer, B producer, one idle warp
+__global__ void __launch_bounds__(kThreadsGroup, 1) cell_group_kernel(const __grid_constant__ CellGroup g) {
   int i = 0;
 #pragma unroll
   for (int k = 1; k < kMaxGroup; ++k)
@@ -1629,7 +1644,7 @@ __global__ void __launch_bounds__(kThreadsUmma, 1) cell_group_kernel(const __gri
 #ifdef RSIS_DEBUG_TIMING
   trace_begin(g.p[0]);
 #endif
-  umma_cta<true, 0, false>(g.maps[i], g.p[i], (int)blockIdx.x - g.first[i], g.first[i + 1] - g.first[i]);
+  umma_cta<true, 0, false, kGroupEpiWarps>(g.maps[i], g.p[i], (int)blockIdx.x - g.first[i], g.first[i + 1] - g.first[i]);
 #ifdef RSIS_DEBUG_TIMING
   trace_end(g.p[0]);
   // per-cell end time (max over its CTAs) and launch start (min over all CTAs): slots 200 + i and 199 of the stamp table
@@ -2324,7 +2339,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.pw = p.BN >= 64 ? 32 : 16;
   // pre_tma (cells with hoisted gates on the row-wise epilogue): two stages of BN/32 boxes of 16 KB take the place of
   // the transpose staging area, which that epilogue does not use
-  p.pre_tma = (g_pre_tma && preact && is_cell && g_cell_rows && p.ksplit == 1 && p.BN <= 64) ? 1 : 0;
+  p.pre_tma = 0;  // (retired with the per-unit distribution of the row-wise epilogue: it measured no gain, profiles/r2bm_*)
   p.p_stage_bytes = (p.BN >> 5) * 16384;
   // the row-wise cell epilogue needs no transpose staging area: its 33 KB go to the operand rings (a third activation
   // stage on the narrow levels, whose 46 KB halo boxes take ~2.5 us from issue to landing: profiles/r2l_group_stamps.txt)
@@ -3112,7 +3127,7 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
   for (int i = n; i <= kMaxGroup; ++i) g.first[i] = first;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(first);
-  cfg.blockDim = dim3(kThreadsUmma);
+  cfg.blockDim = dim3(kThreadsGroup);
   cfg.dynamicSmemBytes = kDynSmem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
