@@ -106,7 +106,11 @@ struct UmmaParams {
   int bg;                  // K blocks per weight box: HALO -> taps of one chunk (1 / 3 / 9), TAP -> chunks of one tap
   int a_flat;              // 1: maps.a[0] is the 4-D flat-pixel view {64, pixels, plane, chunk} of a 1x1 stride-1 input
   int early_b;             // 1: the weight producer does not wait for the previous kernel of the stream (static weights)
-  int a_sw64;              // 1: HALO boxes of 32 channels in SWIZZLE_64B rows of 64 bytes (sources of <= 32 channels: the TMA
+  int a_split_off;         // a_sw64 == 2: byte offset of the 16-channel SWIZZLE_32B part inside an activation stage
+  int a_sw64;              // 2: 33..48-channel cell sources as TWO boxes per tile, 32 channels SWIZZLE_64B + 16 channels
+                           //    SWIZZLE_32B (34.5 KB per stage instead of 46 KB), so that the nine taps of [W_hi | W_lo]
+                           //    (144 KB at 64 gate columns) stay RESIDENT beside two stages instead of streaming per tile;
+                           // 1: HALO boxes of 32 channels in SWIZZLE_64B rows of 64 bytes (sources of <= 32 channels: the TMA
                            //    unit spends ~1.6 ns per box ROW and twice that on rows that are mostly zero fill --
                            //    scripts/halo_probe.cu, profiles/r2ba_halo_probe.txt: 1217 -> 564 ns per 24-channel halo box)
   int b_map3d;             // 1: maps.b is the 3-D view {k, cout, plane} (one K block per box)
@@ -952,6 +956,32 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
   }
 }
 
+// The same for a 33..48-channel source staged as a 32-channel SWIZZLE_64B part (K steps 0, 1) and a 16-channel
+// SWIZZLE_32B part (K step 2): the activation descriptors of the two parts differ in layout type, row size (tap shift
+// of 4 / 2 descriptor units per row) and group stride; the weight tile is the ordinary 64-channel SWIZZLE_128B one.
+__device__ __forceinline__ void issue_halo_resident_split48(uint32_t d, uint64_t a64_hi, uint64_t a64_lo, uint64_t a32_hi,
+                                                            uint64_t a32_lo, uint64_t bdesc0, uint32_t b_stage16,
+                                                            uint32_t idesc, uint32_t accumulate, bool wait_b,
+                                                            uint32_t bfull0, int bg) {
+#pragma unroll
+  for (int bi = 0; bi < 9; ++bi) {
+    if (wait_b && (bg == 1 || bi % bg == 0)) {
+      mbar_wait_lean(bfull0 + 8 * (bg == 1 ? bi : bi / bg), 0);
+      tc_fence_after();
+    }
+    const int row = (bi / 3) * (kHaloBW + 2) + (bi % 3);
+    const uint64_t b = bdesc0 + (uint64_t)((uint32_t)bi * b_stage16);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint64_t adv = (uint64_t)(2 * k);
+      umma_bf16(d, a64_hi + (uint64_t)(row * 4) + adv, b + adv, idesc, (bi == 0 && k == 0) ? accumulate : 1u);
+      umma_bf16(d, a64_lo + (uint64_t)(row * 4) + adv, b + adv, idesc, 1u);
+    }
+    umma_bf16(d, a32_hi + (uint64_t)(row * 2), b + 4, idesc, 1u);
+    umma_bf16(d, a32_lo + (uint64_t)(row * 2), b + 4, idesc, 1u);
+  }
+}
+
 // The MMAs of one (tap, chunk) K block: KS steps of 16 channels, compile-time descriptor offsets.
 template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
 __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t b_plane16,
@@ -1234,6 +1264,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
 
   if (warp == EW && lane == 0) {
     prefetch_tmap(&maps.a[0]);
+    if (p.a_sw64 == 2) prefetch_tmap(&maps.a[1]);
     if (p.stride == 2) {
       prefetch_tmap(&maps.a[1]);
       prefetch_tmap(&maps.a[2]);
@@ -1341,6 +1372,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
           if (ai == item0 && work == bid) STAMP(15);
           if (p.halo) {
             tma_load_5d(sa, &maps.a[0], bar, cc * kBK, w0 - 1, h0 - 1, i0, 0);
+            if (p.a_sw64 == 2) tma_load_5d(sa + p.a_split_off, &maps.a[1], bar, 32, w0 - 1, h0 - 1, i0, 0);
           } else if (p.a_flat) {
             // 1x1, stride 1, the tile is 128 consecutive pixels: `ag` chunks x both planes in one box
             tma_load_4d(sa, &maps.a[0], bar, 0, (i0 * p.Ho + h0) * p.Wo + w0, 0, cc * p.ag);
@@ -1493,7 +1525,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
             if (p.dbg_skip & 4) {  // (diagnostic: no MMAs at all -- what the operand pipeline alone sustains)
             } else
 #endif
-            if (p.a_sw64) {  // <= 32 channels: one or two K steps
+            if (p.a_sw64 == 2) {  // 32 + 16 channels: three K steps
+              const uint32_t part32 = smem_a + (uint32_t)as * (uint32_t)p.a_stage_bytes + (uint32_t)p.a_split_off;
+              const uint64_t a32_hi = make_smem_desc(part32, (uint32_t)(kHaloBW + 2) * 32u, 6u);
+              const uint64_t a32_lo = make_smem_desc(part32 + (uint32_t)kHaloRows * 32u, (uint32_t)(kHaloBW + 2) * 32u, 6u);
+              issue_halo_resident_split48(d, a_hi0, a_lo0, a32_hi, a32_lo, bdesc0, b_chunk16, idesc, accumulate, wb, bfull0,
+                                          bg);
+            } else if (p.a_sw64) {  // <= 32 channels: one or two K steps
               if (ksteps == 1)
                 issue_halo_resident<1, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
               else
@@ -2071,9 +2109,10 @@ int encode_act_map(CUtensorMap* m, const rsis_tensor& t, int sub, int ph, int pw
   cuuint64_t strides[4] = {P * 2 * sub, W * P * 2 * sub, H * W * P * 2, N * H * W * P * 2};
   cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)BI, (cuuint32_t)planes};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  // box_c = 32: rows of 64 bytes, SWIZZLE_64B (UmmaParams::a_sw64)
+  // box_c = 32: rows of 64 bytes, SWIZZLE_64B; box_c = 16: rows of 32 bytes, SWIZZLE_32B (UmmaParams::a_sw64)
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == kBK ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_c == kBK ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? RSIS_OK : RSIS_ERR_CUDA;
 }
@@ -2310,10 +2349,23 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   }
   const int a_rows = p.halo ? kHaloRows : kBM;
   p.a_sw64 = (g_sw64 && p.halo && x.c <= 32 && p.ksplit == 1) ? 1 : 0;
+  const int planes = p.single ? 1 : 2;
+  p.a_split_off = 0;
+  {
+    // split mode: only where it buys weight residency on the unrolled cell issue path (see UmmaParams::a_sw64)
+    const int split_stage = round_up(2 * kHaloRows * (64 + 32), 1024);
+    const long long w_bytes = (long long)p.taps * 2 * p.BN * 128;
+    const bool many = p.num_tiles >= 2 * (cta_share > 0 ? cta_share : g_num_sms);
+    if (g_sw64 && g_b_resident && is_cell && g_cell_rows && p.halo && p.ksplit == 1 && !p.single && p.stacked &&
+        p.chunks == 1 && p.taps == 9 && x.c > 32 && x.c <= 48 && p.tiles_n == 1 && many &&
+        2 * split_stage + w_bytes <= kDynSmem - 1023) {
+      p.a_sw64 = 2;
+      p.a_split_off = 2 * kHaloRows * 64;
+    }
+  }
   const int a_row_bytes = p.a_sw64 ? 64 : 128;
   p.a_plane_bytes = a_rows * a_row_bytes;
-  const int planes = p.single ? 1 : 2;
-  p.a_chunk_bytes = round_up(planes * p.a_plane_bytes, 1024);
+  p.a_chunk_bytes = p.a_sw64 == 2 ? round_up(2 * kHaloRows * (64 + 32), 1024) : round_up(planes * p.a_plane_bytes, 1024);
   p.a_sbo = p.halo ? (uint32_t)((kHaloBW + 2) * a_row_bytes) : 1024u;
   p.b_chunk_bytes = planes * p.BN * 128;
   // K blocks per TMA box (see UmmaParams::ag).  Split-K slices cut the walk anywhere, so they keep one block per box.
@@ -2394,8 +2446,9 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     else if (p.b_resident) { p.b_resident = 0; p.bg = 1; }
     else break;
   }
+  if (p.a_sw64 == 2 && !(p.b_resident && p.a_stages >= 2)) return RSIS_ERR_UNSUPPORTED;  // (chosen only where this holds)
   p.agroups = p.halo ? 1 : ceil_div(p.chunks, p.ag);
-  p.a_tx_bytes = (uint32_t)(p.ag * planes * p.a_plane_bytes);
+  p.a_tx_bytes = p.a_sw64 == 2 ? (uint32_t)(2 * kHaloRows * (64 + 32)) : (uint32_t)(p.ag * planes * p.a_plane_bytes);
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
   if (p.a_stages < 1 || p.b_stages < 1) return RSIS_ERR_UNSUPPORTED;
   if (g_print_plan)
@@ -2429,6 +2482,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   } else if (stride == 1) {
     if (p.halo) {
       if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes, p.a_sw64 ? 32 : kBK)) return e;
+      if (p.a_sw64 == 2)  // channels 32..47 of the same tensor, 16 per row
+        if (int e = encode_act_map(&maps.a[1], x, 1, 0, 0, kHaloBW + 2, kHaloBH + 2, 1, planes, 16)) return e;
     } else {
       if (int e = encode_act_map(&maps.a[0], x, 1, 0, 0, p.BW, p.BH, p.BI, planes)) return e;
     }
@@ -3009,10 +3064,14 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
     tiles[i] = ceil_div(x.n * x.h * x.w, kBM);
     const double cols = w->cout < 16 ? 16 : w->cout;
     // narrow gate blocks are bound by the shared-memory operand reads, not by the tensor pipe: 32 + N/4 vs N/2 cycles
-    const double per_col = cols >= 128 ? 1.0 : (40.0 + cols / 2.0) / cols;
+    // (re-fitted after the three-warps-per-quarter epilogue and the narrow activation boxes: level 4 on 61 CTAs 42 us,
+    // level 3 on 35 CTAs 40 us, profiles/r2by_group_tune.txt)
+    const double per_col = cols >= 128 ? 1.0 : (26.0 + 0.6 * cols) / cols;
     work[i] = (double)tiles[i] * w->kh * w->kw * ceil_div(x.c, 16) * cols * per_col * 2.06e-3;  // ~us on one CTA
     const double w_bytes = 2.0 * w->kh * w->kw * ceil_div(x.c, kBK) * 128.0 * cols;              // [W_hi | W_lo] of a tile
-    fixed[i] = (cols < 128 && w_bytes > 100e3 && tiles[i] >= 2 * g_num_sms / n) ? 5.5 : 0.0;
+    const double a_stage = x.c <= 32 ? 23552.0 : (x.c <= 48 ? 34816.0 : 46080.0 * ceil_div(x.c, kBK));
+    const bool can_reside = x.c <= kBK && 2 * a_stage + w_bytes <= kDynSmem - 1023;
+    fixed[i] = (cols < 128 && !can_reside && tiles[i] >= 2 * g_num_sms / n) ? 5.5 : 0.0;
     tiles[i] *= ceil_div(w->cout, 32);  // most (pixel tile, gate-column tile) units a plan can have
     share[i] = 1;
   }
