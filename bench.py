@@ -541,7 +541,10 @@ def run_ours(a):
                        "events summed", "cuda_graph": True,
                        "decoder_schedule": {"0": "sequential", "1": "wavefront over (level, step), split-K cells",
                                             "2": "wavefront over (level, step), cells without split-K",
-                                            "3": "grouped wavefront: one launch per anti-diagonal of (level, step)"}.get(
+                                            "3": "grouped wavefront: cell (l, t) in wavefront 2l + t, one launch per wavefront, "
+                                                 "upsamplings on a side stream beside the next one"
+                                            if os.environ.get("RSIS_B200_WAVE_SKEW", "2") == "2" else
+                                            "grouped wavefront: one launch per anti-diagonal of (level, step)"}.get(
                            os.environ.get("RSIS_B200_PIPELINE", "3"), "custom"),
                        "impl": {ops.IMPL_SIMT: "simt", ops.IMPL_AUTO: "auto", ops.IMPL_TCGEN05: "tcgen05"}[impl],
                        "tcgen05": bool(ops.has_tcgen05())},

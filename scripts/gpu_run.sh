@@ -1,6 +1,6 @@
 #!/bin/bash
 # One parameterised GPU session (run under gpurun from the repo root):  bash scripts/gpu_run.sh <tag> <step> [<step> ...]
-# steps: tests | smoke | bench | bench_ref | bench_train | launches | ncu_cell | sanitize | decoder_probe
+# steps: tests | smoke | bench | bench_ref | bench_train | launches | ncu_cell | ncu_levels | pass_trace | sanitize | decoder_probe
 TAG=${1:?tag}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -28,6 +28,15 @@ for step in "$@"; do
              timeout 300 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -k "convlstm_cell_hoisted or e2e_b2_64x64_t3" \
                  > $OUT/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?"; tail -4 $OUT/sanitizer_synccheck.log ;;
     decoder_probe) timeout 300 python scripts/decoder_probe.py > $OUT/decoder_probe.txt 2>&1; cat $OUT/decoder_probe.txt ;;
+    ncu_levels) # the grouped cell launch of ONE level at a time (all 148 CTAs) and of all five, one full capture each
+             for lv in 0 1 2 3 4 all; do
+               spec="-;-@$lv"; [ $lv = all ] && spec="-;-"
+               timeout 300 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+                 -k "regex:cell_group_kernel" -s 13 -c 1 -o $OUT/prof_level_$lv -f python scripts/group_tune.py "$spec" > $OUT/ncu_level_$lv.log 2>&1
+             done; ls -la $OUT/*.ncu-rep ;;
+    pass_trace) # needs the -DRSIS_DEBUG_TIMING build at build/librsis_dbg.so (scripts/pass_trace.py)
+             TRACE_LOG=$OUT/trace_shapes.txt RSIS_B200_LIB=$PWD/build/librsis_dbg.so timeout 300 python scripts/pass_trace.py > $OUT/pass_trace.txt 2> $OUT/pass_trace.err
+             tail -2 $OUT/pass_trace.txt ;;
     *) echo "unknown step $step" ;;
   esac
 done

@@ -63,3 +63,18 @@ def test_device_check_fails_loudly_without_gpu():
 def test_status_raises():
     with pytest.raises(RuntimeError, match="bad argument"):
         _lib.check(-1, "unit")
+
+
+def test_static_weights_mode_is_a_host_side_switch():
+    """rsis_set_static_weights (ABI v20) returns the previous setting; ops.static_weights restores it on exit."""
+    from rsis_b200 import ops
+    lib = _lib.load()
+    prev = lib.rsis_set_static_weights(0)
+    try:
+        assert lib.rsis_set_static_weights(1) == 0
+        assert lib.rsis_set_static_weights(0) == 1
+        with ops.static_weights():
+            assert lib.rsis_set_static_weights(1) == 1   # on inside the context
+        assert lib.rsis_set_static_weights(0) == 0       # restored to off
+    finally:
+        lib.rsis_set_static_weights(prev)
