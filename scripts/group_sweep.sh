@@ -1,1 +1,2 @@
-RSIS_B200_PRINT_PLAN=1 python scripts/group_tune.py "-;-" "8,22,22,32,64;-" "8,22,22,30,66;-" "8,22,22,34,62;-" "8,22,25,31,62;-" "-;-@1,2,3,4" "-;-@0,1,2,3" 2>&1 | grep "levels\|rsis group" | uniq
+# bash scripts/group_sweep.sh: the grouped cell launch under a few settings (edit the list; scripts/group_tune.py)
+python scripts/group_tune.py "-;-" "-;-@4" "61;-@4" "-;-@3" "35;-@3" "-;-@2" "-;-@0,1,2" 2>&1 | grep "levels"

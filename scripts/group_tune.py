@@ -9,7 +9,8 @@ import torch
 import rsis_b200
 from rsis_b200 import ops, inference, _lib
 from oracle import ref_shims as rs, synth_weights as sw
-B, H, W, T = 8, 256, 256, 2
+B, H, W = (int(v) for v in os.environ.get("GT_SHAPE", "8,256,256").split(","))  # GT_SHAPE=32,512,512: the configs[4] shard
+T = 2
 args = rs.make_args(maxseqlen=T); args.hidden_size = int(args.hidden_size); args.use_gpu = True
 enc, dec = rsis_b200.FeatureExtractor(args), rsis_b200.RSIS(args)
 enc.load_state_dict(sw.encoder_state_dict(1)); dec.load_state_dict(sw.decoder_state_dict(1))
