@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RSIS_ABI_VERSION 20
+#define RSIS_ABI_VERSION 21
 
 typedef void* rsis_stream_t; /* cudaStream_t */
 
@@ -244,6 +244,12 @@ int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias,
  * C % 4 == 0 and C <= 16 (RSIS_ERR_UNSUPPORTED otherwise -- use the two-call form). */
 int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
                             int out_w, float* logits, float* prob_out, int64_t prob_stride_n, rsis_stream_t stream);
+/* rsis_upsample_mask_head for ALL time-steps of a pass in one launch (the `out_masks.append(out_mask)` ... `torch.cat`
+ * of test.py:41-46 over the T decoder steps): h holds steps * B images, step-major ([t][b][H][W][C] dense float32);
+ * sigmoid(logit) of image (t, b) goes to prob_out[b*prob_stride_n + t*prob_stride_t + pixel]. */
+int rsis_upsample_mask_head_steps(const rsis_tensor* h, int steps, const float* w_oihw, const float* bias, int ksize,
+                                  int out_h, int out_w, float* prob_out, int64_t prob_stride_n, int64_t prob_stride_t,
+                                  rsis_stream_t stream);
 /* fc_class + Softmax + fc_stop on the side features (model.py:169-182).  side_max holds the uint32 keys written by
  * rsis_convlstm_cell; feat_out (optional) receives the decoded float features [N, F].  Outputs: class_probs [N,C]
  * written at class_probs[n*class_stride + c], stop logit at stop_logit[n*stop_stride], and optional sigmoid(stop)
@@ -252,6 +258,12 @@ int rsis_class_stop_heads(const uint32_t* side_max, int n, int f, const float* w
                           int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
                           float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
                           int64_t stop_stride, rsis_stream_t stream);
+/* The same for the side features of ALL time-steps in one launch (test.py:37-50): side_max [steps][n][f] keys;
+ * class_probs[b*class_stride + t*class_stride_t + c], sigmoid(stop) at stop_prob[b*stop_stride + t*stop_stride_t]. */
+int rsis_class_stop_heads_steps(const uint32_t* side_max, int n, int steps, int f, const float* w_class,
+                                const float* b_class, int num_classes, const float* w_stop, const float* b_stop,
+                                float* class_probs, int64_t class_stride, int64_t class_stride_t, float* stop_prob,
+                                int64_t stop_stride, int64_t stop_stride_t, rsis_stream_t stream);
 
 /* ---- backward primitives: `loss.backward()` of train.py:184 through vision.py / model.py / clstm.py ----------- */
 /* All gradients are float32 NHWC.  The DATA gradient of a convolution is itself a forward convolution

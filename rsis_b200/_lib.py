@@ -18,7 +18,7 @@ FMT_SPLIT_BF16 = 1
 IMPL_AUTO = 0
 IMPL_SIMT = 1
 IMPL_TCGEN05 = 2
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 
 class Tensor(C.Structure):
@@ -77,6 +77,9 @@ SIGNATURES = {
     "rsis_mask_head": (_I, [_TP, _P, _P, _I, _P, _P, C.c_int64, _P]),
     "rsis_upsample_mask_head": (_I, [_TP, _P, _P, _I, _I, _I, _P, _P, C.c_int64, _P]),
     "rsis_class_stop_heads": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P]),
+    "rsis_upsample_mask_head_steps": (_I, [_TP, _I, _P, _P, _I, _I, _I, _P, C.c_int64, C.c_int64, _P]),
+    "rsis_class_stop_heads_steps": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int64,
+                                         C.c_int64, _P]),
     # backward primitives
     "rsis_conv_dgrad_weights": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rsis_wgrad_workspace_bytes": (C.c_size_t, []),

@@ -182,10 +182,12 @@ __global__ void mask_head_kernel(const float* __restrict__ x, const float* __res
 // state (which stays L2/L1 resident), so the upsampled tensor -- 4x the hidden state -- never exists in HBM.
 // Interpolation and accumulation orders equal upsample_bilinear_kernel + mask_head_kernel: bit-identical results.
 constexpr int kMaskTile = 32;
+constexpr int kMaskSrc = 20;  // source pixels per side a 34 x 34 upsampled tile can touch at scale <= 1/2 (+ the bilinear neighbour)
 __global__ void __launch_bounds__(256)
 upsample_mask_head_kernel(const float* __restrict__ h, const float* __restrict__ w_oihw, const float* __restrict__ bias,
                           float* __restrict__ logits, float* __restrict__ prob_out, long long prob_stride_n, int H,
-                          int W, int C, int Ho, int Wo, int ks, float sh, float sw) {
+                          int W, int C, int Ho, int Wo, int ks, float sh, float sw, int n_inner,
+                          long long prob_stride_t) {
   pdl_trigger();
   extern __shared__ __align__(16) float smem_mask[];
   const int pad = ks / 2;
@@ -252,7 +254,7 @@ upsample_mask_head_kernel(const float* __restrict__ h, const float* __restrict__
     acc += bs;
     const size_t pix = (size_t)oy * Wo + ox;
     if (logits) logits[(size_t)n * Ho * Wo + pix] = acc;
-    if (prob_out) prob_out[(size_t)n * prob_stride_n + pix] = sigmoidf_acc(acc);
+    if (prob_out) prob_out[(size_t)(n % n_inner) * prob_stride_n + (size_t)(n / n_inner) * prob_stride_t + pix] = sigmoidf_acc(acc);
   }
 }
 
@@ -267,16 +269,35 @@ __global__ void __launch_bounds__(256, 3)
 upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __restrict__ w_oihw,
                                 const float* __restrict__ bias, float* __restrict__ logits,
                                 float* __restrict__ prob_out, long long prob_stride_n, int H, int W, int Ho, int Wo,
-                                float sh, float sw) {
+                                float sh, float sw, int n_inner, long long prob_stride_t) {
   pdl_trigger();
   constexpr int PAD = KS / 2, TW = kMaskTile + 2 * PAD, TAPS = KS * KS, C4 = C / 4;
   extern __shared__ __align__(16) float smem_mask[];
   float* up = smem_mask;                 // [TW][TW][C]
   float* sw_ = smem_mask + TW * TW * C;  // [tap][C]
+  float* src = sw_ + TAPS * C;           // [kMaskSrc][kMaskSrc][C]: the source window of this tile
   const int n = blockIdx.z;
   const int oy0 = blockIdx.y * kMaskTile, ox0 = blockIdx.x * kMaskTile;
   for (int i = threadIdx.x; i < TAPS * C; i += 256) sw_[i] = w_oihw[(i % C) * TAPS + i / C];
   const float* hn = h + (size_t)n * H * W * C;
+  // The interpolation below reads four source pixels per upsampled value.  Straight from global memory that is nine
+  // dependent rounds of loads per thread (~20 us per block when the hidden state comes from HBM: the all-steps launch
+  // took 125 us); the tile's source window (<= 20 x 20 pixels for the x2 case) is therefore brought into shared memory
+  // first, in ONE round of independent, coalesced loads.  Same values, same formula: bit-identical results.
+  const int oyA = max(oy0 - PAD, 0), oyB = min(oy0 + kMaskTile + PAD - 1, Ho - 1);
+  const int oxA = max(ox0 - PAD, 0), oxB = min(ox0 + kMaskTile + PAD - 1, Wo - 1);
+  const int sy0 = min((int)(sh * oyA), H - 1), sy1 = min(min((int)(sh * oyB), H - 1) + 1, H - 1);
+  const int sx0 = min((int)(sw * oxA), W - 1), sx1 = min(min((int)(sw * oxB), W - 1) + 1, W - 1);
+  const int nsy = sy1 - sy0 + 1, nsx = sx1 - sx0 + 1;
+  const bool staged = nsy <= kMaskSrc && nsx <= kMaskSrc;  // (block-uniform; other scales read global memory directly)
+  if (staged) {
+    for (int i = threadIdx.x; i < nsy * nsx * C4; i += 256) {
+      const int c = (i % C4) * 4, p = i / C4, x = p % nsx, y = p / nsx;
+      *reinterpret_cast<float4*>(src + ((size_t)y * kMaskSrc + x) * C + c) =
+          __ldg(reinterpret_cast<const float4*>(hn + ((size_t)(sy0 + y) * W + (sx0 + x)) * C + c));
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < TW * TW * C4; i += 256) {
     const int c = (i % C4) * 4;
     const int t = i / C4;
@@ -289,11 +310,15 @@ upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __rest
       const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
       const float h1l = fminf(fmaxf(fh - h1, 0.f), 1.f), h0l = 1.f - h1l;
       const float w1l = fminf(fmaxf(fw - w1, 0.f), 1.f), w0l = 1.f - w1l;
-      const float* b = hn + ((size_t)h1 * W + w1) * C + c;
-      const float4 v00 = __ldg(reinterpret_cast<const float4*>(b));
-      const float4 v01 = __ldg(reinterpret_cast<const float4*>(b + (size_t)w1p * C));
-      const float4 v10 = __ldg(reinterpret_cast<const float4*>(b + (size_t)h1p * W * C));
-      const float4 v11 = __ldg(reinterpret_cast<const float4*>(b + (size_t)h1p * W * C + (size_t)w1p * C));
+      // one code path for both sources (generic loads), so the interpolation below compiles to ONE instruction sequence
+      // -- the one of upsample_bilinear_kernel, whose results this kernel reproduces bit for bit
+      const float* b = staged ? src + ((size_t)(h1 - sy0) * kMaskSrc + (w1 - sx0)) * C + c
+                              : hn + ((size_t)h1 * W + w1) * C + c;
+      const size_t rstride = staged ? (size_t)kMaskSrc * C : (size_t)W * C;
+      const float4 v00 = *reinterpret_cast<const float4*>(b);
+      const float4 v01 = *reinterpret_cast<const float4*>(b + (size_t)w1p * C);
+      const float4 v10 = *reinterpret_cast<const float4*>(b + (size_t)h1p * rstride);
+      const float4 v11 = *reinterpret_cast<const float4*>(b + (size_t)h1p * rstride + (size_t)w1p * C);
       o.x = h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x);
       o.y = h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y);
       o.z = h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z);
@@ -338,7 +363,7 @@ upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __rest
     const float a = acc[q] + bs;
     const size_t pix = (size_t)oy * Wo + ox;
     if (logits) logits[(size_t)n * Ho * Wo + pix] = a;
-    if (prob_out) prob_out[(size_t)n * prob_stride_n + pix] = sigmoidf_acc(a);
+    if (prob_out) prob_out[(size_t)(n % n_inner) * prob_stride_n + (size_t)(n / n_inner) * prob_stride_t + pix] = sigmoidf_acc(a);
   }
 }
 
@@ -348,12 +373,16 @@ __global__ void class_stop_heads_kernel(const uint32_t* __restrict__ side_max, i
                                         const float* __restrict__ w_stop, const float* __restrict__ b_stop,
                                         float* __restrict__ feat_out, float* __restrict__ class_probs,
                                         long long class_stride, float* __restrict__ stop_logit,
-                                        float* __restrict__ stop_prob, long long stop_stride) {
+                                        float* __restrict__ stop_prob, long long stop_stride, int n_inner,
+                                        long long class_stride_t, long long stop_stride_t) {
   pdl_trigger();
   extern __shared__ float sm[];
   float* feat = sm;            // [F]
   float* logit = sm + F;       // [num_classes + 1]; the last entry is the stop logit
   const int n = blockIdx.x;
+  // image n = step (n / n_inner), batch element (n % n_inner): the all-steps form writes [b][t] outputs
+  const size_t co = (size_t)(n % n_inner) * class_stride + (size_t)(n / n_inner) * class_stride_t;
+  const size_t so = (size_t)(n % n_inner) * stop_stride + (size_t)(n / n_inner) * stop_stride_t;
   for (int i = threadIdx.x; i < F; i += blockDim.x) {
     const float v = key_to_float(side_max[(size_t)n * F + i]);
     feat[i] = v;
@@ -379,11 +408,11 @@ __global__ void class_stop_heads_kernel(const uint32_t* __restrict__ side_max, i
     for (int o = lane; o < num_classes; o += 32) sum += expf(logit[o] - mx);
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
-    for (int o = lane; o < num_classes; o += 32) class_probs[(size_t)n * class_stride + o] = expf(logit[o] - mx) / sum;
+    for (int o = lane; o < num_classes; o += 32) class_probs[co + o] = expf(logit[o] - mx) / sum;
     if (lane == 0) {
       const float s = logit[num_classes];
-      if (stop_logit) stop_logit[(size_t)n * stop_stride] = s;
-      if (stop_prob) stop_prob[(size_t)n * stop_stride] = sigmoidf_acc(s);
+      if (stop_logit) stop_logit[so] = s;
+      if (stop_prob) stop_prob[so] = sigmoidf_acc(s);
     }
   }
 }
@@ -478,18 +507,25 @@ int rsis_mask_head(const rsis_tensor* x, const float* w_oihw, const float* bias,
   return RSIS_OK;
 }
 
-int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
-                            int out_w, float* logits, float* prob_out, int64_t prob_stride_n, rsis_stream_t stream) {
+static int upsample_mask_head_impl(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
+                                   int out_w, float* logits, float* prob_out, int64_t prob_stride_n, int n_inner,
+                                   int64_t prob_stride_t, rsis_stream_t stream) {
   if (!valid_tensor(h) || !w_oihw || (!logits && !prob_out) || out_h < 1 || out_w < 1) return RSIS_ERR_BAD_ARG;
   if (h->fmt != RSIS_FMT_F32 || !is_dense(*h) || h->c % 4 != 0 || h->c > 16 || (ksize != 1 && ksize != 3))
     return RSIS_ERR_UNSUPPORTED;
   if (!aligned16(h->data)) return RSIS_ERR_ALIGN;
   const int pad = ksize / 2, TW = kMaskTile + 2 * pad;
-  const size_t smem = (size_t)(TW * TW * h->c + ksize * ksize * h->c) * sizeof(float);
+  const bool fixed = h->c == 8;  // the unrolled kernels: they also stage the tile's source window (kMaskSrc^2 pixels)
+  const size_t smem = (size_t)(TW * TW * h->c + ksize * ksize * h->c + (fixed ? kMaskSrc * kMaskSrc * h->c : 0)) * sizeof(float);
   static bool attr_set = false;  // idempotent; a race only repeats the call
   if (!attr_set) {
     RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (34 * 34 * 16 + 9 * 16) * (int)sizeof(float)));
+    const int fixed_bytes = (34 * 34 * 8 + 9 * 8 + kMaskSrc * kMaskSrc * 8) * (int)sizeof(float);
+    RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_fixed_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fixed_bytes));
+    RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_fixed_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fixed_bytes));
     attr_set = true;
   }
   const float sh = out_h > 1 ? (float)(h->h - 1) / (float)(out_h - 1) : 0.f;
@@ -499,14 +535,45 @@ int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const flo
   const float* hp = reinterpret_cast<const float*>(h->data);
   if (h->c == 8 && ksize == 3)
     upsample_mask_head_fixed_kernel<8, 3><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        hp, w_oihw, bias, logits, prob_out, (long long)prob_stride_n, h->h, h->w, out_h, out_w, sh, sw);
+        hp, w_oihw, bias, logits, prob_out, (long long)prob_stride_n, h->h, h->w, out_h, out_w, sh, sw, n_inner, (long long)prob_stride_t);
   else if (h->c == 8 && ksize == 1)
     upsample_mask_head_fixed_kernel<8, 1><<<grid, 256, smem, (cudaStream_t)stream>>>(
-        hp, w_oihw, bias, logits, prob_out, (long long)prob_stride_n, h->h, h->w, out_h, out_w, sh, sw);
+        hp, w_oihw, bias, logits, prob_out, (long long)prob_stride_n, h->h, h->w, out_h, out_w, sh, sw, n_inner, (long long)prob_stride_t);
   else
     upsample_mask_head_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(hp, w_oihw, bias, logits, prob_out,
                                                                         (long long)prob_stride_n, h->h, h->w, h->c,
-                                                                        out_h, out_w, ksize, sh, sw);
+                                                                        out_h, out_w, ksize, sh, sw, n_inner, (long long)prob_stride_t);
+  RSIS_CHECK_LAUNCH();
+  return RSIS_OK;
+}
+
+int rsis_upsample_mask_head(const rsis_tensor* h, const float* w_oihw, const float* bias, int ksize, int out_h,
+                            int out_w, float* logits, float* prob_out, int64_t prob_stride_n, rsis_stream_t stream) {
+  return upsample_mask_head_impl(h, w_oihw, bias, ksize, out_h, out_w, logits, prob_out, prob_stride_n,
+                                 h ? (h->n > 0 ? h->n : 1) : 1, 0, stream);
+}
+
+int rsis_upsample_mask_head_steps(const rsis_tensor* h, int steps, const float* w_oihw, const float* bias, int ksize,
+                                  int out_h, int out_w, float* prob_out, int64_t prob_stride_n, int64_t prob_stride_t,
+                                  rsis_stream_t stream) {
+  if (!valid_tensor(h) || steps < 1 || h->n % steps != 0 || !prob_out) return RSIS_ERR_BAD_ARG;
+  return upsample_mask_head_impl(h, w_oihw, bias, ksize, out_h, out_w, nullptr, prob_out, prob_stride_n, h->n / steps,
+                                 prob_stride_t, stream);
+}
+
+static int class_stop_heads_impl(const uint32_t* side_max, int n, int f, const float* w_class, const float* b_class,
+                                 int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
+                                 float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
+                                 int64_t stop_stride, int n_inner, int64_t class_stride_t, int64_t stop_stride_t,
+                                 rsis_stream_t stream) {
+  if (!side_max || !w_class || !b_class || !w_stop || !b_stop || !class_probs) return RSIS_ERR_BAD_ARG;
+  if (n < 1 || f < 1 || num_classes < 1) return RSIS_ERR_BAD_ARG;
+  if (f + num_classes + 1 > 10000) return RSIS_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(f + num_classes + 1) * sizeof(float);
+  class_stop_heads_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(side_max, f, w_class, b_class, num_classes, w_stop,
+                                                                 b_stop, feat_out, class_probs,
+                                                                 (long long)class_stride, stop_logit, stop_prob,
+                                                                 (long long)stop_stride, n_inner, (long long)class_stride_t, (long long)stop_stride_t);
   RSIS_CHECK_LAUNCH();
   return RSIS_OK;
 }
@@ -515,16 +582,17 @@ int rsis_class_stop_heads(const uint32_t* side_max, int n, int f, const float* w
                           int num_classes, const float* w_stop, const float* b_stop, float* feat_out,
                           float* class_probs, int64_t class_stride, float* stop_logit, float* stop_prob,
                           int64_t stop_stride, rsis_stream_t stream) {
-  if (!side_max || !w_class || !b_class || !w_stop || !b_stop || !class_probs) return RSIS_ERR_BAD_ARG;
-  if (n < 1 || f < 1 || num_classes < 1) return RSIS_ERR_BAD_ARG;
-  if (f + num_classes + 1 > 10000) return RSIS_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)(f + num_classes + 1) * sizeof(float);
-  class_stop_heads_kernel<<<n, 256, smem, (cudaStream_t)stream>>>(side_max, f, w_class, b_class, num_classes, w_stop,
-                                                                 b_stop, feat_out, class_probs,
-                                                                 (long long)class_stride, stop_logit, stop_prob,
-                                                                 (long long)stop_stride);
-  RSIS_CHECK_LAUNCH();
-  return RSIS_OK;
+  return class_stop_heads_impl(side_max, n, f, w_class, b_class, num_classes, w_stop, b_stop, feat_out, class_probs,
+                               class_stride, stop_logit, stop_prob, stop_stride, n > 0 ? n : 1, 0, 0, stream);
+}
+
+int rsis_class_stop_heads_steps(const uint32_t* side_max, int n, int steps, int f, const float* w_class,
+                                const float* b_class, int num_classes, const float* w_stop, const float* b_stop,
+                                float* class_probs, int64_t class_stride, int64_t class_stride_t, float* stop_prob,
+                                int64_t stop_stride, int64_t stop_stride_t, rsis_stream_t stream) {
+  if (n < 1 || steps < 1) return RSIS_ERR_BAD_ARG;
+  return class_stop_heads_impl(side_max, n * steps, f, w_class, b_class, num_classes, w_stop, b_stop, nullptr, class_probs,
+                               class_stride, nullptr, stop_prob, stop_stride, n, class_stride_t, stop_stride_t, stream);
 }
 
 }  // extern "C"

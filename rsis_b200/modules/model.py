@@ -175,7 +175,8 @@ class DecoderWorkspace:
         self.h = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.c = [ops.Act.empty(n, h, w, ch, ops.FMT_F32, device) for (h, w), ch in zip(self.sizes, self.hidden)]
         self.up_last = None  # only allocated for hidden sizes the fused upsample + mask head does not take
-        self.h_last = None   # [2] float32 hidden state of the last level, double-buffered (run_wavefront)
+        self.h_last = None   # float32 hidden state of the last level per step (run_wavefront; [2] in the older scheme)
+        self.h_last_all = None
         self.h2 = None       # [level][2] float32 hidden states of the other levels, double-buffered (skewed wavefront)
         self.up_stream = None
         self.side = torch.zeros((n, sum(self.hidden)), dtype=torch.int32, device=device)
@@ -397,8 +398,21 @@ class RSIS(nn.Module):
         hl = ws.h[nlev - 1]
         assert hl.c % 4 == 0 and hl.c <= 16 and ws.t == 0
         ws.prepare_pipeline(T)
-        if ws.h_last is None:
-            ws.h_last = [hl, ops.Act.empty(hl.n, hl.h, hl.w, hl.c, ops.FMT_F32, hl.t.device)]
+        # The mask / class / stop heads of ALL steps run after the last wavefront, one launch each
+        # (`upsample_mask_head_steps`, `class_stop_heads_steps`): the grouped launch leaves no registers for another block
+        # on its SM, so heads launched beside the following wavefronts (RSIS_B200_DEFER_HEADS=0, the earlier scheme)
+        # held back that wavefront's CTAs on every SM they landed on -- ~140 us per pass (profiles/r2cf_*).  The last
+        # level's float32 hidden state of every step is kept for it (T x 4 MB at batch 8).
+        defer = os.environ.get("RSIS_B200_DEFER_HEADS", "1") == "1"
+        nbuf = T if defer else 2
+        if ws.h_last is None or len(ws.h_last) < nbuf:
+            if defer:
+                ws.h_last_all = ops.Act.empty(T * hl.n, hl.h, hl.w, hl.c, ops.FMT_F32, hl.t.device)
+                per = hl.n * hl.h * hl.w * hl.c
+                ws.h_last = [ops.Act(ws.h_last_all.t.view(-1)[t * per:(t + 1) * per].view(hl.n, hl.h, hl.w, hl.c), ops.FMT_F32)
+                             for t in range(T)]
+            else:
+                ws.h_last = [hl] + [ops.Act.empty(hl.n, hl.h, hl.w, hl.c, ops.FMT_F32, hl.t.device) for _ in range(nbuf - 1)]
         dev = hl.t.device
         main = torch.cuda.current_stream(dev)
         B, _, H, W = mask_prob.shape
@@ -427,7 +441,7 @@ class RSIS(nn.Module):
                 p = t & 1
                 _, pc = ws.packs(self, l)
                 if l == nlev - 1:
-                    h_out = ws.h_last[p]
+                    h_out = ws.h_last[t if defer else p]
                 else:
                     h_out = ws.h2[l][p] if skew == 2 else ws.h[l]
                 cells.append(dict(x=ws.X[l][p], pc=pc, c_prev=ws.c[l].t if t > 0 else None, side_max=ws.sides[t],
@@ -438,12 +452,12 @@ class RSIS(nn.Module):
                     ups.append((h_out, ws.up_view(l + 1, p)))
                     assert x_next.h == ws.up_view(l + 1, p).h
             t_last = w - skew * (nlev - 1)   # the step whose last level runs in this wavefront
-            if t_last >= 2 and t_last < T:
+            if t_last >= 2 and t_last < T and not defer:
                 main.wait_event(ev_mask[t_last - 2])   # its mask head read the buffer cell (4, t_last) overwrites
             if skew == 2 and (w - 2) in ev_up:
                 main.wait_event(ev_up[w - 2])          # the upsamplings this wavefront's cells read
             ops.convlstm_cell_group(cells)
-            if 0 <= t_last < T:
+            if 0 <= t_last < T and not defer:
                 done = torch.cuda.Event()
                 done.record(main)
                 with torch.cuda.stream(ws.mask_stream):
@@ -470,7 +484,18 @@ class RSIS(nn.Module):
                 ops.upsample_bilinear_group(ups)
         if skew == 2:
             main.wait_stream(ws.up_stream)
-        main.wait_stream(ws.mask_stream)
+        if defer:
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(ws.side_stream):
+                ws.side_stream.wait_event(done)
+                ops.class_stop_heads_steps(ws.sides[:T], self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight,
+                                           self.fc_stop.bias, class_probs, T * C, C, stop_prob, T, 1)
+            src = ws.h_last_all
+            ops.upsample_mask_head_steps(src, T, 2 * src.h, 2 * src.w, self.conv_out.weight, self.conv_out.bias,
+                                         mask_prob, T * H * W, H * W)
+        if not defer:
+            main.wait_stream(ws.mask_stream)
         main.wait_stream(ws.side_stream)
         ws.t = T
 

@@ -484,6 +484,30 @@ def upsample_mask_head(h: Act, out_h: int, out_w: int, weight: torch.Tensor, bia
     _lib.count_launch(1)
 
 
+def upsample_mask_head_steps(h_all: Act, steps: int, out_h: int, out_w: int, weight: torch.Tensor,
+                             bias: Optional[torch.Tensor], prob_out: torch.Tensor, prob_stride_n: int, prob_stride_t: int):
+    """`upsample_mask_head` of all `steps` time-steps in one launch: `h_all` holds steps * B images, step-major."""
+    lib = _lib.load()
+    ks = weight.shape[-1]
+    check(lib.rsis_upsample_mask_head_steps(h_all.ref(), steps, weight.data_ptr(), _ptr(bias), ks, out_h, out_w,
+                                            prob_out.data_ptr(), prob_stride_n, prob_stride_t, _lib.stream_ptr()),
+          "upsample_mask_head_steps")
+    _lib.count_launch(1)
+
+
+def class_stop_heads_steps(side_max_all: torch.Tensor, w_class, b_class, w_stop, b_stop, class_probs: torch.Tensor,
+                           class_stride: int, class_stride_t: int, stop_prob: torch.Tensor, stop_stride: int,
+                           stop_stride_t: int):
+    """`class_stop_heads` of all time-steps in one launch: `side_max_all` is [steps, n, f] keys."""
+    lib = _lib.load()
+    steps, n, f = side_max_all.shape
+    check(lib.rsis_class_stop_heads_steps(side_max_all.data_ptr(), n, steps, f, w_class.data_ptr(), b_class.data_ptr(),
+                                          w_class.shape[0], w_stop.data_ptr(), b_stop.data_ptr(), class_probs.data_ptr(),
+                                          class_stride, class_stride_t, stop_prob.data_ptr(), stop_stride, stop_stride_t,
+                                          _lib.stream_ptr()), "class_stop_heads_steps")
+    _lib.count_launch(1)
+
+
 def class_stop_heads(side_max: torch.Tensor, w_class, b_class, w_stop, b_stop, class_probs: torch.Tensor,
                      class_stride: int, stop_logit: Optional[torch.Tensor], stop_prob: Optional[torch.Tensor],
                      stop_stride: int, feat_out: Optional[torch.Tensor] = None):

@@ -272,6 +272,39 @@ def test_class_stop_heads_and_side_keys(R, sw):
     assert rel(cls, ref_c) < TOL_FP32 and rel(stop, ref_s) < TOL_FP32 and rel(stop_p, torch.sigmoid(ref_s)) < TOL_FP32
 
 
+@pytest.mark.parametrize("ks", [3, 1])
+def test_heads_of_all_steps_in_one_launch_equal_the_per_step_calls(R, sw, ks):
+    """`upsample_mask_head_steps` / `class_stop_heads_steps` (the T steps of test.py:37-50 in one launch each, step-major
+    inputs, [b][t] outputs) are bit-identical to T per-step calls."""
+    ops = R.ops
+    g = torch.Generator().manual_seed(23)
+    T, B, C, h, w_ = 4, 3, 8, 12, 20
+    x = (torch.rand((T * B, C, h, w_), generator=g) * 2 - 1).cuda()
+    wt = (torch.rand((1, C, ks, ks), generator=g) - 0.5).cuda()
+    b = torch.rand(1, generator=g).cuda()
+    xa = ops.act_from_nchw(x, ops.FMT_F32)
+    H, W = 2 * h, 2 * w_
+    per_step = torch.zeros((B, T, H, W), device="cuda")
+    for t in range(T):
+        xt = ops.act_from_nchw(x[t * B:(t + 1) * B].contiguous(), ops.FMT_F32)
+        ops.upsample_mask_head(xt, H, W, wt, b, None, per_step[:, t], T * H * W)
+    batched = torch.zeros((B, T, H, W), device="cuda")
+    ops.upsample_mask_head_steps(xa, T, H, W, wt, b, batched, T * H * W, H * W)
+    assert torch.equal(batched, per_step)
+
+    feat = torch.rand((T, B, 248), generator=g) * 4 - 2
+    bits = feat.view(torch.int32)
+    keys = torch.where(bits < 0, ~bits, bits | torch.tensor(-2 ** 31, dtype=torch.int32)).cuda()
+    dsd = sw.decoder_state_dict(1)
+    wc, bc, ws, bs = (dsd[k].cuda() for k in ("fc_class.weight", "fc_class.bias", "fc_stop.weight", "fc_stop.bias"))
+    cls_a, stop_a = torch.zeros((B, T, 21), device="cuda"), torch.zeros((B, T, 1), device="cuda")
+    for t in range(T):
+        ops.class_stop_heads(keys[t], wc, bc, ws, bs, cls_a[:, t], T * 21, None, stop_a[:, t], T)
+    cls_b, stop_b = torch.zeros_like(cls_a), torch.zeros_like(stop_a)
+    ops.class_stop_heads_steps(keys, wc, bc, ws, bs, cls_b, T * 21, 21, stop_b, T, 1)
+    assert torch.equal(cls_a, cls_b) and torch.equal(stop_a, stop_b)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # ConvLSTM cell: the reference's own outputs (tests/golden/cells_teacher_forced.npz, made by oracle/make_golden.py)
 # ---------------------------------------------------------------------------------------------------------
