@@ -265,7 +265,7 @@ upsample_mask_head_kernel(const float* __restrict__ h, const float* __restrict__
 // memory once.  The staged tile holds zeros outside the map, so out-of-range taps contribute fma(0, w, acc) = acc:
 // the accumulation order (kh, kw, c) and hence every result bit equals the generic kernel's.
 template <int C, int KS>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 3)  // (4 blocks per SM = 64 registers: spills, measured slower)
 upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __restrict__ w_oihw,
                                 const float* __restrict__ bias, float* __restrict__ logits,
                                 float* __restrict__ prob_out, long long prob_stride_n, int H, int W, int Ho, int Wo,
@@ -296,29 +296,63 @@ upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __rest
       *reinterpret_cast<float4*>(src + ((size_t)y * kMaskSrc + x) * C + c) =
           __ldg(reinterpret_cast<const float4*>(hn + ((size_t)(sy0 + y) * W + (sx0 + x)) * C + c));
     }
-    __syncthreads();
   }
+  // Per tile row / column of the upsampled window: source offset (elements; -1 outside the map), step to the bilinear
+  // neighbour and its weight -- computed ONCE per block (2 x TW threads) instead of once per interpolated value: the
+  // per-value index arithmetic (int <-> float conversions, clamps, divisions) was half of this kernel's instructions.
+  int* roff = reinterpret_cast<int*>(src + kMaskSrc * kMaskSrc * C);  // [TW] row offset, [TW] row step
+  int* coff = roff + 2 * TW;                                           // [TW] column offset, [TW] column step
+  float* rl = reinterpret_cast<float*>(coff + 2 * TW);                 // [TW] h1l, [TW] w1l
+  const int rstride = staged ? kMaskSrc * C : W * C;
+  if (threadIdx.x < TW) {
+    const int oy = oy0 + (int)threadIdx.x - PAD;
+    int off = -1, step = 0;
+    float l = 0.f;
+    if (oy >= 0 && oy < Ho) {
+      const float fh = sh * oy;
+      const int h1 = min((int)fh, H - 1);
+      off = (staged ? h1 - sy0 : h1) * rstride;
+      step = h1 < H - 1 ? rstride : 0;
+      l = fminf(fmaxf(fh - h1, 0.f), 1.f);
+    }
+    roff[threadIdx.x] = off;
+    roff[TW + threadIdx.x] = step;
+    rl[threadIdx.x] = l;
+  } else if (threadIdx.x >= 64 && threadIdx.x < 64 + TW) {
+    const int tx = (int)threadIdx.x - 64;
+    const int ox = ox0 + tx - PAD;
+    int off = -1, step = 0;
+    float l = 0.f;
+    if (ox >= 0 && ox < Wo) {
+      const float fw = sw * ox;
+      const int w1 = min((int)fw, W - 1);
+      off = (staged ? w1 - sx0 : w1) * C;
+      step = w1 < W - 1 ? C : 0;
+      l = fminf(fmaxf(fw - w1, 0.f), 1.f);
+    }
+    coff[tx] = off;
+    coff[TW + tx] = step;
+    rl[TW + tx] = l;
+  }
+  __syncthreads();
+  const float* sbase = staged ? src : hn;
   for (int i = threadIdx.x; i < TW * TW * C4; i += 256) {
     const int c = (i % C4) * 4;
     const int t = i / C4;
     const int tx = t % TW, ty = t / TW;
-    const int oy = oy0 + ty - PAD, ox = ox0 + tx - PAD;
+    const int ro = roff[ty], co = coff[tx];
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
-      const float fh = sh * oy, fw = sw * ox;
-      const int h1 = min((int)fh, H - 1), w1 = min((int)fw, W - 1);
-      const int h1p = h1 < H - 1 ? 1 : 0, w1p = w1 < W - 1 ? 1 : 0;
-      const float h1l = fminf(fmaxf(fh - h1, 0.f), 1.f), h0l = 1.f - h1l;
-      const float w1l = fminf(fmaxf(fw - w1, 0.f), 1.f), w0l = 1.f - w1l;
+    if (ro >= 0 && co >= 0) {
+      const float h1l = rl[ty], h0l = 1.f - h1l;
+      const float w1l = rl[TW + tx], w0l = 1.f - w1l;
       // one code path for both sources (generic loads), so the interpolation below compiles to ONE instruction sequence
       // -- the one of upsample_bilinear_kernel, whose results this kernel reproduces bit for bit
-      const float* b = staged ? src + ((size_t)(h1 - sy0) * kMaskSrc + (w1 - sx0)) * C + c
-                              : hn + ((size_t)h1 * W + w1) * C + c;
-      const size_t rstride = staged ? (size_t)kMaskSrc * C : (size_t)W * C;
+      const float* b = sbase + ro + co + c;
+      const int rs = roff[TW + ty], cs = coff[TW + tx];
       const float4 v00 = *reinterpret_cast<const float4*>(b);
-      const float4 v01 = *reinterpret_cast<const float4*>(b + (size_t)w1p * C);
-      const float4 v10 = *reinterpret_cast<const float4*>(b + (size_t)h1p * rstride);
-      const float4 v11 = *reinterpret_cast<const float4*>(b + (size_t)h1p * rstride + (size_t)w1p * C);
+      const float4 v01 = *reinterpret_cast<const float4*>(b + cs);
+      const float4 v10 = *reinterpret_cast<const float4*>(b + rs);
+      const float4 v11 = *reinterpret_cast<const float4*>(b + rs + cs);
       o.x = h0l * (w0l * v00.x + w1l * v01.x) + h1l * (w0l * v10.x + w1l * v11.x);
       o.y = h0l * (w0l * v00.y + w1l * v01.y) + h1l * (w0l * v10.y + w1l * v11.y);
       o.z = h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z);
@@ -516,12 +550,12 @@ static int upsample_mask_head_impl(const rsis_tensor* h, const float* w_oihw, co
   if (!aligned16(h->data)) return RSIS_ERR_ALIGN;
   const int pad = ksize / 2, TW = kMaskTile + 2 * pad;
   const bool fixed = h->c == 8;  // the unrolled kernels: they also stage the tile's source window (kMaskSrc^2 pixels)
-  const size_t smem = (size_t)(TW * TW * h->c + ksize * ksize * h->c + (fixed ? kMaskSrc * kMaskSrc * h->c : 0)) * sizeof(float);
+  const size_t smem = (size_t)(TW * TW * h->c + ksize * ksize * h->c + (fixed ? kMaskSrc * kMaskSrc * h->c + 6 * TW : 0)) * sizeof(float);
   static bool attr_set = false;  // idempotent; a race only repeats the call
   if (!attr_set) {
     RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (34 * 34 * 16 + 9 * 16) * (int)sizeof(float)));
-    const int fixed_bytes = (34 * 34 * 8 + 9 * 8 + kMaskSrc * kMaskSrc * 8) * (int)sizeof(float);
+    const int fixed_bytes = (34 * 34 * 8 + 9 * 8 + kMaskSrc * kMaskSrc * 8 + 6 * 34) * (int)sizeof(float);
     RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_fixed_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        fixed_bytes));
     RSIS_CUDA_TRY(cudaFuncSetAttribute(upsample_mask_head_fixed_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

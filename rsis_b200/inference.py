@@ -74,10 +74,11 @@ def run_eager(encoder, decoder, x: torch.Tensor, T: int, impl: int, out_masks: t
         if ws is None:
             ws = decoder.workspace(B, feature_sizes(H, W), x.device)
         if feats_op is None:
+            ws.reset(on_side_stream=True)                     # zero fills beside the encoder; encode_into joins the stream
             keep = ws.encode_into(encoder, decoder, x, impl)  # noqa: F841 -- alive until the join is enqueued
         else:
             ws.load_feats(decoder, feats_op, impl)
-        ws.reset()
+            ws.reset()
         # RSIS_B200_PIPELINE: 0 = one step after the other (12 launches in stream order), 1 = wavefront over
         # (level, step) on per-level streams, 2 = wavefront and no split-K in the cells (measured on B200 at
         # B=8 256x256 T=10: 3.60 / 3.40 / 3.24 ms per pass), 3 (default) = grouped wavefront launches

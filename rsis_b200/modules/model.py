@@ -226,13 +226,22 @@ class DecoderWorkspace:
             pc_skip, _ = self.packs(decoder, l)
             ops.conv2d([f], pc_skip, pad=pc_skip.kh // 2, impl=impl, out=self.P[l])
 
-    def reset(self):
-        """New sequence: hidden state None == zeros (clstm.py:26-37)."""
-        for l in range(len(self.X)):
-            sl = slice(self.up_c[l], self.up_c[l] + self.hidden[l])
-            self.X[l][0].t[..., sl].zero_()
-        if self.sides is not None:
-            self.sides.zero_()
+    def reset(self, on_side_stream: bool = False):
+        """New sequence: hidden state None == zeros (clstm.py:26-37).  on_side_stream: the zero fills (six small launches)
+        go to the side stream, ordered after everything enqueued so far -- the caller joins it before the first decoder
+        step (`encode_into` does), so they run beside the encoder instead of between encoder and decoder."""
+        def fills():
+            for l in range(len(self.X)):
+                sl = slice(self.up_c[l], self.up_c[l] + self.hidden[l])
+                self.X[l][0].t[..., sl].zero_()
+            if self.sides is not None:
+                self.sides.zero_()
+        if on_side_stream:
+            self.side_stream.wait_stream(torch.cuda.current_stream(self.side.device))
+            with torch.cuda.stream(self.side_stream):
+                fills()
+        else:
+            fills()
         self.t = 0
 
     def prepare_pipeline(self, T: int):
