@@ -394,17 +394,12 @@ __device__ __forceinline__ void res_prefetch(const UmmaParams& p, ResPiece<PW>& 
 // Lane = (row within the iteration, group of 4 adjacent channels): a pixel's PW channels are one contiguous run.
 template <int PW>
 __device__ __forceinline__ void conv_finish_piece(const UmmaParams& p, const float* stage, int lane, uint32_t mypix,
-                                                  int col0, const ResPiece<PW>& rp) {
+                                                  int col0, const ResPiece<PW>& rp, const float4 sc, const float4 sh) {
   constexpr int LPR = PW / 4;    // lanes per row, four adjacent columns each
   constexpr int RPI = 32 / LPR;  // rows per iteration
   const int c = 4 * (lane % LPR);
   const int col = col0 + c;
   const bool col_ok = col < p.Cout;  // Cout % 4 == 0
-  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
-  if (col_ok) {
-    sc = __ldg(reinterpret_cast<const float4*>(p.scale + col));
-    sh = __ldg(reinterpret_cast<const float4*>(p.shift + col));
-  }
   const float* srow = stage + (lane / LPR) * kStagePitch + c;
 #pragma unroll
   for (int it = 0; it < 32 / RPI; ++it) {
@@ -705,15 +700,26 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
             }
           }
         }
+        // the piece's folded affine first (its L1 / L2 latency hides behind the tensor-memory loads instead of following
+        // the transpose), then BOTH tensor-memory loads of a stacked accumulator before one wait
+        float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
+        if constexpr (!CELL) {
+          const int colq = col0 + 4 * (lane % (PW / 4));
+          if (colq < p.Cout) {
+            sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + colq));
+            sh4 = __ldg(reinterpret_cast<const float4*>(p.shift + colq));
+          }
+        }
         uint32_t r[PW];
         tmem_ld_piece<PW>(taddr + PW * j, r);
-        tmem_ld_wait();
         if (p.stacked) {
           uint32_t r2[PW];
           tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+        } else {
+          tmem_ld_wait();
         }
 #pragma unroll
         for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
@@ -722,7 +728,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           cell_finish_piece<PW>(p, stage, lane, cpz_cur, g.img, col0, seg);
           cpz_cur = cpz_next;
         } else {
-          conv_finish_piece<PW>(p, stage, lane, mypix, col0, res_cur);
+          conv_finish_piece<PW>(p, stage, lane, mypix, col0, res_cur, sc4, sh4);
           if (p.has_res) res_cur = res_next;
         }
         __syncwarp();

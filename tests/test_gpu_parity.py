@@ -603,6 +603,24 @@ def test_cityscapes_shape_cfg3_smoke(R, O, sw, impl):
     assert rel(stops[:, 0], torch.sigmoid(s0)) < _tol(impl)
 
 
+@pytest.mark.parametrize("cfg", [("configs[2] Cityscapes", 2, 512, 1024, 20, 9), ("configs[4] shard", 2, 512, 512, 16, 21)])
+def test_full_length_passes_at_the_large_baseline_shapes_match_the_oracle(R, O, sw, impl, cfg):
+    """BASELINE.json configs[2] (512x1024, T=20, 9 classes) and the configs[4] geometry (512x512, T=16), two images each:
+    EVERY step of the pass against the oracle's test() loop (test.py:16-50) -- masks, class probabilities and stop
+    probabilities of all T steps, so the recurrence's error growth over the full length is inside the tolerance too."""
+    _, B, H, W, T, C = cfg
+    args, enc, dec = _models(R, sw, C, T)
+    x = sw.synthetic_images(321, B, H, W)
+    masks, classes, stops = R.test(args, enc, dec, x.cuda())
+    rm, rc, rs_ = O.test_loop(sw.encoder_state_dict(1), sw.decoder_state_dict(1, num_classes=C), x, T)
+    assert tuple(masks.shape) == (B, T, H, W) and tuple(classes.shape) == (B, T, C) and tuple(stops.shape) == (B, T, 1)
+    tol = _tol(impl)
+    assert rel(masks, rm) < tol and rel(classes, rc) < tol and rel(stops, rs_) < tol
+    # per step, so that a late step cannot hide behind the tensor-wide maximum
+    for t in (0, T // 2, T - 1):
+        assert rel(masks[:, t], rm[:, t]) < tol and rel(classes[:, t], rc[:, t]) < tol
+
+
 # ---------------------------------------------------------------------------------------------------------
 # error behaviour across the ABI
 # ---------------------------------------------------------------------------------------------------------
