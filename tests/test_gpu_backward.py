@@ -484,6 +484,25 @@ def test_cfg4_shard_gradients_tcgen05_vs_exact_fp32_family(R, monkeypatch):
     assert len(rows) > 300 and median <= 5e-2 and rows[0][0] <= 1.5e-1, (median, rows[:5])
 
 
+def test_cfg5_geometry_gradients_tcgen05_vs_exact_fp32_family(R, monkeypatch):
+    """The same gradient-parity statement at the configs[4] geometry (512x512, T=16; two images of the 32 a rank holds):
+    the full-length training iteration (forward, BPTT through 16 decoder steps, train-mode ResNet-101 backward) on the
+    tcgen05 family against the exact-fp32 CUDA-core family.  Same bounds as at the configs[3] shard shape."""
+    from oracle import synth_weights as sw
+    if not R.ops.has_tcgen05():
+        pytest.skip("library built without tcgen05 kernels")
+    l_ref, g_ref = _cfg4_step(R, sw, {"RSIS_B200_IMPL": "simt", "RSIS_B200_BWD_IMPL": "simt"}, monkeypatch, batch=2,
+                              size=512, T=16)
+    l_tc, g_tc = _cfg4_step(R, sw, {"RSIS_B200_IMPL": "auto", "RSIS_B200_BWD_IMPL": "auto"}, monkeypatch, batch=2,
+                            size=512, T=16)
+    assert abs(l_tc - l_ref) <= 1e-4 * abs(l_ref), (l_tc, l_ref)
+    rows = _rel_l2_table(g_tc, g_ref)
+    median = rows[len(rows) // 2][0]
+    print("cfg5 geometry, tcgen05 vs exact fp32: median rel-L2", median, "worst", rows[:5])
+    assert len(rows) > 300 and all(bool(torch.isfinite(g).all()) for g in g_tc.values())
+    assert median <= 5e-2 and rows[0][0] <= 1.5e-1, (median, rows[:5])
+
+
 def test_bf16_training_mode_loss_level_parity(R, monkeypatch):
     """BASELINE.json configs[3] "training step bf16": `args.precision = "bf16"` runs the training-mode forward and
     backward with single-pass bf16 tensor-core products (fp32 accumulation, fp32 master weights and gradients).
