@@ -934,7 +934,8 @@ template <int KS, int PASSES, int ROW16 = 8>  // PASSES: 1 = single-pass bf16, 2
                                               // ROW16: bytes / 16 of an activation row (8: SWIZZLE_128B, 4: SWIZZLE_64B)
 __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
                                                     uint32_t b_stage16, uint32_t b_plane16, uint32_t idesc,
-                                                    uint32_t accumulate, bool wait_b, uint32_t bfull0, int bg) {
+                                                    uint32_t idesc_lo, uint32_t accumulate, bool wait_b, uint32_t bfull0,
+                                                    int bg) {
   // b_stage16: one tap's weights (a K block); the taps arrive in boxes of `bg`, one barrier per box
 #pragma unroll
   for (int bi = 0; bi < 9; ++bi) {
@@ -952,7 +953,7 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
         umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
       } else if (PASSES == 2) {
         umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
-        umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+        umma_bf16(d, a_lo + toff + adv, b + adv, idesc_lo, 1u);
       } else {
         umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
         umma_bf16(d, a_hi + toff + adv, b + b_plane16 + adv, idesc, 1u);
@@ -967,7 +968,7 @@ __device__ __forceinline__ void issue_halo_resident(uint32_t d, uint64_t a_hi, u
 // of 4 / 2 descriptor units per row) and group stride; the weight tile is the ordinary 64-channel SWIZZLE_128B one.
 __device__ __forceinline__ void issue_halo_resident_split48(uint32_t d, uint64_t a64_hi, uint64_t a64_lo, uint64_t a32_hi,
                                                             uint64_t a32_lo, uint64_t bdesc0, uint32_t b_stage16,
-                                                            uint32_t idesc, uint32_t accumulate, bool wait_b,
+                                                            uint32_t idesc, uint32_t idesc_lo, uint32_t accumulate, bool wait_b,
                                                             uint32_t bfull0, int bg) {
 #pragma unroll
   for (int bi = 0; bi < 9; ++bi) {
@@ -981,17 +982,17 @@ __device__ __forceinline__ void issue_halo_resident_split48(uint32_t d, uint64_t
     for (int k = 0; k < 2; ++k) {
       const uint64_t adv = (uint64_t)(2 * k);
       umma_bf16(d, a64_hi + (uint64_t)(row * 4) + adv, b + adv, idesc, (bi == 0 && k == 0) ? accumulate : 1u);
-      umma_bf16(d, a64_lo + (uint64_t)(row * 4) + adv, b + adv, idesc, 1u);
+      umma_bf16(d, a64_lo + (uint64_t)(row * 4) + adv, b + adv, idesc_lo, 1u);
     }
     umma_bf16(d, a32_hi + (uint64_t)(row * 2), b + 4, idesc, 1u);
-    umma_bf16(d, a32_lo + (uint64_t)(row * 2), b + 4, idesc, 1u);
+    umma_bf16(d, a32_lo + (uint64_t)(row * 2), b + 4, idesc_lo, 1u);
   }
 }
 
 // The MMAs of one (tap, chunk) K block: KS steps of 16 channels, compile-time descriptor offsets.
 template <int KS, int PASSES>  // PASSES: 1 = single-pass bf16, 2 = stacked weight planes, 3 = three products
 __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t b_plane16,
-                                             uint32_t idesc, uint32_t accumulate) {
+                                             uint32_t idesc, uint32_t idesc_lo, uint32_t accumulate) {
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     const uint64_t adv = (uint64_t)(2 * k);  // 16 bf16 = 32 bytes along K inside the swizzle row
@@ -1000,7 +1001,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t a_hi, uint64_t
       umma_bf16(d, a_hi + adv, b + adv, idesc, first);
     } else if (PASSES == 2) {
       umma_bf16(d, a_hi + adv, b + adv, idesc, first);
-      umma_bf16(d, a_lo + adv, b + adv, idesc, 1u);
+      umma_bf16(d, a_lo + adv, b + adv, idesc_lo, 1u);
     } else {
       umma_bf16(d, a_hi + adv, b + adv, idesc, first);
       umma_bf16(d, a_hi + adv, b + b_plane16 + adv, idesc, 1u);
@@ -1017,7 +1018,7 @@ __device__ __forceinline__ void issue_kblock(uint32_t d, uint64_t a_hi, uint64_t
 template <int PASSES>  // 2 = stacked weight planes, 3 = three products
 __device__ __forceinline__ void issue_halo_stream3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t bdesc0,
                                                    uint32_t b_stage16, uint32_t b_chunk16, uint32_t b_plane16,
-                                                   uint32_t idesc, uint32_t accumulate, uint32_t bfull0, uint32_t bempty0,
+                                                   uint32_t idesc, uint32_t idesc_lo, uint32_t accumulate, uint32_t bfull0, uint32_t bempty0,
                                                    int& bs, uint32_t& bph, int b_stages) {
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
@@ -1034,7 +1035,7 @@ __device__ __forceinline__ void issue_halo_stream3(uint32_t d, uint64_t a_hi, ui
         const uint32_t first = (g == 0 && j == 0 && k == 0) ? accumulate : 1u;
         if (PASSES == 2) {
           umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
-          umma_bf16(d, a_lo + toff + adv, b + adv, idesc, 1u);
+          umma_bf16(d, a_lo + toff + adv, b + adv, idesc_lo, 1u);
         } else {
           umma_bf16(d, a_hi + toff + adv, b + adv, idesc, first);
           umma_bf16(d, a_hi + toff + adv, b + b_plane16 + adv, idesc, 1u);
@@ -1482,6 +1483,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
       const uint32_t a_row16 = p.a_sw64 ? 4u : 8u;  // descriptor units per activation row (HALO tap shifts)
       const uint32_t n_mma = (uint32_t)(p.stacked ? 2 * p.BN : p.BN);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n_mma >> 3) << 17) | ((kBM >> 4) << 24);
+      // Stacked weight planes: X_hi multiplies [W_hi | W_lo] (N = 2 BN), but X_lo only needs W_hi -- the first BN columns of
+      // the same tile and of the same accumulator -- so its MMA is issued with N = BN: no lo x lo product, half its
+      // weight-operand read and (SS-mode cost max(N/2, 32 + N/4)) 8-50 % less tensor-pipe time for it.
+      const uint32_t idesc_lo = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)p.BN >> 3) << 17) | ((kBM >> 4) << 24);
       const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_stage16 = (uint32_t)p.b_stage_bytes >> 4;
       const uint32_t a_chunk16 = (uint32_t)p.a_chunk_bytes >> 4, b_chunk16 = (uint32_t)p.b_chunk_bytes >> 4;
       const int bg = p.bg, ag = p.ag;
@@ -1522,10 +1527,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
             const bool wb = first_work;  // the nine taps are loaded once, for this CTA's first tile
 #define RSIS_ISSUE_HALO(PASSES)                                                                                          \
   switch (ksteps) {                                                                                                      \
-    case 1: issue_halo_resident<1, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
-    case 2: issue_halo_resident<2, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
-    case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
-    default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg); break; \
+    case 1: issue_halo_resident<1, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg); break; \
+    case 2: issue_halo_resident<2, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg); break; \
+    case 3: issue_halo_resident<3, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg); break; \
+    default: issue_halo_resident<4, PASSES>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg); break; \
   }
 #ifdef RSIS_DEBUG_TIMING
             if (p.dbg_skip & 4) {  // (diagnostic: no MMAs at all -- what the operand pipeline alone sustains)
@@ -1535,13 +1540,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
               const uint32_t part32 = smem_a + (uint32_t)as * (uint32_t)p.a_stage_bytes + (uint32_t)p.a_split_off;
               const uint64_t a32_hi = make_smem_desc(part32, (uint32_t)(kHaloBW + 2) * 32u, 6u);
               const uint64_t a32_lo = make_smem_desc(part32 + (uint32_t)kHaloRows * 32u, (uint32_t)(kHaloBW + 2) * 32u, 6u);
-              issue_halo_resident_split48(d, a_hi0, a_lo0, a32_hi, a32_lo, bdesc0, b_chunk16, idesc, accumulate, wb, bfull0,
+              issue_halo_resident_split48(d, a_hi0, a_lo0, a32_hi, a32_lo, bdesc0, b_chunk16, idesc, idesc_lo, accumulate, wb, bfull0,
                                           bg);
             } else if (p.a_sw64) {  // <= 32 channels: one or two K steps
               if (ksteps == 1)
-                issue_halo_resident<1, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
+                issue_halo_resident<1, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg);
               else
-                issue_halo_resident<2, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, accumulate, wb, bfull0, bg);
+                issue_halo_resident<2, 2, 4>(d, a_hi0, a_lo0, bdesc0, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, wb, bfull0, bg);
             } else {
               RSIS_ISSUE_HALO(2)
             }
@@ -1549,10 +1554,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
             accumulate = 1u;
           } else if (!SPLIT && halo && bg == 3 && !resident && !single && ksteps == kBK / 16) {
             if (stacked)
-              issue_halo_stream3<2>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, accumulate, bfull0,
+              issue_halo_stream3<2>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, bfull0,
                                     bempty0, bs, bph, p.b_stages);
             else
-              issue_halo_stream3<3>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, accumulate, bfull0,
+              issue_halo_stream3<3>(d, a_hi0, a_lo0, bdesc0, b_stage16, b_chunk16, b_plane16, idesc, idesc_lo, accumulate, bfull0,
                                     bempty0, bs, bph, p.b_stages);
             bgi += 3;
             accumulate = 1u;
@@ -1581,16 +1586,16 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
               // partial last chunks and the single-pass bf16 mode take a compact loop (code size: see above)
               if (ksteps == kBK / 16 && !single) {
                 if (stacked)
-                  issue_kblock<kBK / 16, 2>(d, a_hi, a_lo, b_hi, b_plane16, idesc, accumulate);
+                  issue_kblock<kBK / 16, 2>(d, a_hi, a_lo, b_hi, b_plane16, idesc, idesc_lo, accumulate);
                 else
-                  issue_kblock<kBK / 16, 3>(d, a_hi, a_lo, b_hi, b_plane16, idesc, accumulate);
+                  issue_kblock<kBK / 16, 3>(d, a_hi, a_lo, b_hi, b_plane16, idesc, idesc_lo, accumulate);
               } else {
                 for (int k = 0; k < ksteps; ++k) {
                   const uint64_t adv = (uint64_t)(2 * k);
                   umma_bf16(d, a_hi + adv, b_hi + adv, idesc, k == 0 ? accumulate : 1u);
                   if (!single) {
                     if (!stacked) umma_bf16(d, a_hi + adv, b_hi + b_plane16 + adv, idesc, 1u);
-                    umma_bf16(d, a_lo + adv, b_hi + adv, idesc, 1u);
+                    umma_bf16(d, a_lo + adv, b_hi + adv, idesc_lo, 1u);
                   }
                 }
               }
