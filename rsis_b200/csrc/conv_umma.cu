@@ -2032,6 +2032,7 @@ int g_init_status = RSIS_OK;
 int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-B timing)
 int g_early_b = 1;         // RSIS_B200_EARLY_B=0: weight boxes wait for the previous kernel even with static weights (A-B timing)
 int g_max_a_stages = 4;    // RSIS_B200_ASTAGES: most activation stages beside resident weights (cold halo boxes land ~2.5 us after issue)
+int g_plan_lo = 0;         // RSIS_B200_PLAN_LO=1: the planner charges the X_lo MMA of a stacked K step at N = BN
 int g_sw64 = 1;            // RSIS_B200_SW64=0: 64-channel SWIZZLE_128B halo boxes for narrow sources too (A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
@@ -2065,6 +2066,7 @@ cudaError_t set_smem_attr() {
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SW64")) g_sw64 = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_PLAN_LO")) g_plan_lo = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_ASTAGES")) g_max_a_stages = atoi(e) < 2 ? 2 : (atoi(e) > kMaxStages ? kMaxStages : atoi(e));
   if (const char* e = getenv("RSIS_B200_EARLY_B")) g_early_b = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SPLITK")) g_split_k = atoi(e) != 0;
@@ -2231,8 +2233,10 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
     if (g_force_bn && BN != g_force_bn) continue;
     if (t_force_bn && BN != t_force_bn) continue;
     const int stacked = (BN <= 128 && !single) ? 1 : 0;
-    const double mpk = single ? 1 : (stacked ? 2 : 3);
-    const double kMma = mma_ns(stacked ? 2 * BN : BN);
+    // MMAs per K step x their cost: stacked = X_hi x [W_hi | W_lo] (N = 2 BN) + X_lo x W_hi (N = BN); RSIS_B200_PLAN_LO=0
+    // keeps the model of two N = 2 BN MMAs the plans were first calibrated with (A/B timing)
+    const double mpk = single ? 1 : (stacked ? (g_plan_lo ? 1 : 2) : 3);
+    const double kMma = (stacked && g_plan_lo) ? mma_ns(2 * BN) + mma_ns(BN) : mma_ns(stacked ? 2 * BN : BN);
     const int tiles_n = ceil_div(cout, BN);
     const double b_item = (single ? 1.0 : 2.0) * BN * 128;
     const double pieces_per_warp = BN >= 64 ? ceil_div(4 * (BN / 32), kEpiWarps) : 0.6;
