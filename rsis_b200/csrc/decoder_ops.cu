@@ -358,7 +358,7 @@ upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __rest
       o.z = h0l * (w0l * v00.z + w1l * v01.z) + h1l * (w0l * v10.z + w1l * v11.z);
       o.w = h0l * (w0l * v00.w + w1l * v01.w) + h1l * (w0l * v10.w + w1l * v11.w);
     }
-    *reinterpret_cast<float4*>(up + (size_t)t * C + c) = o;
+    *reinterpret_cast<float4*>(up + ((size_t)(c >> 2) * (TW * TW) + t) * 4) = o;  // [c / 4][pixel][4]: see below
   }
   __syncthreads();
   const float bs = bias ? bias[0] : 0.f;
@@ -378,10 +378,13 @@ upsample_mask_head_fixed_kernel(const float* __restrict__ h, const float* __rest
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float* pxl = up + ((size_t)(py0 + q + kh) * TW + (px + kw)) * C;
+        // the window is stored as C / 4 planes of [pixel][4 floats]: the 32 lanes of a warp (32 adjacent pixels) read 512
+        // contiguous bytes per float4 load.  With [pixel][C] (32 bytes per pixel) every such load was a 2-way bank
+        // conflict, and the kernel ran at the shared-memory bandwidth that left (ncu: 115 us for the ten steps of a pass)
+        const float* pxl = up + ((size_t)(py0 + q + kh) * TW + (px + kw)) * 4;
 #pragma unroll
         for (int c = 0; c < C; c += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(pxl + c);
+          const float4 v = *reinterpret_cast<const float4*>(pxl + (size_t)(c >> 2) * (TW * TW * 4));
           acc[q] = fmaf(v.x, wv[c], acc[q]);
           acc[q] = fmaf(v.y, wv[c + 1], acc[q]);
           acc[q] = fmaf(v.z, wv[c + 2], acc[q]);

@@ -11,6 +11,7 @@ from rsis_b200 import ops
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--only", default="", help="substring filter on the case names, e.g. layer4")
 a = ap.parse_args()
 B = a.batch
 CASES = [  # name, Cin, H, W, Cout, k, residual
@@ -20,7 +21,7 @@ CASES = [  # name, Cin, H, W, Cout, k, residual
     ("layer4.conv1", 2048, 8, 8, 512, 1, False), ("layer4.conv2", 512, 8, 8, 512, 3, False), ("layer4.conv3", 512, 8, 8, 2048, 1, True),
 ]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-for name, Cin, H, W, Cout, k, has_res in CASES:
+for name, Cin, H, W, Cout, k, has_res in [c for c in CASES if a.only in c[0]]:
     x = ops.act_from_nchw(torch.rand((B, Cin, H, W), device="cuda") - 0.5, ops.FMT_SPLIT_BF16)
     w = (torch.rand((Cout, Cin, k, k), device="cuda") - 0.5) * 0.05
     pc = ops.PackedConv(w, None, None, want_umma=True)
