@@ -105,6 +105,10 @@ struct UmmaParams {
   int ag;                  // 64-channel chunks per activation box (flat-pixel 1x1 convolutions: up to 2); otherwise 1
   int bg;                  // K blocks per weight box: HALO -> taps of one chunk (1 / 3 / 9), TAP -> chunks of one tap
   int a_flat;              // 1: maps.a[0] is the 4-D flat-pixel view {64, pixels, plane, chunk} of a 1x1 stride-1 input
+  int csplit;              // 1: the two K slices of a tile (ksplit == 2) are the two CTAs of a CLUSTER; rank 1 hands its partial
+                           //    accumulator to rank 0 through distributed shared memory (no global scratch, no counters)
+  int x_off;               // csplit: byte offset of the exchange buffer [128 rows][x_pitch floats] in dynamic smem
+  int x_pitch;             // csplit: floats per exchange row (BN + 4: conflict-free 16-byte accesses with thread = row)
   int early_b;             // 1: the weight producer does not wait for the previous kernel of the stream (static weights)
   int a_split_off;         // a_sw64 == 2: byte offset of the 16-channel SWIZZLE_32B part inside an activation stage
   int a_sw64;              // 2: 33..48-channel cell sources as TWO boxes per tile, 32 channels SWIZZLE_64B + 16 channels
@@ -190,6 +194,43 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// ---- cluster (distributed shared memory) helpers for the cluster split-K
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope, bounded
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -634,7 +675,7 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 template <bool CELL, int PW, bool SPLIT>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, float* stage, int warp, int lane, const int bid,
-                                              const int nblk) {
+                                              const int nblk, uint32_t smem_x = 0, uint32_t xfull = 0) {
   const int quarter = warp & 3;       // TMEM lane quarter this warp may read
   const int half = warp >> 2;         // which pieces (even / odd) of the quarter this warp handles
   const int rows_per_img = p.BW * p.BH;
@@ -667,6 +708,47 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
     if (threadIdx.x == 0) STAMP(7);
     if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
+    // Cluster split-K (csplit; a launch is ONE wave: this CTA has exactly one work unit).  Rank 1 = the second K slice:
+    // its partial tile, already summed over the stacked halves, goes row by row (thread = row, 16-byte stores) into rank
+    // 0's exchange buffer through distributed shared memory, followed by one release-arrive per thread on rank 0's
+    // barrier; it then leaves.  Rank 0 waits for those 256 arrivals and adds the partner's values to its own accumulator
+    // columns as it reads them -- the rest of its epilogue is the ordinary one.
+    uint32_t xrow = 0;
+    if constexpr (!CELL && !SPLIT) {
+      if (p.csplit) {
+        const uint32_t rank = cluster_ctarank();
+        xrow = smem_x + (uint32_t)(quarter * 32 + lane) * (uint32_t)p.x_pitch * 4u;
+        if (rank != 0) {
+          const uint32_t xrow_remote = mapa_shared(xrow, 0);
+          for (int j = half; j < npc; j += 2) {
+            uint32_t r[PW];
+            tmem_ld_piece<PW>(taddr + PW * j, r);
+            if (p.stacked) {
+              uint32_t r2[PW];
+              tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            } else {
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int e = 0; e < PW; e += 4)
+              st_cluster_v4(xrow_remote + (uint32_t)(PW * j + e) * 4u, __uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                            __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          }
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * acc);
+          mbar_arrive_remote(mapa_shared(xfull, 0));
+          if (++acc == kAccStages) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+          continue;
+        }
+        mbar_wait_cluster(xfull, 0);  // (one work unit per CTA: phase 0)
+      }
+    }
     if constexpr (!SPLIT) {
       for (int j = half; j < npc; j += 2) {
         const int col0 = nt * p.BN + PW * j;
@@ -720,6 +802,21 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
         } else {
           tmem_ld_wait();
+        }
+        if constexpr (!CELL) {
+          if (p.csplit) {  // + the partner slice's partial (this thread's row of the exchange buffer)
+#pragma unroll
+            for (int e = 0; e < PW; e += 4) {
+              float4 q;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                           : "r"(xrow + (uint32_t)(PW * j + e) * 4u));
+              r[e] = __float_as_uint(__uint_as_float(r[e]) + q.x);
+              r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + q.y);
+              r[e + 2] = __float_as_uint(__uint_as_float(r[e + 2]) + q.z);
+              r[e + 3] = __float_as_uint(__uint_as_float(r[e + 3]) + q.w);
+            }
+          }
         }
 #pragma unroll
         for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
@@ -1308,6 +1405,10 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (!CELL && !SPLIT) {
+    // cluster split-K: the partner's barriers must be initialised before anything arrives on them remotely
+    if (p.csplit) cluster_sync_all();
+  }
   const uint32_t tmem_base = tmem_slot;
   // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail, and our own
   // dependents may start their prologue right away.  Each role waits for the previous kernel (griddepcontrol.wait) right
@@ -1638,7 +1739,8 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     if (CELL && !SPLIT && p.cell_rows) {
       cell_rows_epilogue(p, tmem_base, tfull0, tempty0, warp, lane, bid, nblk, EW / 4);
     } else if constexpr (PW != 0) {
-      epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk);
+      epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk, smem_a + (uint32_t)p.x_off,
+                                     pempty0);  // (pempty0: 256 arrivals, otherwise unused -- the exchange barrier)
     }
     // PW == 0 (grouped launch): row-wise epilogue only -- convlstm_cell_group_umma refuses to run without it, and
     // leaving the two staged-transpose variants out keeps ~4000 instructions out of the kernel
@@ -2033,6 +2135,7 @@ int g_halo_enabled = 1;    // RSIS_B200_HALO=0 disables HALO staging (debug / A-
 int g_early_b = 1;         // RSIS_B200_EARLY_B=0: weight boxes wait for the previous kernel even with static weights (A-B timing)
 int g_max_a_stages = 4;    // RSIS_B200_ASTAGES: most activation stages beside resident weights (cold halo boxes land ~2.5 us after issue)
 int g_plan_lo = 0;         // RSIS_B200_PLAN_LO=1: the planner charges the X_lo MMA of a stacked K step at N = BN
+int g_csplit = 0;          // RSIS_B200_CSPLIT=1: cluster split-K plans (two-CTA clusters, DSMEM reduction) may be chosen
 int g_sw64 = 1;            // RSIS_B200_SW64=0: 64-channel SWIZZLE_128B halo boxes for narrow sources too (A-B timing)
 int g_split_k = 1;         // RSIS_B200_SPLITK=0 disables split-K (debug / A-B timing)
 int g_force_bn = 0;        // RSIS_B200_BN forces the output-channel tile width (debug)
@@ -2066,6 +2169,7 @@ cudaError_t set_smem_attr() {
 void init_once() {
   if (const char* e = getenv("RSIS_B200_HALO")) g_halo_enabled = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_SW64")) g_sw64 = atoi(e) != 0;
+  if (const char* e = getenv("RSIS_B200_CSPLIT")) g_csplit = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_PLAN_LO")) g_plan_lo = atoi(e) != 0;
   if (const char* e = getenv("RSIS_B200_ASTAGES")) g_max_a_stages = atoi(e) < 2 ? 2 : (atoi(e) > kMaxStages ? kMaxStages : atoi(e));
   if (const char* e = getenv("RSIS_B200_EARLY_B")) g_early_b = atoi(e) != 0;
@@ -2198,6 +2302,7 @@ constexpr size_t kWorkspaceBytes = kCounterBytes + kScratchFloats * sizeof(float
 struct Plan {
   int BN, stacked, ksplit, halo;
   long long cost;
+  int csplit = 0;  // 1: ksplit == 2 as a two-CTA cluster with a DSMEM reduction
 };
 
 // Cost of one tcgen05.mma (M = 128, K = 16, kind::f16, SS mode) in ns, from scripts/mma_probe.cu on B200
@@ -2268,6 +2373,23 @@ Plan make_plan(int m_tiles_halo, int m_tiles_tap, bool halo_ok, int cout, int ta
         if (cost < best.cost) best = Plan{BN, stacked, S, 1, (long long)cost};
       }
     }
+    // (d) cluster split-K (RSIS_B200_CSPLIT=1): the two K halves of a tile on the two CTAs of a cluster, the second half's
+    // partial tile handed over through distributed shared memory (~1.2 us) instead of the L2 scratch + counters of (b) /
+    // (c) (~4.5 us).  For the 16-pixel-tile layers: a wide tile (less shared-memory traffic per output) on all SMs.
+    if (g_csplit && !cell && !single && stacked && BN >= 64 && (halo_ok || taps == 1)) {
+      const double tiles = (double)(halo_ok ? m_tiles_halo : m_tiles_tap) * tiles_n;
+      const bool even = halo_ok ? (chunks % 2 == 0) : (chunks % 4 == 0);
+      if (2 * tiles <= g_num_sms && even && ksteps_tile >= 32 && last_ksteps == kBK / 16) {
+        const double bytes_tile = (halo_ok ? chunks * 2.0 * kHaloRows * 128 : items * 32768.0) + items * b_item;
+        const double mma_tile = ksteps_tile * mpk * kMma;
+        const double tile_t = mma_tile > bytes_tile / kSmBw ? mma_tile : bytes_tile / kSmBw;
+        const double cost = kFixed + tile_t / 2 + 1200 + epi_tile;
+        if (best.cost < 0 || cost < best.cost) {
+          best = Plan{BN, stacked, 2, halo_ok ? 1 : 0, (long long)cost};
+          best.csplit = 1;
+        }
+      }
+    }
     // (b) split-K over (tap, chunk) items, TAP staging, single wave
     if (can_split && g_split_k) {
       const double tiles = (double)m_tiles_tap * tiles_n;
@@ -2330,13 +2452,16 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
             (int)((plan.halo ? mt_halo : mt_tap) * ceil_div(w->cout, plan.BN)) * plan.ksplit);
 #endif
   if (g_print_plan)
-    fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d halo=%d est %lld ns\n",
+    fprintf(stderr, "rsis plan: N=%d %dx%d cin=%d cout=%d k=%d s=%d%s -> BN=%d stacked=%d ksplit=%d%s halo=%d est %lld ns\n",
             x.n, x.h, x.w, x.c, w->cout, w->kh, stride, w->gate_interleaved ? " cell/gates" : "", plan.BN, plan.stacked,
-            plan.ksplit, plan.halo, plan.cost);
+            plan.ksplit, plan.csplit ? " (cluster)" : "", plan.halo, plan.cost);
   p.BN = plan.BN;
   p.stacked = plan.stacked;
   p.ksplit = plan.ksplit;
   p.halo = plan.halo;
+  p.csplit = plan.csplit;
+  p.x_off = 0;
+  p.x_pitch = plan.BN + 4;
   if (p.halo) {
     p.BW = kHaloBW;
     p.BH = kHaloBH;
@@ -2358,7 +2483,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   p.dh = make_fastdiv(p.tiles_h);
   p.dks = make_fastdiv(p.ksplit);
   if (can_split && getenv("RSIS_B200_DEBUG_TIMING")) g_debug_counters = reinterpret_cast<unsigned*>(workspace);
-  if (p.ksplit > 1 || (can_split && getenv("RSIS_B200_DEBUG_TIMING"))) {
+  if ((p.ksplit > 1 && !p.csplit) || (can_split && getenv("RSIS_B200_DEBUG_TIMING"))) {
     p.counters = reinterpret_cast<unsigned*>(workspace);
     p.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
   }
@@ -2386,7 +2511,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   // K blocks per TMA box (see UmmaParams::ag).  Split-K slices cut the walk anywhere, so they keep one block per box.
   p.ag = p.bg = 1;
   p.a_flat = 0;
-  if (g_box_group && p.ksplit == 1) {
+  if (g_box_group && (p.ksplit == 1 || p.csplit)) {  // (the cluster split cuts the walk at a box boundary)
     if (p.halo) {
       p.bg = 3 * p.b_chunk_bytes <= 49152 ? 3 : 1;
     } else {
@@ -2411,7 +2536,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   // the row-wise cell epilogue needs no transpose staging area: its 33 KB go to the operand rings (a third activation
   // stage on the narrow levels, whose 46 KB halo boxes take ~2.5 us from issue to landing: profiles/r2l_group_stamps.txt)
   const bool rows_epi = is_cell && g_cell_rows && p.ksplit == 1;  // (a hoisted-gate CONVOLUTION also has gate-interleaved weights)
-  const int budget = kDynSmem - 1023 - (p.pre_tma ? 2 * p.p_stage_bytes : (rows_epi ? 0 : kStageBytes));
+  const int x_bytes = p.csplit ? kBM * p.x_pitch * 4 : 0;  // exchange buffer of the cluster split-K
+  const int budget = kDynSmem - 1023 - (p.pre_tma ? 2 * p.p_stage_bytes : (rows_epi ? 0 : kStageBytes)) - x_bytes;
   {
     // Weight residency: a persistent CTA that walks several pixel tiles of ONE output-channel tile re-reads the same
     // taps x chunks weight blocks for every tile; when they all fit next to two activation stages, load them once.
@@ -2462,6 +2588,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     else break;
   }
   if (p.a_sw64 == 2 && !(p.b_resident && p.a_stages >= 2)) return RSIS_ERR_UNSUPPORTED;  // (chosen only where this holds)
+  p.x_off = round_up(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes + kStageBytes, 16);
   p.agroups = p.halo ? 1 : ceil_div(p.chunks, p.ag);
   p.a_tx_bytes = p.a_sw64 == 2 ? (uint32_t)(2 * kHaloRows * (64 + 32)) : (uint32_t)(p.ag * planes * p.a_plane_bytes);
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
@@ -2511,17 +2638,28 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
 }
 
 template <bool CELL, int PW, bool SPLIT>
-cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cudaStream_t st, int cluster = 1) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsUmma);
   cfg.dynamicSmemBytes = kDynSmem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {  // cluster split-K: CTAs 2c and 2c + 1 are the two K slices of tile c
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CELL, PW, SPLIT>, maps, p);
 }
 
@@ -2534,7 +2672,9 @@ int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   // a split-K launch needs all its slices co-resident; a plain persistent launch walks its tiles with any grid
   if (CELL && t_cta_cap > 0 && p.ksplit == 1 && grid > t_cta_cap) grid = t_cta_cap;
   cudaError_t e;
-  if (p.ksplit > 1)
+  if (p.csplit)  // one wave, every CTA one (tile, K half): the ordinary kernel with a cluster attribute
+    e = p.pw == 32 ? launch_one<CELL, 32, false>(maps, p, work, st, 2) : launch_one<CELL, 16, false>(maps, p, work, st, 2);
+  else if (p.ksplit > 1)
     e = p.pw == 32 ? launch_one<CELL, 32, true>(maps, p, grid, st) : launch_one<CELL, 16, true>(maps, p, grid, st);
   else
     e = p.pw == 32 ? launch_one<CELL, 32, false>(maps, p, grid, st) : launch_one<CELL, 16, false>(maps, p, grid, st);
