@@ -107,7 +107,8 @@ struct UmmaParams {
   int a_flat;              // 1: maps.a[0] is the 4-D flat-pixel view {64, pixels, plane, chunk} of a 1x1 stride-1 input
   int csplit;              // 1: the two K slices of a tile (ksplit == 2) are the two CTAs of a CLUSTER; rank 1 hands its partial
                            //    accumulator to rank 0 through distributed shared memory (no global scratch, no counters)
-  int x_off;               // csplit: byte offset of the exchange buffer [128 rows][x_pitch floats] in dynamic smem
+  int x_off;               // csplit: byte offset of the exchange buffer [128 rows][x_pitch floats] in dynamic smem (0: it
+                           //    reuses rank 0's operand stages, which are dead once rank 0's accumulator is complete)
   int x_pitch;             // csplit: floats per exchange row (BN + 4: conflict-free 16-byte accesses with thread = row)
   int early_b;             // 1: the weight producer does not wait for the previous kernel of the stream (static weights)
   int a_split_off;         // a_sw64 == 2: byte offset of the 16-channel SWIZZLE_32B part inside an activation stage
@@ -672,7 +673,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 // Epilogue warps: accumulator pieces (32 rows x PW columns) -> staged transpose -> finish.  With split-K the CTA first
 // parks its partial accumulator in the L2-resident scratch (TMEM-native order: for a fixed column the 32 lanes of a
 // warp write 32 consecutive floats), waits for the other K slices of its tile, then reduces and finishes its share.
-template <bool CELL, int PW, bool SPLIT>
+template <bool CELL, int PW, bool SPLIT, bool CS = false>  // CS: the cluster split-K variant (its own instantiations: the
+                                                           // extra epilogue costs the ordinary kernels registers)
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem_base, uint32_t tfull0,
                                               uint32_t tempty0, float* stage, int warp, int lane, const int bid,
                                               const int nblk, uint32_t smem_x = 0, uint32_t xfull = 0) {
@@ -708,45 +710,92 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
     if (threadIdx.x == 0) STAMP(7);
     if (threadIdx.x == 0) STAMP_T(3, (work - bid) / nblk);
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kStageCols;
-    // Cluster split-K (csplit; a launch is ONE wave: this CTA has exactly one work unit).  Rank 1 = the second K slice:
-    // its partial tile, already summed over the stacked halves, goes row by row (thread = row, 16-byte stores) into rank
-    // 0's exchange buffer through distributed shared memory, followed by one release-arrive per thread on rank 0's
-    // barrier; it then leaves.  Rank 0 waits for those 256 arrivals and adds the partner's values to its own accumulator
-    // columns as it reads them -- the rest of its epilogue is the ordinary one.
-    uint32_t xrow = 0;
-    if constexpr (!CELL && !SPLIT) {
-      if (p.csplit) {
-        const uint32_t rank = cluster_ctarank();
-        xrow = smem_x + (uint32_t)(quarter * 32 + lane) * (uint32_t)p.x_pitch * 4u;
-        if (rank != 0) {
-          const uint32_t xrow_remote = mapa_shared(xrow, 0);
-          for (int j = half; j < npc; j += 2) {
-            uint32_t r[PW];
-            tmem_ld_piece<PW>(taddr + PW * j, r);
-            if (p.stacked) {
-              uint32_t r2[PW];
-              tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
-              tmem_ld_wait();
+    // Cluster split-K (csplit; a launch is ONE wave: this CTA has exactly one work unit = one K half of a tile).  The two
+    // CTAs of the cluster split the tile's OUTPUT columns too: rank r finishes pieces [r * npc / 2, (r + 1) * npc / 2).
+    // Each thread (a) tells the partner that this CTA's MMAs are done -- the exchange buffer lies on the operand stages --
+    // (b) once the partner has said the same, writes its partial sums of the PARTNER's pieces, already summed over the
+    // stacked halves, row by row (thread = row, 16-byte stores) into the partner's buffer through distributed shared
+    // memory, (c) release-arrives on the partner's barrier, (d) waits for the partner's 256 arrivals and finishes its own
+    // pieces with the partner's partial sums added.  No scratch in L2, no counters, and the epilogue work is halved.
+    if constexpr (CS && !CELL && !SPLIT) {
+      {
+        const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
+        const uint32_t xrow = smem_x + (uint32_t)(quarter * 32 + lane) * (uint32_t)p.x_pitch * 4u;
+        const uint32_t xrow_remote = mapa_shared(xrow, peer);
+        const int own0 = (int)rank * (npc >> 1), own1 = own0 + (npc >> 1);  // npc is even (BN >= 64)
+        mbar_arrive_remote(mapa_shared(xfull + 8, peer));  // (a) my operand stages are dead
+        mbar_wait_cluster(xfull + 8, 0);                    // (b) ... and so are the partner's
+        for (int j = half; j < npc; j += 2) {
+          if (j >= own0 && j < own1) continue;
+          uint32_t r[PW];
+          tmem_ld_piece<PW>(taddr + PW * j, r);
+          if (p.stacked) {
+            uint32_t r2[PW];
+            tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
+            tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
-            } else {
-              tmem_ld_wait();
-            }
+            for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+          } else {
+            tmem_ld_wait();
+          }
 #pragma unroll
-            for (int e = 0; e < PW; e += 4)
-              st_cluster_v4(xrow_remote + (uint32_t)(PW * j + e) * 4u, __uint_as_float(r[e]), __uint_as_float(r[e + 1]),
-                            __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-          }
-          tc_fence_before();
-          mbar_arrive(tempty0 + 8 * acc);
-          mbar_arrive_remote(mapa_shared(xfull, 0));
-          if (++acc == kAccStages) {
-            acc = 0;
-            acc_phase ^= 1u;
-          }
-          continue;
+          for (int e = 0; e < PW; e += 4)
+            st_cluster_v4(xrow_remote + (uint32_t)(PW * j + e) * 4u, __uint_as_float(r[e]), __uint_as_float(r[e + 1]),
+                          __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
         }
-        mbar_wait_cluster(xfull, 0);  // (one work unit per CTA: phase 0)
+        mbar_arrive_remote(mapa_shared(xfull, peer));       // (c)
+        bool have_partner = false;
+        for (int j = half; j < npc; j += 2) {
+          if (j < own0 || j >= own1) continue;
+          const int col0 = nt * p.BN + PW * j;
+          if (col0 >= p.Cout) break;
+          ResPiece<PW> rp;
+          if (p.has_res) res_prefetch<PW>(p, rp, lane, mypix, col0);
+          float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
+          const int colq = col0 + 4 * (lane % (PW / 4));
+          if (colq < p.Cout) {
+            sc4 = __ldg(reinterpret_cast<const float4*>(p.scale + colq));
+            sh4 = __ldg(reinterpret_cast<const float4*>(p.shift + colq));
+          }
+          uint32_t r[PW];
+          tmem_ld_piece<PW>(taddr + PW * j, r);
+          if (p.stacked) {
+            uint32_t r2[PW];
+            tmem_ld_piece<PW>(taddr + p.BN + PW * j, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+          } else {
+            tmem_ld_wait();
+          }
+          if (!have_partner) {
+            mbar_wait_cluster(xfull, 0);                    // (d)
+            have_partner = true;
+          }
+#pragma unroll
+          for (int e = 0; e < PW; e += 4) {
+            float4 q;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                         : "r"(xrow + (uint32_t)(PW * j + e) * 4u));
+            r[e] = __float_as_uint(__uint_as_float(r[e]) + q.x);
+            r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + q.y);
+            r[e + 2] = __float_as_uint(__uint_as_float(r[e + 2]) + q.z);
+            r[e + 3] = __float_as_uint(__uint_as_float(r[e + 3]) + q.w);
+          }
+#pragma unroll
+          for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
+          __syncwarp();
+          conv_finish_piece<PW>(p, stage, lane, mypix, col0, rp, sc4, sh4);
+          __syncwarp();
+        }
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
       }
     }
     if constexpr (!SPLIT) {
@@ -802,21 +851,6 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, uint32_t tmem
           for (int e = 0; e < PW; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
         } else {
           tmem_ld_wait();
-        }
-        if constexpr (!CELL) {
-          if (p.csplit) {  // + the partner slice's partial (this thread's row of the exchange buffer)
-#pragma unroll
-            for (int e = 0; e < PW; e += 4) {
-              float4 q;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
-                           : "r"(xrow + (uint32_t)(PW * j + e) * 4u));
-              r[e] = __float_as_uint(__uint_as_float(r[e]) + q.x);
-              r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + q.y);
-              r[e + 2] = __float_as_uint(__uint_as_float(r[e + 2]) + q.z);
-              r[e + 3] = __float_as_uint(__uint_as_float(r[e + 3]) + q.w);
-            }
-          }
         }
 #pragma unroll
         for (int e = 0; e < PW; ++e) stage[lane * kStagePitch + e] = __uint_as_float(r[e]);
@@ -1342,7 +1376,8 @@ __device__ __forceinline__ void cell_rows_epilogue(const UmmaParams& p, uint32_t
 // The whole CTA program.  `bid` / `nblk`: this CTA's index among the `nblk` CTAs that share the problem `p` (the whole
 // grid for a plain launch; a contiguous CTA range of a grouped launch, cell_group_kernel).  PW = 0: the epilogue piece
 // width is taken from p.pw at run time (grouped launches mix levels that want 16 and 32).
-template <bool CELL, int PW, bool SPLIT, int EW = kEpiWarps>  // EW epilogue warps (then A producer, MMA issuer, B producer)
+template <bool CELL, int PW, bool SPLIT, int EW = kEpiWarps, bool CS = false>  // EW epilogue warps (then A producer, MMA issuer,
+                                                                                // B producer); CS: cluster split-K
 __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams& p, const int bid, const int nblk) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[4 * kMaxStages + 2 * kAccStages + 4];
@@ -1405,10 +1440,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if constexpr (!CELL && !SPLIT) {
-    // cluster split-K: the partner's barriers must be initialised before anything arrives on them remotely
-    if (p.csplit) cluster_sync_all();
-  }
+  if constexpr (CS) cluster_sync_all();  // the partner's barriers must be initialised before anything arrives on them
   const uint32_t tmem_base = tmem_slot;
   // PDL: everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail, and our own
   // dependents may start their prologue right away.  Each role waits for the previous kernel (griddepcontrol.wait) right
@@ -1739,7 +1771,7 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
     if (CELL && !SPLIT && p.cell_rows) {
       cell_rows_epilogue(p, tmem_base, tfull0, tempty0, warp, lane, bid, nblk, EW / 4);
     } else if constexpr (PW != 0) {
-      epilogue_role<CELL, PW, SPLIT>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk, smem_a + (uint32_t)p.x_off,
+      epilogue_role<CELL, PW, SPLIT, CS>(p, tmem_base, tfull0, tempty0, stage, warp, lane, bid, nblk, smem_a + (uint32_t)p.x_off,
                                      pempty0);  // (pempty0: 256 arrivals, otherwise unused -- the exchange barrier)
     }
     // PW == 0 (grouped launch): row-wise epilogue only -- convlstm_cell_group_umma refuses to run without it, and
@@ -1757,13 +1789,13 @@ __device__ __forceinline__ void umma_cta(const UmmaMaps& maps, const UmmaParams&
 
 // One instantiation per (epilogue kind, piece width, split-K or not): each carries a single epilogue variant, which
 // keeps the 11 differently-specialised warps of a CTA inside the instruction cache.
-template <bool CELL, int PW, bool SPLIT>
+template <bool CELL, int PW, bool SPLIT, bool CS = false>
 __global__ void __launch_bounds__(kThreadsUmma, 1)
 conv_umma_kernel(const __grid_constant__ UmmaMaps maps, const UmmaParams p) {
 #ifdef RSIS_DEBUG_TIMING
   trace_begin(p);
 #endif
-  umma_cta<CELL, PW, SPLIT>(maps, p, (int)blockIdx.x, (int)gridDim.x);
+  umma_cta<CELL, PW, SPLIT, kEpiWarps, CS>(maps, p, (int)blockIdx.x, (int)gridDim.x);
 #ifdef RSIS_DEBUG_TIMING
   trace_end(p);
 #endif
@@ -2161,9 +2193,9 @@ std::once_flag g_once;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kDynSmem = kSmemLimit - 1024;  // static barriers live beside it
 
-template <bool CELL, int PW, bool SPLIT>
+template <bool CELL, int PW, bool SPLIT, bool CS = false>
 cudaError_t set_smem_attr() {
-  return cudaFuncSetAttribute(conv_umma_kernel<CELL, PW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
+  return cudaFuncSetAttribute(conv_umma_kernel<CELL, PW, SPLIT, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
 }
 
 void init_once() {
@@ -2201,6 +2233,7 @@ void init_once() {
       (e = set_smem_attr<false, 16, false>()) != cudaSuccess || (e = set_smem_attr<false, 16, true>()) != cudaSuccess ||
       (e = set_smem_attr<true, 32, false>()) != cudaSuccess || (e = set_smem_attr<true, 32, true>()) != cudaSuccess ||
       (e = set_smem_attr<true, 16, false>()) != cudaSuccess || (e = set_smem_attr<true, 16, true>()) != cudaSuccess ||
+      (e = set_smem_attr<false, 32, false, true>()) != cudaSuccess || (e = set_smem_attr<false, 16, false, true>()) != cudaSuccess ||
       (e = cudaFuncSetAttribute(cell_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
           cudaSuccess ||
       (e = cudaFuncSetAttribute(cell_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem)) !=
@@ -2536,7 +2569,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   // the row-wise cell epilogue needs no transpose staging area: its 33 KB go to the operand rings (a third activation
   // stage on the narrow levels, whose 46 KB halo boxes take ~2.5 us from issue to landing: profiles/r2l_group_stamps.txt)
   const bool rows_epi = is_cell && g_cell_rows && p.ksplit == 1;  // (a hoisted-gate CONVOLUTION also has gate-interleaved weights)
-  const int x_bytes = p.csplit ? kBM * p.x_pitch * 4 : 0;  // exchange buffer of the cluster split-K
+  const int x_bytes = 0;  // (the cluster split-K's exchange buffer, 128 x (BN + 4) floats, reuses the dead operand stages)
   const int budget = kDynSmem - 1023 - (p.pre_tma ? 2 * p.p_stage_bytes : (rows_epi ? 0 : kStageBytes)) - x_bytes;
   {
     // Weight residency: a persistent CTA that walks several pixel tiles of ONE output-channel tile re-reads the same
@@ -2588,7 +2621,8 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
     else break;
   }
   if (p.a_sw64 == 2 && !(p.b_resident && p.a_stages >= 2)) return RSIS_ERR_UNSUPPORTED;  // (chosen only where this holds)
-  p.x_off = round_up(p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes + kStageBytes, 16);
+  p.x_off = 0;  // start of the activation ring
+  if (p.csplit && kBM * p.x_pitch * 4 > p.a_stages * p.a_stage_bytes + p.b_stages * p.b_stage_bytes) return RSIS_ERR_UNSUPPORTED;
   p.agroups = p.halo ? 1 : ceil_div(p.chunks, p.ag);
   p.a_tx_bytes = p.a_sw64 == 2 ? (uint32_t)(2 * kHaloRows * (64 + 32)) : (uint32_t)(p.ag * planes * p.a_plane_bytes);
   p.b_tx_bytes = (uint32_t)p.b_stage_bytes;
@@ -2637,7 +2671,7 @@ int setup(UmmaMaps& maps, UmmaParams& p, const rsis_tensor& x, const rsis_conv_w
   return RSIS_OK;
 }
 
-template <bool CELL, int PW, bool SPLIT>
+template <bool CELL, int PW, bool SPLIT, bool CS = false>
 cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cudaStream_t st, int cluster = 1) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -2660,7 +2694,7 @@ cudaError_t launch_one(const UmmaMaps& maps, const UmmaParams& p, int grid, cuda
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CELL, PW, SPLIT>, maps, p);
+  return cudaLaunchKernelEx(&cfg, conv_umma_kernel<CELL, PW, SPLIT, CS>, maps, p);
 }
 
 thread_local int t_cta_cap = 0;  // > 0: at most this many CTAs for the next cell launch (set by convlstm_cell_umma)
@@ -2673,7 +2707,8 @@ int launch(const UmmaMaps& maps, const UmmaParams& p, cudaStream_t st) {
   if (CELL && t_cta_cap > 0 && p.ksplit == 1 && grid > t_cta_cap) grid = t_cta_cap;
   cudaError_t e;
   if (p.csplit)  // one wave, every CTA one (tile, K half): the ordinary kernel with a cluster attribute
-    e = p.pw == 32 ? launch_one<CELL, 32, false>(maps, p, work, st, 2) : launch_one<CELL, 16, false>(maps, p, work, st, 2);
+    e = p.pw == 32 ? launch_one<false, 32, false, true>(maps, p, work, st, 2)
+                   : launch_one<false, 16, false, true>(maps, p, work, st, 2);
   else if (p.ksplit > 1)
     e = p.pw == 32 ? launch_one<CELL, 32, true>(maps, p, grid, st) : launch_one<CELL, 16, true>(maps, p, grid, st);
   else
