@@ -3256,7 +3256,7 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
     // narrow gate blocks are bound by the shared-memory operand reads, not by the tensor pipe: 32 + N/4 vs N/2 cycles
     // (re-fitted after the three-warps-per-quarter epilogue and the narrow activation boxes: level 4 on 61 CTAs 42 us,
     // level 3 on 35 CTAs 40 us, profiles/r2by_group_tune.txt)
-    const double per_col = cols >= 128 ? 1.0 : (26.0 + 0.6 * cols) / cols;
+    const double per_col = cols >= 128 ? (cols == 256 ? 0.67 : 1.0) : (35.8 + 0.29 * cols) / cols;  // (fitted: r2bl, r2dd)
     work[i] = (double)tiles[i] * w->kh * w->kw * ceil_div(x.c, 16) * cols * per_col * 2.06e-3;  // ~us on one CTA
     const double w_bytes = 2.0 * w->kh * w->kw * ceil_div(x.c, kBK) * 128.0 * cols;              // [W_hi | W_lo] of a tile
     const double a_stage = x.c <= 32 ? 23552.0 : (x.c <= 48 ? 34816.0 : 46080.0 * ceil_div(x.c, kBK));
@@ -3300,6 +3300,9 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
         freed += share[i] - need[i];
         share[i] = need[i];
       }
+      int total = 0;
+      for (int i = 0; i < n; ++i) total += share[i];
+      freed = g_num_sms - total;  // (negative when (1a) rounded shares up)
       for (; freed > 0; --freed) {
         int best = -1;
         double worst = -1;
@@ -3311,7 +3314,74 @@ int convlstm_cell_group_umma(const rsis_cell_args* cells, int n, cudaStream_t st
         if (best < 0) break;
         ++share[best];
       }
+      for (; freed < 0; ++freed) {  // take back from the many-tile cell that finishes first
+        int best = -1;
+        double least = 1e300;
+        for (int i = 0; i < n; ++i) {
+          if (!big[i] || share[i] <= 1) continue;
+          const double t = fixed[i] + work[i] / share[i];
+          if (t < least) { least = t; best = i; }
+        }
+        if (best < 0) break;
+        --share[best];
+      }
     }
+  }
+  // (1c') a small cell's plan changes with its share: with 4 pixel tiles and 512 gate columns, 8 CTAs get 8 units of 256
+  // columns (a 21 us MMA chain and a 10 us epilogue each) where 16 CTAs get 16 units of 128 -- 46 -> 32 us for that cell
+  // alone, and 49 -> 35 us for the wavefront of levels 0-3 it was holding up (profiles/r2dd_group_tune_partial.txt).  When
+  // the cell that finishes last by the model (by a margin) is such a cell, it moves up to its next unit count and the
+  // cells that finish first pay for it.
+  for (int round = 0; round < 2; ++round) {
+    int m = -1, second = -1;
+    double tm = -1, ts = -1;
+    for (int i = 0; i < n; ++i) {
+      const double t = fixed[i] + work[i] / share[i];
+      if (t > tm) { ts = tm; second = m; tm = t; m = i; }
+      else if (t > ts) { ts = t; second = i; }
+    }
+    (void)second;
+    if (m < 0 || n < 2 || tm < 1.25 * ts) break;
+    const rsis_tensor& x = *cells[m].x;
+    const int tiles_px = ceil_div(x.n * x.h * x.w, kBM), cout = cells[m].w->cout;
+    int cand = 0;
+    for (int b = kMaxBN; b >= 32; b >>= 1) {
+      const int c = tiles_px * ceil_div(cout, b);
+      if (c > share[m] && c <= 2 * share[m] + 1 && c <= g_num_sms / 2) { cand = c; break; }
+    }
+    if (!cand) break;
+    int saved[kMaxGroup];
+    for (int i = 0; i < n; ++i) saved[i] = share[i];
+    int need_ctas = cand - share[m];
+    share[m] = cand;
+    while (need_ctas > 0) {  // from the cell that finishes first
+      int best = -1;
+      double least = 1e300;
+      for (int i = 0; i < n; ++i) {
+        if (i == m || share[i] <= 1) continue;
+        const double t = fixed[i] + work[i] / (share[i] - 1);
+        if (t < least) { least = t; best = i; }
+      }
+      if (best < 0) break;
+      --share[best];
+      --need_ctas;
+    }
+    double new_max = 0;
+    for (int i = 0; i < n; ++i) new_max = fmax(new_max, fixed[i] + work[i] / share[i]);
+    if (new_max > 0.85 * tm) {  // the others would pay as much as this cell gains: keep the shares
+      for (int i = 0; i < n; ++i) share[i] = saved[i];
+      break;
+    }
+  }
+  // (1c) never more CTAs than SMs (one wave): whatever was added beyond that comes back from the largest shares
+  for (;;) {
+    int total = 0, big_i = 0;
+    for (int i = 0; i < n; ++i) {
+      total += share[i];
+      if (share[i] > share[big_i]) big_i = i;
+    }
+    if (total <= g_num_sms || share[big_i] <= 1) break;
+    --share[big_i];
   }
   // tuning overrides (development): RSIS_B200_GROUP_SHARES / RSIS_B200_GROUP_BN = comma lists indexed by the cell's
   // position in the group
