@@ -20,7 +20,8 @@
 //   B  packed weights [2 planes][cout_pad][k_pad] bf16 (rsis_conv_pack_umma), one box {64, BN, 2} per (tap, chunk),
 //      in its own smem ring (decoupled from A's: in HALO mode one A stage feeds nine B stages).
 //   D  fp32 accumulators in TMEM, two stages of 128 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (three kind::f16 MMAs per 16-wide K step, fp32 accumulate): relative
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi (fp32 accumulate; for BN <= 128 as TWO MMAs per 16-wide K step: X_hi x [W_hi | W_lo]
+//   with N = 2 BN and X_lo x W_hi with N = BN; three MMAs of N = BN for BN = 256): relative
 //   product error ~2^-16, which keeps the 104-convolution encoder and the T-step recurrence inside the 1e-3 parity
 //   budget (single-pass fp16/bf16/tf32 operands do not: DESIGN.md "precision").
 //   K steps that only cover zero padding (channels beyond C in the last chunk) are not issued.
