@@ -149,6 +149,16 @@ class FeatureExtractor(nn.Module):
         return tuple(outs)
 
 
+def wavefront_schedule(T: int, nlev: int, skew: int):
+    """The decoder's (level, step) loop nest (test.py:37-44 x model.py:129-165) as wavefronts: entry w lists the cells
+    (l, t) that run together in grouped launch w.  Cell (l, t) needs (l, t-1) (its own state) and, through the x2
+    upsampling, (l-1, t).  skew = 1: wavefront l + t, the upsamplings sit between two launches; skew = 2: wavefront
+    2*l + t, the upsampling of (l-1, t) has wavefront 2*(l-1) + t + 1 to itself (a side stream beside that launch) and is
+    consumed one launch later.  Pure function (tests/test_schedule_cpu.py checks its hazards)."""
+    assert skew in (1, 2) and T >= 1 and nlev >= 1
+    return [[(l, w - skew * l) for l in range(nlev) if 0 <= w - skew * l < T] for w in range(T + skew * (nlev - 1))]
+
+
 class DecoderWorkspace:
     """Device buffers of the tcgen05 decoder for one (batch, feature-map sizes).
 
@@ -440,13 +450,11 @@ class RSIS(nn.Module):
                 ws.h2 = [[h, ops.Act.empty(h.n, h.h, h.w, h.c, ops.FMT_F32, dev)] for h in ws.h[:nlev - 1]]
                 ws.up_stream = torch.cuda.Stream(device=dev)
             ev_up = {}
-        n_waves = T + skew * (nlev - 1)
-        for w in range(n_waves):
+        waves = wavefront_schedule(T, nlev, skew)
+        n_waves = len(waves)
+        for w, wave in enumerate(waves):
             cells, ups = [], []
-            for l in range(nlev):
-                t = w - skew * l
-                if t < 0 or t >= T:
-                    continue
+            for l, t in wave:
                 p = t & 1
                 _, pc = ws.packs(self, l)
                 if l == nlev - 1:
@@ -465,7 +473,8 @@ class RSIS(nn.Module):
                 main.wait_event(ev_mask[t_last - 2])   # its mask head read the buffer cell (4, t_last) overwrites
             if skew == 2 and (w - 2) in ev_up:
                 main.wait_event(ev_up[w - 2])          # the upsamplings this wavefront's cells read
-            ops.convlstm_cell_group(cells)
+            if cells:   # (T = 1 on the skewed schedule: every other wavefront is empty)
+                ops.convlstm_cell_group(cells)
             if 0 <= t_last < T and not defer:
                 done = torch.cuda.Event()
                 done.record(main)

@@ -621,6 +621,19 @@ def test_full_length_passes_at_the_large_baseline_shapes_match_the_oracle(R, O, 
         assert rel(masks[:, t], rm[:, t]) < tol and rel(classes[:, t], rc[:, t]) < tol
 
 
+@pytest.mark.parametrize("T", [1, 2])
+def test_short_sequences_match_the_oracle(R, O, sw, impl, T):
+    """maxseqlen = 1 and 2: on the skewed wavefront schedule T = 1 leaves every other wavefront without a cell (found by
+    tests/test_schedule_cpu.py); the pass must still equal the oracle's loop (test.py:16-50)."""
+    args, enc, dec = _models(R, sw, 21, T)
+    x = sw.synthetic_images(77, 2, 128, 128)
+    masks, classes, stops = R.test(args, enc, dec, x.cuda())
+    rm, rc, rs_ = O.test_loop(sw.encoder_state_dict(1), sw.decoder_state_dict(1, num_classes=21), x, T)
+    tol = _tol(impl)
+    assert tuple(masks.shape) == (2, T, 128, 128)
+    assert rel(masks, rm) < tol and rel(classes, rc) < tol and rel(stops, rs_) < tol
+
+
 # ---------------------------------------------------------------------------------------------------------
 # error behaviour across the ABI
 # ---------------------------------------------------------------------------------------------------------
