@@ -510,6 +510,8 @@ class RSIS(nn.Module):
                 ops.class_stop_heads_steps(ws.sides[:T], self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight,
                                            self.fc_stop.bias, class_probs, T * C, C, stop_prob, T, 1)
             src = ws.h_last_all
+            if src.n != T * hl.n:   # the workspace was sized for a longer sequence: the first T steps of the buffer
+                src = ops.Act(src.t[:T * hl.n], ops.FMT_F32)
             ops.upsample_mask_head_steps(src, T, 2 * src.h, 2 * src.w, self.conv_out.weight, self.conv_out.bias,
                                          mask_prob, T * H * W, H * W)
         if not defer:

@@ -634,6 +634,32 @@ def test_short_sequences_match_the_oracle(R, O, sw, impl, T):
     assert rel(masks, rm) < tol and rel(classes, rc) < tol and rel(stops, rs_) < tol
 
 
+def test_decoder_workspace_reused_for_a_shorter_sequence(R, sw):
+    """One DecoderWorkspace, first T = 4, then T = 2 (the all-steps heads read a prefix of the per-step hidden-state buffer
+    that was sized for the longer sequence): the second pass equals a pass on a fresh workspace bit for bit."""
+    from rsis_b200 import inference, ops
+    if not ops.has_tcgen05():
+        pytest.skip("library built without tcgen05 kernels")
+    impl = ops.default_impl()
+    args, enc, dec = _models(R, sw, 21, 4)
+    x = sw.synthetic_images(55, 2, 128, 128).cuda()
+
+    def run(T, ws):
+        m = torch.zeros((2, T, 128, 128), device="cuda")
+        c = torch.zeros((2, T, 21), device="cuda")
+        s_ = torch.zeros((2, T, 1), device="cuda")
+        with torch.no_grad():
+            ws = inference.run_eager(enc, dec, x, T, impl, m, c, s_, ws=ws)
+        torch.cuda.synchronize()
+        return (m, c, s_), ws
+
+    _, ws = run(4, None)
+    second, _ = run(2, ws)
+    fresh, _ = run(2, None)
+    for a, b in zip(second, fresh):
+        assert torch.equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # error behaviour across the ABI
 # ---------------------------------------------------------------------------------------------------------
