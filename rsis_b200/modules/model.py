@@ -405,6 +405,74 @@ class RSIS(nn.Module):
 
     def run_wavefront(self, ws: DecoderWorkspace, impl: int, T: int, class_probs: torch.Tensor,
                       mask_prob: torch.Tensor, stop_prob: torch.Tensor):
+        """All T decoder steps as GROUPED launches: the independent cells of one wavefront of the (level, step) loop nest
+        (model.py:132-153: cell (l, t) needs (l-1, t) through the upsampling and (l, t-1) through its own state; see
+        `wavefront_schedule`) run in ONE kernel launch (`ops.convlstm_cell_group`), so the small levels no longer pay a
+        launch each -- they share the chip with the large ones.
+        Default (skew 2, heads deferred): cell (l, t) in wavefront 2 l + t; the x2 upsamplings of a wavefront's hidden
+        states run on a side stream beside the NEXT grouped launch and are consumed by the one after; the mask head
+        (fused upsample + conv_out + sigmoid) and the class / stop heads of all T steps run as one launch each after the
+        last wavefront.  Per pass at T = 10: 18 + 16 + 2 launches (the sequential schedule: 120).
+        RSIS_B200_WAVE_SKEW=1 / RSIS_B200_DEFER_HEADS=0 restore the first form: wavefront l + t, one upsample launch
+        between two grouped launches, heads on side streams beside the following wavefronts (the last level's hidden state
+        double-buffered for them).  Requires ws.reset() before."""
+        nlev = len(self.clstm_list)
+        hl = ws.h[nlev - 1]
+        assert hl.c % 4 == 0 and hl.c <= 16 and ws.t == 0
+        ws.prepare_pipeline(T)
+        dev = hl.t.device
+        main = torch.cuda.current_stream(dev)
+        B, _, H, W = mask_prob.shape
+        C = class_probs.shape[-1]
+        streams = list(ws.level_streams) + [ws.mask_stream, ws.side_stream]
+        start = torch.cuda.Event()
+        start.record(main)
+        for s_ in streams:
+            s_.wait_event(start)
+        ev_cell, ev_up, ev_mask = {}, {}, {}
+        offs = [sum(ws.hidden[:l]) for l in range(nlev)]
+        for t in range(T):
+            p = t & 1
+            for l in range(nlev):
+                S = ws.level_streams[l]
+                with torch.cuda.stream(S), _lib.lane(2 + l):
+                    x = ws.X[l][p]
+                    if l > 0:
+                        S.wait_event(ev_cell[(l - 1, t)])
+                        ops.upsample_bilinear(ws.h[l - 1], x.h, x.w, out=ws.up_view(l, p))
+                        ev_up[(l, t)] = torch.cuda.Event()
+                        ev_up[(l, t)].record(S)
+                    if t > 0:  # the readers of the h[l] this cell is about to overwrite
+                        S.wait_event(ev_up[(l + 1, t - 1)] if l + 1 < nlev else ev_mask[t - 1])
+                    _, pc = ws.packs(self, l)
+                    cap = int(cta_caps[l]) if cta_caps is not None else 0
+                    if split_k if isinstance(split_k, bool) else bool(split_k[l]):
+                        ops.convlstm_cell_x(x, pc, ws.c[l].t if t > 0 else None, ws.sides[t], offs[l], h_out=ws.h[l],
+                                            c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p), impl=impl, gate_preact=ws.P[l])
+                    else:
+                        with _lib.no_splitk():
+                            ops.convlstm_cell_x(x, pc, ws.c[l].t if t > 0 else None, ws.sides[t], offs[l],
+                                                h_out=ws.h[l], c_out=ws.c[l], h16_out=ws.h_view(l, 1 - p), impl=impl,
+                                                gate_preact=ws.P[l], cta_cap=cap)
+                    ev_cell[(l, t)] = torch.cuda.Event()
+                    ev_cell[(l, t)].record(S)
+            with torch.cuda.stream(ws.mask_stream):
+                ws.mask_stream.wait_event(ev_cell[(nlev - 1, t)])
+                ops.upsample_mask_head(hl, 2 * hl.h, 2 * hl.w, self.conv_out.weight, self.conv_out.bias, None,
+                                       mask_prob[:, t], T * H * W)
+                ev_mask[t] = torch.cuda.Event()
+                ev_mask[t].record(ws.mask_stream)
+            with torch.cuda.stream(ws.side_stream):
+                for l in range(nlev):
+                    ws.side_stream.wait_event(ev_cell[(l, t)])
+                ops.class_stop_heads(ws.sides[t], self.fc_class.weight, self.fc_class.bias, self.fc_stop.weight,
+                                     self.fc_stop.bias, class_probs[:, t], T * C, None, stop_prob[:, t], T)
+        for s_ in streams:
+            main.wait_stream(s_)
+        ws.t = T
+
+    def run_wavefront(self, ws: DecoderWorkspace, impl: int, T: int, class_probs: torch.Tensor,
+                      mask_prob: torch.Tensor, stop_prob: torch.Tensor):
         """All T decoder steps as T + 4 GROUPED launches: wavefront w runs the independent cells {(l, t) : l + t = w}
         (model.py:132-153: cell (l, t) needs (l-1, t) through the upsampling and (l, t-1) through its own state) in ONE
         kernel launch (`ops.convlstm_cell_group`), followed by ONE launch with the x2 upsamplings that feed the next
